@@ -1,0 +1,431 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the `hulk sketch` hot path on B200 (contract: see the task statement).
+
+Workload (BASELINE.json configs[1], "C2"): synthetic 150 bp reads, k=21, w=9, sketch size 512,
+one sketch interval of 100 000 reads per step; `--steps 100` is the whole 10 M-read job.
+A step = minimizer/histogram kernel over the interval's reads + the flush (count-min + CWS sweep).
+
+  value   reads/s with the reads already resident in HBM (device timed, CUDA events on the launch stream)
+  e2e     reads/s through the C ABI with HOST (pinned) input buffers: every step copies its reads
+          host->device and the sketch (mins, weights) device->host inside the timed region
+  --impl reference   the CPU oracle (restatement of the Go reference; no Go toolchain exists here)
+          timed on the host cores with the same metric/config on a bounded sample per step
+
+N > 1 (torchrun, one process per GPU): every rank sketches its own `interval` reads per step, the
+uint32 histograms are NCCL-all-reduced, each rank sweeps its s/N sketch slots (weak scaling in reads).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "reads/sec (150 bp, k=21, s=512)"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--k", type=int, default=21)
+    ap.add_argument("--w", type=int, default=9)
+    ap.add_argument("--s", type=int, default=512)
+    ap.add_argument("--interval", type=int, default=100_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--decay", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": "C2: synthetic %d bp reads, k=%d, w=%d, sketch-size %d, interval=%d reads/step, decay=%g"
+                    % (a.read_len, a.k, a.w, a.s, a.interval, a.decay),
+        "k": a.k, "w": a.w, "sketch_size": a.s, "num_bins": a.k ** 4, "interval_reads": a.interval,
+        "read_len": a.read_len, "decay_ratio": a.decay, "reads_per_step_total": a.interval * n_gpus,
+        "parallelism": "reads sharded over %d GPU(s); histogram all-reduce; CWS slots sharded" % n_gpus
+                       if n_gpus > 1 else "single GPU",
+        "l2_policy": "inputs larger than L2: each step reads fresh reads and streams the %.0f MB CWS table"
+                     % (4.0 * a.s * a.k ** 4 / n_gpus / 1e6),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data on the device (same definition as hulk_b200.seqio.synthetic_reads / BASELINE.md section 3)
+# ------------------------------------------------------------------------------------------------
+def synthetic_reads_torch(torch, n_reads, read_len, seed, first_read, device):
+    wpr = (read_len + 31) // 32
+
+    def lsr(x, n):   # logical shift right on int64
+        return (x >> n) & ((1 << (64 - n)) - 1)
+
+    def c64(v):      # python int -> wrapped int64
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >> 63 else v
+
+    idx = (torch.arange(first_read, first_read + n_reads, dtype=torch.int64, device=device)[:, None] * wpr
+           + torch.arange(wpr, dtype=torch.int64, device=device)[None, :])
+    x = (idx ^ seed) + c64(0x9E3779B97F4A7C15)
+    z = x
+    z = (z ^ lsr(z, 30)) * c64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    shifts = (torch.arange(32, dtype=torch.int64, device=device) * 2)[None, None, :]
+    codes = ((z[:, :, None] >> shifts) & 3).reshape(n_reads, wpr * 32)[:, :read_len]
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    return lut[codes].contiguous()
+
+
+def synthetic_tables_torch(torch, rows, D, seed, device):
+    """Random CWS tables with the reference's distributions (r, exp(c) ~ Gamma(2,1); b = U(0,1)*r)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def gamma2(shape):   # Gamma(2,1) = -ln(U1*U2)
+        u = torch.rand(shape, dtype=torch.float64, device=device, generator=g).clamp_min(1e-300)
+        v = torch.rand(shape, dtype=torch.float64, device=device, generator=g).clamp_min(1e-300)
+        return -(torch.log(u) + torch.log(v))
+
+    r = gamma2((rows, D))
+    c = torch.log(gamma2((rows, D)))
+    b = torch.rand((rows, D), dtype=torch.float64, device=device, generator=g) * r
+    return r, c, b
+
+
+class DevArray:
+    """CUDA array interface view of a raw device pointer (to hand the histogram to torch/NCCL)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, f in self.rows:
+            if len(f) < 9:
+                continue
+            try:
+                mx = max(mx, int(float(f[2])))
+                if t0 - 0.05 <= t <= t1 + 0.15:
+                    sm.append(int(float(f[1])))
+                    for nme, v in zip(names, f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nme)
+            except ValueError:
+                continue
+        if not sm:   # timed region shorter than the sampling period: take the nearest samples
+            sm = [int(float(f[1])) for _, f in self.rows[-3:] if len(f) >= 9 and f[1].replace(".", "").isdigit()]
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(a, steps, warmup):
+    """Time the CPU restatement on bounded samples of the same workload.
+
+    One CPU step = 1/8 of an interval: interval/8 reads through stage 1-2 plus the flush of a DENSE
+    full-interval histogram into s/8 sketch slots (both parts scale linearly, so reads/s of the
+    scaled step equals reads/s of the full interval).  Uses every host thread OpenMP gives it."""
+    import hulk_b200
+    from oracle import oracle as O
+    frac = 8
+    k, w, L = a.k, a.w, a.read_len
+    D = k ** 4
+    s_sub = max(1, a.s // frac)
+    n_sub = max(1, a.interval // frac)
+    threads = O.num_threads()
+    rng = np.random.default_rng(1)
+    r = rng.gamma(2.0, 1.0, (s_sub, D))
+    c = np.log(rng.gamma(2.0, 1.0, (s_sub, D)))
+    b = rng.random((s_sub, D)) * r
+    # dense histogram of one full interval (untimed set-up)
+    full = hulk_b200.synthetic_reads(a.interval, L, seed=1).reshape(-1)
+    offs_full = np.arange(a.interval + 1, dtype=np.uint64) * np.uint64(L)
+    dense, _ = O.count_reads(k, w, D, full, offs_full)
+    hs = O.HistoSketch(k, s_sub, D, a.decay, r, c, b)
+    offs = np.arange(n_sub + 1, dtype=np.uint64) * np.uint64(L)
+    times = []
+    for step in range(warmup + steps):
+        reads = hulk_b200.synthetic_reads(n_sub, L, seed=1, first_read=(step % frac) * n_sub).reshape(-1)
+        t0 = time.perf_counter()
+        O.count_reads(k, w, D, reads, offs)
+        hs.flush(dense.copy(), parallel=True)
+        dt = time.perf_counter() - t0
+        if step >= warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n_sub * len(times) / total
+    sample = ("%d steps of %d reads (1/%d interval) + flush of a dense %d-bin interval histogram into %d of %d "
+              "slots; C oracle (restatement of the Go reference, gcc -O2 -fopenmp), %d threads"
+              % (len(times), n_sub, frac, D, s_sub, a.s, threads))
+    return value, total / len(times) * 1e3, {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                                             "sample": sample}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 6))
+    warm = min(a.warmup, 1)
+    value, ms, base = cpu_arm(a, steps, warm)
+    base["value"] = value
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1), "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "steps_run": steps,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import hulk_b200
+    from hulk_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; hulk_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L_ = hulk_b200.load()
+
+    k, w, s, I, RL = a.k, a.w, a.s, a.interval, a.read_len
+    D = k ** 4
+    if s % world:
+        raise SystemExit("sketch size must divide by the number of GPUs")
+    rows = s // world
+    slots = (rank * rows, (rank + 1) * rows)
+    K, W = a.steps, a.warmup
+    stream = torch.cuda.Stream(device=dev)
+    n_steps_data = K                                   # distinct intervals of reads kept resident
+
+    with torch.cuda.stream(stream):
+        # reads of this rank: rank-th shard of every interval of the global job
+        reads_dev = torch.empty((n_steps_data, I, RL), dtype=torch.uint8, device=dev)
+        for st in range(n_steps_data):
+            first = (st * world + rank) * I
+            reads_dev[st] = synthetic_reads_torch(torch, I, RL, 1, first, dev)
+        r_t, c_t, b_t = synthetic_tables_torch(torch, s, D, 1234, dev)
+        r_t, c_t, b_t = (t[slots[0]:slots[1]].contiguous() for t in (r_t, c_t, b_t))
+    stream.synchronize()
+
+    hs = hulk_b200.HistoSketch(k, w, s, a.decay, device=local, slots=slots, stream=stream.cuda_stream,
+                               async_input=True)
+    hs.set_tables_device(r_t.data_ptr(), c_t.data_ptr(), b_t.data_ptr())
+    del r_t, c_t, b_t
+    torch.cuda.empty_cache()
+    hist_t = torch.as_tensor(DevArray(hs.histogram_device_ptr(), D, "<i4"), device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(st):
+        hs.add_reads_device(reads_dev[st % n_steps_data].data_ptr(), None, I, RL)
+        if world > 1:
+            dist.all_reduce(hist_t)
+        hs.flush()
+
+    def timed(fn, nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for st in range(nsteps):
+                fn(st)
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for st in range(W):
+            step_device(st)
+    hs.sync()
+    hs.reset()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.35)
+    launches0 = hs.stats()["n_kernel_launches"]
+    hs.profile(True)
+    t0 = time.time()
+    ms_value = timed(step_device, K)
+    t1 = time.time()
+    hs.sync()                                          # surfaces deferred errors (short reads, sparse flush)
+    prof = hs.profile_read()
+    hs.profile(False)
+    st_value = hs.stats()
+    launches = st_value["n_kernel_launches"] - launches0
+    assert st_value["n_flushes"] == K, st_value
+    value = world * I * K / (ms_value * 1e-3)
+
+    # ---- e2e: host (pinned) inputs through the C ABI, sketch read back every step -----------------
+    pin_in = C.c_void_p()
+    assert L_.hulk_b200_alloc_pinned(C.byref(pin_in), n_steps_data * I * RL) == 0
+    pin_np = np.ctypeslib.as_array(C.cast(pin_in, C.POINTER(C.c_uint8)), shape=(n_steps_data * I * RL,))
+    pin_np[:] = reads_dev.reshape(-1).cpu().numpy()
+    pin_out = C.c_void_p()
+    assert L_.hulk_b200_alloc_pinned(C.byref(pin_out), 16 * rows) == 0
+    mins_p = pin_out.value
+    weights_p = pin_out.value + 8 * rows
+
+    def step_host(st):
+        off = (st % n_steps_data) * I * RL
+        rc = L_.hulk_b200_push_reads_fixed(hs._ctx, pin_in.value + off, I, RL)
+        assert rc == 0, hs._L.hulk_b200_last_error(hs._ctx)
+        if world > 1:
+            dist.all_reduce(hist_t)
+        hs.flush()
+        rc = L_.hulk_b200_snapshot_async(hs._ctx, mins_p, weights_p)
+        assert rc == 0
+
+    hs.reset()
+    with torch.cuda.stream(stream):
+        for st in range(min(W, n_steps_data)):
+            step_host(st)
+    hs.sync()
+    hs.reset()
+    b0 = hs.stats()
+    ms_e2e = timed(step_host, K)
+    hs.sync()
+    b1 = hs.stats()
+    e2e_value = world * I * K / (ms_e2e * 1e-3)
+    h2d = (b1["h2d_bytes"] - b0["h2d_bytes"]) / K
+    d2h = (b1["d2h_bytes"] - b0["d2h_bytes"]) / K
+    mins_e2e = np.ctypeslib.as_array(C.cast(mins_p, C.POINTER(C.c_uint64)), shape=(rows,)).copy()
+
+    # the two runs sketched the same reads: identical sketches
+    hs_mins, _ = hs.finish()
+    assert (hs_mins == mins_e2e).all()
+    if sampler:
+        sampler.stop()
+        clocks = sampler.summary(t0, t1)
+    L_.hulk_b200_free_pinned(pin_in)
+    L_.hulk_b200_free_pinned(pin_out)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(prof, key=lambda n: prof[n]["ms"])
+    alg_bytes = {
+        "k1_minimizer_histogram": float(I * RL),                    # every base read once
+        "k2_countmin": 16.0 * D,                                    # hist zero+read, f write+read
+        "k3_filter": 4.0 * rows * D,                                # one fp32 coefficient per (slot, bin)
+        "k3_resolve": 4.0 * rows * (D / 512.0),
+    }
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    avg_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
+    achieved = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dom], "avg_launch_ms": avg_ms,
+                "kernel_ms_per_step": {n: prof[n]["ms"] / K for n in prof},
+                "kernel_share_of_step": {n: prof[n]["ms"] / ms_value for n in prof},
+                "k3_filter_GBps": (alg_bytes["k3_filter"] / (prof["k3_filter"]["ms"] / max(1, prof["k3_filter"]["launches"]) * 1e-3) / 1e9)
+                if prof["k3_filter"]["ms"] > 0 else None}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 minimizer/jump-hash, u32 histogram, f32 CWS filter + f64 CWS resolve", "data": "synthetic",
+        "config": workload_config(a, world),
+        "gbases_per_s": value * RL / 1e9,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "n_minimizers": st_value["n_minimizers"], "n_rescans": st_value["n_rescans"],
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            _, _, base = cpu_arm(a, a.cpu_steps, 1)
+            out["cpu_baseline"] = base
+        except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

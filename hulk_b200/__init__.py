@@ -1,0 +1,13 @@
+"""hulk_b200 -- B200-native (sm_100a) implementation of the `hulk sketch` hot path of will-rowe/hulk v1.0.0.
+
+The product is libhulk_b200.so (hand-written CUDA kernels behind the C ABI in include/hulk_b200.h)
+plus the `hulk` command-line front end; this package is the Python mirror of the reference's
+pipeline interface over that ABI.  There is no CPU fallback: every numeric operation fails loudly
+if the CUDA library is missing or no GPU is present.
+"""
+from ._native import load, LIB_PATH, EXPORTS  # noqa: F401
+from .sketch import (HistoSketch, HulkError, md5_mins, new_cws, pack_reads, sketch_json,  # noqa: F401
+                     sketch_reads, spectrum_size)
+from .seqio import read_fastq, read_fasta, synthetic_reads  # noqa: F401
+
+__version__ = "1.0.0"

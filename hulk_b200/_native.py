@@ -1,0 +1,106 @@
+"""ctypes binding of include/hulk_b200.h.  Fails loudly when the CUDA library is missing:
+there is no CPU or pure-Python fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhulk_b200.so")
+
+# names declared in include/hulk_b200.h (tests check the library exports every one of them)
+EXPORTS = [
+    "hulk_b200_version", "hulk_b200_strerror", "hulk_b200_last_error", "hulk_b200_create",
+    "hulk_b200_destroy", "hulk_b200_set_cws_tables", "hulk_b200_generate_cws_tables",
+    "hulk_b200_set_cws_tables_device", "hulk_b200_reset", "hulk_b200_profile_enable", "hulk_b200_profile_read",
+    "hulk_b200_new_cws", "hulk_b200_push_reads", "hulk_b200_push_reads_fixed",
+    "hulk_b200_push_reads_device", "hulk_b200_sync_inputs", "hulk_b200_flush", "hulk_b200_sync",
+    "hulk_b200_finish", "hulk_b200_snapshot_async", "hulk_b200_get_stats", "hulk_b200_histogram_device_ptr", "hulk_b200_stream",
+    "hulk_b200_merge_histogram", "hulk_b200_add_minimizer_count", "hulk_b200_get_histogram", "hulk_b200_get_estimates",
+    "hulk_b200_get_cms", "hulk_b200_minimizers", "hulk_b200_jump_hash", "hulk_b200_get_folded_table",
+    "hulk_b200_md5_mins", "hulk_b200_sketch_json", "hulk_b200_write_json", "hulk_b200_alloc_pinned",
+    "hulk_b200_free_pinned",
+]
+
+OK, EW, EK, EEMPTYSEQ, ESHORTSEQ, ESPARSE = 0, -1, -2, -3, -4, -6
+EHSK, EDECAY, EBINS, ENEGBINS, ENOSKETCH = -10, -11, -12, -13, -14
+EARG, ESTATE, ECUDA, ENOMEM, EIO = -20, -21, -30, -31, -40
+F_ASYNC_INPUT = 1
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("k", C.c_uint32), ("w", C.c_uint32), ("sketch_size", C.c_uint32), ("num_bins", C.c_int32),
+        ("decay_ratio", C.c_double), ("device", C.c_int32), ("slot_begin", C.c_uint32),
+        ("slot_end", C.c_uint32), ("stream", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_reads", "n_bases", "n_minimizers", "n_flushes", "n_adds", "n_kernel_launches", "n_rescans",
+        "h2d_bytes", "d2h_bytes")]
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("launches", C.c_uint64 * 4)]
+
+
+_lib = None
+
+
+def load():
+    """Load libhulk_b200.so (building it is __graft_entry__.build()'s / hulk_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -m hulk_b200.build). "
+            "hulk_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_double
+    sig = {
+        "hulk_b200_version": (C.c_char_p, []),
+        "hulk_b200_strerror": (C.c_char_p, [C.c_int]),
+        "hulk_b200_last_error": (C.c_char_p, [vp]),
+        "hulk_b200_create": (C.c_int, [C.POINTER(Params), C.POINTER(vp)]),
+        "hulk_b200_destroy": (None, [vp]),
+        "hulk_b200_set_cws_tables": (C.c_int, [vp, vp, vp, vp]),
+        "hulk_b200_generate_cws_tables": (C.c_int, [vp]),
+        "hulk_b200_set_cws_tables_device": (C.c_int, [vp, vp, vp, vp]),
+        "hulk_b200_reset": (C.c_int, [vp]),
+        "hulk_b200_profile_enable": (C.c_int, [vp, C.c_int]),
+        "hulk_b200_profile_read": (C.c_int, [vp, C.POINTER(Profile)]),
+        "hulk_b200_new_cws": (C.c_int, [u32, i32, u32, u32, vp, vp, vp]),
+        "hulk_b200_push_reads": (C.c_int, [vp, vp, vp, u64]),
+        "hulk_b200_push_reads_fixed": (C.c_int, [vp, vp, u64, u32]),
+        "hulk_b200_push_reads_device": (C.c_int, [vp, vp, vp, u64, u32]),
+        "hulk_b200_sync_inputs": (C.c_int, [vp]),
+        "hulk_b200_flush": (C.c_int, [vp]),
+        "hulk_b200_sync": (C.c_int, [vp]),
+        "hulk_b200_finish": (C.c_int, [vp, vp, vp]),
+        "hulk_b200_snapshot_async": (C.c_int, [vp, vp, vp]),
+        "hulk_b200_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+        "hulk_b200_histogram_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i32)]),
+        "hulk_b200_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "hulk_b200_merge_histogram": (C.c_int, [vp, vp]),
+        "hulk_b200_add_minimizer_count": (C.c_int, [vp, u64]),
+        "hulk_b200_get_histogram": (C.c_int, [vp, vp]),
+        "hulk_b200_get_estimates": (C.c_int, [vp, vp]),
+        "hulk_b200_get_cms": (C.c_int, [vp, vp]),
+        "hulk_b200_minimizers": (C.c_int, [vp, vp, vp, u64, vp, u32, vp]),
+        "hulk_b200_jump_hash": (C.c_int, [vp, vp, u64, i32, vp]),
+        "hulk_b200_get_folded_table": (C.c_int, [vp, vp, C.POINTER(u64)]),
+        "hulk_b200_md5_mins": (None, [vp, u32, C.c_char_p]),
+        "hulk_b200_sketch_json": (C.c_int64, [C.c_char_p, u64, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int]),
+        "hulk_b200_write_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int]),
+        "hulk_b200_alloc_pinned": (C.c_int, [C.POINTER(vp), u64]),
+        "hulk_b200_free_pinned": (None, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L

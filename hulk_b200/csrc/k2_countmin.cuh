@@ -1,0 +1,292 @@
+// k2_countmin.cuh -- stage 3a of the sketch hot path: the persistent count-min sketch that every
+// non-zero histogram bin passes through before the CWS update.
+//
+// Reference semantics (paths relative to the reference checkout):
+//   src/pipeline/boss.go:112-128      flush: skip if no bin used, Dump, Wipe
+//   src/kmerspectrum/kmerspectrum.go:84-112  Dump: "not used yet" if < 1% of bins used; bins
+//                                     are delivered in ascending order
+//   src/histosketch/histosketch.go:132       estiFreq = cmSketch.Add(bin, value)
+//   src/countmin/countmin.go:28-57,103-147   7 x 2000 float64 counters; key = bin*(d+1);
+//                                     column = jump.Hash(key, 2000); decay scales ALL counters
+//                                     by exp(-ratio) before EVERY Add.
+//
+// The sequential loop "for bin ascending: Q[d][col_d(bin)] += v; f = min_d Q[d][col_d(bin)]" is a
+// segmented inclusive scan: counter (d, col) sees exactly the bins of its static list
+// {bin : jump(bin*(d+1), 2000) == col} in ascending order.  The lists (CSR) are built once per
+// context; per flush one warp per counter scans its list.  Without decay the sums are integers
+// in float64 (exact, order independent).  With decay, counter value after the hit at global add
+// index t is Q(t) = Q(t_prev) * w^(t - t_prev) + v, scanned with the associative operator
+// (t1,B1) o (t2,B2) = (t2, B1 * w^(t2 - t1) + B2); w^n is pow(w, n) instead of n roundings of a
+// repeated product (differs from the reference by <= ~n * 2^-53 relative).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "hd_math.h"
+
+namespace hulk {
+
+constexpr uint32_t CMS_DEPTH = 7;      // ceil(ln(1-0.99)/ln(0.5))   countmin.go:32
+constexpr uint32_t CMS_WIDTH = 2000;   // ceil(2/0.001)              countmin.go:31
+constexpr uint32_t CMS_CELLS = CMS_DEPTH * CMS_WIDTH;
+constexpr unsigned long long F_EMPTY_BITS = 0x7FF0000000000000ull;   // +inf: bin not in this flush
+
+// per-flush control block in device memory
+struct FlushCtl {
+    unsigned int nnz;              // used bins of the histogram being flushed
+    unsigned int go;               // 1: this flush runs; 0: histogram empty (no-op) or error
+    int err;                       // sticky: HULK_B200_ESPARSE once a flush was < 1% used
+    unsigned int pad;
+    unsigned long long t0;         // AddElement calls before this flush
+    unsigned long long n_adds;     // AddElement calls so far
+    unsigned long long n_flushes;  // non-empty flushes so far
+    unsigned long long n_rescans;  // fp64 chunk re-evaluations (k3_resolve)
+};
+
+// ---- context creation: static column map and its CSR ----
+__global__ void k2_build_cols(int32_t D, uint16_t *cols /*[7][D]*/, unsigned int *counts /*[14000]*/) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)D * CMS_DEPTH) return;
+    const uint32_t d = (uint32_t)(i / D);
+    const uint64_t bin = (uint64_t)(i % D);
+    const uint64_t hash = bin + (uint64_t)d * bin;                         // countmin.go:122
+    const int32_t g = jump_hash(hash, (int32_t)CMS_WIDTH);                 // countmin.go:125
+    cols[i] = (uint16_t)g;
+    atomicAdd(&counts[d * CMS_WIDTH + g], 1u);
+}
+// single block: exclusive scan of the 14000 list lengths
+__global__ void k2_scan_counts(const unsigned int *counts, unsigned int *start /*[14001]*/) {
+    __shared__ unsigned int warp_tot[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < CMS_CELLS; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned int v = (i < CMS_CELLS) ? counts[i] : 0;
+        unsigned int s = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) >= o) s += u;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int t = (threadIdx.x < (blockDim.x >> 5)) ? warp_tot[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (threadIdx.x >= o) t += u;
+            }
+            warp_tot[threadIdx.x] = t;   // inclusive
+        }
+        __syncthreads();
+        const unsigned int before = carry + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0);
+        if (i < CMS_CELLS) start[i] = before + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[(blockDim.x >> 5) - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[CMS_CELLS] = carry;
+}
+__global__ void k2_fill_csr(int32_t D, const uint16_t *cols, const unsigned int *start, unsigned int *cursor,
+                            int32_t *csr_bins) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)D * CMS_DEPTH) return;
+    const uint32_t d = (uint32_t)(i / D);
+    const int32_t bin = (int32_t)(i % D);
+    const uint32_t cell = d * CMS_WIDTH + cols[i];
+    const unsigned int at = atomicAdd(&cursor[cell], 1u);
+    csr_bins[start[cell] + at] = bin;
+}
+// one thread per counter: put its list in ascending bin order (insertion sort; lists are short)
+__global__ void k2_sort_csr(const unsigned int *start, int32_t *csr_bins) {
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= CMS_CELLS) return;
+    const unsigned int b = start[cell], e = start[cell + 1];
+    for (unsigned int i = b + 1; i < e; i++) {
+        const int32_t v = csr_bins[i];
+        unsigned int j = i;
+        while (j > b && csr_bins[j - 1] > v) { csr_bins[j] = csr_bins[j - 1]; j--; }
+        csr_bins[j] = v;
+    }
+}
+
+// ---- per flush ----
+// (a) used-bin bitmap, per-32-bin and per-1024-bin used counts, reset of the estimate vector
+__global__ void __launch_bounds__(1024) k2_mask_count(const uint32_t *__restrict__ hist, int32_t D,
+                                                      uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
+                                                      uint32_t *__restrict__ block_count,
+                                                      unsigned long long *__restrict__ fbits, FlushCtl *ctl) {
+    __shared__ uint32_t pc[32];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const bool nz = (i < D) && (hist[i] != 0u);
+    if (i < D) fbits[i] = F_EMPTY_BITS;
+    const uint32_t word = __ballot_sync(0xffffffffu, nz);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        words[(size_t)blockIdx.x * 32 + wid] = word;
+        pc[wid] = __popc(word);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = pc[lane];
+        uint32_t s = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        word_prefix[(size_t)blockIdx.x * 32 + lane] = s - v;   // used bins before this word, inside the block
+        if (lane == 31) {
+            block_count[blockIdx.x] = s;
+            if (s) atomicAdd(&ctl->nnz, s);
+        }
+    }
+}
+// (b) single block: exclusive scan of the per-block counts + the flush decision
+__global__ void __launch_bounds__(1024) k2_flush_decide(const uint32_t *__restrict__ block_count, uint32_t nblocks,
+                                                        uint32_t *__restrict__ block_prefix, int32_t D, FlushCtl *ctl) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < nblocks) ? block_count[i] : 0;
+        uint32_t s = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) >= o) s += u;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t t = warp_tot[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
+                if (threadIdx.x >= o) t += u;
+            }
+            warp_tot[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const uint32_t before = carry + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0);
+        if (i < nblocks) block_prefix[i] = before + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned int nnz = ctl->nnz;
+        unsigned int go = 0;
+        if (nnz != 0) {                                                   // boss.go:117
+            const double prop = (double)nnz / (double)D;                  // kmerspectrum.go:92
+            if (prop < 0.01) {                                            // kmerspectrum.go:94-96
+                if (ctl->err == 0) ctl->err = -6;                         // HULK_B200_ESPARSE
+            } else {
+                go = 1;
+            }
+        }
+        ctl->go = go;
+        ctl->t0 = ctl->n_adds;
+        if (go) {
+            ctl->n_adds += nnz;
+            ctl->n_flushes += 1;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t k2_rank(int32_t bin, const uint32_t *words, const uint32_t *word_prefix,
+                                            const uint32_t *block_prefix) {
+    // number of used bins <= bin (1-based position of `bin` among this flush's AddElement calls)
+    const uint32_t w = words[bin >> 5];
+    return block_prefix[bin >> 10] + word_prefix[bin >> 5] + __popc(w & (0xffffffffu >> (31 - (bin & 31))));
+}
+
+// (c) one warp per counter
+__global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict__ hist,
+                                                     const unsigned int *__restrict__ csr_start,
+                                                     const int32_t *__restrict__ csr_bins,
+                                                     const uint32_t *__restrict__ words,
+                                                     const uint32_t *__restrict__ word_prefix,
+                                                     const uint32_t *__restrict__ block_prefix,
+                                                     double *__restrict__ q, unsigned long long *__restrict__ fbits,
+                                                     const FlushCtl *__restrict__ ctl, const int apply_scaling,
+                                                     const double decay_weight) {
+    if (!ctl->go) return;
+    const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= CMS_CELLS) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned int beg = csr_start[cell], end = csr_start[cell + 1];
+    if (!apply_scaling) {
+        double carry = q[cell];
+        for (unsigned int base = beg; base < end; base += 32) {
+            const unsigned int e = base + lane;
+            int32_t bin = -1;
+            double v = 0.0;
+            if (e < end) { bin = csr_bins[e]; v = (double)hist[bin]; }
+            double s = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += u;
+            }
+            if (v != 0.0) atomicMin(&fbits[bin], (unsigned long long)__double_as_longlong(carry + s));
+            carry += __shfl_sync(0xffffffffu, s, 31);
+        }
+        if (lane == 0) q[cell] = carry;
+    } else {
+        const unsigned long long t0 = ctl->t0;
+        double cval = q[cell];                 // counter value as of add index ct
+        unsigned long long ct = t0;
+        for (unsigned int base = beg; base < end; base += 32) {
+            const unsigned int e = base + lane;
+            int32_t bin = -1;
+            double B = 0.0;
+            unsigned long long t = 0;
+            bool valid = false;
+            if (e < end) {
+                bin = csr_bins[e];
+                const uint32_t c = hist[bin];
+                if (c) {
+                    valid = true;
+                    B = (double)c;
+                    t = t0 + k2_rank(bin, words, word_prefix, block_prefix);
+                }
+            }
+            for (int o = 1; o < 32; o <<= 1) {
+                const double Bl = __shfl_up_sync(0xffffffffu, B, o);
+                const unsigned long long tl = __shfl_up_sync(0xffffffffu, t, o);
+                const int vl = __shfl_up_sync(0xffffffffu, (int)valid, o);
+                if (lane >= o && vl) {
+                    if (valid) B = Bl * pow(decay_weight, (double)(t - tl)) + B;
+                    else { B = Bl; t = tl; valid = true; }
+                }
+            }
+            // B: contribution of this chunk's hits up to and including this lane, as of time t
+            double est = 0.0;
+            if (valid) est = cval * pow(decay_weight, (double)(t - ct)) + B;
+            if (e < end && bin >= 0 && hist[bin] != 0u) atomicMin(&fbits[bin], (unsigned long long)__double_as_longlong(est));
+            const int lastv = __shfl_sync(0xffffffffu, (int)valid, 31);
+            if (lastv) {
+                cval = __shfl_sync(0xffffffffu, est, 31);
+                ct = __shfl_sync(0xffffffffu, t, 31);
+            }
+        }
+        const unsigned long long t1 = t0 + ctl->nnz;
+        if (lane == 0) q[cell] = cval * pow(decay_weight, (double)(t1 - ct));
+    }
+}
+
+// (d) estimate -> fp32 reciprocal for the streaming filter; wipe the histogram (kmerspectrum.go:58-64)
+__global__ void k2_finalize(uint32_t *__restrict__ hist, int32_t D, const unsigned long long *__restrict__ fbits,
+                            float *__restrict__ invf, const FlushCtl *__restrict__ ctl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    const unsigned int go = ctl->go;
+    if (go) {
+        const bool used = hist[i] != 0u;
+        const double f = __longlong_as_double((long long)fbits[i]);
+        invf[i] = used ? (float)(1.0 / f) : __int_as_float(0x7fc00000);
+    }
+    // boss.go:117-128: the spectrum is wiped only when a dump happened (cardinality != 0 and no error)
+    if (go) hist[i] = 0u;
+}
+
+}  // namespace hulk

@@ -1,0 +1,197 @@
+// k3_cws.cuh -- stage 3b of the sketch hot path: the HistoSketch consistent-weighted-sampling
+// update of every sketch slot by every used histogram bin of a flush.
+//
+// Reference semantics (paths relative to the reference checkout):
+//   src/histosketch/histosketch.go:30-33    getSample: A = c / (exp(ln f - b) * exp(r))
+//   src/histosketch/histosketch.go:129-155  AddElement: for every slot j: curMin = W[j] (or
+//       W[j]/decayWeight under concept drift); if A < curMin { Sketch[j] = bin; W[j] = A }
+//   src/pipeline/sketch.go:281-285          called once per used bin, ascending bin order
+//
+// Design.  A = K / f with K = c * exp(b - r) fixed per (slot, bin).  K is folded once into an fp32
+// table K32[rows][Dp] (Dp = bins padded to 512); a flush streams it exactly once:
+//   k3_filter  (HBM-bound): m32[slot][chunk] = min over the chunk's 512 bins of K32 * (1/f)32,
+//              K32 row segments arriving in shared memory through a ring of 1-D bulk TMA copies;
+//   k3_resolve (tiny): per slot walks the chunks in bin order carrying W exactly like the
+//              reference's loop; a chunk whose fp32 minimum could possibly pass the test
+//              (m32 < thr + eps*|thr|, eps covering the fp32 rounding of K32 and 1/f) is
+//              re-evaluated bin by bin in float64 with the reference's own formula from the
+//              float64 r, c, b tables.  Every value that reaches Sketch/Weights therefore comes
+//              from the float64 formula; fp32 only decides which chunks cannot matter.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "k2_countmin.cuh"
+#include "ptx_util.cuh"
+
+namespace hulk {
+
+constexpr int K3_SUB = 512;                         // bins per chunk (one warp-reduction)
+constexpr int K3_SEG = 4096;                        // bins per TMA stage (16 KB)
+constexpr int K3_SUBS_PER_SEG = K3_SEG / K3_SUB;    // 8 = consumer warps
+constexpr int K3_STAGES = 8;                        // 8 x 16 KB ring
+constexpr int K3_CONSUMER_WARPS = K3_SUBS_PER_SEG;
+constexpr int K3_THREADS = (K3_CONSUMER_WARPS + 1) * 32;
+constexpr double K3_EPS = 1e-6;                     // >> 3 * 2^-24 (K32, (1/f)32 and product roundings)
+
+// ---- context creation: fold the float64 tables into K32 ----
+__global__ void k3_fold(const double *__restrict__ r, const double *__restrict__ c, const double *__restrict__ b,
+                        uint32_t rows, int32_t D, uint64_t Dp, float *__restrict__ K32) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)rows * Dp;
+    if (i >= total) return;
+    const uint64_t row = i / Dp, col = i % Dp;
+    float v = __int_as_float(0x7fc00000);
+    if (col < (uint64_t)D) {
+        const uint64_t at = row * (uint64_t)D + col;
+        v = (float)(c[at] * exp(b[at] - r[at]));
+    }
+    K32[i] = v;
+}
+
+// ---- per flush: streaming filter ----
+// tile = (segment, slot); tiles are enumerated segment-major so a CTA's consecutive tiles share
+// the segment's (1/f) values (L1-resident); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G).
+__global__ void __launch_bounds__(K3_THREADS, 1)
+k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restrict__ invf, float *__restrict__ m32,
+          const uint32_t rows, const uint32_t nseg, const FlushCtl *__restrict__ ctl) {
+    if (!ctl->go) return;
+    extern __shared__ __align__(128) uint8_t smem[];
+    float *stage = reinterpret_cast<float *>(smem);                                    // [STAGES][SEG]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)K3_STAGES * K3_SEG * 4);
+    uint64_t *empty = full + K3_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K3_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], K3_CONSUMER_WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t T = (uint64_t)rows * nseg;
+    const uint64_t t_begin = T * blockIdx.x / gridDim.x;
+    const uint64_t t_end = T * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t nsub_row = (uint32_t)(Dp / K3_SUB);
+
+    if (warp == K3_CONSUMER_WARPS) {
+        // producer warp: one lane feeds the ring
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint64_t t = t_begin; t < t_end; t++, it++) {
+                const int s = it % K3_STAGES;
+                const uint32_t round = it / K3_STAGES;
+                if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+                const uint32_t seg = (uint32_t)(t / rows), slot = (uint32_t)(t % rows);
+                const uint64_t col0 = (uint64_t)seg * K3_SEG;
+                const uint32_t ncols = (uint32_t)((Dp - col0 < (uint64_t)K3_SEG) ? (Dp - col0) : K3_SEG);
+                mbar_arrive_expect_tx(&full[s], ncols * 4u);
+                bulk_g2s_evict_first(stage + (size_t)s * K3_SEG, K32 + (uint64_t)slot * Dp + col0, ncols * 4u,
+                                     &full[s]);
+            }
+        }
+    } else {
+        uint32_t it = 0;
+        for (uint64_t t = t_begin; t < t_end; t++, it++) {
+            const int s = it % K3_STAGES;
+            const uint32_t round = it / K3_STAGES;
+            const uint32_t seg = (uint32_t)(t / rows), slot = (uint32_t)(t % rows);
+            const uint64_t col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
+            mbar_wait(&full[s], round & 1);
+            if (col0 < Dp) {
+                const float4 *ks = reinterpret_cast<const float4 *>(stage + (size_t)s * K3_SEG + warp * K3_SUB);
+                const float4 *fs = reinterpret_cast<const float4 *>(invf + col0);
+                float m = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int u = 0; u < K3_SUB / 128; u++) {
+                    const float4 kv = ks[u * 32 + lane];
+                    const float4 fv = __ldg(&fs[u * 32 + lane]);
+                    m = fminf(m, kv.x * fv.x);     // NaN (empty bin / padding) is ignored by fminf
+                    m = fminf(m, kv.y * fv.y);
+                    m = fminf(m, kv.z * fv.z);
+                    m = fminf(m, kv.w * fv.w);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) m32[(uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG + warp] = m;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    }
+}
+
+// reference formula, float64 (histosketch.go:30-33)
+__device__ __forceinline__ double k3_sample(double c, double b, double r, double f) {
+    const double Yka = exp(log(f) - b);
+    return c / (Yka * exp(r));
+}
+
+// ---- per flush: exact resolve, one warp per slot ----
+__global__ void __launch_bounds__(128)
+k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double *__restrict__ r,
+           const double *__restrict__ c, const double *__restrict__ b, const int32_t D,
+           const unsigned long long *__restrict__ fbits, const uint32_t rows, unsigned long long *__restrict__ sketch,
+           double *__restrict__ weights, const int drift, const double decay_weight, FlushCtl *ctl) {
+    if (!ctl->go) return;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= rows) return;
+    const int lane = threadIdx.x & 31;
+    double W = weights[slot];
+    unsigned long long S = sketch[slot];
+    unsigned int rescans = 0;
+    const float *mrow = m32 + (uint64_t)slot * nsub_row;
+    const uint64_t rowoff = (uint64_t)slot * (uint64_t)D;
+
+    for (uint32_t cbase = 0; cbase < nsub_row; cbase += 32) {
+        const uint32_t ci = cbase + lane;
+        const double m = (ci < nsub_row) ? (double)mrow[ci] : INFINITY;
+        uint32_t pending = 0xffffffffu;
+        for (;;) {
+            const double thr = drift ? W / decay_weight : W;             // histosketch.go:141-146
+            // conservative: could any bin of this chunk satisfy A < thr ?  (false for NaN thr)
+            const bool cand = (m < INFINITY) && (m < thr + K3_EPS * fabs(thr) + 1e-37);
+            const uint32_t mask = __ballot_sync(0xffffffffu, cand) & pending;
+            if (mask == 0) break;
+            const int first = __ffs(mask) - 1;
+            pending = (first == 31) ? 0u : (0xffffffffu << (first + 1));
+            // float64 re-evaluation of chunk (cbase + first), bins ascending
+            const uint32_t chunk = cbase + first;
+            rescans++;
+            const int32_t bin_end = min((int32_t)((chunk + 1) * K3_SUB), D);
+            for (int32_t b0 = (int32_t)(chunk * K3_SUB); b0 < bin_end; b0 += 32) {
+                const int32_t bin = b0 + lane;
+                double A = INFINITY;
+                bool used = false;
+                if (bin < bin_end) {
+                    const unsigned long long fb = fbits[bin];
+                    if (fb != F_EMPTY_BITS) {
+                        used = true;
+                        const double f = __longlong_as_double((long long)fb);
+                        A = k3_sample(c[rowoff + bin], b[rowoff + bin], r[rowoff + bin], f);
+                    }
+                }
+                uint32_t todo = 0xffffffffu;
+                for (;;) {
+                    const double th = drift ? W / decay_weight : W;
+                    const bool trig = used && (A < th);                   // histosketch.go:149
+                    const uint32_t tm = __ballot_sync(0xffffffffu, trig) & todo;
+                    if (tm == 0) break;
+                    const int fl = __ffs(tm) - 1;
+                    W = __shfl_sync(0xffffffffu, A, fl);                  // :150-151
+                    S = (unsigned long long)(b0 + fl);
+                    todo = (fl == 31) ? 0u : (0xffffffffu << (fl + 1));
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        weights[slot] = W;
+        sketch[slot] = S;
+        if (rescans) atomicAdd(&ctl->n_rescans, (unsigned long long)rescans);
+    }
+}
+
+}  // namespace hulk

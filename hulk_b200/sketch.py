@@ -1,0 +1,299 @@
+"""Host-side mirror of the reference's sketch pipeline over the C ABI (include/hulk_b200.h).
+
+Names follow the reference: `HistoSketch` stands where histosketch.HistoSketch +
+kmerspectrum.KmerSpectrum + the boss/minion pool stand in src/pipeline (the GPU library fuses
+them), `sketch_reads` is SeqMinimizer.Run + Sketcher.Run (src/pipeline/sketch.go:182-301).
+Everything numeric happens in libhulk_b200.so on the GPU; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+class HulkError(RuntimeError):
+    """A reference-fatal condition (helpers.ErrorCheck -> log.Fatalf, src/helpers/helpers.go:31-35)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+        self.message = message
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def spectrum_size(k: int) -> int:
+    """spectrumSize := int32(helpers.Pow(k, 4))  (cmd/sketch.go:118)"""
+    v = (k ** 4) & 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def new_cws(s: int, num_bins: int, slot_begin: int = 0, slot_end: Optional[int] = None):
+    """HistoSketch.newCWS tables (src/histosketch/histosketch.go:95-126): r, c, b float64[rows, D]."""
+    L = N.load()
+    slot_end = s if slot_end is None else slot_end
+    rows = slot_end - slot_begin
+    r = np.empty((rows, num_bins)); c = np.empty((rows, num_bins)); b = np.empty((rows, num_bins))
+    rc = L.hulk_b200_new_cws(s, num_bins, slot_begin, slot_end, _ptr(r), _ptr(c), _ptr(b))
+    if rc:
+        raise HulkError(rc, L.hulk_b200_strerror(rc).decode())
+    return r, c, b
+
+
+def pack_reads(reads: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
+    if len(reads):
+        offsets[1:] = np.cumsum([len(r) for r in reads], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(reads), dtype=np.uint8).copy() if len(reads) else np.zeros(0, np.uint8)
+    return bases, offsets
+
+
+def md5_mins(mins) -> str:
+    L = N.load()
+    m = np.ascontiguousarray(mins, dtype=np.uint64)
+    out = C.create_string_buffer(33)
+    L.hulk_b200_md5_mins(_ptr(m), m.size, out)
+    return out.value.decode()
+
+
+def sketch_json(filename: str, k: int, mins, weights, num_bins: int, concept_drift: bool,
+                banner_label: str = "blank") -> str:
+    """The JSON document hulk writes to <outFile>.json (src/sketchio/sketchio.go:78-97)."""
+    L = N.load()
+    m = np.ascontiguousarray(mins, dtype=np.uint64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    args = (filename.encode(), banner_label.encode(), k, _ptr(m), _ptr(w), m.size, num_bins, int(concept_drift))
+    need = L.hulk_b200_sketch_json(None, 0, *args)
+    if need < 0:
+        raise HulkError(int(need), L.hulk_b200_strerror(int(need)).decode())
+    buf = C.create_string_buffer(need + 1)
+    L.hulk_b200_sketch_json(buf, need + 1, *args)
+    return buf.raw[:need].decode()
+
+
+class HistoSketch:
+    """One sketching context on one GPU.
+
+    Constructor checks mirror minimizer.NewMinimizerSketch (src/minimizer/minimizer.go:62-67),
+    kmerspectrum.NewKmerSpectrum (src/kmerspectrum/kmerspectrum.go:33-35) and
+    histosketch.NewHistoSketch (src/histosketch/histosketch.go:53-67).
+    """
+
+    def __init__(self, k: int = 21, w: int = 9, sketch_size: int = 50, decay_ratio: float = 1.0,
+                 num_bins: Optional[int] = None, device: int = 0, slots: Optional[Tuple[int, int]] = None,
+                 stream: Optional[int] = None, tables=None, async_input: bool = False):
+        self._L = N.load()
+        self._ctx = C.c_void_p()
+        self.k, self.w, self.sketch_size, self.decay_ratio = k, w, sketch_size, decay_ratio
+        self.num_bins = spectrum_size(k) if num_bins is None else num_bins
+        self.slot_begin, self.slot_end = slots if slots is not None else (0, sketch_size)
+        p = N.Params()
+        p.k, p.w, p.sketch_size = k, w, sketch_size
+        p.num_bins = self.num_bins
+        p.decay_ratio = decay_ratio
+        p.device = device
+        p.slot_begin, p.slot_end = (slots if slots is not None else (0, 0))
+        p.stream = stream
+        p.flags = N.F_ASYNC_INPUT if async_input else 0
+        ctx = C.c_void_p()
+        rc = self._L.hulk_b200_create(C.byref(p), C.byref(ctx))
+        if rc:
+            raise HulkError(rc, self._L.hulk_b200_last_error(None).decode())
+        self._ctx = ctx
+        self._keep = []     # host buffers that must outlive asynchronous copies
+        if tables is not None:
+            self.set_tables(*tables)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.hulk_b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise HulkError(rc, self._L.hulk_b200_last_error(self._ctx).decode())
+
+    @property
+    def rows(self) -> int:
+        return self.slot_end - self.slot_begin
+
+    @property
+    def concept_drift(self) -> bool:
+        return self.decay_ratio != 1.0           # histosketch.go:79-81
+
+    # -- CWS tables --------------------------------------------------------------------------
+    def set_tables(self, r, c, b):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        want = (self.rows, self.num_bins)
+        for t in (r, c, b):
+            if t.shape != want:
+                raise HulkError(N.EARG, f"table shape {t.shape}, expected {want}")
+        self._check(self._L.hulk_b200_set_cws_tables(self._ctx, _ptr(r), _ptr(c), _ptr(b)))
+
+    def set_tables_device(self, d_r: int, d_c: int, d_b: int):
+        """Tables already in device memory (raw device pointers to rows x num_bins float64)."""
+        self._check(self._L.hulk_b200_set_cws_tables_device(self._ctx, d_r, d_c, d_b))
+
+    def reset(self):
+        """Start a new sample with the same parameters and tables."""
+        self._check(self._L.hulk_b200_reset(self._ctx))
+
+    def profile(self, enable: bool):
+        self._check(self._L.hulk_b200_profile_enable(self._ctx, int(enable)))
+
+    def profile_read(self) -> dict:
+        pr = N.Profile()
+        self._check(self._L.hulk_b200_profile_read(self._ctx, C.byref(pr)))
+        names = ("k1_minimizer_histogram", "k2_countmin", "k3_filter", "k3_resolve")
+        return {n: {"ms": pr.ms[i], "launches": int(pr.launches[i])} for i, n in enumerate(names)}
+
+    def generate_tables(self):
+        """newCWS with the reference's seeded streams (histosketch.go:95-126)."""
+        self._check(self._L.hulk_b200_generate_cws_tables(self._ctx))
+
+    # -- stage 1+2 ---------------------------------------------------------------------------
+    def add_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        """theBoss.AddSeq for a batch (src/pipeline/boss.go:24-26)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep = [bases, offsets]
+        self._check(self._L.hulk_b200_push_reads(self._ctx, _ptr(bases), _ptr(offsets), offsets.size - 1))
+
+    def add_seqs(self, reads: Sequence[bytes]):
+        self.add_reads(*pack_reads(reads))
+
+    def add_reads_fixed(self, bases: np.ndarray, n_reads: int, read_len: int):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        self._keep = [bases]
+        self._check(self._L.hulk_b200_push_reads_fixed(self._ctx, _ptr(bases), n_reads, read_len))
+
+    def add_reads_device(self, d_bases_ptr: int, d_offsets_ptr: Optional[int], n_reads: int, read_len: int = 0):
+        self._check(self._L.hulk_b200_push_reads_device(self._ctx, d_bases_ptr, d_offsets_ptr, n_reads, read_len))
+
+    # -- stage 3 -----------------------------------------------------------------------------
+    def flush(self):
+        """theBoss.Flush (src/pipeline/boss.go:112-128).  Asynchronous; errors surface at sync()/finish()."""
+        self._check(self._L.hulk_b200_flush(self._ctx))
+
+    def sync(self):
+        self._check(self._L.hulk_b200_sync(self._ctx))
+
+    def finish(self) -> Tuple[np.ndarray, np.ndarray]:
+        mins = np.zeros(self.rows, dtype=np.uint64)
+        weights = np.zeros(self.rows, dtype=np.float64)
+        self._check(self._L.hulk_b200_finish(self._ctx, _ptr(mins), _ptr(weights)))
+        return mins, weights
+
+    def stats(self) -> dict:
+        st = N.Stats()
+        self._check(self._L.hulk_b200_get_stats(self._ctx, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in N.Stats._fields_}
+
+    # -- multi-GPU plumbing ------------------------------------------------------------------
+    def histogram_device_ptr(self) -> int:
+        p = C.c_void_p()
+        nb = C.c_int32()
+        self._check(self._L.hulk_b200_histogram_device_ptr(self._ctx, C.byref(p), C.byref(nb)))
+        return p.value
+
+    def stream_handle(self) -> int:
+        p = C.c_void_p()
+        self._check(self._L.hulk_b200_stream(self._ctx, C.byref(p)))
+        return p.value or 0
+
+    def merge_histogram(self, hist: np.ndarray):
+        """Add a partial spectrum counted elsewhere (uint32[num_bins]) to this context's histogram."""
+        h = np.ascontiguousarray(hist, dtype=np.uint32)
+        if h.size != self.num_bins:
+            raise HulkError(N.EARG, "histogram size")
+        self._check(self._L.hulk_b200_merge_histogram(self._ctx, _ptr(h)))
+
+    def add_minimizer_count(self, n: int):
+        self._check(self._L.hulk_b200_add_minimizer_count(self._ctx, int(n)))
+
+    # -- parity taps -------------------------------------------------------------------------
+    def histogram(self) -> np.ndarray:
+        h = np.zeros(self.num_bins, dtype=np.uint32)
+        self._check(self._L.hulk_b200_get_histogram(self._ctx, _ptr(h)))
+        return h
+
+    def estimates(self) -> np.ndarray:
+        f = np.zeros(self.num_bins, dtype=np.float64)
+        self._check(self._L.hulk_b200_get_estimates(self._ctx, _ptr(f)))
+        return f
+
+    def cms(self) -> np.ndarray:
+        q = np.zeros((7, 2000), dtype=np.float64)
+        self._check(self._L.hulk_b200_get_cms(self._ctx, _ptr(q)))
+        return q
+
+    def minimizers(self, reads: Sequence[bytes], cap: int = 0):
+        """Per-read minimizer sets computed by the device code (list of sorted uint64 arrays)."""
+        bases, offsets = pack_reads(reads)
+        if cap == 0:
+            cap = max(1, max((len(r) for r in reads), default=1))
+        out = np.zeros((len(reads), cap), dtype=np.uint64)
+        counts = np.zeros(len(reads), dtype=np.uint32)
+        self._check(self._L.hulk_b200_minimizers(self._ctx, _ptr(bases), _ptr(offsets), len(reads), _ptr(out),
+                                                 cap, _ptr(counts)))
+        return [np.sort(out[i, :min(int(counts[i]), cap)]) for i in range(len(reads))], counts
+
+    def jump_hash(self, keys, num_buckets: int) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(keys.size, dtype=np.int32)
+        self._check(self._L.hulk_b200_jump_hash(self._ctx, _ptr(keys), keys.size, num_buckets, _ptr(out)))
+        return out
+
+    def folded_table(self) -> np.ndarray:
+        stride = C.c_uint64()
+        self._check(self._L.hulk_b200_get_folded_table(self._ctx, None, C.byref(stride)))
+        out = np.zeros((self.rows, stride.value), dtype=np.float32)
+        self._check(self._L.hulk_b200_get_folded_table(self._ctx, _ptr(out), C.byref(stride)))
+        return out
+
+
+def sketch_reads(hs: HistoSketch, batches: Iterable[Tuple[np.ndarray, np.ndarray]], interval: int = 0):
+    """SeqMinimizer.Run (src/pipeline/sketch.go:197-224): AddSeq every read, Flush after every
+    `interval`-th read (0 = never) and once more at the end, with the race-free semantics
+    "every read up to the boundary is counted before the flush".
+
+    batches: iterable of (bases uint8[], offsets uint64[n+1]).  Returns (mins, weights, stats)."""
+    seq_count = 0
+    for bases, offsets in batches:
+        n = len(offsets) - 1
+        done = 0
+        while done < n:
+            take = n - done
+            if interval:
+                take = min(take, interval - (seq_count % interval))
+            hs.add_reads(bases, offsets[done:done + take + 1])
+            done += take
+            seq_count += take
+            if interval and seq_count % interval == 0:
+                hs.flush()                                    # sketch.go:211-215
+    hs.flush()                                                # sketch.go:221
+    mins, weights = hs.finish()
+    if seq_count == 0:
+        raise HulkError(N.EARG, "no sequences received")     # sketch.go:237-239
+    return mins, weights, hs.stats()

@@ -1,0 +1,342 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars: bit-exact for minimizer values, jump-hash bins, histogram counts, count-min estimates without
+decay and sketch `mins`; float64 sketch weights within 1e-12 relative (north_star asks 1e-5);
+count-min estimates under decay within 1e-9 relative (pow(w, n) instead of n repeated products).
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, random_reads
+
+pytestmark = pytest.mark.gpu
+
+W_RTOL = 1e-12
+
+
+def _tables(s, D, seed):
+    rng = np.random.default_rng(seed)
+    r = rng.gamma(2.0, 1.0, (s, D))
+    c = np.log(rng.gamma(2.0, 1.0, (s, D)))
+    b = rng.random((s, D)) * r
+    return r, c, b
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hulk_b200
+    hulk_b200.load()
+    return hulk_b200
+
+
+# ---- stage 1: minimizer sets ---------------------------------------------------------------------
+EDGE_READS = [b"A" * 150, b"ACGT" * 40, b"N" * 100, bytes(range(256)), b"AC" * 75, b"acgtnACGTN" * 15,
+              b"ACGTTGCATGCATGCATTACGATCAGCTACGATCAGCATCGACTAGCTANNNNNNACGATCGACTAGCTAGCATCGATCAGCTAGCTAGCATGC",
+              b"GATTACA" * 30, b"T" * 60 + b"N" + b"T" * 60, b"ACGU" * 40, b"\x00\x01\x02\x03" * 40]
+
+
+@pytest.mark.parametrize("k,w", [(21, 9), (31, 9), (11, 9), (4, 4), (21, 1), (15, 32), (5, 9), (3, 7), (7, 40), (21, 200)])
+def test_minimizer_sets_bit_exact(hb, oracle, k, w):
+    reads = random_reads(300, 100, seed=k * 1000 + w, n_frac=0.02, lower_frac=0.1, ragged=120) + EDGE_READS
+    reads = [r for r in reads if len(r) >= k + w - 1]
+    with hb.HistoSketch(k, w, 4) as hs:
+        sets, counts = hs.minimizers(reads)
+    for r, got, n in zip(reads, sets, counts):
+        want = np.sort(oracle.minimizers(k, w, r))
+        assert n == want.size, (k, w, r)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_minimizer_sets_on_reference_fixture(hb, oracle, fixture_reads):
+    with hb.HistoSketch(21, 9, 4) as hs:
+        sets, counts = hs.minimizers(fixture_reads)
+    assert int(counts.sum()) == 17040
+    for r, got in zip(fixture_reads, sets):
+        np.testing.assert_array_equal(got, np.sort(oracle.minimizers(21, 9, r)))
+
+
+def test_long_reads_take_the_generic_path(hb, oracle):
+    # candidate lists longer than the shared-memory capacity are queued for k1_generic
+    reads = random_reads(40, 3000, seed=77, n_frac=0.001, ragged=4000) + [b"ACGTAC" * 2000, b"A" * 5000]
+    reads += random_reads(100, 150, seed=78)
+    with hb.HistoSketch(21, 9, 4) as hs:
+        sets, counts = hs.minimizers(reads, cap=3000)
+        for r, got in zip(reads, sets):
+            np.testing.assert_array_equal(got, np.sort(oracle.minimizers(21, 9, r)))
+        hs.add_seqs(reads)
+        h = hs.histogram()
+    ho, nm = oracle.count_reads(21, 9, 21 ** 4, *oracle.pack_reads(reads))
+    np.testing.assert_array_equal(h, ho.astype(np.uint32))
+
+
+def test_read_length_errors_mirror_reference(hb):
+    with hb.HistoSketch(21, 9, 4) as hs:
+        with pytest.raises(hb.HulkError) as e:
+            hs.minimizers([b"ACGT" * 30, b"ACGTACGTACGTACGTACGTACGTACGT"])      # 28 < k + w - 1 = 29
+        assert e.value.code == -4 and "read 1" in str(e.value)
+        with pytest.raises(hb.HulkError) as e:
+            hs.minimizers([b"ACGT" * 30, b""])
+        assert e.value.code == -3
+    r, c, b = _tables(4, 5 ** 4, 1)
+    with hb.HistoSketch(5, 4, 4, tables=(r, c, b)) as hs:
+        hs.add_seqs([b"ACGTACGTAC", b"ACGTACG"])                                # second read: 7 < 8
+        hs.flush()
+        with pytest.raises(hb.HulkError) as e:
+            hs.finish()
+        assert e.value.code == -4
+
+
+# ---- stage 2: jump hash + histogram --------------------------------------------------------------
+def test_jump_hash_bit_exact(hb, oracle):
+    rng = np.random.default_rng(5)
+    keys = np.concatenate([rng.integers(0, 2 ** 64, 20000, dtype=np.uint64),
+                           np.array([0, 1, 42, 256, 0xDEAD10CC, 2 ** 64 - 1, 2 ** 63, 2 ** 33, 2 ** 33 - 1], dtype=np.uint64)])
+    with hb.HistoSketch(21, 9, 4) as hs:
+        for n in (1, 2, 10, 57, 666, 1024, 2000, 14641, 194481, 923521, 2 ** 31 - 1):
+            got = hs.jump_hash(keys, n)
+            want = np.array([oracle.jump(int(x), n) for x in keys], dtype=np.int32)
+            np.testing.assert_array_equal(got, want)
+        assert hs.jump_hash(np.array([1, 42, 0xDEAD10CC, 0xDEAD10CC, 256], dtype=np.uint64), 1).tolist() == [0] * 5
+        assert int(hs.jump_hash(np.array([42], dtype=np.uint64), 57)[0]) == 43
+        assert int(hs.jump_hash(np.array([0xDEAD10CC], dtype=np.uint64), 666)[0]) == 361
+        assert int(hs.jump_hash(np.array([256], dtype=np.uint64), 1024)[0]) == 520
+
+
+def test_fixture_histogram_matches_anchor(hb, fixture_reads):
+    anchors = json.load(open(os.path.join(GOLDEN, "c1_anchors.json")))
+    with hb.HistoSketch(21, 9, 4) as hs:
+        hs.add_seqs(fixture_reads)
+        h = hs.histogram()
+        st = hs.stats()
+    assert hashlib.md5(h.tobytes()).hexdigest() == anchors["hist_md5"]
+    assert st["n_minimizers"] == anchors["n_minimizers"] and st["n_reads"] == 1000 and st["n_bases"] == 100000
+
+
+@pytest.mark.parametrize("k,w,L", [(21, 9, 150), (31, 9, 150), (11, 9, 150), (21, 9, 250), (15, 5, 100), (21, 16, 151)])
+def test_histogram_bit_exact_synthetic(hb, oracle, k, w, L):
+    n = 20000
+    reads = hb.synthetic_reads(n, L, seed=2)
+    D = hb.spectrum_size(k)
+    offs = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+    ho, nm = oracle.count_reads(k, w, D, reads.reshape(-1), offs)
+    with hb.HistoSketch(k, w, 4) as hs:
+        hs.add_reads_fixed(reads.reshape(-1), n, L)
+        h1 = hs.histogram()
+        assert hs.stats()["n_minimizers"] == nm
+    np.testing.assert_array_equal(h1, ho.astype(np.uint32))
+    # ragged entry point, pushed in three uneven batches: the histogram is a plain sum
+    with hb.HistoSketch(k, w, 4) as hs:
+        for a, z in ((0, 7), (7, 12345), (12345, n)):
+            hs.add_reads(reads.reshape(-1), offs[a:z + 1])
+        np.testing.assert_array_equal(hs.histogram(), h1)
+
+
+def test_histogram_with_n_and_ragged_reads(hb, oracle):
+    reads = random_reads(5000, 60, seed=3, n_frac=0.01, lower_frac=0.3, ragged=200)
+    bases, offs = oracle.pack_reads(reads)
+    ho, nm = oracle.count_reads(21, 9, 21 ** 4, bases, offs)
+    with hb.HistoSketch(21, 9, 4) as hs:
+        hs.add_reads(bases, offs)
+        np.testing.assert_array_equal(hs.histogram(), ho.astype(np.uint32))
+        assert hs.stats()["n_minimizers"] == nm
+
+
+def test_device_resident_input_equals_host_input(hb):
+    import torch
+    n, L = 30000, 150
+    reads = hb.synthetic_reads(n, L, seed=4)
+    with hb.HistoSketch(21, 9, 4) as a, hb.HistoSketch(21, 9, 4) as b:
+        a.add_reads_fixed(reads.reshape(-1), n, L)
+        t = torch.from_numpy(reads.reshape(-1).copy()).cuda()
+        torch.cuda.synchronize()
+        b.add_reads_device(t.data_ptr(), None, n, L)
+        np.testing.assert_array_equal(a.histogram(), b.histogram())
+        offs = torch.arange(0, (n + 1) * L, L, dtype=torch.int64).cuda()
+        torch.cuda.synchronize()
+        b.add_reads_device(t.data_ptr(), offs.data_ptr(), n, 0)
+        np.testing.assert_array_equal(2 * a.histogram(), b.histogram())
+
+
+# ---- stage 3: count-min + CWS ---------------------------------------------------------------------
+def _run_both(hb, oracle, k, w, s, decay, reads_batches, tables, check_estimates=True, rtol_f=0.0):
+    D = hb.spectrum_size(k)
+    r, c, b = tables
+    ref = oracle.HistoSketch(k, s, D, decay, r, c, b)
+    with hb.HistoSketch(k, w, s, decay, tables=tables) as hs:
+        for reads in reads_batches:
+            bases, offs = oracle.pack_reads(reads)
+            hist, _ = oracle.count_reads(k, w, D, bases, offs)
+            f_ref = ref.flush(hist)
+            hs.add_reads(bases, offs)
+            hs.flush()
+            if check_estimates:
+                f = hs.estimates()
+                assert (np.isnan(f) == np.isnan(f_ref)).all()
+                m = ~np.isnan(f)
+                if rtol_f == 0.0:
+                    np.testing.assert_array_equal(f[m], f_ref[m])
+                else:
+                    np.testing.assert_allclose(f[m], f_ref[m], rtol=rtol_f, atol=0)
+            assert (hs.histogram() == 0).all()                       # wiped (kmerspectrum.go:58-64)
+        mins, weights = hs.finish()
+        q = hs.cms()
+        st = hs.stats()
+    mo, wo = ref.get()
+    np.testing.assert_array_equal(mins, mo)
+    np.testing.assert_allclose(weights, wo, rtol=W_RTOL, atol=0)
+    if rtol_f == 0.0:
+        np.testing.assert_array_equal(q, ref.cms())
+    else:
+        np.testing.assert_allclose(q, ref.cms(), rtol=rtol_f, atol=1e-300)
+    return st
+
+
+@pytest.mark.parametrize("k,s", [(11, 64), (21, 50), (7, 33)])
+def test_sketch_no_decay_exact(hb, oracle, k, s):
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 21)
+    batches = [random_reads(3000, 100, seed=100 + i, n_frac=0.002) for i in range(3)]
+    st = _run_both(hb, oracle, k, 9, s, 1.0, batches, tables)
+    assert st["n_flushes"] == 3
+
+
+@pytest.mark.parametrize("decay", [0.02, 0.5, 0.999, 0.0])
+def test_sketch_with_concept_drift(hb, oracle, decay):
+    k, s = 9, 48
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 22)
+    batches = [random_reads(1500, 100, seed=200 + i) for i in range(4)]
+    _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=(0.0 if decay == 0.0 else 1e-9))
+
+
+def test_c1_golden_json(hb, fixture_reads):
+    # BASELINE config C1: hulk sketch -f testing/test-reads-small.fq.gz -k 21 -s 50, Go-compatible tables
+    for name, decay, interval in (("c1_k21_s50.json", 1.0, 0), ("c1_k21_s50_x02_i250.json", 0.2, 250)):
+        want = open(os.path.join(GOLDEN, name)).read()
+        with hb.HistoSketch(21, 9, 50, decay) as hs:
+            hs.generate_tables()
+            mins, weights, st = hb.sketch_reads(hs, [hb.pack_reads(fixture_reads)], interval=interval)
+        doc = hb.sketch_json("testing/test-reads-small.fq.gz,", 21, mins, weights, 194481, decay != 1.0)
+        wj, gj = json.loads(want), json.loads(doc)
+        ws, gs = wj["signatures"][0]["Sketch"], gj["signatures"][0]["Sketch"]
+        assert gs["mins"] == ws["mins"] and gs["md5sum"] == ws["md5sum"]
+        np.testing.assert_allclose(gs["weights"], ws["weights"], rtol=W_RTOL)
+        assert st["n_minimizers"] == 17040 and st["n_reads"] == 1000
+        if doc != want:      # byte-compatibility up to the last float64 ulp of the GPU's exp/log
+            assert [ln for ln in doc.split("\n") if "e" not in ln and "." not in ln] == \
+                   [ln for ln in want.split("\n") if "e" not in ln and "." not in ln]
+
+
+def test_flush_semantics(hb):
+    k, s = 5, 8
+    D = k ** 4
+    tables = _tables(s, D, 3)
+    with hb.HistoSketch(k, 4, s, tables=tables) as hs:
+        hs.flush()                                           # empty spectrum: no-op (boss.go:117)
+        mins, weights = hs.finish()
+        assert (mins == 0).all() and (weights == 1.7976931348623157e308).all()
+        assert hs.stats()["n_flushes"] == 0
+        hs.add_seqs([b"ACGTACGTAC"])                         # 3 minimizers -> 3/625 bins < 1 %
+        hs.flush()
+        with pytest.raises(hb.HulkError) as e:
+            hs.finish()
+        assert e.value.code == -6 and "not used yet" in str(e.value)
+    with hb.HistoSketch(k, 4, s) as hs:
+        with pytest.raises(hb.HulkError) as e:
+            hs.flush()                                       # tables never set
+        assert e.value.code == -21
+
+
+def test_intervals_match_oracle_run(hb, oracle):
+    k, w, s = 11, 9, 40
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 9)
+    reads = random_reads(2500, 120, seed=12)
+    bases, offs = oracle.pack_reads(reads)
+    for interval in (0, 1000, 500, 2500):
+        ref = oracle.HistoSketch(k, s, D, 1.0, *tables)
+        nm, nf = ref.run(w, bases, offs, interval=interval)
+        with hb.HistoSketch(k, w, s, tables=tables) as hs:
+            mins, weights, st = hb.sketch_reads(hs, [(bases, offs)], interval=interval)
+        np.testing.assert_array_equal(mins, ref.get()[0])
+        np.testing.assert_allclose(weights, ref.get()[1], rtol=W_RTOL)
+        assert st["n_minimizers"] == nm
+
+
+def test_slot_sharding_is_identical_to_single_context(hb):
+    # multi-GPU layout: every rank counts a read shard, histograms are summed, each rank sweeps its slots
+    k, w, s = 11, 9, 64
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 31)
+    reads = [random_reads(2000, 150, seed=40 + i) for i in range(2)]
+    with hb.HistoSketch(k, w, s, tables=tables) as whole:
+        for rd in reads:
+            whole.add_seqs(rd)
+        whole.flush()
+        mins, weights = whole.finish()
+    parts = []
+    shards = [hb.HistoSketch(k, w, s, slots=(g * 16, (g + 1) * 16), tables=tuple(t[g * 16:(g + 1) * 16] for t in tables))
+              for g in range(4)]
+    try:
+        shards[0].add_seqs(reads[0])
+        shards[1].add_seqs(reads[1])
+        h0, h1 = shards[0].histogram(), shards[1].histogram()
+        # what the NCCL all-reduce leaves in every rank's histogram: the sum of all partial spectra
+        shards[0].merge_histogram(h1)
+        shards[1].merge_histogram(h0)
+        shards[2].merge_histogram(h0 + h1)
+        shards[3].merge_histogram(h0 + h1)
+        for sh in shards:
+            sh.flush()
+            parts.append(sh.finish())
+    finally:
+        for sh in shards:
+            sh.close()
+    np.testing.assert_array_equal(np.concatenate([p[0] for p in parts]), mins)
+    np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), weights)
+
+
+def test_folded_table_is_the_fp32_rounding_of_the_float64_coefficient(hb):
+    k, s = 7, 5
+    D = k ** 4
+    r, c, b = _tables(s, D, 2)
+    with hb.HistoSketch(k, 5, s, tables=(r, c, b)) as hs:
+        K = hs.folded_table()
+    assert K.shape[1] % 512 == 0 and np.isnan(K[:, D:]).all()
+    np.testing.assert_allclose(K[:, :D], (c * np.exp(b - r)).astype(np.float32), rtol=2e-7)
+
+
+# ---- size-independent properties at a larger size -------------------------------------------------
+def test_properties_one_million_reads(hb):
+    n, L, k, s = 1_000_000, 150, 21, 64
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 55)
+    reads = hb.synthetic_reads(n, L, seed=1).reshape(-1)
+    with hb.HistoSketch(k, 9, s, tables=tables) as a:
+        a.add_reads_fixed(reads, n, L)
+        h = a.histogram()
+        st = a.stats()
+        assert int(h.astype(np.int64).sum()) == st["n_minimizers"]          # every set member lands in one bin
+        assert 26.0 < st["n_minimizers"] / n < 28.0
+        a.flush()
+        mins_a, w_a = a.finish()
+    # linearity: two half-batches into one context == one batch; order of batches is irrelevant
+    with hb.HistoSketch(k, 9, s, tables=tables) as b:
+        half = (n // 2) * L
+        b.add_reads_fixed(reads[half:], n - n // 2, L)
+        b.add_reads_fixed(reads[:half], n // 2, L)
+        np.testing.assert_array_equal(b.histogram(), h)
+        b.flush()
+        mins_b, w_b = b.finish()
+        # idempotence: flushing an empty spectrum changes nothing
+        b.flush()
+        mins_c, w_c = b.finish()
+    np.testing.assert_array_equal(mins_a, mins_b)
+    np.testing.assert_array_equal(w_a, w_b)
+    np.testing.assert_array_equal(mins_b, mins_c)
+    np.testing.assert_array_equal(w_b, w_c)
+    assert (w_a < 0).all() and (mins_a < D).all()

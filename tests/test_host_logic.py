@@ -1,0 +1,179 @@
+"""CPU-only checks of the product's host side: the C ABI library loads and exports every symbol of
+include/hulk_b200.h, fails loudly without a GPU, and its host-only pieces (CWS table generator,
+md5, JSON writer, the device math header compiled for the host) agree with the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, has_gpu
+from oracle import pyref as P
+
+import hulk_b200
+from hulk_b200 import _native as N
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hulk_b200.h")).read()
+    declared = sorted(set(re.findall(r"HULK_B200_API[^;(]*?(hulk_b200_\w+)\s*\(", hdr)))
+    assert declared == sorted(N.EXPORTS)
+    L = hulk_b200.load()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.hulk_b200_version() == b"1.0.0"
+    assert L.hulk_b200_strerror(-4) == b"sequence length must be >= w + k - 1"
+    assert L.hulk_b200_strerror(-6) == b"not used yet"
+
+
+def test_product_does_not_touch_the_oracle():
+    # the product tree must never import, link or execute anything under oracle/
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hulk_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_create_fails_loudly_without_gpu():
+    with pytest.raises(hulk_b200.HulkError) as e:
+        hulk_b200.HistoSketch(21, 9, 50)
+    assert e.value.code == N.ECUDA and "no CPU fallback" in str(e.value)
+
+
+def test_parameter_validation_order():
+    # argument checks happen before any CUDA call, so they are testable here
+    L = hulk_b200.load()
+    for kw, code in [(dict(k=32), N.EK), (dict(w=257), N.EW), (dict(decay_ratio=1.5), N.EDECAY),
+                     (dict(decay_ratio=-0.1), N.EDECAY), (dict(k=1), N.EBINS), (dict(num_bins=-5), N.ENEGBINS)]:
+        p = N.Params()
+        p.k, p.w, p.sketch_size, p.decay_ratio = 21, 9, 50, 1.0
+        for a, v in kw.items():
+            setattr(p, a, v)
+        ctx = C.c_void_p()
+        assert L.hulk_b200_create(C.byref(p), C.byref(ctx)) == code, kw
+
+
+def test_new_cws_equals_oracle(oracle):
+    s, D = 5, 14641
+    r, c, b = hulk_b200.new_cws(s, D)
+    ro, co, bo = oracle.new_cws(s, D)
+    np.testing.assert_array_equal(r, ro)
+    np.testing.assert_array_equal(c, co)
+    np.testing.assert_array_equal(b, bo)
+    r2, c2, b2 = hulk_b200.new_cws(s, D, 2, 4)
+    np.testing.assert_array_equal(r2, ro[2:4])
+    np.testing.assert_array_equal(b2, bo[2:4])
+
+
+def test_md5_and_json_equal_oracle_side():
+    rng = np.random.default_rng(0)
+    mins = rng.integers(0, 923521, 64).astype(np.uint64)
+    weights = np.concatenate([-rng.random(40) * 10.0 ** rng.integers(-12, 3, 40), rng.random(20) * 1e-8,
+                              [1.7976931348623157e308, 0.0, -0.0, 123456789012345678901234.0]])
+    assert hulk_b200.md5_mins(mins) == P.md5_of_mins(mins)
+    for fn, banner in (("a.fq,b.fq.gz,", "blank"), ("STDIN", "label <&> \"q\" \\ \t  é")):
+        mine = hulk_b200.sketch_json(fn, 21, mins, weights, 194481, True, banner)
+        assert mine == P.sketch_json(fn, 21, mins, weights, 194481, True, banner)
+    import json
+    doc = json.loads(hulk_b200.sketch_json("x,", 31, mins, weights, 923521, False))
+    assert list(doc) == ["class", "filename", "hash_function", "license", "signatures", "version", "banner_label"]
+    sk = doc["signatures"][0]["Sketch"]
+    assert list(sk) == ["ksize", "md5sum", "mins", "weights", "num", "num_histogram_bins", "concept_drift"]
+    assert sk["weights"] == [float(x) for x in weights] and sk["mins"] == mins.tolist()
+
+
+def test_go_float_formatting_cases():
+    cases = {1.7976931348623157e308: "1.7976931348623157e+308", 1e-7: "1e-7", 1.5e-9: "1.5e-9", 1e-6: "0.000001",
+             9.999e-7: "9.999e-7", 1e21: "1e+21", 1e20: "100000000000000000000", -3.25: "-3.25", 100.0: "100",
+             5e-324: "5e-324", -0.0123: "-0.0123", 2.5e-10: "2.5e-10", 0.1: "0.1"}
+    mins = np.zeros(len(cases), dtype=np.uint64)
+    doc = hulk_b200.sketch_json("f,", 21, mins, np.array(list(cases)), 16, False)
+    got = [ln.strip().rstrip(",") for ln in doc.split('"weights": [')[1].split("]")[0].strip().split("\n")]
+    assert got == list(cases.values())
+    assert [P.go_float(v) for v in cases] == list(cases.values())
+
+
+def test_fastq_reader_on_reference_fixture(fixture_reads):
+    reads = hulk_b200.read_fastq(os.path.join(GOLDEN, "c1_reads.fq.gz"))
+    assert reads == fixture_reads
+
+
+def test_fastq_reader_quirks(tmp_path):
+    # empty lines are nil in the reference and re-fill the same slot (src/pipeline/sketch.go:50,139-159)
+    p = tmp_path / "q.fq"
+    p.write_bytes(b"@r1\n\nACGT\n+\nIIII\n@r2\r\nGGCC\r\n+\r\nIIII")
+    assert hulk_b200.read_fastq(str(p)) == [b"ACGT", b"GGCC"]
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"r1\nACGT\n+\nIIII\n")
+    with pytest.raises(ValueError):
+        hulk_b200.read_fastq(str(bad))
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b">c1 desc\nACGT\nTTAA\n>c2\nGG\n\n>c3\nAAAA\n")
+    assert hulk_b200.read_fasta(str(fa)) == [b"ACGTTTAA", b"GG"]        # stops at the empty line
+
+
+def test_synthetic_reads_definition():
+    a = hulk_b200.synthetic_reads(64, 150, seed=1)
+    b = hulk_b200.synthetic_reads(32, 150, seed=1, first_read=32)
+    assert a.shape == (64, 150) and (a[32:] == b).all()
+    assert set(np.unique(a).tolist()) <= set(b"ACGT")
+    # base j of read i from the definition in BASELINE.md section 3
+    def splitmix(x):
+        x = (x + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return z ^ (z >> 31)
+    for i, j in ((0, 0), (3, 31), (3, 32), (63, 149)):
+        word = splitmix(1 ^ (i * 5 + j // 32))
+        assert a[i, j] == b"ACGT"[(word >> (2 * (j % 32))) & 3]
+
+
+HD_TEST_SRC = r"""
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include "hd_math.h"
+int main(int argc, char** argv) {
+    // stdin: lines "h key mask" | "j key n" | "n byte"; stdout: results
+    char op; unsigned long long a, b;
+    while (scanf(" %c %llu %llu", &op, &a, &b) == 3) {
+        if (op == 'h') printf("%llu\n", (unsigned long long)hulk::hash64(a, b));
+        else if (op == 'j') printf("%d\n", hulk::jump_hash(a, (int32_t)b));
+        else printf("%u\n", hulk::nt4((uint32_t)a));
+    }
+    return 0;
+}
+"""
+
+
+def test_device_math_header_compiled_for_host_matches_oracle(oracle, tmp_path):
+    # hd_math.h is the exact source the kernels use (multiply forms of hash64, arithmetic nt4)
+    src = tmp_path / "hd_test.cpp"
+    src.write_text(HD_TEST_SRC)
+    exe = tmp_path / "hd_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "hulk_b200", "csrc"),
+                    "-o", str(exe), str(src)], check=True)
+    rng = np.random.default_rng(1)
+    lines, want = [], []
+    for k in (2, 4, 11, 21, 31):
+        mask = (1 << (2 * k)) - 1
+        for key in [0, 1, mask] + [int(x) & mask for x in rng.integers(0, 2 ** 63, 300, dtype=np.uint64)]:
+            lines.append(f"h {key} {mask}")
+            want.append(oracle.hash64(key, mask))
+    for n in (1, 2, 10, 2000, 14641, 194481, 923521, 2 ** 31 - 1):
+        for key in [0, 1, 2 ** 64 - 1] + [int(x) for x in rng.integers(0, 2 ** 64, 200, dtype=np.uint64)]:
+            lines.append(f"j {key} {n}")
+            want.append(oracle.jump(key, n))
+    for b in range(256):
+        lines.append(f"n {b} 0")
+        want.append(oracle.nt4(b))
+    out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+    got = [int(x) for x in out.split()]
+    assert got == want
