@@ -1,0 +1,111 @@
+// UNCOMPILED: no Go toolchain exists in the authoring image (see INTEGRATION.md).
+// Drop into src/pipeline/ of will-rowe/hulk v1.0.0 and build with `-tags b200`.
+// +build b200
+
+package pipeline
+
+/*
+#cgo CFLAGS:  -I${SRCDIR}/../../third_party/hulk_b200/include
+#cgo LDFLAGS: -L${SRCDIR}/../../third_party/hulk_b200/lib -lhulk_b200 -Wl,-rpath,$ORIGIN
+#include <stdlib.h>
+#include "hulk_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"log"
+	"runtime"
+	"unsafe"
+
+	"github.com/will-rowe/hulk/src/helpers"
+	"github.com/will-rowe/hulk/src/histosketch"
+	"github.com/will-rowe/hulk/src/seqio"
+	"github.com/will-rowe/hulk/src/sketchio"
+)
+
+// GPUSketcher replaces SeqMinimizer + Sketcher (src/pipeline/sketch.go:163-301).
+type GPUSketcher struct {
+	info  *Info
+	input chan *seqio.FASTQread
+}
+
+func NewGPUSketcher(info *Info) *GPUSketcher      { return &GPUSketcher{info: info} }
+func (proc *GPUSketcher) Connect(p *FastqHandler) { proc.input = p.output }
+
+const batchBytes = 64 << 20 // reads are handed to the GPU in ~64 MB batches
+
+func (proc *GPUSketcher) Run() {
+	runtime.LockOSThread() // a context is single-caller (include/hulk_b200.h)
+	defer runtime.UnlockOSThread()
+	s := proc.info.Sketch
+	var ctx *C.hulk_b200_ctx
+	p := C.hulk_b200_params{k: C.uint32_t(s.KmerSize), w: C.uint32_t(s.WindowSize),
+		sketch_size: C.uint32_t(s.SketchSize), num_bins: C.int32_t(s.SpectrumSize),
+		decay_ratio: C.double(s.DecayRatio)}
+	check := func(rc C.int) {
+		if rc != 0 {
+			helpers.ErrorCheck(fmt.Errorf("%s", C.GoString(C.hulk_b200_last_error(ctx))))
+		}
+	}
+	check(C.hulk_b200_create(&p, &ctx))
+	defer C.hulk_b200_destroy(ctx)
+	check(C.hulk_b200_generate_cws_tables(ctx)) // newCWS, histosketch.go:95-126
+
+	bases := make([]byte, 0, batchBytes+1<<20)
+	offsets := []C.uint64_t{0}
+	push := func() {
+		if len(offsets) > 1 {
+			check(C.hulk_b200_push_reads(ctx, (*C.uint8_t)(unsafe.Pointer(&bases[0])),
+				&offsets[0], C.uint64_t(len(offsets)-1)))
+			bases, offsets = bases[:0], offsets[:1]
+		}
+	}
+	log.Printf("finding minimizers...")
+	seqCount, interval, sketchingInterval := uint(0), s.Interval, 0
+	for sequence := range proc.input { // sketch.go:197
+		bases = append(bases, sequence.Seq...)
+		offsets = append(offsets, C.uint64_t(len(bases)))
+		seqCount++
+		if seqCount%100000 == 0 {
+			log.Printf("\tprocessed %d sequences", seqCount)
+		}
+		if interval != 0 && seqCount%interval == 0 { // sketch.go:211-215
+			push()
+			sketchingInterval++
+			log.Printf("\treached interval %d -> histosketching", sketchingInterval)
+			check(C.hulk_b200_flush(ctx))
+		} else if len(bases) >= batchBytes {
+			push()
+		}
+	}
+	log.Printf("generating final histosketch of k-mer spectra...")
+	push()
+	check(C.hulk_b200_flush(ctx)) // sketch.go:221
+	if seqCount == 0 {
+		helpers.ErrorCheck(fmt.Errorf("no sequences received")) // sketch.go:237-239
+	}
+	mins := make([]C.uint64_t, s.SketchSize)
+	weights := make([]C.double, s.SketchSize)
+	check(C.hulk_b200_finish(ctx, &mins[0], &weights[0]))
+	var st C.hulk_b200_stats
+	check(C.hulk_b200_get_stats(ctx, &st))
+	log.Printf("\tprocessed %d sequences in total\n", seqCount)
+	log.Printf("\tmean sequence length: %d\n", uint(float64(st.n_bases)/float64(seqCount)))
+	log.Printf("\tfound %d minimizers\n", uint64(st.n_minimizers))
+	log.Printf("\thistosketching across %d bins\n", s.SpectrumSize)
+
+	// hand the result to the reference's own output code (sketchio.go:56-97); `algorithm`, `cwsSamples`
+	// and `cmSketch` are unexported, so the histosketch package gains the 12-line constructor below
+	sk := make([]uint, s.SketchSize)
+	wt := make([]float64, s.SketchSize)
+	for i := range mins {
+		sk[i], wt[i] = uint(mins[i]), float64(weights[i])
+	}
+	hs := histosketch.FromSlots(s.KmerSize, s.SpectrumSize, s.DecayRatio != 1.0, sk, wt)
+	hulkData := sketchio.NewHULKdata()
+	helpers.ErrorCheck(hulkData.Add(hs))
+	hulkData.FileName, hulkData.Banner = s.FileName, s.BannerLabel
+	hulkData.WriteJSON(s.OutFile + ".json")
+	log.Printf("\twritten sketch to disk: %v\n", s.OutFile+".json")
+}

@@ -14,6 +14,11 @@
 #else
 #define HULK_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define HULK_UNROLL _Pragma("unroll")
+#else
+#define HULK_UNROLL
+#endif
 
 namespace hulk {
 
@@ -58,6 +63,121 @@ HULK_HD int32_t jump_hash(uint64_t key, int32_t num_buckets) {
         j = (int64_t)((double)(b + 1) * (2147483648.0 / (double)((key >> 33) + 1)));
     }
     return (int32_t)b;
+}
+
+// ---- fast path of the Lamping-Veach step -------------------------------------------------
+// One step is j' = trunc(fl(fl(2^31 / q) * (j + 1))) with q = (key >> 33) + 1.  The exact IEEE
+// quotient is only needed when the product lies within a few ulps of an integer, so the hot
+// loop evaluates x ~= (j + 1) * 2^31 / q from the hardware reciprocal seed plus one Newton
+// step (relative error <= JUMP_RCP_ERR, measured on the device by the self-test tap) and
+// brackets the reference value: with EPS >= JUMP_RCP_ERR + 2^-50 the reference product lies
+// in [x(1-EPS), x(1+EPS)], so when both ends truncate to the same integer that integer IS the
+// reference's result.  Otherwise (probability ~ 2 EPS x per step) the caller recomputes the
+// step with the true division.  No rounding-mode or fast-math assumptions leak out: the
+// result is bit-identical to jump_hash() above by construction.
+constexpr double JUMP_EPS = 9.094947017729282e-13;        // 2^-40
+constexpr double JUMP_TWO52 = 4503599627370496.0;         // 2^52
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double u32_to_double(uint32_t v) {   // exact, no conversion unit
+    return __hiloint2double(0x43300000, (int)v) - JUMP_TWO52;
+}
+__device__ __forceinline__ double rcp_seed(double x) {          // MUFU.RCP64H, ~2^-23 relative
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double fma_down(double a, double b, double c) { return __fma_rd(a, b, c); }
+__device__ __forceinline__ uint32_t dbl_lo(double x) { return (uint32_t)__double2loint(x); }
+__device__ __forceinline__ uint32_t dbl_hi(double x) { return (uint32_t)__double2hiint(x); }
+__device__ __forceinline__ double dbl_make(uint32_t hi, uint32_t lo) { return __hiloint2double((int)hi, (int)lo); }
+#else
+}  // namespace hulk
+#include <cfenv>
+#include <cmath>
+#include <cstring>
+namespace hulk {
+inline uint32_t dbl_lo(double x) { uint64_t u; std::memcpy(&u, &x, 8); return (uint32_t)u; }
+inline uint32_t dbl_hi(double x) { uint64_t u; std::memcpy(&u, &x, 8); return (uint32_t)(u >> 32); }
+inline double dbl_make(uint32_t hi, uint32_t lo) { uint64_t u = ((uint64_t)hi << 32) | lo; double x; std::memcpy(&x, &u, 8); return x; }
+inline double u32_to_double(uint32_t v) { return dbl_make(0x43300000u, v) - JUMP_TWO52; }
+// host stand-in for the hardware seed: 1/x with the mantissa cut to 24 bits (same error class)
+inline double rcp_seed(double x) { const double r = 1.0 / x; return dbl_make(dbl_hi(r), dbl_lo(r) & 0xF0000000u); }
+inline double fma_down(double a, double b, double c) {
+    const int old = std::fegetround();
+    std::fesetround(FE_DOWNWARD);
+    volatile double va = a, vb = b, vc = c;
+    const double r = std::fma(va, vb, vc);
+    std::fesetround(old);
+    return r;
+}
+#endif
+
+// state of one chain: key, current bucket b, jd1 = (double)(b + 1)
+// returns 0: stepped (b, jd1 updated), 1: finished (b is the answer), 2: ambiguous -> use jump_step_exact
+HULK_HD int jump_step_fast(uint64_t &key, uint32_t &b, double &jd1, uint32_t num_buckets) {
+    key = key * 2862933555777941757ull + 1ull;
+    const uint32_t q = (uint32_t)(key >> 33) + 1u;                       // 1 .. 2^31
+    const double qd = u32_to_double(q);
+    const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
+    const double r0 = rcp_seed(Q);
+    const double e = fma(-Q, r0, 1.0);
+    const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
+    const double x = jd1 * R;
+    const double tl = fma_down(x, 1.0 - JUMP_EPS, JUMP_TWO52);           // 2^52 + floor(x (1-EPS))
+    const double th = fma_down(x, 1.0 + JUMP_EPS, JUMP_TWO52);
+    const uint32_t nl = dbl_lo(tl), nh = dbl_lo(th);
+    if (dbl_hi(th) != 0x43300000u || nl >= num_buckets) return 1;        // x(1-EPS) >= 2^32 - 1 or >= n
+    if (nl != nh) return 2;
+    b = nl;
+    jd1 = tl - (JUMP_TWO52 - 1.0);                                       // (double)(nl + 1), exact
+    return 0;
+}
+// the same step with the reference's arithmetic; `key` has already been advanced by jump_step_fast
+HULK_HD int jump_step_exact(uint64_t key, uint32_t &b, double &jd1, uint32_t num_buckets) {
+    const int64_t j = (int64_t)((double)((int64_t)b + 1) * (2147483648.0 / (double)((key >> 33) + 1)));
+    if (j >= (int64_t)num_buckets) return 1;
+    b = (uint32_t)j;
+    jd1 = (double)(j + 1);
+    return 0;
+}
+// jump_hash() evaluated through the fast step (what the kernel's chains compute)
+HULK_HD int32_t jump_hash_fast(uint64_t key, int32_t num_buckets, uint32_t *n_ambiguous = nullptr) {
+    uint32_t b = 0;
+    double jd1 = 1.0;
+    for (;;) {
+        int rc = jump_step_fast(key, b, jd1, (uint32_t)num_buckets);
+        if (rc == 2) {
+            if (n_ambiguous) ++*n_ambiguous;
+            rc = jump_step_exact(key, b, jd1, (uint32_t)num_buckets);
+        }
+        if (rc) return (int32_t)b;
+    }
+}
+
+// ---- word-wise base encoding ---------------------------------------------------------------
+// Four ASCII bases in one little-endian word -> four 2-bit codes (byte j of the result = code of
+// base j) and a flag telling whether every byte was one of ACGTUacgtu.  (b >> 1 ^ b >> 2) & 3
+// maps A,C,G,T/U -> 0,1,2,3 for either case; the check rebuilds the expected letters from the
+// codes with a byte permute and compares.  Words that fail fall back to nt4() per byte.
+HULK_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+#endif
+}
+HULK_HD uint32_t nt4x4(uint32_t w, bool &all_acgtu) {
+    const uint32_t v = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+    const uint32_t s1 = v | (v >> 4);
+    const uint32_t sel = byte_perm(s1, 0u, 0x4420u) & 0xffffu;           // nibble j = code of base j
+    const uint32_t expect = byte_perm(0x54474341u /* "ACGT" */, 0u, sel);
+    const uint32_t is_t = v & (v >> 1) & 0x01010101u;                    // code 3: accept T and U
+    all_acgtu = (((w & 0xDFDFDFDFu) ^ expect) & ~is_t) == 0u;
+    return v;
 }
 
 }  // namespace hulk

@@ -2,27 +2,25 @@
 //   reads (ASCII, in HBM) -> per-read SET of window minimizers -> jump-hash bin -> histogram.
 //
 // Reference semantics (paths relative to the reference checkout):
-//   src/minimizer/minimizer.go:96-204  findMinimizers (rolling 2-bit k-mer pair, canonical pick,
-//       X = hash64(canon)<<8 | kmerSpan, monotone-deque window minimum, per-read set)
+//   src/minimizer/minimizer.go:96-204  findMinimizers (see k1_scan.h for the scan itself)
 //   src/pipeline/minion.go:51-57 + boss.go:90-95 -> src/kmerspectrum/kmerspectrum.go:67-81 AddHash
-//
-// What the deque computes, restated for a SIMT machine: position i (i >= k-1, fwd != rev) emits
-//   m_i = min{ X_j : i-w < j <= i, j >= k-1, fwd_j != rev_j }   when i >= w-1,
-// and the read contributes the SET {m_i}.  (The deque's tie rule only affects the stored
-// position, which never leaves the function.)  The window minimum is evaluated with the
-// two-pass block decomposition (prefix minima of the current block of w k-mers, suffix minima
-// of the previous one) so every lane runs the same instruction stream regardless of data.
 //
 // Work decomposition: one thread per read, 128 reads per CTA tile; the tile's bytes are one
 // contiguous range of the batch and are staged into shared memory with a single 1-D bulk TMA
-// copy (the other resident CTAs of the SM cover its latency).  Candidates (window minima that
-// differ from the previous one) go to a per-thread shared-memory list; after the scan the list
-// is de-duplicated exactly and every distinct minimizer is jump-hashed and counted with a
-// global (L2) atomic -- the k^4-bin histogram does not fit shared memory for k > 11.
+// copy (the other resident CTAs of the SM cover its latency).  Three phases per tile:
+//   scan    every lane walks its read four bases at a time (k1_scan.h); window minima that differ
+//           from the previous one go to the lane's private list in shared memory;
+//   de-dup  the list is reduced in place to the exact per-read set (minimizer.go:189-198);
+//   jump    the warp's 32 lists form one work queue; every lane keeps TWO jump-hash chains in
+//           flight (ILP), runs them K1_JUMP_BATCH steps at a time with the fast step of
+//           hd_math.h, and finished chains are refilled from the queue, so lanes stay busy
+//           whatever the per-read set sizes and per-key step counts are.  Bins are counted
+//           with global (L2) atomics -- the k^4-bin histogram does not fit shared memory for k > 11.
 #pragma once
 #include <stdint.h>
 
 #include "hd_math.h"
+#include "k1_scan.h"
 #include "ptx_util.cuh"
 
 namespace hulk {
@@ -70,62 +68,43 @@ __device__ __forceinline__ void k1_report(const K1Params &p, uint64_t r, uint32_
     atomicMin(p.err_word, (unsigned long long)(((p.read_base + r) << 8) | code));
 }
 
-// Scan one read.  `vh(t)` is the w-entry block buffer, `emit(m)` receives every window minimum
-// (position order).  Returns false if the read fails the reference's length checks.
-template <class VH, class Emit>
-__device__ __forceinline__ void k1_scan_read(const uint8_t *__restrict__ seq, int32_t len, int32_t k, int32_t w,
-                                             VH vh, Emit emit) {
-    const uint64_t mask = (1ull << (2 * k)) - 1ull;       // minimizer.go:103  (k <= 31)
-    const int shift = 2 * (k - 1);                        // minimizer.go:104
-    uint64_t fwd = 0, rev = 0;
-    uint64_t pref = ~0ull;                                // prefix minimum of the current block
-    int t = 0;                                            // position inside the current block
-    for (int x = 0; x < w; x++) vh(x) = ~0ull;
-    for (int32_t i = 0; i < len; i++) {
-        const uint32_t c = nt4(seq[i]);                                   // minimizer.go:115
-        fwd = ((fwd << 2) | (uint64_t)c) & mask;                          // :134
-        rev = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);                 // :137 (not masked)
-        if (i < k - 1) continue;                                          // :140-142
-        const bool skip = (fwd == rev);                                   // :145-147
-        uint64_t X = ~0ull;
-        if (!skip) {
-            const int32_t wi = i - w + 1;                                 // windowIndex :112
-            const int32_t span = (wi + 1 < k) ? (wi + 1) : k;             // :127-131
-            const uint64_t canon = (fwd > rev) ? rev : fwd;               // :150-153
-            X = (hash64(canon, mask) << 8) | (uint64_t)(int64_t)span;     // :156-159
-        }
-        pref = (X < pref) ? X : pref;
-        const uint64_t suf = (t + 1 < w) ? vh(t + 1) : ~0ull;             // previous block, positions t+1..w-1
-        vh(t) = X;
-        if (!skip && i >= w - 1) emit((pref < suf) ? pref : suf);         // :186-199
-        if (++t == w) {                                                   // block complete: suffix minima in place
-            uint64_t run = ~0ull;
-            for (int x = w - 1; x >= 0; x--) {
-                const uint64_t v = vh(x);
-                run = (v < run) ? v : run;
-                vh(x) = run;
-            }
-            t = 0;
-            pref = ~0ull;
-        }
-    }
-}
-
 struct K1SmemVH {
     uint64_t *base;   // [w][K1_TPB], this thread's column
     __device__ __forceinline__ uint64_t &operator()(int t) const { return base[t * K1_TPB]; }
 };
 
+// bases of a read staged in shared memory: aligned 32-bit loads + funnel shift (the buffer has
+// 16 bytes of slack behind the tile, so the word behind the last base may be read, never used)
+struct SmemWordSrc {
+    const uint32_t *words;    // aligned word that holds base 0
+    uint32_t sh;              // (byte offset of base 0 inside that word) * 8
+    __device__ __forceinline__ uint32_t get4(int32_t i) const {
+        const uint32_t lo = words[i >> 2], hi = words[(i >> 2) + 1];
+        return __funnelshift_r(lo, hi, sh);
+    }
+};
+
+constexpr int K1_JUMP_BATCH = 4;      // jump steps between two refills of a lane's chains
+constexpr int K1_WARPS = K1_TPB / 32;
+
+struct K1Chain {
+    uint64_t key;
+    double jd1;
+    uint32_t b;
+    bool busy;                // holds a key whose walk has not finished
+};
+
 template <bool DUMP>
 __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *tile = smem;                                                          // tile_cap bytes
-    uint64_t *vh_all = reinterpret_cast<uint64_t *>(smem + (size_t)p.tile_cap);    // [w][K1_TPB]
-    uint64_t *list_all = vh_all + (size_t)p.w * K1_TPB;                            // [list_cap][K1_TPB]
-    uint64_t *bar = list_all + (size_t)p.list_cap * K1_TPB;                        // mbarrier
+    uint8_t *tile = smem;                                                          // tile_cap + 16 bytes
+    uint64_t *vh_all = reinterpret_cast<uint64_t *>(smem + (size_t)p.tile_cap + 16);   // [w][K1_TPB]
+    uint64_t *list_all = vh_all + (size_t)p.w * K1_TPB;                            // [K1_TPB][list_cap]
+    uint32_t *prefix_all = reinterpret_cast<uint32_t *>(list_all + (size_t)p.list_cap * K1_TPB);   // [warps][34]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(prefix_all + K1_WARPS * 34);      // mbarrier
     uint64_t *tile_src = bar + 1;                  // global address the tile was staged from (0 = not staged)
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t ntiles = (p.n_reads + K1_TPB - 1) / K1_TPB;
     if (blockIdx.x >= ntiles) return;
 
@@ -137,9 +116,12 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
 
     uint32_t phase = 0;
     uint64_t *my_vh = vh_all + tid;
-    uint64_t *my_list = list_all + tid;
     const uint32_t list_cap = p.list_cap;
+    uint64_t *my_list = list_all + (size_t)tid * list_cap;
+    uint64_t *warp_lists = list_all + (size_t)(warp * 32) * list_cap;
+    uint32_t *P = prefix_all + warp * 34;          // P[l] = first queue index of lane l's set; P[32] = total
     unsigned long long local_minimizers = 0;
+    const uint32_t nb = (uint32_t)p.D;
 
     for (uint64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         if (tid == 0) {
@@ -162,6 +144,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
         mbar_wait(bar, phase);
         phase ^= 1;
 
+        // ---- scan ----------------------------------------------------------------------------
         const uint64_t r = tl * K1_TPB + tid;
         uint32_t n = 0;            // entries in my list
         bool overflow = false;
@@ -176,17 +159,23 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
             } else {
                 valid = true;
                 const uint64_t src = *tile_src;
-                const uint8_t *seq = src ? tile + (reinterpret_cast<uintptr_t>(p.bases) + b0 - src)
-                                         : p.bases + b0;
-                uint64_t last = 0;
-                k1_scan_read(seq, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh},
-                             [&](uint64_t m) {
-                                 if (n == 0 || m != last) {
-                                     if (n < list_cap) { my_list[(size_t)n * K1_TPB] = m; n++; }
-                                     else overflow = true;
-                                     last = m;
-                                 }
-                             });
+                uint64_t last = ~0ull;                                           // never a minimizer (low byte <= 31)
+                auto emit = [&](uint64_t m) {
+                    if (m != last) {
+                        if (n < list_cap) my_list[n] = m;
+                        else overflow = true;
+                        n++;
+                        last = m;
+                    }
+                };
+                if (src) {
+                    const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases) + b0 - src);
+                    const SmemWordSrc ws{reinterpret_cast<const uint32_t *>(tile + (off & ~3u)), (off & 3u) * 8u};
+                    k1_scan_read(ws, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh}, emit);
+                } else {
+                    const ByteSrc bs{p.bases + b0, (int32_t)len64};
+                    k1_scan_read(bs, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh}, emit);
+                }
             }
         }
         if (valid && overflow) {
@@ -197,43 +186,72 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
             n = 0;
             valid = false;
         }
-        // exact per-read set: drop values already present earlier in the list (minimizer.go:189-198)
+        // ---- exact per-read set: drop values already present earlier in the list (minimizer.go:189-198)
         uint32_t m_out = 0;
         for (uint32_t a = 0; a < n; a++) {
-            const uint64_t x = my_list[(size_t)a * K1_TPB];
+            const uint64_t x = my_list[a];
             bool dup = false;
-            for (uint32_t b = 0; b < m_out; b++) dup |= (my_list[(size_t)b * K1_TPB] == x);
-            if (!dup) { my_list[(size_t)m_out * K1_TPB] = x; m_out++; }
+            for (uint32_t b = 0; b < m_out; b++) dup |= (my_list[b] == x);
+            if (!dup) { my_list[m_out] = x; m_out++; }
         }
         if (DUMP) {
             if (valid) {
-                for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++)
-                    p.dump[r * p.dump_cap + e] = my_list[(size_t)e * K1_TPB];
+                for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++) p.dump[r * p.dump_cap + e] = my_list[e];
                 p.dump_counts[r] = m_out;
             } else if (r < p.n_reads && !overflow) {
                 p.dump_counts[r] = 0;
             }
         } else {
-            // kmerspectrum.go:67-81: bins[jump.Hash(kmer, numBins)]++ for every set member.
-            // Each lane walks its own list; a lane that finishes a key immediately starts the next
-            // one, so the warp only idles for the difference in total jump steps between lanes.
+            // ---- jump: kmerspectrum.go:67-81, bins[jump.Hash(kmer, numBins)]++ for every set member
             local_minimizers += m_out;
-            if (m_out > 0) {
-                uint32_t e = 0;
-                uint64_t key = my_list[0];
-                int64_t b = -1, j = 0;
-                const int64_t nb = p.D;
-                for (;;) {
-                    if (j >= nb) {
-                        atomicAdd(&p.hist[(int32_t)b], 1u);
-                        if (++e >= m_out) break;
-                        key = my_list[(size_t)e * K1_TPB];
-                        b = -1;
-                        j = 0;
+            uint32_t incl = m_out;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            P[lane] = incl - m_out;
+            if (lane == 31) P[32] = incl;
+            __syncwarp();
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t next_f = 0;       // warp-uniform: first unclaimed queue index
+            uint32_t o_cur = 0;        // warp-uniform: P[o_cur] <= next_f (owner search starts here)
+            K1Chain ch[2];
+            ch[0].busy = ch[1].busy = false;
+            ch[0].key = ch[1].key = 0; ch[0].jd1 = ch[1].jd1 = 1.0; ch[0].b = ch[1].b = 0;
+            for (;;) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {                                    // refill idle chains
+                    const bool need = !ch[c].busy;
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, need);
+                    const uint32_t f = next_f + __popc(ballot & ((1u << lane) - 1u));
+                    next_f += __popc(ballot);
+                    if (need && f < total) {
+                        uint32_t o = o_cur;
+                        while (f >= P[o + 1]) o++;                               // P[32] = total > f
+                        ch[c].key = warp_lists[(size_t)o * list_cap + (f - P[o])];
+                        ch[c].b = 0;                                             // first step of jump.Hash: b = 0
+                        ch[c].jd1 = 1.0;
+                        ch[c].busy = true;
                     }
-                    b = j;
-                    key = key * 2862933555777941757ull + 1ull;
-                    j = (int64_t)((double)(b + 1) * (2147483648.0 / (double)((key >> 33) + 1)));
+                    while (o_cur < 31 && P[o_cur + 1] <= next_f) o_cur++;
+                }
+                if (!__any_sync(0xffffffffu, ch[0].busy || ch[1].busy)) break;
+#pragma unroll
+                for (int it = 0; it < K1_JUMP_BATCH; it++) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        uint64_t key = ch[c].key;
+                        uint32_t b = ch[c].b;
+                        double jd1 = ch[c].jd1;
+                        int rc = jump_step_fast(key, b, jd1, nb);
+                        if (rc == 2 && ch[c].busy) rc = jump_step_exact(key, b, jd1, nb);   // rare
+                        if (ch[c].busy) {
+                            ch[c].key = key;
+                            if (rc == 0) { ch[c].b = b; ch[c].jd1 = jd1; }
+                            else { atomicAdd(&p.hist[ch[c].b], 1u); ch[c].busy = false; }
+                        }
+                    }
                 }
             }
         }
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
     }
     if (!DUMP) {
         for (int o = 16; o > 0; o >>= 1) local_minimizers += __shfl_down_sync(0xffffffffu, local_minimizers, o);
-        if ((tid & 31) == 0 && local_minimizers) atomicAdd(p.n_minimizers, local_minimizers);
+        if (lane == 0 && local_minimizers) atomicAdd(p.n_minimizers, local_minimizers);
     }
 }
 
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(64) k1_generic(const K1Params p, const bool us
         uint32_t n_set = 0;
         uint64_t last = 0;
         bool have_last = false;
-        k1_scan_read(p.bases + b0, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1LocalVH{vhbuf}, [&](uint64_t m) {
+        k1_scan_read(ByteSrc{p.bases + b0, (int32_t)len64}, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1LocalVH{vhbuf}, [&](uint64_t m) {
             if (have_last && m == last) return;
             last = m;
             have_last = true;

@@ -177,3 +177,103 @@ def test_device_math_header_compiled_for_host_matches_oracle(oracle, tmp_path):
     out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
     got = [int(x) for x in out.split()]
     assert got == want
+
+
+SCAN_TEST_SRC = r"""
+#include <algorithm>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "k1_scan.h"
+struct VH { uint64_t* b; uint64_t& operator()(int t) const { return b[t]; } };
+// same role as the kernel's SmemWordSrc: aligned word loads + funnel shift
+struct WordSrc {
+    const uint32_t* words; uint32_t sh;
+    uint32_t get4(int32_t i) const {
+        const uint64_t two = ((uint64_t)words[(i >> 2) + 1] << 32) | words[i >> 2];
+        return (uint32_t)(two >> sh);
+    }
+};
+int main() {
+    // stdin: "s k w seq" -> sorted distinct window minima (byte source and word source must agree)
+    //        "J key n"   -> jump_hash_fast + number of ambiguous steps
+    char op[4];
+    while (scanf(" %3s", op) == 1) {
+        if (op[0] == 's') {
+            int k, w; static char buf[1 << 20];
+            if (scanf("%d %d %1048575s", &k, &w, buf) != 3) return 1;
+            const int len = (int)strlen(buf);
+            for (int i = 0; i < len; i++) if (buf[i] >= '0' && buf[i] <= '3') buf[i] -= '0';   // raw 0..3 bytes
+            std::vector<uint64_t> a, b, vh(w);
+            hulk::k1_scan_read(hulk::ByteSrc{(const uint8_t*)buf, len}, len, k, w, VH{vh.data()},
+                               [&](uint64_t m) { a.push_back(m); });
+            for (int mis = 0; mis < 4; mis++) {      // every misalignment of the word source
+                std::vector<uint32_t> words((len + mis) / 4 + 4, 0xA5A5A5A5u);
+                memcpy((uint8_t*)words.data() + mis, buf, len);
+                std::vector<uint64_t> c;
+                hulk::k1_scan_read(WordSrc{words.data(), (uint32_t)mis * 8u}, len, k, w, VH{vh.data()},
+                                   [&](uint64_t m) { c.push_back(m); });
+                if (c != a) { printf("MISMATCH\n"); return 2; }
+            }
+            std::sort(a.begin(), a.end());
+            a.erase(std::unique(a.begin(), a.end()), a.end());
+            printf("%zu", a.size());
+            for (uint64_t x : a) printf(" %llu", (unsigned long long)x);
+            printf("\n");
+        } else {
+            unsigned long long key; long long n;
+            if (scanf("%llu %lld", &key, &n) != 2) return 1;
+            uint32_t amb = 0;
+            printf("%d %u\n", hulk::jump_hash_fast(key, (int32_t)n, &amb), amb);
+        }
+    }
+    return 0;
+}
+"""
+
+
+def test_kernel_scan_and_fast_jump_compiled_for_host_match_oracle(oracle, tmp_path):
+    # k1_scan.h / hd_math.h are the exact sources the CUDA kernel compiles: the 4-bases-per-word scan,
+    # the word-wise encoder with its fallback, and the bracketed fast jump step
+    src = tmp_path / "scan_test.cpp"
+    src.write_text(SCAN_TEST_SRC)
+    exe = tmp_path / "scan_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math", "-I",
+                    os.path.join(ROOT, "hulk_b200", "csrc"), "-o", str(exe), str(src)], check=True)
+    from conftest import random_reads
+    rng = np.random.default_rng(7)
+    lines, want = [], []
+    cases = [(21, 9, 150), (31, 9, 151), (11, 9, 149), (4, 4, 60), (21, 1, 80), (15, 32, 200), (5, 9, 40),
+             (3, 7, 30), (7, 40, 120), (21, 200, 400), (2, 2, 5)]
+    for k, w, L in cases:
+        reads = (random_reads(6, L, seed=k * 100 + w) + random_reads(4, L, seed=k + w, n_frac=0.05, lower_frac=0.3)
+                 + [b"A" * L, (b"ACGTU" * L)[:L], (b"acgn0123RYKM" * L)[:L], (b"AC" * L)[:L]])
+        for rd in reads:
+            if len(rd) < k + w - 1:
+                continue
+            lines.append("s %d %d %s" % (k, w, rd.decode()))
+            raw = bytes((c - 48) if 48 <= c <= 51 else c for c in rd)
+            m = np.sort(oracle.minimizers(k, w, raw))
+            want.append(" ".join([str(len(m))] + [str(int(x)) for x in m]))
+    n_jump = 0
+    for n in (2, 10, 2000, 14641, 194481, 923521, 2 ** 31 - 1):
+        for key in [0, 1, 2 ** 64 - 1] + [int(x) for x in rng.integers(0, 2 ** 64, 400, dtype=np.uint64)]:
+            lines.append("J %d %d" % (key, n))
+            want.append(oracle.jump(key, n))
+            n_jump += 1
+    out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+    got = out.strip().split("\n")
+    assert len(got) == len(want)
+    n_amb = 0
+    for g, w_ in zip(got, want):
+        if isinstance(w_, str):
+            assert g == w_
+        else:
+            b, amb = g.split()
+            assert int(b) == w_
+            n_amb += int(amb)
+    # the exact step is a rare fallback, not the common path (only buckets near 2^31 see it at all)
+    assert n_amb < n_jump
