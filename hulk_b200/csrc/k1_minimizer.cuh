@@ -87,19 +87,43 @@ struct SmemWordSrc {
 constexpr int K1_JUMP_BATCH = 4;      // jump steps between two refills of a lane's chains
 constexpr int K1_WARPS = K1_TPB / 32;
 
+// One jump-hash walk in flight (dgryski/go-jump Hash, kmerspectrum.go:70): key, current bucket b,
+// jd1 = (double)(b + 1).  See hd_math.h jump_step_fast for the arithmetic; this is the same step
+// split into "evaluate" (no side effects, so two chains interleave freely) and "commit".
 struct K1Chain {
     uint64_t key;
     double jd1;
     uint32_t b;
     bool busy;                // holds a key whose walk has not finished
 };
+struct K1Step {
+    uint64_t key;             // advanced key
+    double tl;                // 2^52 + floor(x (1 - EPS))
+    bool fin, amb;
+};
+__device__ __forceinline__ K1Step k1_jump_eval(const K1Chain &c, const uint32_t nb) {
+    K1Step s;
+    s.key = c.key * 2862933555777941757ull + 1ull;
+    const uint32_t q = (uint32_t)(s.key >> 33) + 1u;                     // 1 .. 2^31
+    const double qd = u32_to_double(q);
+    const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
+    const double r0 = rcp_seed(Q);
+    const double e = fma(-Q, r0, 1.0);
+    const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
+    const double x = c.jd1 * R;
+    s.tl = __fma_rd(x, 1.0 - JUMP_EPS, JUMP_TWO52);
+    const double th = __fma_rd(x, 1.0 + JUMP_EPS, JUMP_TWO52);
+    s.fin = (dbl_hi(th) != 0x43300000u) | (dbl_lo(s.tl) >= nb);
+    s.amb = !s.fin & (dbl_lo(s.tl) != dbl_lo(th));
+    return s;
+}
 
-template <bool DUMP>
+template <bool DUMP, bool FP>
 __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *tile = smem;                                                          // tile_cap + 16 bytes
-    uint64_t *vh_all = reinterpret_cast<uint64_t *>(smem + (size_t)p.tile_cap + 16);   // [w][K1_TPB]
-    uint64_t *list_all = vh_all + (size_t)p.w * K1_TPB;                            // [K1_TPB][list_cap]
+    uint64_t *vh_all = reinterpret_cast<uint64_t *>(smem + (size_t)p.tile_cap + 16);   // [w + 1][K1_TPB]
+    uint64_t *list_all = vh_all + (size_t)(p.w + 1) * K1_TPB;                      // [K1_TPB][list_cap]
     uint32_t *prefix_all = reinterpret_cast<uint32_t *>(list_all + (size_t)p.list_cap * K1_TPB);   // [warps][34]
     uint64_t *bar = reinterpret_cast<uint64_t *>(prefix_all + K1_WARPS * 34);      // mbarrier
     uint64_t *tile_src = bar + 1;                  // global address the tile was staged from (0 = not staged)
@@ -146,8 +170,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
 
         // ---- scan ----------------------------------------------------------------------------
         const uint64_t r = tl * K1_TPB + tid;
-        uint32_t n = 0;            // entries in my list
-        bool overflow = false;
+        uint32_t n = 0;            // window minima that differ from their predecessor (all of them, even past list_cap)
         bool valid = false;
         if (r < p.n_reads) {
             const uint64_t b0 = k1_read_off(p, r), b1 = k1_read_off(p, r + 1);
@@ -159,26 +182,25 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
             } else {
                 valid = true;
                 const uint64_t src = *tile_src;
-                uint64_t last = ~0ull;                                           // never a minimizer (low byte <= 31)
-                auto emit = [&](uint64_t m) {
-                    if (m != last) {
-                        if (n < list_cap) my_list[n] = m;
-                        else overflow = true;
-                        n++;
-                        last = m;
-                    }
+                uint64_t last = Sentinel<FP>::value;                             // never a minimizer
+                auto emit = [&](uint64_t m, bool on) {
+                    const bool fresh = on && !ueq64<FP>(m, last);
+                    if (fresh) my_list[min(n, list_cap - 1u)] = m;               // entries past the cap are dropped,
+                    n += fresh ? 1u : 0u;                                        // n still counts them (overflow test)
+                    last = fresh ? m : last;
                 };
                 if (src) {
                     const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases) + b0 - src);
                     const SmemWordSrc ws{reinterpret_cast<const uint32_t *>(tile + (off & ~3u)), (off & 3u) * 8u};
-                    k1_scan_read(ws, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh}, emit);
+                    k1_scan_read<FP>(ws, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh}, emit);
                 } else {
                     const ByteSrc bs{p.bases + b0, (int32_t)len64};
-                    k1_scan_read(bs, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh}, emit);
+                    k1_scan_read<FP>(bs, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1SmemVH{my_vh}, emit);
                 }
             }
         }
-        if (valid && overflow) {
+        const bool overflow = valid && n > list_cap;
+        if (overflow) {
             // hand the read to the generic kernel (exact de-dup with an unbounded set)
             const unsigned int slot = atomicAdd(p.ovf_count, 1u);
             if (slot < p.ovf_cap) p.ovf_list[slot] = r;
@@ -191,7 +213,8 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
         for (uint32_t a = 0; a < n; a++) {
             const uint64_t x = my_list[a];
             bool dup = false;
-            for (uint32_t b = 0; b < m_out; b++) dup |= (my_list[b] == x);
+#pragma unroll 4
+            for (uint32_t b = 0; b < m_out; b++) dup |= ueq64<FP>(my_list[b], x);
             if (!dup) { my_list[m_out] = x; m_out++; }
         }
         if (DUMP) {
@@ -239,18 +262,28 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
                 if (!__any_sync(0xffffffffu, ch[0].busy || ch[1].busy)) break;
 #pragma unroll
                 for (int it = 0; it < K1_JUMP_BATCH; it++) {
+                    K1Step s[2];
+                    s[0] = k1_jump_eval(ch[0], nb);
+                    s[1] = k1_jump_eval(ch[1], nb);
+                    if ((s[0].amb & ch[0].busy) | (s[1].amb & ch[1].busy)) {     // ~2^-21 per step: exact division
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            if (s[c].amb & ch[c].busy) {
+                                uint32_t b = ch[c].b;
+                                double jd1 = ch[c].jd1;
+                                s[c].fin = jump_step_exact(s[c].key, b, jd1, nb) != 0;
+                                s[c].tl = JUMP_TWO52 + (double)b;                // as the fast step reports it
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int c = 0; c < 2; c++) {
-                        uint64_t key = ch[c].key;
-                        uint32_t b = ch[c].b;
-                        double jd1 = ch[c].jd1;
-                        int rc = jump_step_fast(key, b, jd1, nb);
-                        if (rc == 2 && ch[c].busy) rc = jump_step_exact(key, b, jd1, nb);   // rare
-                        if (ch[c].busy) {
-                            ch[c].key = key;
-                            if (rc == 0) { ch[c].b = b; ch[c].jd1 = jd1; }
-                            else { atomicAdd(&p.hist[ch[c].b], 1u); ch[c].busy = false; }
-                        }
+                        const bool adv = ch[c].busy & !s[c].fin;
+                        if (ch[c].busy & s[c].fin) atomicAdd(&p.hist[ch[c].b], 1u);
+                        ch[c].key = s[c].key;
+                        ch[c].b = adv ? dbl_lo(s[c].tl) : ch[c].b;
+                        ch[c].jd1 = adv ? s[c].tl - (JUMP_TWO52 - 1.0) : ch[c].jd1;
+                        ch[c].busy = adv;
                     }
                 }
             }
@@ -275,7 +308,7 @@ struct K1LocalVH {
 
 template <bool DUMP>
 __global__ void __launch_bounds__(64) k1_generic(const K1Params p, const bool use_queue) {
-    uint64_t vhbuf[256];
+    uint64_t vhbuf[257];
     const uint64_t total = use_queue ? (uint64_t)min(*p.ovf_count, p.ovf_cap) : p.n_reads;
     unsigned long long local_minimizers = 0;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
@@ -298,7 +331,8 @@ __global__ void __launch_bounds__(64) k1_generic(const K1Params p, const bool us
         uint32_t n_set = 0;
         uint64_t last = 0;
         bool have_last = false;
-        k1_scan_read(ByteSrc{p.bases + b0, (int32_t)len64}, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1LocalVH{vhbuf}, [&](uint64_t m) {
+        k1_scan_read<false>(ByteSrc{p.bases + b0, (int32_t)len64}, (int32_t)len64, (int32_t)p.k, (int32_t)p.w, K1LocalVH{vhbuf}, [&](uint64_t m, bool on) {
+            if (!on) return;
             if (have_last && m == last) return;
             last = m;
             have_last = true;

@@ -36,44 +36,75 @@ HULK_UNROLL
     }
 };
 
-// One window-minimum state machine (block decomposition).  vh(t): w-entry buffer.
-template <class VH, class Emit>
+// 64-bit unsigned minimum / equality.  When every value is below 0x7FF0'0000'0000'0000 the bit
+// patterns are non-negative finite doubles (or +inf for the sentinel), whose IEEE order equals the
+// integer order, so one DSETP on the otherwise idle FP64 pipe replaces the two-instruction 64-bit integer
+// compare on the (busiest) ALU pipe.  FP = false keeps the plain integer forms (k > 27, or w > k + 1 where the reference's
+// kmerSpan goes negative and sign-extends into the top bits).
+template <bool FP>
+HULK_HD uint64_t umin64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    if (FP) return (__longlong_as_double((long long)a) < __longlong_as_double((long long)b)) ? a : b;   // DSETP + 2 SEL
+#endif
+    return (a < b) ? a : b;
+}
+template <bool FP>
+HULK_HD bool ueq64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    if (FP) return __longlong_as_double((long long)a) == __longlong_as_double((long long)b);
+#endif
+    return a == b;
+}
+template <bool FP>
+struct Sentinel {   // "no k-mer": larger than every minimizer value, never emitted
+    static constexpr uint64_t value = FP ? 0x7FF0000000000000ull : ~0ull;
+};
+HULK_HD bool k1_fp_compare_ok(int32_t k, int32_t w) { return k <= 27 && w <= k + 1; }
+
+// One window-minimum state machine (block decomposition).  vh(t): buffer of w + 1 entries, entry w
+// stays at the sentinel so the look-ahead load needs no bounds test.  Written so that the only
+// branch is the (warp-uniform) end-of-block test.
+template <bool FP, class VH, class Emit>
 struct WinMin {
+    static constexpr uint64_t SENT = Sentinel<FP>::value;
     VH vh;
     Emit emit;
     int32_t w;
     int32_t t;
     uint64_t pref;
-    HULK_HD WinMin(VH vh_, Emit emit_, int32_t w_) : vh(vh_), emit(emit_), w(w_), t(0), pref(~0ull) {
-        for (int x = 0; x < w; x++) vh(x) = ~0ull;
+    HULK_HD WinMin(VH vh_, Emit emit_, int32_t w_) : vh(vh_), emit(emit_), w(w_), t(0), pref(SENT) {
+        for (int x = 0; x <= w; x++) vh(x) = SENT;
     }
-    // X == ~0 marks a skipped k-mer (fwd == rev): it never wins and emits nothing
-    HULK_HD void step(uint64_t X, bool may_emit) {
-        pref = (X < pref) ? X : pref;
-        const uint64_t suf = (t + 1 < w) ? vh(t + 1) : ~0ull;            // previous block, positions t+1..w-1
-        vh(t) = X;
-        if (may_emit) emit((pref < suf) ? pref : suf);                   // minimizer.go:186-199
-        if (++t == w) {                                                  // block complete: suffix minima in place
-            uint64_t run = ~0ull;
+    // act: this position holds a k-mer (i >= k-1, inside the read); X == SENT marks a skipped
+    // k-mer (fwd == rev): it never wins and emits nothing
+    HULK_HD void step(uint64_t X, bool act, bool may_emit) {
+        X = act ? X : SENT;
+        pref = umin64<FP>(pref, X);
+        const uint64_t suf = vh(t + 1);                                  // previous block, positions t+1..w-1
+        if (act) vh(t) = X;
+        emit(umin64<FP>(pref, suf), may_emit);                           // minimizer.go:186-199
+        t += act ? 1 : 0;
+        if (t == w) {                                                    // block complete: suffix minima in place
+            uint64_t run = SENT;
             for (int x = w - 1; x >= 0; x--) {
-                const uint64_t v = vh(x);
-                run = (v < run) ? v : run;
+                run = umin64<FP>(run, vh(x));
                 vh(x) = run;
             }
             t = 0;
-            pref = ~0ull;
+            pref = SENT;
         }
     }
 };
 
-// Scan one read.  `emit(m)` receives every window minimum in position order.
-// The caller has already applied the reference's length checks (minimizer.go:62-76).
-template <class Src, class VH, class Emit>
+// Scan one read.  `emit(m, on)` is called for every position; when `on` is true m is that position's
+// window minimum (position order).  The caller has already applied the reference's length checks
+// (minimizer.go:62-76) and provides a buffer of w + 1 entries.
+template <bool FP, class Src, class VH, class Emit>
 HULK_HD void k1_scan_read(const Src src, int32_t len, int32_t k, int32_t w, VH vh, Emit emit) {
     const uint64_t mask = (1ull << (2 * k)) - 1ull;       // minimizer.go:103  (k <= 31)
     const int shift = 2 * (k - 1);                        // minimizer.go:104
     uint64_t fwd = 0, rev = 0;
-    WinMin<VH, Emit> win(vh, emit, w);
+    WinMin<FP, VH, Emit> win(vh, emit, w);
     for (int32_t i0 = 0; i0 < len; i0 += 4) {
         const uint32_t word = src.get4(i0);
         bool fast;
@@ -88,12 +119,14 @@ HULK_UNROLL
 HULK_UNROLL
         for (int u = 0; u < 4; u++) {
             const uint32_t c = (codes >> (8 * u)) & 0xffu;               // 0..4
-            if (i0 + u < len) {
-                fwd = ((fwd << 2) | (uint64_t)c) & mask;                  // :134
-                rev = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);         // :137 (not masked)
-            }
-            skip[u] = (fwd == rev);                                       // :145-147
-            canon[u] = (fwd > rev) ? rev : fwd;                           // :150-153
+            const bool in = i0 + u < len;
+            const uint64_t f2 = ((fwd << 2) | (uint64_t)c) & mask;        // :134
+            const uint64_t r2 = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);   // :137 (not masked)
+            fwd = in ? f2 : fwd;
+            rev = in ? r2 : rev;
+            // (a k = 31 read with N's can set bit 62 of rev; the integer forms are used there)
+            skip[u] = ueq64<FP>(fwd, rev);                                // :145-147
+            canon[u] = umin64<FP>(fwd, rev);                              // :150-153
         }
         if (i0 + 3 < k - 1) continue;                                     // :140-142 (whole group before the first k-mer)
 HULK_UNROLL
@@ -105,8 +138,8 @@ HULK_UNROLL
 HULK_UNROLL
         for (int u = 0; u < 4; u++) {
             const int32_t i = i0 + u;
-            if (i >= k - 1 && i < len)                                    // :140-142
-                win.step(skip[u] ? ~0ull : X[u], !skip[u] && i >= w - 1);
+            const bool act = (i >= k - 1) && (i < len);                   // :140-142
+            win.step(skip[u] ? WinMin<FP, VH, Emit>::SENT : X[u], act, act && !skip[u] && i >= w - 1);
         }
     }
 }

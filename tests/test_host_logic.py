@@ -206,15 +206,20 @@ int main() {
             if (scanf("%d %d %1048575s", &k, &w, buf) != 3) return 1;
             const int len = (int)strlen(buf);
             for (int i = 0; i < len; i++) if (buf[i] >= '0' && buf[i] <= '3') buf[i] -= '0';   // raw 0..3 bytes
-            std::vector<uint64_t> a, b, vh(w);
-            hulk::k1_scan_read(hulk::ByteSrc{(const uint8_t*)buf, len}, len, k, w, VH{vh.data()},
-                               [&](uint64_t m) { a.push_back(m); });
+            std::vector<uint64_t> a, b, vh(w + 1);
+            hulk::k1_scan_read<false>(hulk::ByteSrc{(const uint8_t*)buf, len}, len, k, w, VH{vh.data()},
+                                      [&](uint64_t m, bool on) { if (on) a.push_back(m); });
+            if (hulk::k1_fp_compare_ok(k, w)) {       // the sentinel of the FP-compare variant (host: integer compares)
+                hulk::k1_scan_read<true>(hulk::ByteSrc{(const uint8_t*)buf, len}, len, k, w, VH{vh.data()},
+                                         [&](uint64_t m, bool on) { if (on) b.push_back(m); });
+                if (b != a) { printf("MISMATCH\n"); return 2; }
+            }
             for (int mis = 0; mis < 4; mis++) {      // every misalignment of the word source
                 std::vector<uint32_t> words((len + mis) / 4 + 4, 0xA5A5A5A5u);
                 memcpy((uint8_t*)words.data() + mis, buf, len);
                 std::vector<uint64_t> c;
-                hulk::k1_scan_read(WordSrc{words.data(), (uint32_t)mis * 8u}, len, k, w, VH{vh.data()},
-                                   [&](uint64_t m) { c.push_back(m); });
+                hulk::k1_scan_read<false>(WordSrc{words.data(), (uint32_t)mis * 8u}, len, k, w, VH{vh.data()},
+                                          [&](uint64_t m, bool on) { if (on) c.push_back(m); });
                 if (c != a) { printf("MISMATCH\n"); return 2; }
             }
             std::sort(a.begin(), a.end());
