@@ -87,35 +87,11 @@ struct SmemWordSrc {
 constexpr int K1_JUMP_BATCH = 4;      // jump steps between two refills of a lane's chains
 constexpr int K1_WARPS = K1_TPB / 32;
 
-// One jump-hash walk in flight (dgryski/go-jump Hash, kmerspectrum.go:70): key, current bucket b,
-// jd1 = (double)(b + 1).  See hd_math.h jump_step_fast for the arithmetic; this is the same step
-// split into "evaluate" (no side effects, so two chains interleave freely) and "commit".
-struct K1Chain {
-    uint64_t key;
-    double jd1;
-    uint32_t b;
-    bool busy;                // holds a key whose walk has not finished
-};
-struct K1Step {
-    uint64_t key;             // advanced key
-    double tl;                // 2^52 + floor(x (1 - EPS))
-    bool fin, amb;
-};
-__device__ __forceinline__ K1Step k1_jump_eval(const K1Chain &c, const uint32_t nb) {
-    K1Step s;
-    s.key = c.key * 2862933555777941757ull + 1ull;
-    const uint32_t q = (uint32_t)(s.key >> 33) + 1u;                     // 1 .. 2^31
-    const double qd = u32_to_double(q);
-    const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
-    const double r0 = rcp_seed(Q);
-    const double e = fma(-Q, r0, 1.0);
-    const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
-    const double x = c.jd1 * R;
-    s.tl = __fma_rd(x, 1.0 - JUMP_EPS, JUMP_TWO52);
-    const double th = __fma_rd(x, 1.0 + JUMP_EPS, JUMP_TWO52);
-    s.fin = (dbl_hi(th) != 0x43300000u) | (dbl_lo(s.tl) >= nb);
-    s.amb = !s.fin & (dbl_lo(s.tl) != dbl_lo(th));
-    return s;
+// keeps a loop-invariant double in registers (the compiler would otherwise re-materialise the
+// 64-bit immediate with two moves in front of every use)
+__device__ __forceinline__ double k1_pin(double x) {
+    asm volatile("" : "+d"(x));
+    return x;
 }
 
 template <bool DUMP, bool FP>
@@ -213,8 +189,14 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
         for (uint32_t a = 0; a < n; a++) {
             const uint64_t x = my_list[a];
             bool dup = false;
-#pragma unroll 4
-            for (uint32_t b = 0; b < m_out; b++) dup |= ueq64<FP>(my_list[b], x);
+            uint32_t b = 0;
+            for (; b + 4 <= m_out; b += 4) {
+                const bool e0 = ueq64<FP>(my_list[b], x), e1 = ueq64<FP>(my_list[b + 1], x);
+                const bool e2 = ueq64<FP>(my_list[b + 2], x), e3 = ueq64<FP>(my_list[b + 3], x);
+                if (e0 | e1 | e2 | e3) dup = true;
+            }
+            for (; b < m_out; b++)
+                if (ueq64<FP>(my_list[b], x)) dup = true;
             if (!dup) { my_list[m_out] = x; m_out++; }
         }
         if (DUMP) {
@@ -225,7 +207,11 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
                 p.dump_counts[r] = 0;
             }
         } else {
-            // ---- jump: kmerspectrum.go:67-81, bins[jump.Hash(kmer, numBins)]++ for every set member
+            // ---- jump: kmerspectrum.go:67-81, bins[jump.Hash(kmer, numBins)]++ for every set member.
+            // The warp's 32 sets are one queue of `total` keys (P = exclusive prefix of the set sizes);
+            // lane l walks keys l, l + 32, l + 64, ... so every lane gets the same number of keys
+            // whatever its own read produced.  Two walks per lane are in flight (ILP); they advance
+            // K1_JUMP_BATCH steps between two refill points.  See hd_math.h jump_step_fast for the step.
             local_minimizers += m_out;
             uint32_t incl = m_out;
 #pragma unroll
@@ -237,53 +223,70 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
             if (lane == 31) P[32] = incl;
             __syncwarp();
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t next_f = 0;       // warp-uniform: first unclaimed queue index
-            uint32_t o_cur = 0;        // warp-uniform: P[o_cur] <= next_f (owner search starts here)
-            K1Chain ch[2];
-            ch[0].busy = ch[1].busy = false;
-            ch[0].key = ch[1].key = 0; ch[0].jd1 = ch[1].jd1 = 1.0; ch[0].b = ch[1].b = 0;
+            uint32_t f = lane;         // this lane's next queue index
+            uint32_t own = 0;          // set that holds f (monotone cursor)
+            uint64_t key[2] = {0, 0};
+            double jd1[2] = {1.0, 1.0};
+            uint32_t bkt[2] = {0, 0};
+            bool busy[2] = {false, false}, loaded[2] = {false, false};
+            const double c_lo = k1_pin(1.0 - JUMP_EPS), c_hi = k1_pin(1.0 + JUMP_EPS);
+            const double two52 = k1_pin(JUMP_TWO52), two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0);
+            uint32_t *const hist = p.hist;
             for (;;) {
 #pragma unroll
-                for (int c = 0; c < 2; c++) {                                    // refill idle chains
-                    const bool need = !ch[c].busy;
-                    const uint32_t ballot = __ballot_sync(0xffffffffu, need);
-                    const uint32_t f = next_f + __popc(ballot & ((1u << lane) - 1u));
-                    next_f += __popc(ballot);
-                    if (need && f < total) {
-                        uint32_t o = o_cur;
-                        while (f >= P[o + 1]) o++;                               // P[32] = total > f
-                        ch[c].key = warp_lists[(size_t)o * list_cap + (f - P[o])];
-                        ch[c].b = 0;                                             // first step of jump.Hash: b = 0
-                        ch[c].jd1 = 1.0;
-                        ch[c].busy = true;
+                for (int c = 0; c < 2; c++) {
+                    if (!busy[c]) {
+                        if (loaded[c]) {                                         // its walk ended in the last batch
+                            atomicAdd(&hist[bkt[c]], 1u);
+                            loaded[c] = false;
+                        }
+                        if (f < total) {
+                            while (f >= P[own + 1]) own++;                       // P[32] = total > f
+                            key[c] = warp_lists[(size_t)own * list_cap + (f - P[own])];
+                            f += 32;
+                            bkt[c] = 0;                                          // first step of jump.Hash: b = 0
+                            jd1[c] = one;
+                            busy[c] = loaded[c] = true;
+                        }
                     }
-                    while (o_cur < 31 && P[o_cur + 1] <= next_f) o_cur++;
                 }
-                if (!__any_sync(0xffffffffu, ch[0].busy || ch[1].busy)) break;
+                if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
 #pragma unroll
                 for (int it = 0; it < K1_JUMP_BATCH; it++) {
-                    K1Step s[2];
-                    s[0] = k1_jump_eval(ch[0], nb);
-                    s[1] = k1_jump_eval(ch[1], nb);
-                    if ((s[0].amb & ch[0].busy) | (s[1].amb & ch[1].busy)) {     // ~2^-21 per step: exact division
+                    double tlo[2];
+                    bool fin[2], amb[2];
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
+                        key[c] = key[c] * 2862933555777941757ull + 1ull;
+                        const uint32_t q = (uint32_t)(key[c] >> 33) + 1u;                    // 1 .. 2^31
+                        const double qd = dbl_make(0x43300000u, q) - two52;                  // (double)q, exact
+                        const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
+                        const double r0 = rcp_seed(Q);
+                        const double e = fma(-Q, r0, one);
+                        const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
+                        const double x = jd1[c] * R;
+                        tlo[c] = __fma_rd(x, c_lo, two52);                                   // 2^52 + floor(x (1 - EPS))
+                        const double thi = __fma_rd(x, c_hi, two52);
+                        fin[c] = (dbl_hi(thi) != 0x43300000u) || (dbl_lo(tlo[c]) >= nb);
+                        amb[c] = !fin[c] && (dbl_lo(tlo[c]) != dbl_lo(thi));
+                    }
+                    if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-21 per step: the true division
 #pragma unroll
                         for (int c = 0; c < 2; c++) {
-                            if (s[c].amb & ch[c].busy) {
-                                uint32_t b = ch[c].b;
-                                double jd1 = ch[c].jd1;
-                                s[c].fin = jump_step_exact(s[c].key, b, jd1, nb) != 0;
-                                s[c].tl = JUMP_TWO52 + (double)b;                // as the fast step reports it
+                            if (amb[c] && busy[c]) {
+                                uint32_t b = bkt[c];
+                                double j1 = jd1[c];
+                                fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
+                                tlo[c] = JUMP_TWO52 + (double)b;                 // as the fast step reports it
                             }
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const bool adv = ch[c].busy & !s[c].fin;
-                        if (ch[c].busy & s[c].fin) atomicAdd(&p.hist[ch[c].b], 1u);
-                        ch[c].key = s[c].key;
-                        ch[c].b = adv ? dbl_lo(s[c].tl) : ch[c].b;
-                        ch[c].jd1 = adv ? s[c].tl - (JUMP_TWO52 - 1.0) : ch[c].jd1;
-                        ch[c].busy = adv;
+                    for (int c = 0; c < 2; c++) {                                // commit
+                        const bool adv = busy[c] && !fin[c];
+                        bkt[c] = adv ? dbl_lo(tlo[c]) : bkt[c];
+                        jd1[c] = adv ? tlo[c] - two52m1 : jd1[c];                // (double)(bucket + 1), exact
+                        busy[c] = adv;
                     }
                 }
             }

@@ -75,10 +75,10 @@ struct WinMin {
     HULK_HD WinMin(VH vh_, Emit emit_, int32_t w_) : vh(vh_), emit(emit_), w(w_), t(0), pref(SENT) {
         for (int x = 0; x <= w; x++) vh(x) = SENT;
     }
-    // act: this position holds a k-mer (i >= k-1, inside the read); X == SENT marks a skipped
-    // k-mer (fwd == rev): it never wins and emits nothing
-    HULK_HD void step(uint64_t X, bool act, bool may_emit) {
-        X = act ? X : SENT;
+    // act: this position holds a k-mer (i >= k-1, inside the read); !real marks a skipped k-mer
+    // (fwd == rev): it occupies its window position but never wins and emits nothing
+    HULK_HD void step(uint64_t X, bool act, bool real, bool may_emit) {
+        X = real ? X : SENT;
         pref = umin64<FP>(pref, X);
         const uint64_t suf = vh(t + 1);                                  // previous block, positions t+1..w-1
         if (act) vh(t) = X;
@@ -119,11 +119,9 @@ HULK_UNROLL
 HULK_UNROLL
         for (int u = 0; u < 4; u++) {
             const uint32_t c = (codes >> (8 * u)) & 0xffu;               // 0..4
-            const bool in = i0 + u < len;
-            const uint64_t f2 = ((fwd << 2) | (uint64_t)c) & mask;        // :134
-            const uint64_t r2 = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);   // :137 (not masked)
-            fwd = in ? f2 : fwd;
-            rev = in ? r2 : rev;
+            // (positions at or past the read's end roll garbage in; nothing after them is ever used)
+            fwd = ((fwd << 2) | (uint64_t)c) & mask;                      // :134
+            rev = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);             // :137 (not masked)
             // (a k = 31 read with N's can set bit 62 of rev; the integer forms are used there)
             skip[u] = ueq64<FP>(fwd, rev);                                // :145-147
             canon[u] = umin64<FP>(fwd, rev);                              // :150-153
@@ -139,7 +137,7 @@ HULK_UNROLL
         for (int u = 0; u < 4; u++) {
             const int32_t i = i0 + u;
             const bool act = (i >= k - 1) && (i < len);                   // :140-142
-            win.step(skip[u] ? WinMin<FP, VH, Emit>::SENT : X[u], act, act && !skip[u] && i >= w - 1);
+            win.step(X[u], act, act && !skip[u], act && !skip[u] && i >= w - 1);
         }
     }
 }
