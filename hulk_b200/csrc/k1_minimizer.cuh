@@ -99,9 +99,8 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *tile = smem;                                                          // tile_cap + 16 bytes
     uint64_t *vh_all = reinterpret_cast<uint64_t *>(smem + (size_t)p.tile_cap + 16);   // [w + 1][K1_TPB]
-    uint64_t *list_all = vh_all + (size_t)(p.w + 1) * K1_TPB;                      // [K1_TPB][list_cap]
-    uint32_t *prefix_all = reinterpret_cast<uint32_t *>(list_all + (size_t)p.list_cap * K1_TPB);   // [warps][34]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(prefix_all + K1_WARPS * 34);      // mbarrier
+    uint64_t *list_all = vh_all + (size_t)(p.w + 1) * K1_TPB;                      // [warps][list_cap][32]
+    uint64_t *bar = list_all + (size_t)p.list_cap * K1_TPB;                        // mbarrier
     uint64_t *tile_src = bar + 1;                  // global address the tile was staged from (0 = not staged)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,9 +116,8 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
     uint32_t phase = 0;
     uint64_t *my_vh = vh_all + tid;
     const uint32_t list_cap = p.list_cap;
-    uint64_t *my_list = list_all + (size_t)tid * list_cap;
-    uint64_t *warp_lists = list_all + (size_t)(warp * 32) * list_cap;
-    uint32_t *P = prefix_all + warp * 34;          // P[l] = first queue index of lane l's set; P[32] = total
+    uint64_t *wl = list_all + (size_t)warp * list_cap * 32;    // this warp's lists: entry e of lane l at wl[e * 32 + l]
+    uint64_t *my_list = wl + lane;                             // this lane's column (stride 32)
     unsigned long long local_minimizers = 0;
     const uint32_t nb = (uint32_t)p.D;
 
@@ -161,7 +159,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
                 uint64_t last = Sentinel<FP>::value;                             // never a minimizer
                 auto emit = [&](uint64_t m, bool on) {
                     const bool fresh = on && !ueq64<FP>(m, last);
-                    if (fresh) my_list[min(n, list_cap - 1u)] = m;               // entries past the cap are dropped,
+                    if (fresh) my_list[min(n, list_cap - 1u) * 32u] = m;         // entries past the cap are dropped,
                     n += fresh ? 1u : 0u;                                        // n still counts them (overflow test)
                     last = fresh ? m : last;
                 };
@@ -187,44 +185,47 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
         // ---- exact per-read set: drop values already present earlier in the list (minimizer.go:189-198)
         uint32_t m_out = 0;
         for (uint32_t a = 0; a < n; a++) {
-            const uint64_t x = my_list[a];
+            const uint64_t x = my_list[a * 32];
             bool dup = false;
             uint32_t b = 0;
             for (; b + 4 <= m_out; b += 4) {
-                const bool e0 = ueq64<FP>(my_list[b], x), e1 = ueq64<FP>(my_list[b + 1], x);
-                const bool e2 = ueq64<FP>(my_list[b + 2], x), e3 = ueq64<FP>(my_list[b + 3], x);
+                const bool e0 = ueq64<FP>(my_list[b * 32], x), e1 = ueq64<FP>(my_list[(b + 1) * 32], x);
+                const bool e2 = ueq64<FP>(my_list[(b + 2) * 32], x), e3 = ueq64<FP>(my_list[(b + 3) * 32], x);
                 if (e0 | e1 | e2 | e3) dup = true;
             }
             for (; b < m_out; b++)
-                if (ueq64<FP>(my_list[b], x)) dup = true;
-            if (!dup) { my_list[m_out] = x; m_out++; }
+                if (ueq64<FP>(my_list[b * 32], x)) dup = true;
+            if (!dup) { my_list[m_out * 32] = x; m_out++; }
         }
         if (DUMP) {
             if (valid) {
-                for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++) p.dump[r * p.dump_cap + e] = my_list[e];
+                for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++) p.dump[r * p.dump_cap + e] = my_list[e * 32];
                 p.dump_counts[r] = m_out;
             } else if (r < p.n_reads && !overflow) {
                 p.dump_counts[r] = 0;
             }
         } else {
             // ---- jump: kmerspectrum.go:67-81, bins[jump.Hash(kmer, numBins)]++ for every set member.
-            // The warp's 32 sets are one queue of `total` keys (P = exclusive prefix of the set sizes);
-            // lane l walks keys l, l + 32, l + 64, ... so every lane gets the same number of keys
-            // whatever its own read produced.  Two walks per lane are in flight (ILP); they advance
-            // K1_JUMP_BATCH steps between two refill points.  See hd_math.h jump_step_fast for the step.
+            // Rows 0 .. m_min-1 of the warp's list block are full; the entries of the longer sets
+            // behind them are packed row by row right after, so the block becomes one dense queue of
+            // `total` keys and lane l simply walks keys l, l + 32, l + 64, ...: every lane gets the
+            // same number of keys whatever its own read produced.  Two walks per lane are in flight
+            // (ILP); they advance K1_JUMP_BATCH steps between two refill points.  The step itself is
+            // hd_math.h jump_step_fast, split into evaluate / commit.
             local_minimizers += m_out;
-            uint32_t incl = m_out;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += u;
+            const uint32_t m_min = __reduce_min_sync(0xffffffffu, m_out);
+            const uint32_t m_max = __reduce_max_sync(0xffffffffu, m_out);
+            uint32_t total = m_min * 32;
+            for (uint32_t e = m_min; e < m_max; e++) {
+                const bool has = m_out > e;
+                const uint64_t x = has ? wl[e * 32 + lane] : 0ull;
+                const uint32_t mask = __ballot_sync(0xffffffffu, has);
+                __syncwarp();                                    // row e is in registers before anyone overwrites it
+                if (has) wl[total + __popc(mask & ((1u << lane) - 1u))] = x;     // total <= e * 32: never a later row
+                total += __popc(mask);
             }
-            P[lane] = incl - m_out;
-            if (lane == 31) P[32] = incl;
             __syncwarp();
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t f = lane;         // this lane's next queue index
-            uint32_t own = 0;          // set that holds f (monotone cursor)
+            uint32_t g = lane;         // this lane's next queue index
             uint64_t key[2] = {0, 0};
             double jd1[2] = {1.0, 1.0};
             uint32_t bkt[2] = {0, 0};
@@ -240,10 +241,9 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
                             atomicAdd(&hist[bkt[c]], 1u);
                             loaded[c] = false;
                         }
-                        if (f < total) {
-                            while (f >= P[own + 1]) own++;                       // P[32] = total > f
-                            key[c] = warp_lists[(size_t)own * list_cap + (f - P[own])];
-                            f += 32;
+                        if (g < total) {
+                            key[c] = wl[g];
+                            g += 32;
                             bkt[c] = 0;                                          // first step of jump.Hash: b = 0
                             jd1[c] = one;
                             busy[c] = loaded[c] = true;
