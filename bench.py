@@ -108,13 +108,6 @@ def synthetic_tables_torch(torch, rows, D, seed, device):
     return r, c, b
 
 
-class DevArray:
-    """CUDA array interface view of a raw device pointer (to hand the histogram to torch/NCCL)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 class ClockSampler(threading.Thread):
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -268,7 +261,9 @@ def run_b200(a):
     hs.set_tables_device(r_t.data_ptr(), c_t.data_ptr(), b_t.data_ptr())
     del r_t, c_t, b_t
     torch.cuda.empty_cache()
-    hist_t = torch.as_tensor(DevArray(hs.histogram_device_ptr(), D, "<i4"), device=dev) if world > 1 else None
+    # multi-GPU: the same ShardedSketch the CPU (gloo) tests drive; its flush = spectrum all-reduce + local flush
+    sh = hulk_b200.ShardedSketch(hs, s, world, rank)
+    assert sh.slots == slots
 
     def barrier():
         if world > 1:
@@ -277,9 +272,7 @@ def run_b200(a):
 
     def step_device(st):
         hs.add_reads_device(reads_dev[st % n_steps_data].data_ptr(), None, I, RL)
-        if world > 1:
-            dist.all_reduce(hist_t)
-        hs.flush()
+        sh.flush()
 
     def timed(fn, nsteps):
         barrier()
@@ -334,9 +327,7 @@ def run_b200(a):
         off = (st % n_steps_data) * I * RL
         rc = L_.hulk_b200_push_reads_fixed(hs._ctx, pin_in.value + off, I, RL)
         assert rc == 0, hs._L.hulk_b200_last_error(hs._ctx)
-        if world > 1:
-            dist.all_reduce(hist_t)
-        hs.flush()
+        sh.flush()
         rc = L_.hulk_b200_snapshot_async(hs._ctx, mins_p, weights_p)
         assert rc == 0
 

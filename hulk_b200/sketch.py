@@ -93,6 +93,7 @@ class HistoSketch:
         self.k, self.w, self.sketch_size, self.decay_ratio = k, w, sketch_size, decay_ratio
         self.num_bins = spectrum_size(k) if num_bins is None else num_bins
         self.slot_begin, self.slot_end = slots if slots is not None else (0, sketch_size)
+        self.device = device
         p = N.Params()
         p.k, p.w, p.sketch_size = k, w, sketch_size
         p.num_bins = self.num_bins
@@ -216,6 +217,20 @@ class HistoSketch:
         nb = C.c_int32()
         self._check(self._L.hulk_b200_histogram_device_ptr(self._ctx, C.byref(p), C.byref(nb)))
         return p.value
+
+    def histogram_tensor(self):
+        """The device spectrum as a torch int32 tensor aliasing the context's memory (for the per-flush
+        all-reduce of hulk_b200.distributed; uint32 sums wrap identically in two's complement)."""
+        import torch
+
+        class _Dev:
+            pass
+        v = _Dev()
+        v.__cuda_array_interface__ = {"shape": (self.num_bins,), "typestr": "<i4",
+                                      "data": (self.histogram_device_ptr(), False), "version": 2}
+        t = torch.as_tensor(v, device=torch.device("cuda", self.device))
+        self._keep_hist = v
+        return t
 
     def stream_handle(self) -> int:
         p = C.c_void_p()
