@@ -9,6 +9,10 @@ from ._native import load, LIB_PATH, EXPORTS  # noqa: F401
 from .sketch import (HistoSketch, HulkError, md5_mins, new_cws, pack_reads, sketch_json,  # noqa: F401
                      sketch_reads, spectrum_size)
 from .distributed import ShardedSketch, chunk_range, sketch_reads_sharded, slot_range  # noqa: F401
-from .seqio import read_fastq, read_fasta, synthetic_reads  # noqa: F401
+from .seqio import NativeReader, read_fastq, read_fasta, synthetic_reads  # noqa: F401
+
+import os as _os
+
+CLI_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "bin", "hulk")   # the `hulk` front end
 
 __version__ = "1.0.0"

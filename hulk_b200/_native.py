@@ -19,12 +19,15 @@ EXPORTS = [
     "hulk_b200_merge_histogram", "hulk_b200_add_minimizer_count", "hulk_b200_get_histogram", "hulk_b200_get_estimates",
     "hulk_b200_get_cms", "hulk_b200_minimizers", "hulk_b200_jump_hash", "hulk_b200_get_folded_table",
     "hulk_b200_md5_mins", "hulk_b200_sketch_json", "hulk_b200_write_json", "hulk_b200_alloc_pinned",
-    "hulk_b200_free_pinned",
+    "hulk_b200_free_pinned", "hulk_b200_reader_open", "hulk_b200_reader_next", "hulk_b200_reader_error",
+    "hulk_b200_reader_close", "hulk_b200_sketch_reader",
 ]
 
 OK, EW, EK, EEMPTYSEQ, ESHORTSEQ, ESPARSE = 0, -1, -2, -3, -4, -6
 EHSK, EDECAY, EBINS, ENEGBINS, ENOSKETCH = -10, -11, -12, -13, -14
 EARG, ESTATE, ECUDA, ENOMEM, EIO = -20, -21, -30, -31, -40
+EFASTQ, ETOOLONG, ENOSEQ = -41, -42, -43
+LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 F_ASYNC_INPUT = 1
 
 
@@ -97,6 +100,11 @@ def load():
         "hulk_b200_write_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int]),
         "hulk_b200_alloc_pinned": (C.c_int, [C.POINTER(vp), u64]),
         "hulk_b200_free_pinned": (None, [vp]),
+        "hulk_b200_reader_open": (C.c_int, [C.POINTER(C.c_char_p), u32, C.c_int, u64, C.POINTER(vp)]),
+        "hulk_b200_reader_next": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "hulk_b200_reader_error": (C.c_char_p, [vp]),
+        "hulk_b200_reader_close": (None, [vp]),
+        "hulk_b200_sketch_reader": (C.c_int, [vp, vp, u64, LOG_FN, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

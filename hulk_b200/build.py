@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libhulk_b200.so")
 CLI = os.path.join(HERE, "bin", "hulk")
 
 CUDA_SOURCES = ["api.cu"]
-HOST_SOURCES = ["host_io.cpp"]
+HOST_SOURCES = ["host_io.cpp", "ingest.cpp"]
 DEPS = CUDA_SOURCES + HOST_SOURCES + ["hd_math.h", "ptx_util.cuh", "k1_minimizer.cuh", "k1_scan.h", "k2_countmin.cuh",
                                       "k3_cws.cuh", "go_rng_cooked.inc", "../../include/hulk_b200.h"]
 CLI_SOURCES = ["cli/hulk_main.cpp"]
@@ -42,7 +42,8 @@ def _stale(target: str, deps) -> bool:
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     deps = [os.path.join(CSRC, d) for d in DEPS]
     if force or _stale(LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES] + \
+              ["-lz", "-lpthread"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

@@ -1,0 +1,450 @@
+// hulk_main.cpp -- `hulk sketch` front end over libhulk_b200.so: the reference's flags, log lines and
+// JSON output, with everything numeric running on the GPU behind the C ABI (include/hulk_b200.h).
+//
+// The reference's host is Go (cobra); no Go toolchain exists in this image, so the tested host above
+// the C ABI is this C++ program (and the Python mirror).  What it follows:
+//   cmd/root.go:62-66        persistent flags  -k/--kmerSize -o/--outFile --log -p/--processors --profiling
+//   cmd/sketch.go:50-59      sketch flags      -f/--fastq --fasta -w -i -s -x --stream -b --khf --kmv
+//   cmd/sketch.go:64-179     runSketch: log lines, parameter checks, pipeline wiring
+//   cmd/sketch.go:185-214    sketchParamCheck
+//   src/pipeline/sketch.go:182-301  SeqMinimizer.Run / Sketcher.Run log lines and the output file
+// Not here (out of scope): `hulk smash`, --profiling (pprof), KMV/KHF side sketches
+// (unwired in the reference, src/pipeline/boss.go:18-19: the flags are accepted and logged, like there).
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "hulk_b200.h"
+
+namespace {
+
+FILE *g_log = stdout;
+
+// Go's log package with LstdFlags: "2006/01/02 15:04:05 " + message + '\n'
+void logf(const char *fmt, ...) {
+    char msg[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof msg, fmt, ap);
+    va_end(ap);
+    const time_t t = time(nullptr);
+    struct tm tmv;
+    localtime_r(&t, &tmv);
+    char ts[32];
+    strftime(ts, sizeof ts, "%Y/%m/%d %H:%M:%S", &tmv);
+    size_t n = strlen(msg);
+    while (n && msg[n - 1] == '\n') msg[--n] = 0;
+    fprintf(g_log, "%s %s\n", ts, msg);
+    fflush(g_log);
+}
+void log_line(void *, const char *line) { logf("%s", line); }
+
+[[noreturn]] void fatal(const std::string &msg) {     // helpers.ErrorCheck -> log.Fatalf("ERROR---> %v\n")
+    logf("ERROR---> %s", msg.c_str());
+    exit(1);
+}
+
+struct Options {
+    // root (cmd/root.go:62-66)
+    unsigned long kmer_size = 21;
+    std::string out_file, log_file;
+    long proc = 1;
+    bool profiling = false;
+    // sketch (cmd/sketch.go:50-59)
+    std::vector<std::string> fastq;
+    bool fasta = false;
+    unsigned long window_size = 9, interval = 0, sketch_size = 50;
+    double decay_ratio = 1.0;
+    bool streaming = false;
+    std::string banner_label = "blank";
+    bool add_khf = false, add_kmv = false;
+    // this build only
+    long device = 0;
+};
+
+struct FlagDef {
+    const char *name;
+    char shorthand;
+    enum Kind { UINT, INT, FLOAT, STRING, SLICE, BOOL } kind;
+    void *dst;
+    const char *usage;
+};
+
+void usage_sketch(const std::vector<FlagDef> &defs, FILE *out) {
+    fprintf(out, "Usage:\n  hulk sketch [flags]\n\nFlags:\n");
+    for (const FlagDef &d : defs) {
+        if (d.shorthand) fprintf(out, "  -%c, --%-14s %s\n", d.shorthand, d.name, d.usage);
+        else fprintf(out, "      --%-14s %s\n", d.name, d.usage);
+    }
+}
+
+[[noreturn]] void flag_error(const std::vector<FlagDef> &defs, const std::string &msg) {
+    printf("Error: %s\n", msg.c_str());
+    usage_sketch(defs, stdout);
+    printf("\n%s\n", msg.c_str());
+    exit(1);
+}
+
+void set_flag(const std::vector<FlagDef> &defs, const FlagDef &d, const std::string &v, const std::string &shown) {
+    char *end = nullptr;
+    errno = 0;
+    switch (d.kind) {
+        case FlagDef::UINT: {
+            if (v.empty() || v[0] == '-') flag_error(defs, "invalid argument \"" + v + "\" for \"" + shown + "\" flag");
+            const unsigned long x = strtoul(v.c_str(), &end, 0);
+            if (*end || errno) flag_error(defs, "invalid argument \"" + v + "\" for \"" + shown + "\" flag");
+            *static_cast<unsigned long *>(d.dst) = x;
+            break;
+        }
+        case FlagDef::INT: {
+            const long x = strtol(v.c_str(), &end, 0);
+            if (v.empty() || *end || errno) flag_error(defs, "invalid argument \"" + v + "\" for \"" + shown + "\" flag");
+            *static_cast<long *>(d.dst) = x;
+            break;
+        }
+        case FlagDef::FLOAT: {
+            const double x = strtod(v.c_str(), &end);
+            if (v.empty() || *end) flag_error(defs, "invalid argument \"" + v + "\" for \"" + shown + "\" flag");
+            *static_cast<double *>(d.dst) = x;
+            break;
+        }
+        case FlagDef::STRING:
+            *static_cast<std::string *>(d.dst) = v;
+            break;
+        case FlagDef::SLICE: {                              // pflag StringSlice: comma separated, repeats append
+            auto *dst = static_cast<std::vector<std::string> *>(d.dst);
+            size_t at = 0;
+            for (;;) {
+                const size_t c = v.find(',', at);
+                dst->push_back(v.substr(at, c == std::string::npos ? c : c - at));
+                if (c == std::string::npos) break;
+                at = c + 1;
+            }
+            break;
+        }
+        case FlagDef::BOOL: {
+            bool x;
+            if (v == "true" || v == "1" || v == "t" || v == "T" || v == "TRUE" || v == "True") x = true;
+            else if (v == "false" || v == "0" || v == "f" || v == "F" || v == "FALSE" || v == "False") x = false;
+            else flag_error(defs, "invalid argument \"" + v + "\" for \"" + shown + "\" flag");
+            *static_cast<bool *>(d.dst) = x;
+            break;
+        }
+    }
+}
+
+// pflag-style parsing: --name value, --name=value, -n value, -nvalue, -n=value, grouped bool shorthands
+void parse_flags(const std::vector<FlagDef> &defs, int argc, char **argv, int first) {
+    for (int i = first; i < argc; i++) {
+        const std::string a = argv[i];
+        if (a == "--") break;
+        if (a.size() >= 3 && a[0] == '-' && a[1] == '-') {
+            const size_t eq = a.find('=');
+            const std::string name = a.substr(2, eq == std::string::npos ? eq : eq - 2);
+            if (name == "help") { usage_sketch(defs, stdout); exit(0); }
+            const FlagDef *d = nullptr;
+            for (const FlagDef &x : defs)
+                if (name == x.name) d = &x;
+            if (!d) flag_error(defs, "unknown flag: --" + name);
+            if (eq != std::string::npos) set_flag(defs, *d, a.substr(eq + 1), "--" + name);
+            else if (d->kind == FlagDef::BOOL) *static_cast<bool *>(d->dst) = true;
+            else if (i + 1 < argc) set_flag(defs, *d, argv[++i], "--" + name);
+            else flag_error(defs, "flag needs an argument: --" + name);
+        } else if (a.size() >= 2 && a[0] == '-') {
+            for (size_t j = 1; j < a.size(); j++) {
+                const char c = a[j];
+                if (c == 'h') { usage_sketch(defs, stdout); exit(0); }
+                const FlagDef *d = nullptr;
+                for (const FlagDef &x : defs)
+                    if (x.shorthand == c) d = &x;
+                if (!d) flag_error(defs, std::string("unknown shorthand flag: '") + c + "' in " + a);
+                const std::string shown = std::string("-") + c + ", --" + d->name;
+                if (d->kind == FlagDef::BOOL) { *static_cast<bool *>(d->dst) = true; continue; }
+                std::string rest = a.substr(j + 1);
+                if (!rest.empty()) {
+                    if (rest[0] == '=') rest = rest.substr(1);
+                    set_flag(defs, *d, rest, shown);
+                } else if (i + 1 < argc) {
+                    set_flag(defs, *d, argv[++i], shown);
+                } else {
+                    flag_error(defs, std::string("flag needs an argument: '") + c + "' in " + a);
+                }
+                break;
+            }
+        }
+        // positional arguments are ignored, as cobra does for a command without Args validation
+    }
+}
+
+bool is_not_exist(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) != 0 && errno == ENOENT;
+}
+std::string dir_of(const std::string &p) {                 // filepath.Dir
+    const size_t s = p.find_last_of('/');
+    if (s == std::string::npos) return ".";
+    std::string d = p.substr(0, s);
+    while (d.size() > 1 && d.back() == '/') d.pop_back();
+    if (d.empty()) return "/";
+    // filepath.Clean of the common "./x" shapes
+    while (d.size() > 2 && d.compare(0, 2, "./") == 0) d = d.substr(2);
+    return d;
+}
+bool mkdir_all(const std::string &p, mode_t mode) {
+    std::string cur;
+    size_t at = 0;
+    while (at <= p.size()) {
+        const size_t s = p.find('/', at);
+        cur = p.substr(0, s == std::string::npos ? p.size() : s);
+        at = (s == std::string::npos) ? p.size() + 1 : s + 1;
+        if (cur.empty()) continue;
+        if (mkdir(cur.c_str(), mode) != 0 && errno != EEXIST) return false;
+    }
+    return true;
+}
+std::vector<std::string> split(const std::string &s, char c) {
+    std::vector<std::string> out;
+    size_t at = 0;
+    for (;;) {
+        const size_t p = s.find(c, at);
+        out.push_back(s.substr(at, p == std::string::npos ? p : p - at));
+        if (p == std::string::npos) break;
+        at = p + 1;
+    }
+    return out;
+}
+
+// helpers.CheckFile / CheckExt (src/helpers/helpers.go:112-141)
+void check_file(const std::string &file) {
+    struct stat st;
+    if (stat(file.c_str(), &st) != 0) {
+        if (errno == ENOENT) fatal("file does not exist: " + file);
+        fatal("can't access file (check permissions): " + file);
+    }
+}
+void check_ext(const std::string &file) {
+    const std::vector<std::string> parts = split(file, '.');
+    size_t last = parts.size() - 1;
+    if (parts[last] == "gz" && last > 0) last--;
+    else if (parts[last] == "gz") fatal("file does not have recognised extension: " + file);
+    for (const char *e : {"fastq", "fq", "fasta", "fna", "fa"})
+        if (parts[last] == e) return;
+    fatal("file does not have recognised extension: " + file);
+}
+
+std::string go_duration(double seconds) {                  // time.Duration.String()
+    const long long ns = (long long)(seconds * 1e9);
+    auto trimmed = [](long long whole, long long frac, int digits) {   // whole.frac without trailing zeros
+        char buf[64];
+        snprintf(buf, sizeof buf, "%lld.%0*lld", whole, digits, frac);
+        std::string s = buf;
+        while (s.back() == '0') s.pop_back();
+        if (s.back() == '.') s.pop_back();
+        return s;
+    };
+    if (ns < 1000) return std::to_string(ns) + "ns";
+    if (ns < 1000000) return trimmed(ns / 1000, ns % 1000, 3) + "\xc2\xb5s";
+    if (ns < 1000000000) return trimmed(ns / 1000000, ns % 1000000, 6) + "ms";
+    const long long total_s = ns / 1000000000, h = total_s / 3600, m = (total_s / 60) % 60;
+    std::string out;
+    if (h) out += std::to_string(h) + "h";
+    if (h || m) out += std::to_string(m) + "m";
+    return out + trimmed(total_s % 60, ns % 1000000000, 9) + "s";
+}
+
+int run_sketch(int argc, char **argv) {
+    Options o;
+    char stamp[32];
+    const time_t t0 = time(nullptr);
+    struct tm tmv;
+    localtime_r(&t0, &tmv);
+    strftime(stamp, sizeof stamp, "%Y%m%d%H%M%S", &tmv);
+    o.out_file = std::string("./hulk-") + stamp;            // cmd/root.go:35
+    const std::vector<FlagDef> defs = {
+        {"fastq", 'f', FlagDef::SLICE, &o.fastq, "FASTQ file(s) to sketch (can also pipe in STDIN)"},
+        {"fasta", 0, FlagDef::BOOL, &o.fasta, "tells HULK that the input file is actually FASTA format (.fna/.fasta/.fa), not FASTQ (experimental feature)"},
+        {"windowSize", 'w', FlagDef::UINT, &o.window_size, "minimizer window size (default 9)"},
+        {"interval", 'i', FlagDef::UINT, &o.interval, "size of k-mer sampling interval (default 0 (= no interval))"},
+        {"sketchSize", 's', FlagDef::UINT, &o.sketch_size, "size of sketch (default 50)"},
+        {"decayRatio", 'x', FlagDef::FLOAT, &o.decay_ratio, "decay ratio used for concept drift (1.0 = concept drift disabled) (default 1)"},
+        {"stream", 0, FlagDef::BOOL, &o.streaming, "prints the sketches to STDOUT after every interval is reached, whilst still writting them to disk (log file is redirected to disk))"},
+        {"bannerLabel", 'b', FlagDef::STRING, &o.banner_label, "adds a label to the sketch object, for use with BANNER (default \"blank\")"},
+        {"khf", 0, FlagDef::BOOL, &o.add_khf, "also generate a MinHash K-Hash Functions sketch"},
+        {"kmv", 0, FlagDef::BOOL, &o.add_kmv, "also generate a MinHash K-Minimum Values (bottom-k) sketch"},
+        {"kmerSize", 'k', FlagDef::UINT, &o.kmer_size, "minimizer k-mer length (default 21)"},
+        {"outFile", 'o', FlagDef::STRING, &o.out_file, "directory and basename for saving the outfile(s)"},
+        {"log", 0, FlagDef::STRING, &o.log_file, "filename for log file, if omitted then STDOUT used by default"},
+        {"processors", 'p', FlagDef::INT, &o.proc, "number of processors to use (default 1)"},
+        {"profiling", 0, FlagDef::BOOL, &o.profiling, "create the files needed to profile HULK using the go tool pprof"},
+        {"device", 0, FlagDef::INT, &o.device, "CUDA device ordinal (this build; default 0)"},
+    };
+    parse_flags(defs, argc, argv, 2);
+
+    // cmd/sketch.go:74-87
+    if (o.streaming) {
+        if (o.log_file.empty()) o.log_file = o.out_file + ".log";
+        const std::string dir = dir_of(o.log_file);       // helpers.StartLogging
+        if (o.log_file.find('/') != std::string::npos && is_not_exist(dir) && !mkdir_all(dir, 0700)) {
+            fprintf(stderr, "can't create specified directory for log\n");
+            return 1;
+        }
+        g_log = fopen(o.log_file.c_str(), "a");
+        if (!g_log) { perror(o.log_file.c_str()); return 1; }
+    }
+
+    const auto start = std::chrono::steady_clock::now();
+    logf("this is hulk (version %s)", hulk_b200_version());
+    logf("please cite Rowe et al. 2019, doi: https://doi.org/10.1186/s40168-019-0653-2");
+    logf("starting the sketch subcommand");
+    logf("checking parameters...");
+
+    // sketchParamCheck (cmd/sketch.go:185-214)
+    const std::string out_dir = dir_of(o.out_file);
+    if (out_dir != "." && is_not_exist(out_dir) && !mkdir_all(out_dir, 0700))
+        fatal(std::string("can't create specified output directory: mkdir ") + out_dir + ": " + strerror(errno));
+    const long ncpu = (long)std::max(1u, std::thread::hardware_concurrency());
+    if (o.proc <= 0 || o.proc > ncpu) o.proc = ncpu;
+    if (o.fastq.empty()) {
+        struct stat st;
+        if (fstat(0, &st) != 0) fatal("error with STDIN");
+        if (!S_ISFIFO(st.st_mode)) fatal("no STDIN found");
+        logf("\tinput file: using STDIN");
+    } else {
+        for (const std::string &f : o.fastq) {
+            check_file(f);
+            check_ext(f);
+        }
+    }
+    logf(o.fasta ? "\tmode: FASTA" : "\tmode: FASTQ");
+    logf("\tno. processors: %ld", o.proc);
+    logf("\tminimizer k-mer size: %lu", o.kmer_size);
+    logf("\tminimizer window size: %lu", o.window_size);
+    logf("\tsketch size: %lu", o.sketch_size);
+    logf(o.streaming ? "\tstreaming: enabled" : "\tstreaming: disabled");
+    if (o.decay_ratio == 1.0) {
+        logf("\tconcept drift: disabled");
+    } else {
+        logf("\tconcept drift: enabled");
+        logf("\tdecay ratio: %.2f", o.decay_ratio);
+    }
+    // spectrumSize := int32(helpers.Pow(k, 4)) in uint (64-bit) arithmetic  cmd/sketch.go:118
+    const uint64_t k64 = o.kmer_size;
+    const int32_t spectrum = (int32_t)(uint32_t)(k64 * k64 * k64 * k64);
+    logf("\tnumber of bins in k-mer spectrum: %d", spectrum);
+    logf("\tadding KHF sketch: %s", o.add_khf ? "true" : "false");
+    logf("\tadding KMV sketch: %s", o.add_kmv ? "true" : "false");
+
+    std::string file_name = "STDIN";                        // cmd/sketch.go:147-155 (trailing comma kept)
+    if (!o.fastq.empty()) {
+        file_name.clear();
+        for (const std::string &f : o.fastq) file_name += f + ",";
+    }
+
+    logf("initialising sketching pipeline...");
+    logf("\tinitialising the processes");
+    logf("\tconnecting data streams");
+    logf("\tnumber of processes added to the sketching pipeline: %d", 4);
+    logf("\tnumber of minions in the sketching pool: %ld", o.proc);
+
+    // the reader starts first: reading/inflating overlaps context creation and the CWS table draw
+    std::vector<const char *> paths;
+    for (const std::string &f : o.fastq) paths.push_back(f.c_str());
+    hulk_b200_reader *rd = nullptr;
+    int rc = hulk_b200_reader_open(paths.data(), (uint32_t)paths.size(), o.fasta ? 1 : 0, 0, &rd);
+    if (rc) fatal(hulk_b200_strerror(rc));
+
+    logf("finding minimizers...");                          // SeqMinimizer.Run  src/pipeline/sketch.go:183
+    hulk_b200_params P;
+    memset(&P, 0, sizeof P);
+    P.k = (uint32_t)std::min<unsigned long>(o.kmer_size, 0xffffffffu);
+    P.w = (uint32_t)std::min<unsigned long>(o.window_size, 0xffffffffu);
+    P.sketch_size = (uint32_t)std::min<unsigned long>(o.sketch_size, 0xffffffffu);
+    P.num_bins = spectrum;
+    P.decay_ratio = o.decay_ratio;
+    P.device = (int32_t)o.device;
+    hulk_b200_ctx *ctx = nullptr;
+    rc = hulk_b200_create(&P, &ctx);                        // findMinimizers + NewHistoSketch parameter checks
+    if (rc) fatal(hulk_b200_last_error(nullptr));
+    rc = hulk_b200_generate_cws_tables(ctx);                // NewHistoSketch -> newCWS
+    if (rc) fatal(hulk_b200_last_error(ctx));
+
+    rc = hulk_b200_sketch_reader(ctx, rd, o.interval, log_line, nullptr);
+    if (rc) {
+        const char *rerr = hulk_b200_reader_error(rd);
+        if (rc == HULK_B200_EFASTQ || rc == HULK_B200_ETOOLONG || rc == HULK_B200_EIO) {
+            // log.Fatal(err) in the reader processes: no "ERROR--->" prefix  src/pipeline/sketch.go:53-55,75-77,150-152
+            logf("%s", (rerr && *rerr) ? rerr : hulk_b200_strerror(rc));
+            return 1;
+        }
+        if (rc == HULK_B200_ENOSEQ) fatal("no sequences received");
+        fatal(hulk_b200_last_error(ctx));
+    }
+    hulk_b200_stats st;
+    rc = hulk_b200_get_stats(ctx, &st);
+    if (rc) fatal(hulk_b200_last_error(ctx));
+    const unsigned long mean_rl = (unsigned long)((double)st.n_bases / (double)st.n_reads);
+    logf("\tprocessed %llu sequences in total", (unsigned long long)st.n_reads);
+    logf("\tmean sequence length: %lu", mean_rl);
+    logf("\tfound %llu minimizers", (unsigned long long)st.n_minimizers);
+    logf("\thistosketching across %d bins", spectrum);
+    logf(o.proc > 1 ? "merging sketches and cleaning up..." : "cleaning up...");
+
+    std::vector<uint64_t> mins(P.sketch_size);
+    std::vector<double> weights(P.sketch_size);
+    rc = hulk_b200_finish(ctx, mins.data(), weights.data());
+    if (rc) fatal(hulk_b200_last_error(ctx));
+    const std::string out_json = o.out_file + ".json";
+    rc = hulk_b200_write_json(out_json.c_str(), file_name.c_str(), o.banner_label.c_str(), P.k, mins.data(),
+                              weights.data(), P.sketch_size, spectrum, o.decay_ratio != 1.0);
+    if (rc == HULK_B200_ENOSKETCH) fatal("no sketch was generated by the histosketch algorithm");
+    if (rc == HULK_B200_EARG) fatal("json: unsupported value: a sketch weight is not finite");
+    if (rc) fatal("open " + out_json + ": " + strerror(errno));
+    logf("\twritten sketch to disk: %s", out_json.c_str());
+    hulk_b200_reader_close(rd);
+    hulk_b200_destroy(ctx);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    logf("finished in %s", go_duration(secs).c_str());
+    return 0;
+}
+
+void usage_root() {
+    printf("\n\tHULK is a tool that creates small, fixed-size sketches from streaming microbiome sequencing data,\n"
+           "\tenabling rapid metagenomic dissimilarity analysis. HULK generates an approximate k-mer spectrum from\n"
+           "\ta FASTQ data stream, incrementally sketches it and makes similarity search queries against other microbiome sketches.\n\n"
+           "Usage:\n  hulk [command]\n\nAvailable Commands:\n"
+           "  help        Help about any command\n"
+           "  sketch      Create a sketch from a set of reads\n"
+           "  version     Prints the current version and exits\n\n"
+           "Use \"hulk [command] --help\" for more information about a command.\n");
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2 || !strcmp(argv[1], "help") || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
+        usage_root();
+        return 0;
+    }
+    if (!strcmp(argv[1], "version")) {                      // cmd/version.go
+        printf("%s\n", hulk_b200_version());
+        return 0;
+    }
+    if (!strcmp(argv[1], "sketch")) return run_sketch(argc, argv);
+    if (!strcmp(argv[1], "smash")) {
+        printf("Error: `hulk smash` is not part of the B200 build (only the sketch hot path is; see DESIGN.md)\n");
+        return 1;
+    }
+    printf("Error: unknown command \"%s\" for \"hulk\"\nRun 'hulk --help' for usage.\n", argv[1]);
+    return 1;
+}

@@ -1,0 +1,421 @@
+// ingest.cpp -- the input side of `hulk sketch`: line reader + FASTQ/FASTA framing, feeding the GPU.
+//
+// Reference semantics (paths relative to the reference checkout):
+//   src/pipeline/sketch.go:40-79    DataStreamer.Run: every input file in order (or STDIN) through a
+//                                   bufio.Scanner, gzip when the last '.'-component of the name is "gz";
+//                                   `append([]byte(nil), line...)` makes an EMPTY line nil
+//   src/pipeline/sketch.go:99-161   FastqHandler.Run: FASTQ = fill l1..l4 with the next non-nil lines,
+//                                   FASTA = '>' starts a record, other lines are appended, an empty line
+//                                   stops the input
+//   src/seqio/seqio.go:37-48        NewFASTQread: only l1[0] == '@' is checked
+//   src/pipeline/sketch.go:197-224  SeqMinimizer.Run: AddSeq / progress lines / Flush per interval
+//
+// Design: one producer thread reads (read(2) or zlib), splits lines with memchr and frames records
+// straight into a ring of page-locked batches (bases + offsets), so the consumer can hand a batch to
+// hulk_b200_push_reads without another copy while the producer fills the next one.  No CUDA kernels
+// here; the only CUDA dependency is the pinned allocation (plain memory when no device exists, so the
+// reader itself can be tested on a CPU-only box -- it computes nothing).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/hulk_b200.h"
+
+namespace {
+
+constexpr size_t kBlock = 4u << 20;             // bytes per read()/gzread()
+constexpr size_t kMaxToken = 64 * 1024;         // bufio.MaxScanTokenSize
+constexpr int kRing = 4;                        // batches in flight
+
+struct HostBuf {                                // page-locked when a device exists
+    void *p = nullptr;
+    bool pinned = false;
+    size_t bytes = 0;
+    bool alloc(size_t n) {
+        release();
+        void *q = nullptr;
+        if (hulk_b200_alloc_pinned(&q, n) == HULK_B200_OK) {
+            p = q; pinned = true; bytes = n;
+            return true;
+        }
+        if (posix_memalign(&q, 4096, n ? n : 1) != 0) return false;
+        p = q; pinned = false; bytes = n;
+        return true;
+    }
+    void release() {
+        if (!p) return;
+        if (pinned) hulk_b200_free_pinned(p);
+        else free(p);
+        p = nullptr; bytes = 0;
+    }
+};
+
+struct Batch {
+    HostBuf bases, offsets;
+    uint64_t n_reads = 0, n_bytes = 0;          // committed
+    uint64_t cap_reads() const { return offsets.bytes / 8 - 1; }
+    uint8_t *b() { return static_cast<uint8_t *>(bases.p); }
+    uint64_t *o() { return static_cast<uint64_t *>(offsets.p); }
+};
+
+}  // namespace
+
+struct hulk_b200_reader {
+    std::vector<std::string> paths;
+    bool fasta = false;
+    uint64_t batch_bytes = 0;
+
+    Batch ring[kRing];
+    std::deque<Batch *> free_q, full_q;
+    Batch *held = nullptr;                      // batch currently lent to the consumer
+    std::mutex mu;
+    std::condition_variable cv_free, cv_full;
+    bool done = false, stop = false;
+    int err = 0;                                // producer's terminal error (delivered after the full batches)
+    std::string err_text, last_error;
+    std::thread th;
+
+    // producer state
+    Batch *cur = nullptr;
+    // FASTQ framing: which of l1..l4 are filled (the sequence itself is parked in the batch, uncommitted)
+    int slot = 0;
+    uint8_t l1_first = 0;
+    std::string l1_text;
+    uint64_t pend_bytes = 0;
+    // FASTA framing
+    bool have_header = false, fasta_stop = false;
+    std::vector<uint8_t> fa_seq;
+
+    bool fail(int code, const std::string &text) {
+        err = code;
+        err_text = text;
+        return false;
+    }
+
+    Batch *take_free() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_free.wait(lk, [&] { return stop || !free_q.empty(); });
+        if (stop) return nullptr;
+        Batch *b = free_q.front();
+        free_q.pop_front();
+        b->n_reads = b->n_bytes = 0;
+        b->o()[0] = 0;
+        return b;
+    }
+    void publish(Batch *b) {
+        std::lock_guard<std::mutex> lk(mu);
+        full_q.push_back(b);
+        cv_full.notify_one();
+    }
+    // make room for `len` more bases and one more read in the current batch; false = stopped / OOM
+    bool reserve(uint64_t len) {
+        if (!cur && !(cur = take_free())) return false;
+        const bool full = cur->n_bytes + len > cur->bases.bytes || cur->n_reads + 1 > cur->cap_reads();
+        if (full && cur->n_reads > 0) {
+            publish(cur);
+            if (!(cur = take_free())) return false;
+        }
+        if (len > cur->bases.bytes) {                       // one sequence larger than a whole batch
+            if (!cur->bases.alloc((size_t)((len + 4095) & ~4095ull))) return fail(HULK_B200_ENOMEM, "batch buffer");
+        }
+        return true;
+    }
+    bool commit(uint64_t len) {
+        cur->n_bytes += len;
+        cur->n_reads += 1;
+        cur->o()[cur->n_reads] = cur->n_bytes;
+        return true;
+    }
+
+    // one bufio.Scanner line (CR already dropped); an empty line is Go's nil slice
+    bool on_line(const uint8_t *p, size_t len) {
+        if (fasta) {
+            if (fasta_stop) return true;
+            if (len == 0) { fasta_stop = true; return true; }            // sketch.go:103-105
+            if (p[0] == '>') {                                           // :107
+                if (have_header) {                                       // :108-119
+                    if (!reserve(fa_seq.size())) return false;
+                    if (!fa_seq.empty()) memcpy(cur->b() + cur->n_bytes, fa_seq.data(), fa_seq.size());
+                    commit(fa_seq.size());
+                }
+                have_header = true;                                      // l1, l2 = line, nil   :120
+                fa_seq.clear();
+            } else {
+                fa_seq.insert(fa_seq.end(), p, p + len);                 // l2 = append(l2, line...)  :122
+            }
+            return true;
+        }
+        if (len == 0) return true;                                       // nil line: no slot takes it  :140-147
+        switch (slot) {
+            case 0:
+                l1_first = p[0];
+                if (l1_first != '@') l1_text.assign(reinterpret_cast<const char *>(p), len);
+                slot = 1;
+                break;
+            case 1:
+                if (!reserve(len)) return false;
+                memcpy(cur->b() + cur->n_bytes, p, len);                 // parked behind the committed reads
+                pend_bytes = len;
+                slot = 2;
+                break;
+            case 2:
+                slot = 3;
+                break;
+            default:
+                if (l1_first != '@')                                     // seqio.go:38-40 (checked when l4 arrives)
+                    return fail(HULK_B200_EFASTQ, "read ID in fastq file does not begin with @: " + l1_text);
+                commit(pend_bytes);
+                slot = 0;
+                break;
+        }
+        return true;
+    }
+
+    // split one file's byte stream into lines (bufio.ScanLines): `carry` holds an unfinished line
+    bool feed(const uint8_t *data, size_t n, std::vector<uint8_t> &carry) {
+        size_t pos = 0;
+        while (pos < n && !fasta_stop) {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(data + pos, '\n', n - pos));
+            if (!nl) {
+                carry.insert(carry.end(), data + pos, data + n);
+                if (carry.size() >= kMaxToken) return fail(HULK_B200_ETOOLONG, "bufio.Scanner: token too long");
+                return true;
+            }
+            const uint8_t *lp = data + pos;
+            size_t len = (size_t)(nl - lp);
+            if (!carry.empty()) {
+                carry.insert(carry.end(), lp, nl);
+                lp = carry.data();
+                len = carry.size();
+            }
+            if (len >= kMaxToken) return fail(HULK_B200_ETOOLONG, "bufio.Scanner: token too long");
+            if (len && lp[len - 1] == '\r') len--;
+            if (!on_line(lp, len)) return false;
+            carry.clear();
+            pos = (size_t)(nl - data) + 1;
+        }
+        return true;
+    }
+    bool end_of_file(std::vector<uint8_t> &carry) {
+        if (!carry.empty() && !fasta_stop) {                 // final line without a newline is still a token
+            size_t len = carry.size();
+            if (carry[len - 1] == '\r') len--;
+            if (!on_line(carry.data(), len)) return false;
+        }
+        carry.clear();
+        return true;
+    }
+
+    bool read_plain(int fd, const std::string &name) {
+        std::vector<uint8_t> block(kBlock), carry;
+        for (;;) {
+            if (stop) return false;
+            const ssize_t got = ::read(fd, block.data(), block.size());
+            if (got < 0) {
+                if (errno == EINTR) continue;
+                return fail(HULK_B200_EIO, "read " + name + ": " + strerror(errno));
+            }
+            if (got == 0) break;
+            if (!feed(block.data(), (size_t)got, carry)) return false;
+            if (fasta_stop) return true;
+        }
+        return end_of_file(carry);
+    }
+    bool read_gz(int fd, const std::string &name) {
+        uint8_t magic[2];
+        const ssize_t m = ::pread(fd, magic, 2, 0);
+        if (m == 0) return fail(HULK_B200_EIO, "EOF");                                    // gzip.NewReader on an empty file
+        if (m != 2 || magic[0] != 0x1f || magic[1] != 0x8b) return fail(HULK_B200_EIO, "gzip: invalid header");
+        gzFile gz = gzdopen(dup(fd), "rb");
+        if (!gz) return fail(HULK_B200_EIO, "gzdopen " + name);
+        gzbuffer(gz, 1u << 20);
+        std::vector<uint8_t> block(kBlock), carry;
+        bool ok = true;
+        for (;;) {
+            if (stop) { ok = false; break; }
+            const int got = gzread(gz, block.data(), (unsigned)block.size());
+            if (got < 0) {
+                int zerr = 0;
+                const char *msg = gzerror(gz, &zerr);
+                ok = fail(HULK_B200_EIO, std::string("gzip: ") + (msg ? msg : "read error"));
+                break;
+            }
+            if (got == 0) break;
+            if (!(ok = feed(block.data(), (size_t)got, carry))) break;
+            if (fasta_stop) break;
+        }
+        gzclose(gz);
+        if (!ok) return false;
+        return fasta_stop ? true : end_of_file(carry);
+    }
+
+    void produce() {
+        bool ok = true;
+        if (paths.empty()) {
+            ok = read_plain(0, "STDIN");
+        } else {
+            for (size_t i = 0; ok && i < paths.size() && !fasta_stop; i++) {
+                const std::string &name = paths[i];
+                const int fd = ::open(name.c_str(), O_RDONLY);
+                if (fd < 0) { ok = fail(HULK_B200_EIO, "open " + name + ": " + strerror(errno)); break; }
+#ifdef POSIX_FADV_SEQUENTIAL
+                posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+                const size_t dot = name.rfind('.');
+                const bool gz = dot != std::string::npos && name.compare(dot + 1, std::string::npos, "gz") == 0;
+                ok = gz ? read_gz(fd, name) : read_plain(fd, name);
+                ::close(fd);
+            }
+        }
+        if (ok && fasta) {                                               // "flush final fasta"  sketch.go:126-135
+            if (!have_header) {
+                ok = fail(HULK_B200_EFASTQ, "no FASTA record in the input (the reference indexes a nil header here)");
+            } else if (reserve(fa_seq.size())) {
+                if (!fa_seq.empty()) memcpy(cur->b() + cur->n_bytes, fa_seq.data(), fa_seq.size());
+                commit(fa_seq.size());
+            } else {
+                ok = false;
+            }
+        }
+        // (an unfinished FASTQ record at the end of the input is never emitted by the reference)
+        if (cur && cur->n_reads > 0) { publish(cur); cur = nullptr; }
+        std::lock_guard<std::mutex> lk(mu);
+        done = true;
+        cv_full.notify_all();
+    }
+};
+
+extern "C" {
+
+int hulk_b200_reader_open(const char *const *paths, uint32_t n_paths, int fasta, uint64_t batch_bytes,
+                          hulk_b200_reader **out) {
+    if (!out || (n_paths && !paths)) return HULK_B200_EARG;
+    *out = nullptr;
+    hulk_b200_reader *rd = new (std::nothrow) hulk_b200_reader();
+    if (!rd) return HULK_B200_ENOMEM;
+    for (uint32_t i = 0; i < n_paths; i++) {
+        if (!paths[i]) { delete rd; return HULK_B200_EARG; }
+        rd->paths.emplace_back(paths[i]);
+    }
+    rd->fasta = fasta != 0;
+    rd->batch_bytes = batch_bytes ? batch_bytes : (32ull << 20);
+    if (rd->batch_bytes < 4096) rd->batch_bytes = 4096;
+    // offsets: room for reads as short as 32 bases on average (shorter reads just close the batch earlier)
+    const uint64_t cap_reads = std::max<uint64_t>(1024, rd->batch_bytes / 32);
+    for (int i = 0; i < kRing; i++) {
+        if (!rd->ring[i].bases.alloc((size_t)rd->batch_bytes) || !rd->ring[i].offsets.alloc((size_t)(cap_reads + 1) * 8)) {
+            for (int j = 0; j <= i; j++) { rd->ring[j].bases.release(); rd->ring[j].offsets.release(); }
+            delete rd;
+            return HULK_B200_ENOMEM;
+        }
+        rd->free_q.push_back(&rd->ring[i]);
+    }
+    rd->th = std::thread([rd] { rd->produce(); });
+    *out = rd;
+    return HULK_B200_OK;
+}
+
+int hulk_b200_reader_next(hulk_b200_reader *rd, const uint8_t **bases, const uint64_t **offsets, uint64_t *n_reads) {
+    if (!rd || !bases || !offsets || !n_reads) return HULK_B200_EARG;
+    *n_reads = 0;
+    *bases = nullptr;
+    *offsets = nullptr;
+    std::unique_lock<std::mutex> lk(rd->mu);
+    if (rd->held) {
+        rd->free_q.push_back(rd->held);
+        rd->held = nullptr;
+        rd->cv_free.notify_one();
+    }
+    rd->cv_full.wait(lk, [&] { return rd->done || !rd->full_q.empty(); });
+    if (!rd->full_q.empty()) {
+        Batch *b = rd->full_q.front();
+        rd->full_q.pop_front();
+        rd->held = b;
+        *bases = b->b();
+        *offsets = b->o();
+        *n_reads = b->n_reads;
+        return HULK_B200_OK;
+    }
+    if (rd->err) {
+        rd->last_error = rd->err_text;
+        return rd->err;
+    }
+    return HULK_B200_OK;                                                  // end of input
+}
+
+const char *hulk_b200_reader_error(const hulk_b200_reader *rd) { return rd ? rd->last_error.c_str() : ""; }
+
+void hulk_b200_reader_close(hulk_b200_reader *rd) {
+    if (!rd) return;
+    {
+        std::lock_guard<std::mutex> lk(rd->mu);
+        rd->stop = true;
+        rd->cv_free.notify_all();
+    }
+    if (rd->th.joinable()) rd->th.join();
+    for (int i = 0; i < kRing; i++) { rd->ring[i].bases.release(); rd->ring[i].offsets.release(); }
+    delete rd;
+}
+
+int hulk_b200_sketch_reader(hulk_b200_ctx *ctx, hulk_b200_reader *rd, uint64_t interval, hulk_b200_log_fn log,
+                            void *user) {
+    if (!ctx || !rd) return HULK_B200_EARG;
+    char line[128];
+    uint64_t seq_count = 0, sketching_interval = 0;
+    for (;;) {
+        const uint8_t *bases = nullptr;
+        const uint64_t *offsets = nullptr;
+        uint64_t n = 0;
+        const int rc = hulk_b200_reader_next(rd, &bases, &offsets, &n);
+        if (rc) return rc;
+        if (n == 0) break;
+        uint64_t done = 0;
+        while (done < n) {
+            uint64_t take = n - done;
+            if (interval) take = std::min<uint64_t>(take, interval - (seq_count % interval));
+            // the sub-range [done, done + take] of the batch's offsets addresses the same `bases`
+            const int prc = hulk_b200_push_reads(ctx, bases, offsets + done, take);     // theBoss.AddSeq  :200
+            if (prc) return prc;
+            const uint64_t before = seq_count;
+            seq_count += take;
+            done += take;
+            if (log)
+                for (uint64_t m = before / 100000 + 1; m * 100000 <= seq_count; m++) {  // :203-207
+                    snprintf(line, sizeof line, "\tprocessed %llu sequences", (unsigned long long)(m * 100000));
+                    log(user, line);
+                }
+            if (interval && seq_count % interval == 0) {                                // :211-215
+                sketching_interval++;
+                if (log) {
+                    snprintf(line, sizeof line, "\treached interval %llu -> histosketching",
+                             (unsigned long long)sketching_interval);
+                    log(user, line);
+                }
+                const int frc = hulk_b200_flush(ctx);
+                if (frc) return frc;
+            }
+        }
+    }
+    if (log) log(user, "generating final histosketch of k-mer spectra...");              // :220
+    const int frc = hulk_b200_flush(ctx);                                               // :221
+    if (frc) return frc;
+    const int src = hulk_b200_sync(ctx);
+    if (src) return src;
+    if (seq_count == 0) return HULK_B200_ENOSEQ;                                        // :237-239
+    return HULK_B200_OK;
+}
+
+}  // extern "C"

@@ -28,7 +28,7 @@ def _lines(path: str) -> Iterator[bytes]:
     for ln in parts:
         if ln.endswith(b"\r"):
             ln = ln[:-1]
-        if len(ln) > 64 * 1024:
+        if len(ln) >= 64 * 1024:          # bufio.MaxScanTokenSize: the line and its "\n" must fit the buffer
             raise ValueError("bufio.Scanner: token too long")
         yield ln
 
@@ -68,6 +68,64 @@ def read_fasta(path: str) -> List[bytes]:
         raise ValueError("no FASTA record")      # the reference panics on l1[0] of a nil slice
     reads.append(seq if seq is not None else b"")
     return reads
+
+
+class NativeReader:
+    """The library's threaded line reader + FASTQ/FASTA framing (hulk_b200_reader_*, csrc/ingest.cpp):
+    what the `hulk` front end feeds the GPU from.  Iterating yields (bases uint8[], offsets uint64[n+1])
+    batches in input order; the arrays alias the reader's pinned ring and are valid until the next batch."""
+
+    def __init__(self, paths, fasta: bool = False, batch_bytes: int = 0):
+        import ctypes as C
+        from . import _native as N
+        self._C, self._N, self._L = C, N, N.load()
+        arr = (C.c_char_p * max(1, len(paths)))(*[p.encode() for p in paths])
+        self._rd = C.c_void_p()
+        rc = self._L.hulk_b200_reader_open(arr, len(paths), int(fasta), batch_bytes, C.byref(self._rd))
+        if rc:
+            raise OSError(self._L.hulk_b200_strerror(rc).decode())
+
+    def __iter__(self):
+        C = self._C
+        while True:
+            bases, offsets, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+            rc = self._L.hulk_b200_reader_next(self._rd, C.byref(bases), C.byref(offsets), C.byref(n))
+            if rc:
+                raise ValueError(self._L.hulk_b200_reader_error(self._rd).decode())
+            if n.value == 0:
+                return
+            offs = np.ctypeslib.as_array(C.cast(offsets, C.POINTER(C.c_uint64)), shape=(n.value + 1,))
+            nb = int(offs[-1])
+            b = (np.ctypeslib.as_array(C.cast(bases, C.POINTER(C.c_uint8)), shape=(nb,)) if nb
+                 else np.zeros(0, np.uint8))
+            yield b, offs
+
+    def reads(self) -> List[bytes]:
+        out: List[bytes] = []
+        for b, offs in self:
+            raw = b.tobytes()
+            out.extend(raw[int(offs[i]):int(offs[i + 1])] for i in range(len(offs) - 1))
+        return out
+
+    def handle(self):
+        return self._rd
+
+    def close(self):
+        if getattr(self, "_rd", None):
+            self._L.hulk_b200_reader_close(self._rd)
+            self._rd = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)

@@ -1,0 +1,203 @@
+"""The input stage (csrc/ingest.cpp: line reader + FASTQ/FASTA framing, reference src/pipeline/sketch.go:40-161)
+and the `hulk` front end (csrc/cli/hulk_main.cpp: flags and log lines of cmd/root.go, cmd/sketch.go).
+
+CPU tests cover the reader against the Python restatement of the reference's framing (hulk_b200.seqio) and the
+front end's argument handling; the GPU tests run `hulk sketch` end to end on the reference's own fixture."""
+import gzip
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import hulk_b200
+from conftest import GOLDEN, has_gpu, random_reads
+
+FIXTURE = os.path.join(GOLDEN, "c1_reads.fq.gz")
+TS = r"^\d{4}/\d{2}/\d{2} \d{2}:\d{2}:\d{2} "
+
+
+def _native(paths, fasta=False, batch_bytes=0):
+    with hulk_b200.NativeReader([str(p) for p in paths], fasta=fasta, batch_bytes=batch_bytes) as rd:
+        return rd.reads()
+
+
+def test_native_reader_on_reference_fixture(fixture_reads):
+    assert _native([FIXTURE]) == fixture_reads
+    # tiny batches: every batch boundary falls between two records
+    assert _native([FIXTURE], batch_bytes=4096) == fixture_reads
+
+
+def test_native_reader_framing_quirks(tmp_path):
+    # empty lines are nil in the reference and re-fill the same slot; CRLF; last line without newline
+    p = tmp_path / "q.fq"
+    p.write_bytes(b"@r1\n\nACGT\n+\nIIII\n@r2\r\nGGCC\r\n+\r\nIIII")
+    assert _native([p]) == hulk_b200.read_fastq(str(p)) == [b"ACGT", b"GGCC"]
+    # an unfinished record at the end is never emitted; '@' is the only check and only on line 1
+    q = tmp_path / "t.fq"
+    q.write_bytes(b"@r1\nAC\nwhatever\n!!\n@r2\nGG\n+\n")
+    assert _native([q]) == [b"AC"]
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"@ok\nAAAA\n+\nIIII\nr1\nACGT\n+\nIIII\n")
+    with pytest.raises(ValueError, match="read ID in fastq file does not begin with @: r1"):
+        _native([bad])
+    # the line stream runs across files: a record may straddle two files, and a final line
+    # without newline does not join the next file's first line
+    a, b = tmp_path / "a.fq", tmp_path / "b.fq"
+    a.write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nTTTT")
+    b.write_bytes(b"+\nIIII\n@r3\nCC\n+\nII\n")
+    assert _native([a, b]) == [b"ACGT", b"TTTT", b"CC"]
+
+
+def test_native_reader_gzip_multimember_and_long_lines(tmp_path):
+    reads = random_reads(5000, 150, seed=3, ragged=100)
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
+    half = len(rec) // 2
+    cut = rec.index(b"\n@", half) + 1
+    gz = tmp_path / "m.fastq.gz"
+    gz.write_bytes(gzip.compress(rec[:cut]) + gzip.compress(rec[cut:]))      # two gzip members (Go: multistream)
+    assert _native([gz], batch_bytes=1 << 16) == reads
+    notgz = tmp_path / "n.fq.gz"
+    notgz.write_bytes(rec[:1000])
+    with pytest.raises(ValueError, match="gzip: invalid header"):
+        _native([notgz])
+    # bufio.Scanner: a line of 64 KiB or more is fatal, 64 KiB - 1 is fine
+    ok = tmp_path / "ok.fq"
+    ok.write_bytes(b"@r\n" + b"A" * 65535 + b"\n+\n" + b"I" * 65535 + b"\n")
+    assert _native([ok], batch_bytes=4096) == [b"A" * 65535]                # also: one read larger than a batch
+    long = tmp_path / "long.fq"
+    long.write_bytes(b"@r\n" + b"A" * 65536 + b"\n+\n" + b"I" * 10 + b"\n")
+    with pytest.raises(ValueError, match="token too long"):
+        _native([long])
+    with pytest.raises(ValueError, match="token too long"):
+        hulk_b200.read_fastq(str(long))
+
+
+def test_native_reader_fasta(tmp_path):
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b"stray\n>c1 desc\nACGT\nTTAA\n>c2\n>c3\nGG\n\n>c4\nAAAA\n")
+    want = hulk_b200.read_fasta(str(fa))
+    assert want == [b"ACGTTTAA", b"", b"GG"]                                # stops at the empty line
+    assert _native([fa], fasta=True) == want
+    big = tmp_path / "g.fna"
+    seq = random_reads(1, 300000, seed=9)[0]
+    big.write_bytes(b">chr\n" + b"\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + b"\n")
+    assert _native([big], fasta=True, batch_bytes=8192) == [seq]
+    none = tmp_path / "none.fa"
+    none.write_bytes(b"ACGT\n")
+    with pytest.raises(ValueError):
+        _native([none], fasta=True)
+
+
+def _hulk(*args, stdin=None):
+    assert os.path.exists(hulk_b200.CLI_PATH), "build the front end first (python -m hulk_b200.build)"
+    return subprocess.run([hulk_b200.CLI_PATH, *args], capture_output=True, text=True, timeout=600, stdin=stdin)
+
+
+def test_cli_version_and_flag_errors(tmp_path):
+    r = _hulk("version")
+    assert r.returncode == 0 and r.stdout == "1.0.0\n"
+    r = _hulk("sketch", "--nope")
+    assert r.returncode == 1 and "unknown flag: --nope" in r.stdout
+    r = _hulk("sketch", "-k", "x")
+    assert r.returncode == 1 and 'invalid argument "x" for "-k, --kmerSize" flag' in r.stdout
+    # helpers.CheckFile / CheckExt messages through helpers.ErrorCheck
+    r = _hulk("sketch", "-f", str(tmp_path / "missing.fq"), "-o", str(tmp_path / "o"))
+    assert r.returncode == 1 and re.search(TS + r"ERROR---> file does not exist: .*missing.fq$", r.stdout.strip().split("\n")[-1])
+    odd = tmp_path / "reads.txt"
+    odd.write_text("@r\nACGT\n+\nIIII\n")
+    r = _hulk("sketch", "-f", str(odd), "-o", str(tmp_path / "o"))
+    assert r.returncode == 1 and "ERROR---> file does not have recognised extension" in r.stdout
+    r = _hulk("sketch", "-o", str(tmp_path / "o"), stdin=subprocess.DEVNULL)
+    assert r.returncode == 1 and "ERROR---> no STDIN found" in r.stdout
+    # the banner lines of cmd/sketch.go:90-122 come before any GPU work
+    lines = _hulk("sketch", "-f", str(odd), "-o", str(tmp_path / "o")).stdout.split("\n")
+    assert re.match(TS + r"this is hulk \(version 1\.0\.0\)$", lines[0])
+    assert lines[2].endswith("starting the sketch subcommand") and lines[3].endswith("checking parameters...")
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    r = _hulk("sketch", "-f", FIXTURE, "-o", str(tmp_path / "o"))
+    assert r.returncode == 1 and "ERROR---> CUDA error: no CUDA device (no CPU fallback exists)" in r.stdout
+    assert not os.path.exists(str(tmp_path / "o.json"))
+
+
+# ---- GPU: the front end end to end ------------------------------------------------------------------
+EXPECTED_LOG = [
+    r"this is hulk \(version 1\.0\.0\)", r"please cite Rowe et al\. 2019, doi: https://doi\.org/10\.1186/s40168-019-0653-2",
+    r"starting the sketch subcommand", r"checking parameters\.\.\.", r"\tmode: FASTQ", r"\tno\. processors: 1",
+    r"\tminimizer k-mer size: 21", r"\tminimizer window size: 9", r"\tsketch size: 50", r"\tstreaming: disabled",
+    r"\tconcept drift: disabled", r"\tnumber of bins in k-mer spectrum: 194481", r"\tadding KHF sketch: false",
+    r"\tadding KMV sketch: false", r"initialising sketching pipeline\.\.\.", r"\tinitialising the processes",
+    r"\tconnecting data streams", r"\tnumber of processes added to the sketching pipeline: 4",
+    r"\tnumber of minions in the sketching pool: 1", r"finding minimizers\.\.\.",
+    r"generating final histosketch of k-mer spectra\.\.\.", r"\tprocessed 1000 sequences in total",
+    r"\tmean sequence length: 100", r"\tfound 17040 minimizers", r"\thistosketching across 194481 bins",
+    r"cleaning up\.\.\.", r"\twritten sketch to disk: .*\.json", r"finished in [0-9.]+(µs|ms|s)",
+]
+
+
+def _same_sketch(doc, want, filename):
+    gj, wj = json.loads(doc), json.loads(want)
+    assert gj["filename"] == filename
+    gs, ws = gj["signatures"][0]["Sketch"], wj["signatures"][0]["Sketch"]
+    assert gs["mins"] == ws["mins"] and gs["md5sum"] == ws["md5sum"]
+    np.testing.assert_allclose(gs["weights"], ws["weights"], rtol=1e-12)
+    strip = lambda d: [ln for ln in d.split("\n") if "e" not in ln and "." not in ln and "filename" not in ln]
+    assert strip(doc) == strip(want)                         # byte-identical layout, key order, integers
+
+
+@pytest.mark.gpu
+def test_cli_sketch_c1_matches_golden(tmp_path):
+    # BASELINE config C1 (.travis.yml:22 of the reference): hulk sketch -f testing/test-reads-small.fq.gz -k 21 -s 50
+    out = str(tmp_path / "run" / "c1")                       # the output directory is created (cmd/sketch.go:188-195)
+    r = _hulk("sketch", "-f", FIXTURE, "-k", "21", "-s", "50", "-o", out)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.rstrip("\n").split("\n")
+    assert len(lines) == len(EXPECTED_LOG), r.stdout
+    for ln, pat in zip(lines, EXPECTED_LOG):
+        assert re.match(TS + pat + "$", ln), (ln, pat)
+    _same_sketch(open(out + ".json").read(), open(os.path.join(GOLDEN, "c1_k21_s50.json")).read(), FIXTURE + ",")
+
+
+@pytest.mark.gpu
+def test_cli_intervals_drift_stream_and_stdin(tmp_path):
+    out = str(tmp_path / "c1x")
+    r = _hulk("sketch", "--fastq=" + FIXTURE, "-x", "0.2", "-i", "250", "-s50", "--stream", "-b", "lbl", "-p", "2", "-o", out)
+    assert r.returncode == 0 and r.stdout == ""             # --stream moves the log to <outFile>.log
+    log = open(out + ".log").read()
+    assert "\tconcept drift: enabled\n" in log and "\tdecay ratio: 0.20\n" in log and "\tstreaming: enabled\n" in log
+    assert [m for m in re.findall(r"\treached interval (\d+) -> histosketching", log)] == ["1", "2", "3", "4"]
+    assert "merging sketches and cleaning up..." in log
+    doc = open(out + ".json").read()
+    _same_sketch(doc.replace('"banner_label": "lbl"', '"banner_label": "blank"'),
+                 open(os.path.join(GOLDEN, "c1_k21_s50_x02_i250.json")).read(), FIXTURE + ",")
+    assert '"banner_label": "lbl"' in doc and '"concept_drift": true' in doc
+    # STDIN (plain FASTQ through a pipe) gives the same sketch, filename "STDIN"
+    raw = gzip.open(FIXTURE, "rb").read()
+    p = subprocess.run([hulk_b200.CLI_PATH, "sketch", "-k", "21", "-s", "50", "-o", str(tmp_path / "pipe")],
+                       input=raw, capture_output=True, timeout=600)
+    assert p.returncode == 0, p.stdout
+    assert b"\tinput file: using STDIN" in p.stdout
+    _same_sketch(open(str(tmp_path / "pipe.json")).read(), open(os.path.join(GOLDEN, "c1_k21_s50.json")).read(), "STDIN")
+
+
+@pytest.mark.gpu
+def test_cli_reference_fatals(tmp_path):
+    short = tmp_path / "short.fq"
+    short.write_bytes(b"@r1\n" + b"ACGT" * 30 + b"\n+\n" + b"I" * 120 + b"\n@r2\nACGTACGT\n+\nIIIIIIII\n")
+    r = _hulk("sketch", "-f", str(short), "-o", str(tmp_path / "s"))
+    assert r.returncode == 1 and "ERROR---> sequence length must be >= w + k - 1" in r.stdout
+    r = _hulk("sketch", "-f", FIXTURE, "-k", "32", "-o", str(tmp_path / "s"))
+    assert r.returncode == 1 and "ERROR---> k size must be: 0 < k < 32" in r.stdout
+    # fewer than 1 % of the bins used at the flush: "not used yet" (src/kmerspectrum/kmerspectrum.go:94-96)
+    r = _hulk("sketch", "-f", FIXTURE, "-i", "10", "-o", str(tmp_path / "s"))
+    assert r.returncode == 1 and "ERROR---> not used yet" in r.stdout
+    empty = tmp_path / "empty.fq"
+    empty.write_bytes(b"")
+    r = _hulk("sketch", "-f", str(empty), "-o", str(tmp_path / "s"))
+    assert r.returncode == 1 and "ERROR---> no sequences received" in r.stdout
+    assert not os.path.exists(str(tmp_path / "s.json"))
