@@ -257,7 +257,7 @@ def run_b200(a):
     stream.synchronize()
 
     hs = hulk_b200.HistoSketch(k, w, s, a.decay, device=local, slots=slots, stream=stream.cuda_stream,
-                               async_input=True)
+                               async_input=True, input_ready=True)
     hs.set_tables_device(r_t.data_ptr(), c_t.data_ptr(), b_t.data_ptr())
     del r_t, c_t, b_t
     torch.cuda.empty_cache()

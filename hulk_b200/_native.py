@@ -29,6 +29,7 @@ EARG, ESTATE, ECUDA, ENOMEM, EIO = -20, -21, -30, -31, -40
 EFASTQ, ETOOLONG, ENOSEQ = -41, -42, -43
 LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 F_ASYNC_INPUT = 1
+F_INPUT_READY = 2
 
 
 class Params(C.Structure):

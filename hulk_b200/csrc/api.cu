@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -33,6 +34,7 @@ struct hulk_b200_ctx {
     uint64_t Dp = 0;
     uint32_t nsub_row = 0, nseg = 0, nblk = 0;
     bool drift = false, apply_scaling = false;
+    bool force_tile_path = false;   // HULK_B200_K1_TILE=1: use the staged-tile kernel even for w = 9 (A/B measurements)
     double decay_weight = 0.0;
     int sm_count = 148;
 
@@ -40,7 +42,15 @@ struct hulk_b200_ctx {
     bool own_stream = false;
 
     // stage 1+2
-    uint32_t *d_hist = nullptr;
+    // The spectrum is double-buffered: the reads of interval i+1 are counted into the other buffer (on
+    // their own stream) while interval i is still being flushed on the main stream.
+    uint32_t *d_hist[2] = {nullptr, nullptr};
+    int cur_hist = 0;                          // buffer (and k1 stream) of the interval being counted
+    cudaStream_t k1_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k1_last[2] = {nullptr, nullptr};    // last k1 launch into buffer b
+    cudaEvent_t ev_hist_free[2] = {nullptr, nullptr};  // buffer b consumed and wiped by its flush
+    cudaEvent_t ev_main = nullptr;
+    bool k1_pending[2] = {false, false};       // k1 launches into buffer b since its last flush
     unsigned long long *d_nmin = nullptr, *d_errword = nullptr;
     uint8_t *d_stage[2] = {nullptr, nullptr};
     uint64_t stage_cap[2] = {0, 0};
@@ -48,12 +58,12 @@ struct hulk_b200_ctx {
     uint64_t off_cap[2] = {0, 0};
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr};
     int cur_buf = 0;
-    unsigned int *d_ovf_count = nullptr;
-    unsigned long long *d_ovf_list = nullptr;
+    unsigned int *d_ovf_count[2] = {nullptr, nullptr};          // one overflow queue + scratch arena per k1 stream
+    unsigned long long *d_ovf_list[2] = {nullptr, nullptr};
     uint32_t ovf_cap = 0;
-    uint64_t *d_arena = nullptr;
-    unsigned long long *d_arena_cursor = nullptr;
-    uint64_t arena_entries = 0;
+    uint64_t *d_arena[2] = {nullptr, nullptr};
+    unsigned long long *d_arena_cursor[2] = {nullptr, nullptr};
+    uint64_t arena_entries[2] = {0, 0};
 
     // stage 3a
     FlushCtl *d_ctl = nullptr;
@@ -98,15 +108,16 @@ struct ProfScope {
         cudaEventCreate(&e);
         return e;
     }
-    ProfScope(hulk_b200_ctx *c, int k) : ctx(c), cls(k) {
+    cudaStream_t st;
+    ProfScope(hulk_b200_ctx *c, int k, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : c->stream) {
         if (!ctx->profiling) return;
         e0 = get(ctx);
         e1 = get(ctx);
-        cudaEventRecord(e0, ctx->stream);
+        cudaEventRecord(e0, st);
     }
     ~ProfScope() {
         if (!e0) return;
-        cudaEventRecord(e1, ctx->stream);
+        cudaEventRecord(e1, st);
         ctx->prof_events[cls].emplace_back(e0, e1);
     }
 };
@@ -180,10 +191,13 @@ static cudaError_t dmalloc(T **p, uint64_t n) {
 void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->P.device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    void *ptrs[] = {ctx->d_hist, ctx->d_nmin, ctx->d_errword, ctx->d_stage[0], ctx->d_stage[1], ctx->d_off[0],
-                    ctx->d_off[1], ctx->d_ovf_count, ctx->d_ovf_list, ctx->d_arena, ctx->d_arena_cursor, ctx->d_ctl,
+    for (int i = 0; i < 2; i++)
+        if (ctx->k1_stream[i]) cudaStreamSynchronize(ctx->k1_stream[i]);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = {ctx->d_hist[0], ctx->d_hist[1], ctx->d_nmin, ctx->d_errword, ctx->d_stage[0], ctx->d_stage[1], ctx->d_off[0],
+                    ctx->d_off[1], ctx->d_ovf_count[0], ctx->d_ovf_count[1], ctx->d_ovf_list[0], ctx->d_ovf_list[1],
+                    ctx->d_arena[0], ctx->d_arena[1], ctx->d_arena_cursor[0], ctx->d_arena_cursor[1], ctx->d_ctl,
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits, ctx->d_invf, ctx->d_r, ctx->d_c,
                     ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights};
@@ -192,13 +206,26 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]);
+        if (ctx->ev_k1_last[i]) cudaEventDestroy(ctx->ev_k1_last[i]);
+        if (ctx->ev_hist_free[i]) cudaEventDestroy(ctx->ev_hist_free[i]);
+        if (ctx->k1_stream[i]) cudaStreamDestroy(ctx->k1_stream[i]);
     }
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
     for (int c = 0; c < 4; c++)
         for (auto &pr : ctx->prof_events[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// every stream of the context idle (inputs copied, all k1 launches and flushes done)
+static int sync_all(hulk_b200_ctx *ctx) {
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->k1_stream[0]));
+    CU(cudaStreamSynchronize(ctx->k1_stream[1]));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HULK_B200_OK;
 }
 
 static int create_impl(hulk_b200_ctx *ctx) {
@@ -217,7 +244,11 @@ static int create_impl(hulk_b200_ctx *ctx) {
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_k1[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_k1_last[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_hist_free[i], cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&ctx->k1_stream[i], cudaStreamNonBlocking));
     }
+    CU(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
     const int32_t D = ctx->D;
     const uint32_t rows = ctx->rows;
     ctx->Dp = ((uint64_t)D + K3_SUB - 1) / K3_SUB * K3_SUB;
@@ -225,13 +256,16 @@ static int create_impl(hulk_b200_ctx *ctx) {
     ctx->nseg = (uint32_t)((ctx->Dp + K3_SEG - 1) / K3_SEG);
     ctx->nblk = (uint32_t)(((uint64_t)D + 1023) / 1024);
 
-    CU(dmalloc(&ctx->d_hist, D));
+    CU(dmalloc(&ctx->d_hist[0], D));
+    CU(dmalloc(&ctx->d_hist[1], D));
     CU(dmalloc(&ctx->d_nmin, 1));
     CU(dmalloc(&ctx->d_errword, 1));
     ctx->ovf_cap = 1u << 20;
-    CU(dmalloc(&ctx->d_ovf_count, 1));
-    CU(dmalloc(&ctx->d_ovf_list, ctx->ovf_cap));
-    CU(dmalloc(&ctx->d_arena_cursor, 1));
+    for (int i = 0; i < 2; i++) {
+        CU(dmalloc(&ctx->d_ovf_count[i], 1));
+        CU(dmalloc(&ctx->d_ovf_list[i], ctx->ovf_cap));
+        CU(dmalloc(&ctx->d_arena_cursor[i], 1));
+    }
     CU(dmalloc(&ctx->d_ctl, 1));
     CU(dmalloc(&ctx->d_cols, (uint64_t)D * CMS_DEPTH));
     CU(dmalloc(&ctx->d_csr_start, CMS_CELLS + 1));
@@ -248,11 +282,13 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(dmalloc(&ctx->d_weights, rows));
 
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (size_t)D, st));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)D, st));
+        CU(cudaMemsetAsync(ctx->d_ovf_count[i], 0, 4, st));
+        CU(cudaMemsetAsync(ctx->d_arena_cursor[i], 0, 8, st));
+    }
     CU(cudaMemsetAsync(ctx->d_nmin, 0, 8, st));
     CU(cudaMemsetAsync(ctx->d_errword, 0xff, 8, st));
-    CU(cudaMemsetAsync(ctx->d_ovf_count, 0, 4, st));
-    CU(cudaMemsetAsync(ctx->d_arena_cursor, 0, 8, st));
     CU(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(FlushCtl), st));
     CU(cudaMemsetAsync(ctx->d_q, 0, sizeof(double) * CMS_CELLS, st));
     CU(cudaMemsetAsync(ctx->d_invf, 0xff, sizeof(float) * ctx->Dp, st));            // NaN padding
@@ -289,6 +325,14 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k1_minimizer_histogram<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k1_minimizer_histogram<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    {
+        const char *e = getenv("HULK_B200_K1_TILE");
+        ctx->force_tile_path = e && *e == '1';
+    }
     return HULK_B200_OK;
 }
 
@@ -402,8 +446,12 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
     cudaStream_t st = ctx->stream;
-    CU(cudaStreamSynchronize(ctx->copy_stream));
-    CU(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (size_t)ctx->D, st));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)ctx->D, st));
+        ctx->k1_pending[i] = false;
+    }
+    ctx->cur_hist = 0;
     CU(cudaMemsetAsync(ctx->d_nmin, 0, 8, st));
     CU(cudaMemsetAsync(ctx->d_errword, 0xff, 8, st));
     CU(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(FlushCtl), st));
@@ -428,7 +476,7 @@ int hulk_b200_profile_enable(hulk_b200_ctx *ctx, int enable) {
 int hulk_b200_profile_read(hulk_b200_ctx *ctx, hulk_b200_profile *out) {
     if (!ctx || !out) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
     for (int c = 0; c < 4; c++) {
         for (auto &pr : ctx->prof_events[c]) {
             float ms = 0.f;
@@ -480,10 +528,11 @@ static void k1_geometry(const hulk_b200_ctx *ctx, uint64_t n_reads, uint64_t tot
 }
 
 // enqueue the minimizer/histogram kernels over one device-resident batch
+// hs: which spectrum buffer / overflow set to use; st: the stream to enqueue on
 template <bool DUMP>
-static int launch_k1(hulk_b200_ctx *ctx, const uint8_t *d_bases, uint64_t bases_bytes, const uint64_t *d_offsets,
-                     uint64_t off_base, uint32_t fixed_len, uint64_t n_reads, uint64_t total_bytes, uint64_t *d_dump,
-                     uint32_t dump_cap, uint32_t *d_dump_counts) {
+static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t *d_bases, uint64_t bases_bytes,
+                     const uint64_t *d_offsets, uint64_t off_base, uint32_t fixed_len, uint64_t n_reads,
+                     uint64_t total_bytes, uint64_t *d_dump, uint32_t dump_cap, uint32_t *d_dump_counts) {
     if (n_reads == 0) return HULK_B200_OK;
     K1Params p{};
     p.bases = d_bases;
@@ -496,11 +545,11 @@ static int launch_k1(hulk_b200_ctx *ctx, const uint8_t *d_bases, uint64_t bases_
     p.k = ctx->P.k;
     p.w = ctx->P.w;
     p.D = ctx->D;
-    p.hist = ctx->d_hist;
+    p.hist = ctx->d_hist[hs];
     p.n_minimizers = ctx->d_nmin;
     p.err_word = ctx->d_errword;
-    p.ovf_count = ctx->d_ovf_count;
-    p.ovf_list = ctx->d_ovf_list;
+    p.ovf_count = ctx->d_ovf_count[hs];
+    p.ovf_list = ctx->d_ovf_list[hs];
     p.ovf_cap = ctx->ovf_cap;
     p.dump = d_dump;
     p.dump_cap = dump_cap;
@@ -509,32 +558,40 @@ static int launch_k1(hulk_b200_ctx *ctx, const uint8_t *d_bases, uint64_t bases_
     uint64_t want = std::max<uint64_t>(1ull << 22, 4 * total_bytes + (n_reads << 7));
     // only reserve the large arena when the generic path will take whole batches
     if (ctx->P.w <= (uint32_t)K1_W_FAST) want = std::min<uint64_t>(want, 1ull << 26);
-    if (want > ctx->arena_entries) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_arena) cudaFree(ctx->d_arena);
-        ctx->d_arena = nullptr;
-        ctx->arena_entries = 0;
-        CU(dmalloc(&ctx->d_arena, want));
-        ctx->arena_entries = want;
+    if (want > ctx->arena_entries[hs]) {
+        CU(cudaStreamSynchronize(st));
+        if (ctx->d_arena[hs]) cudaFree(ctx->d_arena[hs]);
+        ctx->d_arena[hs] = nullptr;
+        ctx->arena_entries[hs] = 0;
+        CU(dmalloc(&ctx->d_arena[hs], want));
+        ctx->arena_entries[hs] = want;
     }
-    p.arena = ctx->d_arena;
-    p.arena_cursor = ctx->d_arena_cursor;
-    p.arena_entries = ctx->arena_entries;
-    cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(ctx->d_ovf_count, 0, 4, st));
-    CU(cudaMemsetAsync(ctx->d_arena_cursor, 0, 8, st));
+    p.arena = ctx->d_arena[hs];
+    p.arena_cursor = ctx->d_arena_cursor[hs];
+    p.arena_entries = ctx->arena_entries[hs];
+    CU(cudaMemsetAsync(ctx->d_ovf_count[hs], 0, 4, st));
+    CU(cudaMemsetAsync(ctx->d_arena_cursor[hs], 0, 8, st));
     const bool fast = ctx->P.w <= (uint32_t)K1_W_FAST;
-    ProfScope prof_scope(ctx, 0);
+    ProfScope prof_scope(ctx, 0, st);
     if (fast) {
         size_t smem;
         k1_geometry(ctx, n_reads, total_bytes, &p.tile_cap, &p.list_cap, &smem);
         const uint64_t ntiles = (n_reads + K1_TPB - 1) / K1_TPB;
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
         const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * per_sm);
-        if (k1_fp_compare_ok((int32_t)ctx->P.k, (int32_t)ctx->P.w))
+        const bool fp = k1_fp_compare_ok((int32_t)ctx->P.k, (int32_t)ctx->P.w);
+        if (ctx->P.w == 9 && !ctx->force_tile_path) {
+            // register-resident window, no staged tile: shared memory is the candidate lists only
+            const size_t smem9 = (size_t)p.list_cap * K1_TPB * 8;
+            const uint64_t nctas = (n_reads + K1_TPB - 1) / K1_TPB;
+            const unsigned grid9 = (unsigned)std::min<uint64_t>(nctas, (uint64_t)ctx->sm_count * K1_W9_CTAS_PER_SM);
+            if (fp) k1_minimizer_histogram_w9<DUMP, true><<<grid9, K1_TPB, smem9, st>>>(p);
+            else k1_minimizer_histogram_w9<DUMP, false><<<grid9, K1_TPB, smem9, st>>>(p);
+        } else if (fp) {
             k1_minimizer_histogram<DUMP, true><<<grid, K1_TPB, smem, st>>>(p);
-        else
+        } else {
             k1_minimizer_histogram<DUMP, false><<<grid, K1_TPB, smem, st>>>(p);
+        }
         LAUNCH_CHECK("k1_minimizer_histogram");
         k1_generic<DUMP><<<ctx->sm_count * 2, 64, 0, st>>>(p, true);
         LAUNCH_CHECK("k1_generic");
@@ -600,12 +657,17 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
             CU(cudaMemcpyAsync(ctx->d_off[buf], offsets + done, sizeof(uint64_t) * (nr + 1), cudaMemcpyHostToDevice,
                                ctx->copy_stream));
         CU(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+        const int hs = ctx->cur_hist;
+        cudaStream_t ks = ctx->k1_stream[hs];
+        CU(cudaStreamWaitEvent(ks, ctx->ev_copy[buf], 0));
+        if (!ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ks, ctx->ev_hist_free[hs], 0));   // its last flush wiped it
         ctx->st.h2d_bytes += nb + (offsets ? sizeof(uint64_t) * (nr + 1) : 0);
-        rc = launch_k1<false>(ctx, ctx->d_stage[buf], (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr, b0,
-                              fixed_len, nr, nb, nullptr, 0, nullptr);
+        rc = launch_k1<false>(ctx, hs, ks, ctx->d_stage[buf], (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr,
+                              b0, fixed_len, nr, nb, nullptr, 0, nullptr);
         if (rc) return rc;
-        CU(cudaEventRecord(ctx->ev_k1[buf], ctx->stream));
+        CU(cudaEventRecord(ctx->ev_k1[buf], ks));
+        CU(cudaEventRecord(ctx->ev_k1_last[hs], ks));
+        ctx->k1_pending[hs] = true;
         ctx->st.n_reads += nr;
         ctx->st.n_bases += nb;
         ctx->cur_buf ^= 1;
@@ -652,10 +714,19 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
         extent = ends[1];
         total_bytes = ends[1] - ends[0];
     }
-    // bytes that may be touched: the batch itself, rounded DOWN to 16 so bulk copies never overrun it
-    const int rc = launch_k1<false>(ctx, d_bases, extent & ~15ull, d_offsets, off_base, read_len, n_reads,
+    const int hs = ctx->cur_hist;
+    cudaStream_t ks = ctx->k1_stream[hs];
+    if (!(ctx->P.flags & HULK_B200_F_INPUT_READY)) {          // order behind whatever produced the input on the main stream
+        CU(cudaEventRecord(ctx->ev_main, ctx->stream));
+        CU(cudaStreamWaitEvent(ks, ctx->ev_main, 0));
+    }
+    if (!ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ks, ctx->ev_hist_free[hs], 0));
+    // bytes that may be touched: the batch itself, rounded DOWN to 16 so wide loads never overrun it
+    const int rc = launch_k1<false>(ctx, hs, ks, d_bases, extent & ~15ull, d_offsets, off_base, read_len, n_reads,
                                     total_bytes, nullptr, 0, nullptr);
     if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_k1_last[hs], ks));
+    ctx->k1_pending[hs] = true;
     ctx->st.n_reads += n_reads;
     ctx->st.n_bases += total_bytes;
     return HULK_B200_OK;
@@ -677,23 +748,30 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
     CU(cudaSetDevice(ctx->P.device));
     cudaStream_t st = ctx->stream;
     const int32_t D = ctx->D;
+    const int hs = ctx->cur_hist;
+    uint32_t *const hist = ctx->d_hist[hs];
+    if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(st, ctx->ev_k1_last[hs], 0));   // every read of the interval is counted
     CU(cudaMemsetAsync(&ctx->d_ctl->nnz, 0, 4, st));
     {
     ProfScope prof_scope(ctx, 1);
-    k2_mask_count<<<ctx->nblk, 1024, 0, st>>>(ctx->d_hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count,
+    k2_mask_count<<<ctx->nblk, 1024, 0, st>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count,
                                               ctx->d_fbits, ctx->d_ctl);
     LAUNCH_CHECK("k2_mask_count");
     k2_flush_decide<<<1, 1024, 0, st>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl);
     LAUNCH_CHECK("k2_flush_decide");
-    k2_cms_update<<<(CMS_CELLS * 32 + 255) / 256, 256, 0, st>>>(ctx->d_hist, ctx->d_csr_start, ctx->d_csr_bins,
+    k2_cms_update<<<(CMS_CELLS * 32 + 255) / 256, 256, 0, st>>>(hist, ctx->d_csr_start, ctx->d_csr_bins,
                                                                 ctx->d_words, ctx->d_word_prefix, ctx->d_block_prefix,
                                                                 ctx->d_q, ctx->d_fbits, ctx->d_ctl,
                                                                 ctx->apply_scaling ? 1 : 0, ctx->decay_weight);
     LAUNCH_CHECK("k2_cms_update");
-    k2_finalize<<<(unsigned)(((uint64_t)D + 255) / 256), 256, 0, st>>>(ctx->d_hist, D, ctx->d_fbits, ctx->d_invf,
+    k2_finalize<<<(unsigned)(((uint64_t)D + 255) / 256), 256, 0, st>>>(hist, D, ctx->d_fbits, ctx->d_invf,
                                                                        ctx->d_ctl);
     LAUNCH_CHECK("k2_finalize");
     }
+    // the buffer is wiped: the next interval but one may count into it while the CWS sweep below runs
+    CU(cudaEventRecord(ctx->ev_hist_free[hs], st));
+    ctx->k1_pending[hs] = false;
+    ctx->cur_hist = hs ^ 1;
     if (ctx->rows) {
         const size_t smem = (size_t)K3_STAGES * K3_SEG * 4 + 2 * K3_STAGES * 8;
         const uint64_t T = (uint64_t)ctx->rows * ctx->nseg;
@@ -738,8 +816,7 @@ static int deferred_error(hulk_b200_ctx *ctx) {
 int hulk_b200_sync(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
-    CU(cudaStreamSynchronize(ctx->copy_stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
     return deferred_error(ctx);
 }
 
@@ -756,11 +833,38 @@ int hulk_b200_finish(hulk_b200_ctx *ctx, uint64_t *mins, double *weights) {
     return HULK_B200_OK;
 }
 
+// copies the sketch straight into page-locked host memory from a kernel: no copy-engine round trip behind
+// whatever host->device batch is in flight on the same engine
+__global__ void k_snapshot(const unsigned long long *__restrict__ sketch, const double *__restrict__ weights,
+                           unsigned long long *__restrict__ h_mins, double *__restrict__ h_weights, uint32_t rows) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        h_mins[i] = sketch[i];
+        h_weights[i] = weights[i];
+    }
+}
+static bool device_can_write(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+
 int hulk_b200_snapshot_async(hulk_b200_ctx *ctx, uint64_t *mins, double *weights) {
     if (!ctx) return HULK_B200_EARG;
     if (!ctx->rows) return HULK_B200_OK;
     if (!mins || !weights) return fail(ctx, HULK_B200_EARG, "mins/weights is NULL");
     CU(cudaSetDevice(ctx->P.device));
+    if (device_can_write(mins) && device_can_write(weights)) {
+        k_snapshot<<<(ctx->rows + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_sketch, ctx->d_weights,
+                                                                     reinterpret_cast<unsigned long long *>(mins),
+                                                                     weights, ctx->rows);
+        LAUNCH_CHECK("k_snapshot");
+        ctx->st.d2h_bytes += 16ull * ctx->rows;
+        return HULK_B200_OK;
+    }
     CU(cudaMemcpyAsync(mins, ctx->d_sketch, sizeof(uint64_t) * ctx->rows, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(weights, ctx->d_weights, sizeof(double) * ctx->rows, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->st.d2h_bytes += 16ull * ctx->rows;
@@ -770,7 +874,7 @@ int hulk_b200_snapshot_async(hulk_b200_ctx *ctx, uint64_t *mins, double *weights
 int hulk_b200_get_stats(hulk_b200_ctx *ctx, hulk_b200_stats *out) {
     if (!ctx || !out) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
     unsigned long long nm = 0;
     FlushCtl ctl;
     CU(cudaMemcpy(&nm, ctx->d_nmin, 8, cudaMemcpyDeviceToHost));
@@ -785,7 +889,12 @@ int hulk_b200_get_stats(hulk_b200_ctx *ctx, hulk_b200_stats *out) {
 
 int hulk_b200_histogram_device_ptr(hulk_b200_ctx *ctx, void **d_hist_u32, int32_t *num_bins) {
     if (!ctx || !d_hist_u32) return HULK_B200_EARG;
-    *d_hist_u32 = ctx->d_hist;
+    CU(cudaSetDevice(ctx->P.device));
+    // the spectrum of the interval being counted; work enqueued on the context's stream after this
+    // call (e.g. the all-reduce across GPUs) sees every read pushed so far
+    const int hs = ctx->cur_hist;
+    if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_k1_last[hs], 0));
+    *d_hist_u32 = ctx->d_hist[hs];
     if (num_bins) *num_bins = ctx->D;
     return HULK_B200_OK;
 }
@@ -801,10 +910,12 @@ __global__ void k_merge_hist(uint32_t *__restrict__ dst, const uint32_t *__restr
 int hulk_b200_merge_histogram(hulk_b200_ctx *ctx, const uint32_t *hist) {
     if (!ctx || !hist) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
     uint32_t *d_tmp = nullptr;
     CU(dmalloc(&d_tmp, ctx->D));
     CU(cudaMemcpyAsync(d_tmp, hist, sizeof(uint32_t) * (size_t)ctx->D, cudaMemcpyHostToDevice, ctx->stream));
-    k_merge_hist<<<(unsigned)(((uint64_t)ctx->D + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_hist, d_tmp, ctx->D);
+    k_merge_hist<<<(unsigned)(((uint64_t)ctx->D + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_hist[ctx->cur_hist], d_tmp,
+                                                                                    ctx->D);
     LAUNCH_CHECK("k_merge_hist");
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_tmp);
@@ -823,8 +934,8 @@ int hulk_b200_add_minimizer_count(hulk_b200_ctx *ctx, uint64_t n) {
 int hulk_b200_get_histogram(hulk_b200_ctx *ctx, uint32_t *hist) {
     if (!ctx || !hist) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpy(hist, ctx->d_hist, sizeof(uint32_t) * (size_t)ctx->D, cudaMemcpyDeviceToHost));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    CU(cudaMemcpy(hist, ctx->d_hist[ctx->cur_hist], sizeof(uint32_t) * (size_t)ctx->D, cudaMemcpyDeviceToHost));
     return HULK_B200_OK;
 }
 int hulk_b200_get_estimates(hulk_b200_ctx *ctx, double *f) {
@@ -857,12 +968,14 @@ int hulk_b200_minimizers(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_
     CU(dmalloc(&d_offsets, n_reads + 1));
     CU(dmalloc(&d_dump, n_reads * cap));
     CU(dmalloc(&d_counts, n_reads));
+    { const int rc0 = sync_all(ctx); if (rc0) return rc0; }
     cudaStream_t st = ctx->stream;
     if (nb) CU(cudaMemcpyAsync(d_bases, bases + b0, nb, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_offsets, offsets, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_reads, st));
     const uint64_t saved_reads = ctx->st.n_reads;
-    int rc = launch_k1<true>(ctx, d_bases, (nb + 15) & ~15ull, d_offsets, b0, 0, n_reads, nb, d_dump, cap, d_counts);
+    int rc = launch_k1<true>(ctx, 0, st, d_bases, (nb + 15) & ~15ull, d_offsets, b0, 0, n_reads, nb, d_dump, cap,
+                             d_counts);
     ctx->st.n_reads = saved_reads;
     if (rc == HULK_B200_OK) {
         cudaError_t e = cudaStreamSynchronize(st);

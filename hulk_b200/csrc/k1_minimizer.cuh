@@ -94,6 +94,125 @@ __device__ __forceinline__ double k1_pin(double x) {
     return x;
 }
 
+// ---- the part of a warp's work behind the scan: exact per-read sets, then jump-hash binning -------
+// wl: the warp's list block [list_cap][32] (entry e of lane l at wl[e * 32 + l]); n: this lane's number
+// of adjacent-distinct window minima (0 when the read is invalid or was queued for k1_generic).
+template <bool DUMP, bool FP>
+__device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl, uint64_t *my_list, const int lane,
+                                                const uint32_t list_cap, uint32_t n, const bool valid,
+                                                const bool overflow, const uint64_t r, const uint32_t nb,
+                                                unsigned long long &local_minimizers) {
+    // ---- exact per-read set: drop values already present earlier in the list (minimizer.go:189-198)
+    uint32_t m_out = 0;
+    for (uint32_t a = 0; a < n; a++) {
+        const uint64_t x = my_list[a * 32];
+        bool dup = false;
+        uint32_t b = 0;
+        for (; b + 4 <= m_out; b += 4) {
+            const bool e0 = ueq64<FP>(my_list[b * 32], x), e1 = ueq64<FP>(my_list[(b + 1) * 32], x);
+            const bool e2 = ueq64<FP>(my_list[(b + 2) * 32], x), e3 = ueq64<FP>(my_list[(b + 3) * 32], x);
+            if (e0 | e1 | e2 | e3) dup = true;
+        }
+        for (; b < m_out; b++)
+            if (ueq64<FP>(my_list[b * 32], x)) dup = true;
+        if (!dup) { my_list[m_out * 32] = x; m_out++; }
+    }
+    if (DUMP) {
+        if (valid) {
+            for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++) p.dump[r * p.dump_cap + e] = my_list[e * 32];
+            p.dump_counts[r] = m_out;
+        } else if (r < p.n_reads && !overflow) {
+            p.dump_counts[r] = 0;
+        }
+    } else {
+        // ---- jump: kmerspectrum.go:67-81, bins[jump.Hash(kmer, numBins)]++ for every set member.
+        // Rows 0 .. m_min-1 of the warp's list block are full; the entries of the longer sets
+        // behind them are packed row by row right after, so the block becomes one dense queue of
+        // `total` keys and lane l simply walks keys l, l + 32, l + 64, ...: every lane gets the
+        // same number of keys whatever its own read produced.  Two walks per lane are in flight
+        // (ILP); they advance K1_JUMP_BATCH steps between two refill points.  The step itself is
+        // hd_math.h jump_step_fast, split into evaluate / commit.
+        local_minimizers += m_out;
+        const uint32_t m_min = __reduce_min_sync(0xffffffffu, m_out);
+        const uint32_t m_max = __reduce_max_sync(0xffffffffu, m_out);
+        uint32_t total = m_min * 32;
+        for (uint32_t e = m_min; e < m_max; e++) {
+            const bool has = m_out > e;
+            const uint64_t x = has ? wl[e * 32 + lane] : 0ull;
+            const uint32_t mask = __ballot_sync(0xffffffffu, has);
+            __syncwarp();                                    // row e is in registers before anyone overwrites it
+            if (has) wl[total + __popc(mask & ((1u << lane) - 1u))] = x;     // total <= e * 32: never a later row
+            total += __popc(mask);
+        }
+        __syncwarp();
+        uint32_t g = lane;         // this lane's next queue index
+        uint64_t key[2] = {0, 0};
+        double jd1[2] = {1.0, 1.0};
+        uint32_t bkt[2] = {0, 0};
+        bool busy[2] = {false, false}, loaded[2] = {false, false};
+        const double c_lo = k1_pin(1.0 - JUMP_EPS), c_hi = k1_pin(1.0 + JUMP_EPS);
+        const double two52 = k1_pin(JUMP_TWO52), two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0);
+        uint32_t *const hist = p.hist;
+        for (;;) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if (!busy[c]) {
+                    if (loaded[c]) {                                         // its walk ended in the last batch
+                        atomicAdd(&hist[bkt[c]], 1u);
+                        loaded[c] = false;
+                    }
+                    if (g < total) {
+                        key[c] = wl[g];
+                        g += 32;
+                        bkt[c] = 0;                                          // first step of jump.Hash: b = 0
+                        jd1[c] = one;
+                        busy[c] = loaded[c] = true;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
+#pragma unroll
+            for (int it = 0; it < K1_JUMP_BATCH; it++) {
+                double tlo[2];
+                bool fin[2], amb[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
+                    key[c] = key[c] * 2862933555777941757ull + 1ull;
+                    const uint32_t q = (uint32_t)(key[c] >> 33) + 1u;                    // 1 .. 2^31
+                    const double qd = dbl_make(0x43300000u, q) - two52;                  // (double)q, exact
+                    const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
+                    const double r0 = rcp_seed(Q);
+                    const double e = fma(-Q, r0, one);
+                    const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
+                    const double x = jd1[c] * R;
+                    tlo[c] = __fma_rd(x, c_lo, two52);                                   // 2^52 + floor(x (1 - EPS))
+                    const double thi = __fma_rd(x, c_hi, two52);
+                    fin[c] = (dbl_hi(thi) != 0x43300000u) || (dbl_lo(tlo[c]) >= nb);
+                    amb[c] = !fin[c] && (dbl_lo(tlo[c]) != dbl_lo(thi));
+                }
+                if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-21 per step: the true division
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        if (amb[c] && busy[c]) {
+                            uint32_t b = bkt[c];
+                            double j1 = jd1[c];
+                            fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
+                            tlo[c] = JUMP_TWO52 + (double)b;                 // as the fast step reports it
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; c++) {                                // commit
+                    const bool adv = busy[c] && !fin[c];
+                    bkt[c] = adv ? dbl_lo(tlo[c]) : bkt[c];
+                    jd1[c] = adv ? tlo[c] - two52m1 : jd1[c];                // (double)(bucket + 1), exact
+                    busy[c] = adv;
+                }
+            }
+        }
+    }
+}
+
 template <bool DUMP, bool FP>
 __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -182,116 +301,104 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
             n = 0;
             valid = false;
         }
-        // ---- exact per-read set: drop values already present earlier in the list (minimizer.go:189-198)
-        uint32_t m_out = 0;
-        for (uint32_t a = 0; a < n; a++) {
-            const uint64_t x = my_list[a * 32];
-            bool dup = false;
-            uint32_t b = 0;
-            for (; b + 4 <= m_out; b += 4) {
-                const bool e0 = ueq64<FP>(my_list[b * 32], x), e1 = ueq64<FP>(my_list[(b + 1) * 32], x);
-                const bool e2 = ueq64<FP>(my_list[(b + 2) * 32], x), e3 = ueq64<FP>(my_list[(b + 3) * 32], x);
-                if (e0 | e1 | e2 | e3) dup = true;
-            }
-            for (; b < m_out; b++)
-                if (ueq64<FP>(my_list[b * 32], x)) dup = true;
-            if (!dup) { my_list[m_out * 32] = x; m_out++; }
-        }
-        if (DUMP) {
-            if (valid) {
-                for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++) p.dump[r * p.dump_cap + e] = my_list[e * 32];
-                p.dump_counts[r] = m_out;
-            } else if (r < p.n_reads && !overflow) {
-                p.dump_counts[r] = 0;
-            }
-        } else {
-            // ---- jump: kmerspectrum.go:67-81, bins[jump.Hash(kmer, numBins)]++ for every set member.
-            // Rows 0 .. m_min-1 of the warp's list block are full; the entries of the longer sets
-            // behind them are packed row by row right after, so the block becomes one dense queue of
-            // `total` keys and lane l simply walks keys l, l + 32, l + 64, ...: every lane gets the
-            // same number of keys whatever its own read produced.  Two walks per lane are in flight
-            // (ILP); they advance K1_JUMP_BATCH steps between two refill points.  The step itself is
-            // hd_math.h jump_step_fast, split into evaluate / commit.
-            local_minimizers += m_out;
-            const uint32_t m_min = __reduce_min_sync(0xffffffffu, m_out);
-            const uint32_t m_max = __reduce_max_sync(0xffffffffu, m_out);
-            uint32_t total = m_min * 32;
-            for (uint32_t e = m_min; e < m_max; e++) {
-                const bool has = m_out > e;
-                const uint64_t x = has ? wl[e * 32 + lane] : 0ull;
-                const uint32_t mask = __ballot_sync(0xffffffffu, has);
-                __syncwarp();                                    // row e is in registers before anyone overwrites it
-                if (has) wl[total + __popc(mask & ((1u << lane) - 1u))] = x;     // total <= e * 32: never a later row
-                total += __popc(mask);
-            }
-            __syncwarp();
-            uint32_t g = lane;         // this lane's next queue index
-            uint64_t key[2] = {0, 0};
-            double jd1[2] = {1.0, 1.0};
-            uint32_t bkt[2] = {0, 0};
-            bool busy[2] = {false, false}, loaded[2] = {false, false};
-            const double c_lo = k1_pin(1.0 - JUMP_EPS), c_hi = k1_pin(1.0 + JUMP_EPS);
-            const double two52 = k1_pin(JUMP_TWO52), two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0);
-            uint32_t *const hist = p.hist;
-            for (;;) {
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    if (!busy[c]) {
-                        if (loaded[c]) {                                         // its walk ended in the last batch
-                            atomicAdd(&hist[bkt[c]], 1u);
-                            loaded[c] = false;
-                        }
-                        if (g < total) {
-                            key[c] = wl[g];
-                            g += 32;
-                            bkt[c] = 0;                                          // first step of jump.Hash: b = 0
-                            jd1[c] = one;
-                            busy[c] = loaded[c] = true;
-                        }
-                    }
-                }
-                if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
-#pragma unroll
-                for (int it = 0; it < K1_JUMP_BATCH; it++) {
-                    double tlo[2];
-                    bool fin[2], amb[2];
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
-                        key[c] = key[c] * 2862933555777941757ull + 1ull;
-                        const uint32_t q = (uint32_t)(key[c] >> 33) + 1u;                    // 1 .. 2^31
-                        const double qd = dbl_make(0x43300000u, q) - two52;                  // (double)q, exact
-                        const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
-                        const double r0 = rcp_seed(Q);
-                        const double e = fma(-Q, r0, one);
-                        const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
-                        const double x = jd1[c] * R;
-                        tlo[c] = __fma_rd(x, c_lo, two52);                                   // 2^52 + floor(x (1 - EPS))
-                        const double thi = __fma_rd(x, c_hi, two52);
-                        fin[c] = (dbl_hi(thi) != 0x43300000u) || (dbl_lo(tlo[c]) >= nb);
-                        amb[c] = !fin[c] && (dbl_lo(tlo[c]) != dbl_lo(thi));
-                    }
-                    if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-21 per step: the true division
-#pragma unroll
-                        for (int c = 0; c < 2; c++) {
-                            if (amb[c] && busy[c]) {
-                                uint32_t b = bkt[c];
-                                double j1 = jd1[c];
-                                fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
-                                tlo[c] = JUMP_TWO52 + (double)b;                 // as the fast step reports it
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {                                // commit
-                        const bool adv = busy[c] && !fin[c];
-                        bkt[c] = adv ? dbl_lo(tlo[c]) : bkt[c];
-                        jd1[c] = adv ? tlo[c] - two52m1 : jd1[c];                // (double)(bucket + 1), exact
-                        busy[c] = adv;
-                    }
-                }
-            }
-        }
+        k1_finish_lists<DUMP, FP>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
         __syncthreads();   // everyone is done with the tile before thread 0 refills it
+    }
+    if (!DUMP) {
+        for (int o = 16; o > 0; o >>= 1) local_minimizers += __shfl_down_sync(0xffffffffu, local_minimizers, o);
+        if (lane == 0 && local_minimizers) atomicAdd(p.n_minimizers, local_minimizers);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// w = 9 path (the reference's default window, cmd/sketch.go:52): k1_scan_read_w9 keeps the whole
+// window state in registers, so shared memory only holds the candidate lists and five CTAs
+// (20 warps) fit one SM instead of three.  No tile is staged: every lane streams its own read
+// from global memory with aligned 8-byte loads issued one block (8 bases, ~600 instructions)
+// ahead of their use; the batch is read exactly once from HBM, sectors are shared through L2.
+// Warps are independent (no CTA barrier anywhere): warp g takes reads [32 g', 32 g' + 32) for
+// g' = g, g + #warps, ...
+// ------------------------------------------------------------------------------------------
+constexpr int K1_W9_CTAS_PER_SM = 5;
+
+struct GlobalSrc8 {
+    const uint64_t *p;      // aligned unit that holds the next unread base
+    uint64_t cur, nxt;
+    uint32_t sh;            // (byte offset of the read inside its first unit) * 8
+    uintptr_t lim;          // no 8-byte load may touch this address or beyond
+    uintptr_t end;          // end of this read: bytes at or past it are never interpreted
+    __device__ __forceinline__ uint64_t ld(const uint64_t *q) const {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        if (a + 8 <= lim) return __ldg(reinterpret_cast<const unsigned long long *>(q));
+        uint64_t v = 0;                                    // the last few bytes of the batch
+        for (int j = 0; j < 8; j++)
+            if (a + j < end) v |= (uint64_t)reinterpret_cast<const uint8_t *>(q)[j] << (8 * j);
+        return v;
+    }
+    __device__ __forceinline__ GlobalSrc8(const uint8_t *read, uint64_t len, uintptr_t lim_)
+        : lim(lim_), end(reinterpret_cast<uintptr_t>(read) + len) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(read);
+        p = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+        sh = (uint32_t)(a & 7) * 8u;
+        cur = ld(p);
+        nxt = ld(p + 1);
+    }
+    __device__ __forceinline__ uint64_t next8() {
+        const uint64_t r = (cur >> sh) | ((nxt << 1) << (63u - sh));
+        cur = nxt;
+        p++;
+        nxt = ld(p + 1);
+        return r;
+    }
+};
+
+template <bool DUMP, bool FP>
+__global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histogram_w9(const K1Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *list_all = reinterpret_cast<uint64_t *>(smem);                       // [warps][list_cap][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t list_cap = p.list_cap;
+    uint64_t *wl = list_all + (size_t)warp * list_cap * 32;
+    uint64_t *my_list = wl + lane;
+    unsigned long long local_minimizers = 0;
+    const uint32_t nb = (uint32_t)p.D;
+    const uint64_t ntasks = (p.n_reads + 31) / 32;
+    const uintptr_t lim = reinterpret_cast<uintptr_t>(p.bases) + p.bases_bytes;
+
+    for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp; task < ntasks; task += (uint64_t)gridDim.x * K1_WARPS) {
+        const uint64_t r = task * 32 + lane;
+        uint32_t n = 0;
+        bool valid = false;
+        if (r < p.n_reads) {
+            const uint64_t b0 = k1_read_off(p, r), b1 = k1_read_off(p, r + 1);
+            const uint64_t len64 = b1 - b0;
+            if (len64 < 1) {
+                k1_report(p, r, K1_ERR_EMPTY);                                   // minimizer.go:71-73
+            } else if (len64 < (uint64_t)(9 + p.k - 1)) {
+                k1_report(p, r, K1_ERR_SHORT);                                   // minimizer.go:74-76
+            } else {
+                valid = true;
+                uint64_t last = Sentinel<FP>::value;                             // never a minimizer
+                auto emit = [&](uint64_t m, bool on) {
+                    const bool fresh = on && !ueq64<FP>(m, last);
+                    if (fresh) my_list[min(n, list_cap - 1u) * 32u] = m;         // entries past the cap are dropped,
+                    n += fresh ? 1u : 0u;                                        // n still counts them (overflow test)
+                    last = fresh ? m : last;
+                };
+                k1_scan_read_w9<FP>(GlobalSrc8(p.bases + b0, len64, lim), (int32_t)len64, (int32_t)p.k, emit);
+            }
+        }
+        const bool overflow = valid && n > list_cap;
+        if (overflow) {
+            const unsigned int slot = atomicAdd(p.ovf_count, 1u);
+            if (slot < p.ovf_cap) p.ovf_list[slot] = r;
+            else k1_report(p, r, K1_ERR_OVF);
+            n = 0;
+            valid = false;
+        }
+        __syncwarp();
+        k1_finish_lists<DUMP, FP>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
+        __syncwarp();                                                            // the queue is drained before the lists refill
     }
     if (!DUMP) {
         for (int o = 16; o > 0; o >>= 1) local_minimizers += __shfl_down_sync(0xffffffffu, local_minimizers, o);

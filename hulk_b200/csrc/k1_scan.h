@@ -142,4 +142,96 @@ HULK_UNROLL
     }
 }
 
+// ---- w = 9 (the reference's default, cmd/sketch.go:52): the whole window state in registers -----
+// With blocks of B = w - 1 = 8 positions a window of w positions always spans exactly two consecutive
+// blocks: the suffix of the previous block from offset t and the prefix of the current block up to
+// offset t.  So m_i = min(S_prev[t], P_cur[t]) with every index a compile-time constant once the block
+// is unrolled, the suffix minima S live in eight registers, and no shared-memory window buffer (nor
+// the loads/stores that maintain it) is needed.  Blocks are the absolute base ranges [8j, 8j + 8);
+// positions that hold no k-mer (i < k-1, i >= len, fwd == rev) carry the sentinel, which is exactly
+// "not in the deque" of the reference.
+
+// Source of bases, eight at a time: next8() returns bytes i..i+7 of the read (i = 0, 8, 16, ...) as a
+// little-endian 64-bit word; bytes at or beyond the read's end are unspecified (never interpreted).
+struct ByteSrc8 {
+    const uint8_t *p;
+    int32_t len;
+    int32_t i;
+    HULK_HD uint64_t next8() {
+        uint64_t v = 0;
+HULK_UNROLL
+        for (int u = 0; u < 8; u++)
+            if (i + u < len) v |= (uint64_t)p[i + u] << (8 * u);
+        i += 8;
+        return v;
+    }
+};
+
+template <bool FP, class Src8, class Emit>
+HULK_HD void k1_scan_read_w9(Src8 src, int32_t len, int32_t k, Emit emit) {
+    constexpr int32_t W = 9, B = 8;
+    constexpr uint64_t SENT = Sentinel<FP>::value;
+    const uint64_t mask = (1ull << (2 * k)) - 1ull;       // minimizer.go:103  (k <= 31)
+    const int shift = 2 * (k - 1);                        // minimizer.go:104
+    uint64_t fwd = 0, rev = 0, pref = SENT;
+    uint64_t A[B];                                        // A[t..7]: suffix minima of the previous block; A[0..t-1]: this block's values
+HULK_UNROLL
+    for (int x = 0; x < B; x++) A[x] = SENT;
+    for (int32_t i0 = 0; i0 < len; i0 += B) {
+        const uint64_t word = src.next8();
+        uint32_t codes[2];
+HULK_UNROLL
+        for (int h = 0; h < 2; h++) {
+            const uint32_t w32 = (uint32_t)(word >> (32 * h));
+            bool fast;
+            codes[h] = nt4x4(w32, fast);
+            if (!fast) {                                                  // N, IUPAC, raw 0..3 bytes, ...
+                codes[h] = 0;
+HULK_UNROLL
+                for (int u = 0; u < 4; u++) codes[h] |= nt4((w32 >> (8 * u)) & 0xffu) << (8 * u);   // minimizer.go:115
+            }
+        }
+        const bool warm = i0 + (B - 1) < k - 1;                           // whole block in front of the first k-mer
+HULK_UNROLL
+        for (int h = 0; h < 2; h++) {                                     // two groups of four independent hash chains
+            uint64_t X[4], canon[4];
+            bool skip[4];
+HULK_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const uint32_t c = (codes[h] >> (8 * u)) & 0xffu;         // 0..4
+                fwd = ((fwd << 2) | (uint64_t)c) & mask;                  // :134
+                rev = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);         // :137 (not masked)
+                skip[u] = ueq64<FP>(fwd, rev);                            // :145-147
+                canon[u] = umin64<FP>(fwd, rev);                          // :150-153
+            }
+            if (warm) continue;                                           // :140-142
+HULK_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const int32_t wi = i0 + 4 * h + u - W + 1;                // windowIndex :112
+                const int32_t span = (wi + 1 < k) ? (wi + 1) : k;         // :127-131
+                X[u] = (hash64(canon[u], mask) << 8) | (uint64_t)(int64_t)span;   // :156-159
+            }
+HULK_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const int t = 4 * h + u;
+                const int32_t i = i0 + t;
+                const bool real = (i >= k - 1) && (i < len) && !skip[u];
+                const uint64_t Xe = real ? X[u] : SENT;
+                pref = umin64<FP>(pref, Xe);
+                const uint64_t m = umin64<FP>(pref, A[t]);                // prefix of this block, suffix of the previous one
+                A[t] = Xe;
+                emit(m, real && i >= W - 1);                              // minimizer.go:186-199
+            }
+        }
+        if (warm) continue;
+        uint64_t run = SENT;
+HULK_UNROLL
+        for (int x = B - 1; x >= 0; x--) {                                // suffix minima in place
+            run = umin64<FP>(run, A[x]);
+            A[x] = run;
+        }
+        pref = SENT;
+    }
+}
+
 }  // namespace hulk

@@ -68,12 +68,13 @@ class ShardedSketch:
     def flush(self):
         """theBoss.Flush (src/pipeline/boss.go:112-128) over the spectrum summed across ranks."""
         if self.world > 1:
+            hist = self.engine.histogram_tensor()      # the engine double-buffers its spectrum: ask every flush
             if self._stream is not None:
                 import torch
                 with torch.cuda.stream(self._stream):
-                    self._dist.all_reduce(self._hist, op=self._dist.ReduceOp.SUM, group=self.group)
+                    self._dist.all_reduce(hist, op=self._dist.ReduceOp.SUM, group=self.group)
             else:
-                self._dist.all_reduce(self._hist, op=self._dist.ReduceOp.SUM, group=self.group)
+                self._dist.all_reduce(hist, op=self._dist.ReduceOp.SUM, group=self.group)
         self.engine.flush()
 
     def finish(self) -> Tuple[np.ndarray, np.ndarray]:

@@ -87,7 +87,8 @@ class HistoSketch:
 
     def __init__(self, k: int = 21, w: int = 9, sketch_size: int = 50, decay_ratio: float = 1.0,
                  num_bins: Optional[int] = None, device: int = 0, slots: Optional[Tuple[int, int]] = None,
-                 stream: Optional[int] = None, tables=None, async_input: bool = False):
+                 stream: Optional[int] = None, tables=None, async_input: bool = False,
+                 input_ready: bool = False):
         self._L = N.load()
         self._ctx = C.c_void_p()
         self.k, self.w, self.sketch_size, self.decay_ratio = k, w, sketch_size, decay_ratio
@@ -101,7 +102,7 @@ class HistoSketch:
         p.device = device
         p.slot_begin, p.slot_end = (slots if slots is not None else (0, 0))
         p.stream = stream
-        p.flags = N.F_ASYNC_INPUT if async_input else 0
+        p.flags = (N.F_ASYNC_INPUT if async_input else 0) | (N.F_INPUT_READY if input_ready else 0)
         ctx = C.c_void_p()
         rc = self._L.hulk_b200_create(C.byref(p), C.byref(ctx))
         if rc:
@@ -219,18 +220,20 @@ class HistoSketch:
         return p.value
 
     def histogram_tensor(self):
-        """The device spectrum as a torch int32 tensor aliasing the context's memory (for the per-flush
-        all-reduce of hulk_b200.distributed; uint32 sums wrap identically in two's complement)."""
+        """The device spectrum of the interval being counted, as a torch int32 tensor aliasing the context's
+        memory (for the per-flush all-reduce of hulk_b200.distributed; uint32 sums wrap identically in two's
+        complement).  The spectrum is double-buffered, so ask again after every flush; work enqueued on the
+        context's stream after this call sees every read pushed so far."""
         import torch
-
-        class _Dev:
-            pass
-        v = _Dev()
-        v.__cuda_array_interface__ = {"shape": (self.num_bins,), "typestr": "<i4",
-                                      "data": (self.histogram_device_ptr(), False), "version": 2}
-        t = torch.as_tensor(v, device=torch.device("cuda", self.device))
-        self._keep_hist = v
-        return t
+        ptr = self.histogram_device_ptr()
+        cache = self.__dict__.setdefault("_hist_tensors", {})
+        if ptr not in cache:
+            class _Dev:
+                pass
+            v = _Dev()
+            v.__cuda_array_interface__ = {"shape": (self.num_bins,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+            cache[ptr] = (torch.as_tensor(v, device=torch.device("cuda", self.device)), v)
+        return cache[ptr][0]
 
     def stream_handle(self) -> int:
         p = C.c_void_p()

@@ -222,6 +222,16 @@ int main() {
                                           [&](uint64_t m, bool on) { if (on) c.push_back(m); });
                 if (c != a) { printf("MISMATCH\n"); return 2; }
             }
+            if (w == 9) {                             // the register-resident w = 9 scan emits the same sequence
+                for (int fp = 0; fp < 2; fp++) {
+                    if (fp && !hulk::k1_fp_compare_ok(k, w)) continue;
+                    std::vector<uint64_t> d;
+                    auto em = [&](uint64_t m, bool on) { if (on) d.push_back(m); };
+                    if (fp) hulk::k1_scan_read_w9<true>(hulk::ByteSrc8{(const uint8_t*)buf, len, 0}, len, k, em);
+                    else hulk::k1_scan_read_w9<false>(hulk::ByteSrc8{(const uint8_t*)buf, len, 0}, len, k, em);
+                    if (d != a) { printf("MISMATCH_W9\n"); return 2; }
+                }
+            }
             std::sort(a.begin(), a.end());
             a.erase(std::unique(a.begin(), a.end()), a.end());
             printf("%zu", a.size());
@@ -252,7 +262,8 @@ def test_kernel_scan_and_fast_jump_compiled_for_host_match_oracle(oracle, tmp_pa
     rng = np.random.default_rng(7)
     lines, want = [], []
     cases = [(21, 9, 150), (31, 9, 151), (11, 9, 149), (4, 4, 60), (21, 1, 80), (15, 32, 200), (5, 9, 40),
-             (3, 7, 30), (7, 40, 120), (21, 200, 400), (2, 2, 5)]
+             (3, 7, 30), (7, 40, 120), (21, 200, 400), (2, 2, 5), (27, 9, 35), (28, 9, 100), (1, 9, 9), (8, 9, 16),
+             (9, 9, 17), (21, 9, 29), (21, 9, 33)]
     for k, w, L in cases:
         reads = (random_reads(6, L, seed=k * 100 + w) + random_reads(4, L, seed=k + w, n_frac=0.05, lower_frac=0.3)
                  + [b"A" * L, (b"ACGTU" * L)[:L], (b"acgn0123RYKM" * L)[:L], (b"AC" * L)[:L]])
