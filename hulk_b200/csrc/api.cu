@@ -27,6 +27,9 @@
 
 using namespace hulk;
 
+constexpr int NBUF = 4;     // spectrum buffers allocated; ctx->nbuf of them are cycled = intervals in flight at once
+constexpr int NSTAGE = 4;   // host-input staging buffers (ring)
+
 struct hulk_b200_ctx {
     hulk_b200_params P{};
     int32_t D = 0;
@@ -34,6 +37,7 @@ struct hulk_b200_ctx {
     uint64_t Dp = 0;
     uint32_t nsub_row = 0, nseg = 0, nblk = 0;
     bool drift = false, apply_scaling = false;
+    bool overlap = true;            // k1 on its own streams (false: everything in order on the main stream)
     bool force_tile_path = false;   // HULK_B200_K1_TILE=1: use the staged-tile kernel even for w = 9 (A/B measurements)
     double decay_weight = 0.0;
     int sm_count = 148;
@@ -44,26 +48,31 @@ struct hulk_b200_ctx {
     // stage 1+2
     // The spectrum is double-buffered: the reads of interval i+1 are counted into the other buffer (on
     // their own stream) while interval i is still being flushed on the main stream.
-    uint32_t *d_hist[2] = {nullptr, nullptr};
+    uint32_t *d_hist[NBUF] = {};
     int cur_hist = 0;                          // buffer (and k1 stream) of the interval being counted
-    cudaStream_t k1_stream[2] = {nullptr, nullptr};
-    cudaEvent_t ev_k1_last[2] = {nullptr, nullptr};    // last k1 launch into buffer b
-    cudaEvent_t ev_hist_free[2] = {nullptr, nullptr};  // buffer b consumed and wiped by its flush
+    int nbuf = 3;
+    cudaStream_t k1_stream[NBUF] = {};
+    cudaEvent_t ev_k1_last[NBUF] = {};         // last k1 launch into buffer b
+    cudaEvent_t ev_hist_free[NBUF] = {};       // buffer b consumed and wiped by its flush
     cudaEvent_t ev_main = nullptr;
-    bool k1_pending[2] = {false, false};       // k1 launches into buffer b since its last flush
+    bool k1_pending[NBUF] = {};                // k1 launches into buffer b since its last flush
     unsigned long long *d_nmin = nullptr, *d_errword = nullptr;
-    uint8_t *d_stage[2] = {nullptr, nullptr};
-    uint64_t stage_cap[2] = {0, 0};
-    uint64_t *d_off[2] = {nullptr, nullptr};
-    uint64_t off_cap[2] = {0, 0};
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr};
+    uint8_t *d_stage[NSTAGE] = {};
+    uint64_t stage_cap[NSTAGE] = {};
+    uint64_t *d_off[NSTAGE] = {};
+    uint64_t off_cap[NSTAGE] = {};
+    cudaEvent_t ev_copy[NSTAGE] = {}, ev_k1[NSTAGE] = {};
     int cur_buf = 0;
-    unsigned int *d_ovf_count[2] = {nullptr, nullptr};          // one overflow queue + scratch arena per k1 stream
-    unsigned long long *d_ovf_list[2] = {nullptr, nullptr};
+    unsigned int *d_ovf_count[NBUF] = {};      // one overflow queue + scratch arena per k1 stream
+    unsigned long long *d_ovf_list[NBUF] = {};
     uint32_t ovf_cap = 0;
-    uint64_t *d_arena[2] = {nullptr, nullptr};
-    unsigned long long *d_arena_cursor[2] = {nullptr, nullptr};
-    uint64_t arena_entries[2] = {0, 0};
+    uint64_t *d_queue[NBUF] = {};              // per-batch minimizer queue (k1 scan -> k1_jump_queue)
+    unsigned long long *d_queue_cursor[NBUF] = {};
+    uint64_t queue_cap[NBUF] = {};
+    bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
+    uint64_t *d_arena[NBUF] = {};
+    unsigned long long *d_arena_cursor[NBUF] = {};
+    uint64_t arena_entries[NBUF] = {};
 
     // stage 3a
     FlushCtl *d_ctl = nullptr;
@@ -78,6 +87,8 @@ struct hulk_b200_ctx {
     // stage 3b
     double *d_r = nullptr, *d_c = nullptr, *d_b = nullptr;
     float *d_K32 = nullptr, *d_m32 = nullptr;
+    unsigned int *d_cand = nullptr;            // per slot: some chunk of the current flush may change it
+    int k3_stages = 4, k3_ctas_per_sm = 2;     // 2 x (4 x 16 KB) per SM: 5.7 TB/s alone, and k1 CTAs still fit next to it
     unsigned long long *d_sketch = nullptr;
     double *d_weights = nullptr;
     bool tables_set = false;
@@ -192,20 +203,30 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->P.device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < NBUF; i++)
         if (ctx->k1_stream[i]) cudaStreamSynchronize(ctx->k1_stream[i]);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->d_hist[0], ctx->d_hist[1], ctx->d_nmin, ctx->d_errword, ctx->d_stage[0], ctx->d_stage[1], ctx->d_off[0],
-                    ctx->d_off[1], ctx->d_ovf_count[0], ctx->d_ovf_count[1], ctx->d_ovf_list[0], ctx->d_ovf_list[1],
-                    ctx->d_arena[0], ctx->d_arena[1], ctx->d_arena_cursor[0], ctx->d_arena_cursor[1], ctx->d_ctl,
+    for (int i = 0; i < NBUF; i++) {
+        void *per[] = {ctx->d_hist[i], ctx->d_ovf_count[i], ctx->d_ovf_list[i], ctx->d_arena[i], ctx->d_arena_cursor[i],
+                       ctx->d_queue[i], ctx->d_queue_cursor[i]};
+        for (void *p : per)
+            if (p) cudaFree(p);
+    }
+    for (int i = 0; i < NSTAGE; i++) {
+        if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+        if (ctx->d_off[i]) cudaFree(ctx->d_off[i]);
+    }
+    void *ptrs[] = {ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits, ctx->d_invf, ctx->d_r, ctx->d_c,
-                    ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights};
+                    ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights, ctx->d_cand};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSTAGE; i++) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]);
+    }
+    for (int i = 0; i < NBUF; i++) {
         if (ctx->ev_k1_last[i]) cudaEventDestroy(ctx->ev_k1_last[i]);
         if (ctx->ev_hist_free[i]) cudaEventDestroy(ctx->ev_hist_free[i]);
         if (ctx->k1_stream[i]) cudaStreamDestroy(ctx->k1_stream[i]);
@@ -222,8 +243,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
 // every stream of the context idle (inputs copied, all k1 launches and flushes done)
 static int sync_all(hulk_b200_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->copy_stream));
-    CU(cudaStreamSynchronize(ctx->k1_stream[0]));
-    CU(cudaStreamSynchronize(ctx->k1_stream[1]));
+    for (int i = 0; i < NBUF; i++) CU(cudaStreamSynchronize(ctx->k1_stream[i]));
     CU(cudaStreamSynchronize(ctx->stream));
     return HULK_B200_OK;
 }
@@ -234,19 +254,25 @@ static int create_impl(hulk_b200_ctx *ctx) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P.device));
     ctx->sm_count = prop.multiProcessorCount;
+    // the flush chain (k2, k3) is the critical path of a pipelined run: it gets the SMs first, the k1 streams
+    // (counting the NEXT interval) fill what is left
+    int prio_least = 0, prio_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     if (P.stream) {
         ctx->stream = reinterpret_cast<cudaStream_t>(P.stream);
     } else {
-        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
         ctx->own_stream = true;
     }
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSTAGE; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_k1[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < NBUF; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_k1_last[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_hist_free[i], cudaEventDisableTiming));
-        CU(cudaStreamCreateWithFlags(&ctx->k1_stream[i], cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&ctx->k1_stream[i], cudaStreamNonBlocking, prio_least));
     }
     CU(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
     const int32_t D = ctx->D;
@@ -256,15 +282,15 @@ static int create_impl(hulk_b200_ctx *ctx) {
     ctx->nseg = (uint32_t)((ctx->Dp + K3_SEG - 1) / K3_SEG);
     ctx->nblk = (uint32_t)(((uint64_t)D + 1023) / 1024);
 
-    CU(dmalloc(&ctx->d_hist[0], D));
-    CU(dmalloc(&ctx->d_hist[1], D));
+    for (int i = 0; i < NBUF; i++) CU(dmalloc(&ctx->d_hist[i], D));
     CU(dmalloc(&ctx->d_nmin, 1));
     CU(dmalloc(&ctx->d_errword, 1));
     ctx->ovf_cap = 1u << 20;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NBUF; i++) {
         CU(dmalloc(&ctx->d_ovf_count[i], 1));
         CU(dmalloc(&ctx->d_ovf_list[i], ctx->ovf_cap));
         CU(dmalloc(&ctx->d_arena_cursor[i], 1));
+        CU(dmalloc(&ctx->d_queue_cursor[i], 1));
     }
     CU(dmalloc(&ctx->d_ctl, 1));
     CU(dmalloc(&ctx->d_cols, (uint64_t)D * CMS_DEPTH));
@@ -279,10 +305,11 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(dmalloc(&ctx->d_invf, ctx->Dp));
     CU(dmalloc(&ctx->d_m32, (uint64_t)rows * ctx->nsub_row));
     CU(dmalloc(&ctx->d_sketch, rows));
+    CU(dmalloc(&ctx->d_cand, rows));
     CU(dmalloc(&ctx->d_weights, rows));
 
     cudaStream_t st = ctx->stream;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NBUF; i++) {
         CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)D, st));
         CU(cudaMemsetAsync(ctx->d_ovf_count[i], 0, 4, st));
         CU(cudaMemsetAsync(ctx->d_arena_cursor[i], 0, 8, st));
@@ -293,6 +320,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->d_q, 0, sizeof(double) * CMS_CELLS, st));
     CU(cudaMemsetAsync(ctx->d_invf, 0xff, sizeof(float) * ctx->Dp, st));            // NaN padding
     CU(cudaMemsetAsync(ctx->d_sketch, 0, sizeof(unsigned long long) * (rows ? rows : 1), st));   // histosketch.go:84-87
+    CU(cudaMemsetAsync(ctx->d_cand, 0, sizeof(unsigned int) * (rows ? rows : 1), st));
     {
         std::vector<double> w(rows ? rows : 1, 1.7976931348623157e308);             // math.MaxFloat64
         CU(cudaMemcpyAsync(ctx->d_weights, w.data(), sizeof(double) * rows, cudaMemcpyHostToDevice, st));
@@ -319,19 +347,40 @@ static int create_impl(hulk_b200_ctx *ctx) {
         cudaFree(d_counts);
         cudaFree(d_cursor);
     }
-    CU(cudaFuncSetAttribute(k3_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            K3_STAGES * K3_SEG * 4 + 2 * K3_STAGES * 8));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k3_filter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * K3_SEG * 4 + 2 * 4 * 8));
+    CU(cudaFuncSetAttribute(k3_filter<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * K3_SEG * 4 + 2 * 6 * 8));
+    CU(cudaFuncSetAttribute(k3_filter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * K3_SEG * 4 + 2 * 8 * 8));
+    {
+        const char *e = getenv("HULK_B200_K3_STAGES");
+        if (e && (*e == '4' || *e == '6' || *e == '8')) ctx->k3_stages = *e - '0';
+        e = getenv("HULK_B200_NBUF");
+        if (e && *e >= '2' && *e <= '0' + NBUF) ctx->nbuf = *e - '0';
+        e = getenv("HULK_B200_K3_CTAS");
+        if (e && (*e == '1' || *e == '2' || *e == '3')) ctx->k3_ctas_per_sm = *e - '0';
+    }
+    {
+        const int big = 200 * 1024;
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, false, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, true, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, false, true>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram<false, true, true>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram<true, false, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram<true, true, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false, true>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, false, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, true, false>, attr, big));
+    }
     {
         const char *e = getenv("HULK_B200_K1_TILE");
         ctx->force_tile_path = e && *e == '1';
+        e = getenv("HULK_B200_K1_FUSED");
+        ctx->fused_jump = e && *e == '1';
+        e = getenv("HULK_B200_SERIAL");
+        if (e && *e == '1') ctx->overlap = false;
     }
     return HULK_B200_OK;
 }
@@ -447,7 +496,7 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     CU(cudaSetDevice(ctx->P.device));
     cudaStream_t st = ctx->stream;
     { const int rc = sync_all(ctx); if (rc) return rc; }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NBUF; i++) {
         CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)ctx->D, st));
         ctx->k1_pending[i] = false;
     }
@@ -457,6 +506,7 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(FlushCtl), st));
     CU(cudaMemsetAsync(ctx->d_q, 0, sizeof(double) * CMS_CELLS, st));
     CU(cudaMemsetAsync(ctx->d_sketch, 0, sizeof(unsigned long long) * (ctx->rows ? ctx->rows : 1), st));
+    CU(cudaMemsetAsync(ctx->d_cand, 0, sizeof(unsigned int) * (ctx->rows ? ctx->rows : 1), st));
     std::vector<double> w(ctx->rows ? ctx->rows : 1, 1.7976931348623157e308);
     CU(cudaMemcpyAsync(ctx->d_weights, w.data(), sizeof(double) * ctx->rows, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
@@ -465,6 +515,14 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     ctx->st.n_kernel_launches = launches;
     ctx->extra_minimizers = 0;
     ctx->err.clear();
+    return HULK_B200_OK;
+}
+
+int hulk_b200_set_overlap(hulk_b200_ctx *ctx, int enable) {
+    if (!ctx) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    ctx->overlap = enable != 0;
     return HULK_B200_OK;
 }
 
@@ -566,33 +624,64 @@ static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t 
         CU(dmalloc(&ctx->d_arena[hs], want));
         ctx->arena_entries[hs] = want;
     }
+    // minimizer queue of the batch: at most list_cap keys per read (longer lists go to k1_generic)
+    const bool fast = ctx->P.w <= (uint32_t)K1_W_FAST;
+    const bool use_queue = fast && !DUMP && !ctx->fused_jump;
+    size_t smem = 0;
+    if (fast) k1_geometry(ctx, n_reads, total_bytes, &p.tile_cap, &p.list_cap, &smem);
+    if (use_queue) {
+        const uint64_t need = n_reads * (uint64_t)p.list_cap;
+        if (need >= (1ull << 31)) return fail(ctx, HULK_B200_EARG, "batch too large for one minimizer queue");
+        if (need > ctx->queue_cap[hs]) {
+            CU(cudaStreamSynchronize(st));
+            if (ctx->d_queue[hs]) cudaFree(ctx->d_queue[hs]);
+            ctx->d_queue[hs] = nullptr;
+            ctx->queue_cap[hs] = 0;
+            CU(dmalloc(&ctx->d_queue[hs], need));
+            ctx->queue_cap[hs] = need;
+        }
+        p.queue = ctx->d_queue[hs];
+        p.queue_cursor = ctx->d_queue_cursor[hs];
+        p.queue_cap = ctx->queue_cap[hs];
+        CU(cudaMemsetAsync(ctx->d_queue_cursor[hs], 0, 8, st));
+    }
     p.arena = ctx->d_arena[hs];
     p.arena_cursor = ctx->d_arena_cursor[hs];
     p.arena_entries = ctx->arena_entries[hs];
     CU(cudaMemsetAsync(ctx->d_ovf_count[hs], 0, 4, st));
     CU(cudaMemsetAsync(ctx->d_arena_cursor[hs], 0, 8, st));
-    const bool fast = ctx->P.w <= (uint32_t)K1_W_FAST;
     ProfScope prof_scope(ctx, 0, st);
     if (fast) {
-        size_t smem;
-        k1_geometry(ctx, n_reads, total_bytes, &p.tile_cap, &p.list_cap, &smem);
         const uint64_t ntiles = (n_reads + K1_TPB - 1) / K1_TPB;
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
         const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * per_sm);
         const bool fp = k1_fp_compare_ok((int32_t)ctx->P.k, (int32_t)ctx->P.w);
+        // template dispatch: <DUMP, FP-compares, QUEUE>
+#define K1_DISPATCH(KERNEL, GRID, SMEM)                                                      \
+        do {                                                                                  \
+            if (use_queue) {                                                                  \
+                if (fp) KERNEL<false, true, true><<<GRID, K1_TPB, SMEM, st>>>(p);             \
+                else KERNEL<false, false, true><<<GRID, K1_TPB, SMEM, st>>>(p);               \
+            } else {                                                                          \
+                if (fp) KERNEL<DUMP, true, false><<<GRID, K1_TPB, SMEM, st>>>(p);             \
+                else KERNEL<DUMP, false, false><<<GRID, K1_TPB, SMEM, st>>>(p);               \
+            }                                                                                 \
+        } while (0)
         if (ctx->P.w == 9 && !ctx->force_tile_path) {
             // register-resident window, no staged tile: shared memory is the candidate lists only
             const size_t smem9 = (size_t)p.list_cap * K1_TPB * 8;
             const uint64_t nctas = (n_reads + K1_TPB - 1) / K1_TPB;
             const unsigned grid9 = (unsigned)std::min<uint64_t>(nctas, (uint64_t)ctx->sm_count * K1_W9_CTAS_PER_SM);
-            if (fp) k1_minimizer_histogram_w9<DUMP, true><<<grid9, K1_TPB, smem9, st>>>(p);
-            else k1_minimizer_histogram_w9<DUMP, false><<<grid9, K1_TPB, smem9, st>>>(p);
-        } else if (fp) {
-            k1_minimizer_histogram<DUMP, true><<<grid, K1_TPB, smem, st>>>(p);
+            K1_DISPATCH(k1_minimizer_histogram_w9, grid9, smem9);
         } else {
-            k1_minimizer_histogram<DUMP, false><<<grid, K1_TPB, smem, st>>>(p);
+            K1_DISPATCH(k1_minimizer_histogram, grid, smem);
         }
+#undef K1_DISPATCH
         LAUNCH_CHECK("k1_minimizer_histogram");
+        if (use_queue) {
+            k1_jump_queue<<<ctx->sm_count * 8, K1_JUMP_TPB, 0, st>>>(p);
+            LAUNCH_CHECK("k1_jump_queue");
+        }
         k1_generic<DUMP><<<ctx->sm_count * 2, 64, 0, st>>>(p, true);
         LAUNCH_CHECK("k1_generic");
     } else {
@@ -658,7 +747,7 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
                                ctx->copy_stream));
         CU(cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
         const int hs = ctx->cur_hist;
-        cudaStream_t ks = ctx->k1_stream[hs];
+        cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
         CU(cudaStreamWaitEvent(ks, ctx->ev_copy[buf], 0));
         if (!ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ks, ctx->ev_hist_free[hs], 0));   // its last flush wiped it
         ctx->st.h2d_bytes += nb + (offsets ? sizeof(uint64_t) * (nr + 1) : 0);
@@ -670,7 +759,7 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
         ctx->k1_pending[hs] = true;
         ctx->st.n_reads += nr;
         ctx->st.n_bases += nb;
-        ctx->cur_buf ^= 1;
+        ctx->cur_buf = (ctx->cur_buf + 1) % NSTAGE;
         done = upto;
         if (!(ctx->P.flags & HULK_B200_F_ASYNC_INPUT)) CU(cudaEventSynchronize(ctx->ev_copy[buf]));
     }
@@ -715,8 +804,8 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
         total_bytes = ends[1] - ends[0];
     }
     const int hs = ctx->cur_hist;
-    cudaStream_t ks = ctx->k1_stream[hs];
-    if (!(ctx->P.flags & HULK_B200_F_INPUT_READY)) {          // order behind whatever produced the input on the main stream
+    cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
+    if (ctx->overlap && !(ctx->P.flags & HULK_B200_F_INPUT_READY)) {          // order behind whatever produced the input on the main stream
         CU(cudaEventRecord(ctx->ev_main, ctx->stream));
         CU(cudaStreamWaitEvent(ks, ctx->ev_main, 0));
     }
@@ -771,22 +860,27 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
     // the buffer is wiped: the next interval but one may count into it while the CWS sweep below runs
     CU(cudaEventRecord(ctx->ev_hist_free[hs], st));
     ctx->k1_pending[hs] = false;
-    ctx->cur_hist = hs ^ 1;
+    ctx->cur_hist = (hs + 1) % ctx->nbuf;
     if (ctx->rows) {
-        const size_t smem = (size_t)K3_STAGES * K3_SEG * 4 + 2 * K3_STAGES * 8;
+        const int stages = ctx->k3_stages;
+        const size_t smem = (size_t)stages * K3_SEG * 4 + 2 * stages * 8;
         const uint64_t T = (uint64_t)ctx->rows * ctx->nseg;
-        const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)ctx->sm_count);
+        const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)ctx->sm_count * ctx->k3_ctas_per_sm);
         {
             ProfScope prof_scope(ctx, 2);
-            k3_filter<<<grid, K3_THREADS, smem, st>>>(ctx->d_K32, ctx->Dp, ctx->d_invf, ctx->d_m32, ctx->rows,
-                                                      ctx->nseg, ctx->d_ctl);
+#define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, ctx->d_invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_weights, ctx->d_cand, \
+                       ctx->drift ? 1 : 0, ctx->d_ctl
+            if (stages == 4) k3_filter<4><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
+            else if (stages == 6) k3_filter<6><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
+            else k3_filter<8><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
+#undef K3_FILTER_ARGS
             LAUNCH_CHECK("k3_filter");
         }
         ProfScope prof_scope(ctx, 3);
         k3_resolve<<<(ctx->rows * 32 + 127) / 128, 128, 0, st>>>(ctx->d_m32, ctx->nsub_row, ctx->d_r, ctx->d_c, ctx->d_b,
                                                                  D, ctx->d_fbits, ctx->rows, ctx->d_sketch,
                                                                  ctx->d_weights, ctx->drift ? 1 : 0, ctx->decay_weight,
-                                                                 ctx->d_ctl);
+                                                                 ctx->d_cand, ctx->d_ctl);
         LAUNCH_CHECK("k3_resolve");
     }
     return HULK_B200_OK;

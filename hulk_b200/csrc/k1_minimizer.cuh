@@ -51,6 +51,10 @@ struct K1Params {
     uint64_t *dump;
     uint32_t dump_cap;
     uint32_t *dump_counts;
+    // the batch's minimizer queue: k1 scan kernels append their per-read sets, k1_jump_queue bins them
+    uint64_t *queue;
+    unsigned long long *queue_cursor;
+    uint64_t queue_cap;
     // generic path scratch
     uint64_t *arena;
     unsigned long long *arena_cursor;
@@ -94,10 +98,82 @@ __device__ __forceinline__ double k1_pin(double x) {
     return x;
 }
 
+// ---- jump.Hash walks over a key queue (kmerspectrum.go:67-81: bins[jump.Hash(kmer, numBins)]++) ----
+// This thread bins keys g, g + stride, g + 2 stride, ... < total.  Two walks per thread are in flight
+// (ILP); they advance K1_JUMP_BATCH steps between two refill points.  The step itself is hd_math.h
+// jump_step_fast, split into evaluate / commit.  Must be entered by whole warps.
+template <class Load>
+__device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32_t stride, const uint32_t total,
+                                             uint32_t *const hist, const uint32_t nb) {
+    uint64_t key[2] = {0, 0};
+    double jd1[2] = {1.0, 1.0};
+    uint32_t bkt[2] = {0, 0};
+    bool busy[2] = {false, false}, loaded[2] = {false, false};
+    const double c_lo = k1_pin(1.0 - JUMP_EPS), c_hi = k1_pin(1.0 + JUMP_EPS);
+    const double two52 = k1_pin(JUMP_TWO52), two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0);
+    for (;;) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (!busy[c]) {
+                if (loaded[c]) {                                         // its walk ended in the last batch
+                    atomicAdd(&hist[bkt[c]], 1u);
+                    loaded[c] = false;
+                }
+                if (g < total) {
+                    key[c] = load(g);
+                    g += stride;
+                    bkt[c] = 0;                                          // first step of jump.Hash: b = 0
+                    jd1[c] = one;
+                    busy[c] = loaded[c] = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
+#pragma unroll
+        for (int it = 0; it < K1_JUMP_BATCH; it++) {
+            double tlo[2];
+            bool fin[2], amb[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
+                key[c] = key[c] * 2862933555777941757ull + 1ull;
+                const uint32_t q = (uint32_t)(key[c] >> 33) + 1u;                    // 1 .. 2^31
+                const double qd = dbl_make(0x43300000u, q) - two52;                  // (double)q, exact
+                const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
+                const double r0 = rcp_seed(Q);
+                const double e = fma(-Q, r0, one);
+                const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
+                const double x = jd1[c] * R;
+                tlo[c] = __fma_rd(x, c_lo, two52);                                   // 2^52 + floor(x (1 - EPS))
+                const double thi = __fma_rd(x, c_hi, two52);
+                fin[c] = (dbl_hi(thi) != 0x43300000u) || (dbl_lo(tlo[c]) >= nb);
+                amb[c] = !fin[c] && (dbl_lo(tlo[c]) != dbl_lo(thi));
+            }
+            if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-21 per step: the true division
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (amb[c] && busy[c]) {
+                        uint32_t b = bkt[c];
+                        double j1 = jd1[c];
+                        fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
+                        tlo[c] = JUMP_TWO52 + (double)b;                 // as the fast step reports it
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {                                // commit
+                const bool adv = busy[c] && !fin[c];
+                bkt[c] = adv ? dbl_lo(tlo[c]) : bkt[c];
+                jd1[c] = adv ? tlo[c] - two52m1 : jd1[c];                // (double)(bucket + 1), exact
+                busy[c] = adv;
+            }
+        }
+    }
+}
+
 // ---- the part of a warp's work behind the scan: exact per-read sets, then jump-hash binning -------
 // wl: the warp's list block [list_cap][32] (entry e of lane l at wl[e * 32 + l]); n: this lane's number
 // of adjacent-distinct window minima (0 when the read is invalid or was queued for k1_generic).
-template <bool DUMP, bool FP>
+template <bool DUMP, bool FP, bool QUEUE>
 __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl, uint64_t *my_list, const int lane,
                                                 const uint32_t list_cap, uint32_t n, const bool valid,
                                                 const bool overflow, const uint64_t r, const uint32_t nb,
@@ -145,75 +221,24 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
             total += __popc(mask);
         }
         __syncwarp();
-        uint32_t g = lane;         // this lane's next queue index
-        uint64_t key[2] = {0, 0};
-        double jd1[2] = {1.0, 1.0};
-        uint32_t bkt[2] = {0, 0};
-        bool busy[2] = {false, false}, loaded[2] = {false, false};
-        const double c_lo = k1_pin(1.0 - JUMP_EPS), c_hi = k1_pin(1.0 + JUMP_EPS);
-        const double two52 = k1_pin(JUMP_TWO52), two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0);
-        uint32_t *const hist = p.hist;
-        for (;;) {
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                if (!busy[c]) {
-                    if (loaded[c]) {                                         // its walk ended in the last batch
-                        atomicAdd(&hist[bkt[c]], 1u);
-                        loaded[c] = false;
-                    }
-                    if (g < total) {
-                        key[c] = wl[g];
-                        g += 32;
-                        bkt[c] = 0;                                          // first step of jump.Hash: b = 0
-                        jd1[c] = one;
-                        busy[c] = loaded[c] = true;
-                    }
-                }
+        if (QUEUE) {
+            // hand the warp's dense key block to the batch queue (one reservation per warp, coalesced copy);
+            // k1_jump_queue bins the whole batch afterwards without any shared memory
+            unsigned long long base = 0;
+            if (lane == 0 && total) base = atomicAdd(p.queue_cursor, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + total > p.queue_cap) {
+                if (lane == 0) k1_report(p, r, K1_ERR_OVF);
+            } else {
+                for (uint32_t j = lane; j < total; j += 32) p.queue[base + j] = wl[j];
             }
-            if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
-#pragma unroll
-            for (int it = 0; it < K1_JUMP_BATCH; it++) {
-                double tlo[2];
-                bool fin[2], amb[2];
-#pragma unroll
-                for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
-                    key[c] = key[c] * 2862933555777941757ull + 1ull;
-                    const uint32_t q = (uint32_t)(key[c] >> 33) + 1u;                    // 1 .. 2^31
-                    const double qd = dbl_make(0x43300000u, q) - two52;                  // (double)q, exact
-                    const double Q = dbl_make(dbl_hi(qd) - (31u << 20), dbl_lo(qd));     // q * 2^-31, exact
-                    const double r0 = rcp_seed(Q);
-                    const double e = fma(-Q, r0, one);
-                    const double R = fma(r0, e, r0);                                     // ~ 2^31 / q
-                    const double x = jd1[c] * R;
-                    tlo[c] = __fma_rd(x, c_lo, two52);                                   // 2^52 + floor(x (1 - EPS))
-                    const double thi = __fma_rd(x, c_hi, two52);
-                    fin[c] = (dbl_hi(thi) != 0x43300000u) || (dbl_lo(tlo[c]) >= nb);
-                    amb[c] = !fin[c] && (dbl_lo(tlo[c]) != dbl_lo(thi));
-                }
-                if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-21 per step: the true division
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        if (amb[c] && busy[c]) {
-                            uint32_t b = bkt[c];
-                            double j1 = jd1[c];
-                            fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
-                            tlo[c] = JUMP_TWO52 + (double)b;                 // as the fast step reports it
-                        }
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 2; c++) {                                // commit
-                    const bool adv = busy[c] && !fin[c];
-                    bkt[c] = adv ? dbl_lo(tlo[c]) : bkt[c];
-                    jd1[c] = adv ? tlo[c] - two52m1 : jd1[c];                // (double)(bucket + 1), exact
-                    busy[c] = adv;
-                }
-            }
+        } else {
+            k1_jump_walk([&](uint32_t g) { return wl[g]; }, (uint32_t)lane, 32u, total, p.hist, nb);
         }
     }
 }
 
-template <bool DUMP, bool FP>
+template <bool DUMP, bool FP, bool QUEUE>
 __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *tile = smem;                                                          // tile_cap + 16 bytes
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
             n = 0;
             valid = false;
         }
-        k1_finish_lists<DUMP, FP>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
+        k1_finish_lists<DUMP, FP, QUEUE>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
         __syncthreads();   // everyone is done with the tile before thread 0 refills it
     }
     if (!DUMP) {
@@ -352,7 +377,7 @@ struct GlobalSrc8 {
     }
 };
 
-template <bool DUMP, bool FP>
+template <bool DUMP, bool FP, bool QUEUE>
 __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histogram_w9(const K1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *list_all = reinterpret_cast<uint64_t *>(smem);                       // [warps][list_cap][32]
@@ -397,13 +422,28 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
             valid = false;
         }
         __syncwarp();
-        k1_finish_lists<DUMP, FP>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
+        k1_finish_lists<DUMP, FP, QUEUE>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
         __syncwarp();                                                            // the queue is drained before the lists refill
     }
     if (!DUMP) {
         for (int o = 16; o > 0; o >>= 1) local_minimizers += __shfl_down_sync(0xffffffffu, local_minimizers, o);
         if (lane == 0 && local_minimizers) atomicAdd(p.n_minimizers, local_minimizers);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Second half of stage 1+2 when the scan kernels run in QUEUE mode: bin every key of the batch queue.
+// No shared memory and few registers, so it runs at full occupancy and shares an SM with the CWS
+// filter's TMA ring or the next interval's scan CTAs; the queue is dense, so the walks are balanced
+// across the whole grid whatever the per-read set sizes were.
+// ------------------------------------------------------------------------------------------
+constexpr int K1_JUMP_TPB = 256;
+__global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue(const K1Params p) {
+    const unsigned long long filled = *p.queue_cursor;
+    const uint32_t total = (uint32_t)(filled < p.queue_cap ? filled : p.queue_cap);
+    const uint32_t g = blockIdx.x * K1_JUMP_TPB + threadIdx.x;
+    const uint64_t *const q = p.queue;
+    k1_jump_walk([&](uint32_t i) { return q[i]; }, g, gridDim.x * K1_JUMP_TPB, total, p.hist, (uint32_t)p.D);
 }
 
 // ------------------------------------------------------------------------------------------

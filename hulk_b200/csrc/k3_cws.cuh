@@ -29,7 +29,7 @@ namespace hulk {
 constexpr int K3_SUB = 512;                         // bins per chunk (one warp-reduction)
 constexpr int K3_SEG = 4096;                        // bins per TMA stage (16 KB)
 constexpr int K3_SUBS_PER_SEG = K3_SEG / K3_SUB;    // 8 = consumer warps
-constexpr int K3_STAGES = 8;                        // 8 x 16 KB ring
+constexpr int K3_STAGES_MAX = 8;                    // ring depth (template parameter): 4 x 16 KB leaves room for k1 CTAs
 constexpr int K3_CONSUMER_WARPS = K3_SUBS_PER_SEG;
 constexpr int K3_THREADS = (K3_CONSUMER_WARPS + 1) * 32;
 constexpr double K3_EPS = 1e-6;                     // >> 3 * 2^-24 (K32, (1/f)32 and product roundings)
@@ -52,9 +52,14 @@ __global__ void k3_fold(const double *__restrict__ r, const double *__restrict__
 // ---- per flush: streaming filter ----
 // tile = (segment, slot); tiles are enumerated segment-major so a CTA's consecutive tiles share
 // the segment's (1/f) values (L1-resident); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G).
-__global__ void __launch_bounds__(K3_THREADS, 1)
+// cand[slot] is raised when a chunk minimum could pass the slot's test as it stands at the start of the
+// flush; without concept drift W only decreases during a flush, so a slot whose flag stays down cannot
+// change and k3_resolve skips it (with drift the flag is raised unconditionally).
+template <int K3_STAGES>
+__global__ void __launch_bounds__(K3_THREADS, 2)
 k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restrict__ invf, float *__restrict__ m32,
-          const uint32_t rows, const uint32_t nseg, const FlushCtl *__restrict__ ctl) {
+          const uint32_t rows, const uint32_t nseg, const double *__restrict__ weights, unsigned int *__restrict__ cand,
+          const int drift, const FlushCtl *__restrict__ ctl) {
     if (!ctl->go) return;
     extern __shared__ __align__(128) uint8_t smem[];
     float *stage = reinterpret_cast<float *>(smem);                                    // [STAGES][SEG]
@@ -99,11 +104,13 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
             const uint32_t round = it / K3_STAGES;
             const uint32_t seg = (uint32_t)(t / rows), slot = (uint32_t)(t % rows);
             const uint64_t col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
+            double thr = 0.0;
+            if (lane == 0) thr = weights[slot];     // issued ahead of the wait: its latency hides behind the stage
             mbar_wait(&full[s], round & 1);
+            float m = __int_as_float(0x7f800000);
             if (col0 < Dp) {
                 const float4 *ks = reinterpret_cast<const float4 *>(stage + (size_t)s * K3_SEG + warp * K3_SUB);
                 const float4 *fs = reinterpret_cast<const float4 *>(invf + col0);
-                float m = __int_as_float(0x7f800000);
 #pragma unroll
                 for (int u = 0; u < K3_SUB / 128; u++) {
                     const float4 kv = ks[u * 32 + lane];
@@ -113,12 +120,18 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
                     m = fminf(m, kv.z * fv.z);
                     m = fminf(m, kv.w * fv.w);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if (lane == 0) m32[(uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG + warp] = m;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive(&empty[s]);  // the stage is free before the (global) epilogue
+            if (col0 < Dp) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) {
+                    m32[(uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG + warp] = m;
+                    const bool c = drift || ((double)m < thr + K3_EPS * fabs(thr) + 1e-37);   // same test as k3_resolve
+                    if (c && m < __int_as_float(0x7f800000)) atomicOr(&cand[slot], 1u);
+                }
+            }
         }
     }
 }
@@ -134,20 +147,34 @@ __global__ void __launch_bounds__(128)
 k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double *__restrict__ r,
            const double *__restrict__ c, const double *__restrict__ b, const int32_t D,
            const unsigned long long *__restrict__ fbits, const uint32_t rows, unsigned long long *__restrict__ sketch,
-           double *__restrict__ weights, const int drift, const double decay_weight, FlushCtl *ctl) {
+           double *__restrict__ weights, const int drift, const double decay_weight, unsigned int *__restrict__ cand,
+           FlushCtl *ctl) {
     if (!ctl->go) return;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= rows) return;
     const int lane = threadIdx.x & 31;
+    if (cand[slot] == 0u) return;                   // no chunk of this flush can change the slot
+    __syncwarp();
+    if (lane == 0) cand[slot] = 0u;                 // lowered for the next flush
     double W = weights[slot];
     unsigned long long S = sketch[slot];
     unsigned int rescans = 0;
     const float *mrow = m32 + (uint64_t)slot * nsub_row;
     const uint64_t rowoff = (uint64_t)slot * (uint64_t)D;
 
-    for (uint32_t cbase = 0; cbase < nsub_row; cbase += 32) {
-        const uint32_t ci = cbase + lane;
-        const double m = (ci < nsub_row) ? (double)mrow[ci] : INFINITY;
+    constexpr int PRE = 8;                          // chunk minima fetched per lane before they are walked
+    for (uint32_t cbase0 = 0; cbase0 < nsub_row; cbase0 += 32 * PRE) {
+      float mv[PRE];
+#pragma unroll
+      for (int j = 0; j < PRE; j++) {
+          const uint32_t ci = cbase0 + 32 * j + lane;
+          mv[j] = (ci < nsub_row) ? mrow[ci] : INFINITY;
+      }
+#pragma unroll
+      for (int j = 0; j < PRE; j++) {
+        const uint32_t cbase = cbase0 + 32 * j;
+        if (cbase >= nsub_row) break;
+        const double m = (double)mv[j];
         uint32_t pending = 0xffffffffu;
         for (;;) {
             const double thr = drift ? W / decay_weight : W;             // histosketch.go:141-146
@@ -186,6 +213,7 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
                 }
             }
         }
+      }
     }
     if (lane == 0) {
         weights[slot] = W;

@@ -164,6 +164,10 @@ class HistoSketch:
     def profile(self, enable: bool):
         self._check(self._L.hulk_b200_profile_enable(self._ctx, int(enable)))
 
+    def set_overlap(self, enable: bool):
+        """Counting interval i+1 while interval i is flushed (default on); off = strict call order on one stream."""
+        self._check(self._L.hulk_b200_set_overlap(self._ctx, int(enable)))
+
     def profile_read(self) -> dict:
         pr = N.Profile()
         self._check(self._L.hulk_b200_profile_read(self._ctx, C.byref(pr)))
