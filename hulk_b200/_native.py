@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libhulk_b200.so")
 EXPORTS = [
     "hulk_b200_version", "hulk_b200_strerror", "hulk_b200_last_error", "hulk_b200_create",
     "hulk_b200_destroy", "hulk_b200_set_cws_tables", "hulk_b200_generate_cws_tables",
-    "hulk_b200_set_cws_tables_device", "hulk_b200_reset", "hulk_b200_profile_enable", "hulk_b200_profile_read", "hulk_b200_set_overlap",
+    "hulk_b200_set_cws_tables_device", "hulk_b200_reset", "hulk_b200_profile_enable", "hulk_b200_profile_read", "hulk_b200_profile_timeline", "hulk_b200_set_overlap",
     "hulk_b200_new_cws", "hulk_b200_push_reads", "hulk_b200_push_reads_fixed",
     "hulk_b200_push_reads_device", "hulk_b200_sync_inputs", "hulk_b200_flush", "hulk_b200_sync",
     "hulk_b200_finish", "hulk_b200_snapshot_async", "hulk_b200_get_stats", "hulk_b200_histogram_device_ptr", "hulk_b200_stream",
@@ -76,6 +76,7 @@ def load():
         "hulk_b200_reset": (C.c_int, [vp]),
         "hulk_b200_profile_enable": (C.c_int, [vp, C.c_int]),
         "hulk_b200_set_overlap": (C.c_int, [vp, C.c_int]),
+        "hulk_b200_profile_timeline": (C.c_int, [vp, vp, u64, C.POINTER(u64)]),
         "hulk_b200_profile_read": (C.c_int, [vp, C.POINTER(Profile)]),
         "hulk_b200_new_cws": (C.c_int, [u32, i32, u32, u32, vp, vp, vp]),
         "hulk_b200_push_reads": (C.c_int, [vp, vp, vp, u64]),

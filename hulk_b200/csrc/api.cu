@@ -69,6 +69,9 @@ struct hulk_b200_ctx {
     uint64_t *d_queue[NBUF] = {};              // per-batch minimizer queue (k1 scan -> k1_jump_queue)
     unsigned long long *d_queue_cursor[NBUF] = {};
     uint64_t queue_cap[NBUF] = {};
+    int k1_ctas_per_sm = 4;                    // scan CTAs per SM in queue mode (tasks are handed out dynamically):
+                                               // one short of what fits, so the flush chain always finds SM room
+    int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
     bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
     unsigned long long *d_arena_cursor[NBUF] = {};
@@ -290,7 +293,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(dmalloc(&ctx->d_ovf_count[i], 1));
         CU(dmalloc(&ctx->d_ovf_list[i], ctx->ovf_cap));
         CU(dmalloc(&ctx->d_arena_cursor[i], 1));
-        CU(dmalloc(&ctx->d_queue_cursor[i], 1));
+        CU(dmalloc(&ctx->d_queue_cursor[i], 2));
     }
     CU(dmalloc(&ctx->d_ctl, 1));
     CU(dmalloc(&ctx->d_cols, (uint64_t)D * CMS_DEPTH));
@@ -377,6 +380,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
     {
         const char *e = getenv("HULK_B200_K1_TILE");
         ctx->force_tile_path = e && *e == '1';
+        e = getenv("HULK_B200_K1_CTAS");
+        if (e && *e >= '1' && *e <= '0' + K1_W9_CTAS_PER_SM) ctx->k1_ctas_per_sm = *e - '0';
+        e = getenv("HULK_B200_JUMP_BATCH");
+        if (e && (*e == '2' || *e == '4')) ctx->jump_batch = *e - '0';
         e = getenv("HULK_B200_K1_FUSED");
         ctx->fused_jump = e && *e == '1';
         e = getenv("HULK_B200_SERIAL");
@@ -552,6 +559,33 @@ int hulk_b200_profile_read(hulk_b200_ctx *ctx, hulk_b200_profile *out) {
     return HULK_B200_OK;
 }
 
+// raw timeline of the recorded scopes (debug tap): rows of (class, start ms, end ms) relative to the
+// earliest recorded start; consumes the records like profile_read
+int hulk_b200_profile_timeline(hulk_b200_ctx *ctx, double *rows, uint64_t cap, uint64_t *n_out) {
+    if (!ctx || !rows || !n_out) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    cudaEvent_t base = nullptr;
+    for (int c = 0; c < 4 && !base; c++)
+        if (!ctx->prof_events[c].empty()) base = ctx->prof_events[c].front().first;
+    uint64_t n = 0;
+    for (int c = 0; c < 4; c++) {
+        for (auto &pr : ctx->prof_events[c]) {
+            float a = 0.f, b = 0.f;
+            if (base && n < cap && cudaEventElapsedTime(&a, base, pr.first) == cudaSuccess &&
+                cudaEventElapsedTime(&b, base, pr.second) == cudaSuccess) {
+                rows[3 * n] = c; rows[3 * n + 1] = a; rows[3 * n + 2] = b;
+                n++;
+            }
+            ctx->prof_pool.push_back(pr.first);
+            ctx->prof_pool.push_back(pr.second);
+        }
+        ctx->prof_events[c].clear();
+    }
+    *n_out = n;
+    return HULK_B200_OK;
+}
+
 int hulk_b200_generate_cws_tables(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
@@ -643,7 +677,7 @@ static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t 
         p.queue = ctx->d_queue[hs];
         p.queue_cursor = ctx->d_queue_cursor[hs];
         p.queue_cap = ctx->queue_cap[hs];
-        CU(cudaMemsetAsync(ctx->d_queue_cursor[hs], 0, 8, st));
+        CU(cudaMemsetAsync(ctx->d_queue_cursor[hs], 0, 16, st));
     }
     p.arena = ctx->d_arena[hs];
     p.arena_cursor = ctx->d_arena_cursor[hs];
@@ -671,7 +705,8 @@ static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t 
             // register-resident window, no staged tile: shared memory is the candidate lists only
             const size_t smem9 = (size_t)p.list_cap * K1_TPB * 8;
             const uint64_t nctas = (n_reads + K1_TPB - 1) / K1_TPB;
-            const unsigned grid9 = (unsigned)std::min<uint64_t>(nctas, (uint64_t)ctx->sm_count * K1_W9_CTAS_PER_SM);
+            const int per_sm9 = use_queue ? ctx->k1_ctas_per_sm : K1_W9_CTAS_PER_SM;
+            const unsigned grid9 = (unsigned)std::min<uint64_t>(nctas, (uint64_t)ctx->sm_count * per_sm9);
             K1_DISPATCH(k1_minimizer_histogram_w9, grid9, smem9);
         } else {
             K1_DISPATCH(k1_minimizer_histogram, grid, smem);
@@ -679,7 +714,9 @@ static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t 
 #undef K1_DISPATCH
         LAUNCH_CHECK("k1_minimizer_histogram");
         if (use_queue) {
-            k1_jump_queue<<<ctx->sm_count * 8, K1_JUMP_TPB, 0, st>>>(p);
+            const unsigned gridj = (unsigned)(ctx->sm_count * K1_JUMP_CTAS_PER_SM);
+            if (ctx->jump_batch == 2) k1_jump_queue<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+            else k1_jump_queue<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             LAUNCH_CHECK("k1_jump_queue");
         }
         k1_generic<DUMP><<<ctx->sm_count * 2, 64, 0, st>>>(p, true);

@@ -53,7 +53,7 @@ struct K1Params {
     uint32_t *dump_counts;
     // the batch's minimizer queue: k1 scan kernels append their per-read sets, k1_jump_queue bins them
     uint64_t *queue;
-    unsigned long long *queue_cursor;
+    unsigned long long *queue_cursor;      // [0]: keys appended so far, [1]: next 32-read task (dynamic scheduling)
     uint64_t queue_cap;
     // generic path scratch
     uint64_t *arena;
@@ -102,9 +102,14 @@ __device__ __forceinline__ double k1_pin(double x) {
 // This thread bins keys g, g + stride, g + 2 stride, ... < total.  Two walks per thread are in flight
 // (ILP); they advance K1_JUMP_BATCH steps between two refill points.  The step itself is hd_math.h
 // jump_step_fast, split into evaluate / commit.  Must be entered by whole warps.
-template <class Load>
+// DYN = false: static assignment, this thread's keys are g, g + stride, ...
+// DYN = true : the warp owns keys [g, total) (g warp-uniform, stride unused); a walk that ends takes the
+//              warp's next unclaimed key (ballot + popc, no atomics), so every lane stays busy until the
+//              segment is exhausted, whatever the per-key step counts are.
+template <bool DYN, int BATCH, class Load>
 __device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32_t stride, const uint32_t total,
                                              uint32_t *const hist, const uint32_t nb) {
+    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     uint64_t key[2] = {0, 0};
     double jd1[2] = {1.0, 1.0};
     uint32_t bkt[2] = {0, 0};
@@ -119,18 +124,24 @@ __device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32
                     atomicAdd(&hist[bkt[c]], 1u);
                     loaded[c] = false;
                 }
-                if (g < total) {
-                    key[c] = load(g);
-                    g += stride;
-                    bkt[c] = 0;                                          // first step of jump.Hash: b = 0
-                    jd1[c] = one;
-                    busy[c] = loaded[c] = true;
-                }
+            }
+            uint32_t mine = g;
+            if (DYN) {
+                const uint32_t need = __ballot_sync(0xffffffffu, !busy[c]);
+                mine = g + __popc(need & lane_lt);
+                g = min(g + (uint32_t)__popc(need), total);
+            }
+            if (!busy[c] && mine < total) {
+                key[c] = load(mine);
+                if (!DYN) g += stride;
+                bkt[c] = 0;                                              // first step of jump.Hash: b = 0
+                jd1[c] = one;
+                busy[c] = loaded[c] = true;
             }
         }
         if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
 #pragma unroll
-        for (int it = 0; it < K1_JUMP_BATCH; it++) {
+        for (int it = 0; it < BATCH; it++) {
             double tlo[2];
             bool fin[2], amb[2];
 #pragma unroll
@@ -233,7 +244,7 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
                 for (uint32_t j = lane; j < total; j += 32) p.queue[base + j] = wl[j];
             }
         } else {
-            k1_jump_walk([&](uint32_t g) { return wl[g]; }, (uint32_t)lane, 32u, total, p.hist, nb);
+            k1_jump_walk<false, K1_JUMP_BATCH>([&](uint32_t g) { return wl[g]; }, (uint32_t)lane, 32u, total, p.hist, nb);
         }
     }
 }
@@ -390,7 +401,16 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
     const uint64_t ntasks = (p.n_reads + 31) / 32;
     const uintptr_t lim = reinterpret_cast<uintptr_t>(p.bases) + p.bases_bytes;
 
-    for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp; task < ntasks; task += (uint64_t)gridDim.x * K1_WARPS) {
+    // tasks (32 reads) are handed out dynamically when a counter exists: the grid may be smaller than the
+    // task count without a straggler round, so it can be sized to leave SM room for the flush chain
+    unsigned long long *const task_counter = QUEUE ? p.queue_cursor + 1 : nullptr;
+    for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp;;) {
+        if (task_counter) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(task_counter, 1ull);
+            task = __shfl_sync(0xffffffffu, t, 0);
+        }
+        if (task >= ntasks) break;
         const uint64_t r = task * 32 + lane;
         uint32_t n = 0;
         bool valid = false;
@@ -424,6 +444,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
         __syncwarp();
         k1_finish_lists<DUMP, FP, QUEUE>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
         __syncwarp();                                                            // the queue is drained before the lists refill
+        if (!task_counter) task += (uint64_t)gridDim.x * K1_WARPS;
     }
     if (!DUMP) {
         for (int o = 16; o > 0; o >>= 1) local_minimizers += __shfl_down_sync(0xffffffffu, local_minimizers, o);
@@ -438,12 +459,16 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
 // across the whole grid whatever the per-read set sizes were.
 // ------------------------------------------------------------------------------------------
 constexpr int K1_JUMP_TPB = 256;
+constexpr int K1_JUMP_CTAS_PER_SM = 4;      // 32 warps per SM, one wave: every warp walks one contiguous segment
+template <int BATCH>
 __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue(const K1Params p) {
     const unsigned long long filled = *p.queue_cursor;
-    const uint32_t total = (uint32_t)(filled < p.queue_cap ? filled : p.queue_cap);
-    const uint32_t g = blockIdx.x * K1_JUMP_TPB + threadIdx.x;
+    const uint64_t total = filled < p.queue_cap ? filled : p.queue_cap;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (K1_JUMP_TPB / 32);
+    const uint64_t gw = (uint64_t)blockIdx.x * (K1_JUMP_TPB / 32) + (threadIdx.x >> 5);
+    const uint32_t seg_begin = (uint32_t)(total * gw / nwarps), seg_end = (uint32_t)(total * (gw + 1) / nwarps);
     const uint64_t *const q = p.queue;
-    k1_jump_walk([&](uint32_t i) { return q[i]; }, g, gridDim.x * K1_JUMP_TPB, total, p.hist, (uint32_t)p.D);
+    k1_jump_walk<true, BATCH>([&](uint32_t i) { return q[i]; }, seg_begin, 0u, seg_end, p.hist, (uint32_t)p.D);
 }
 
 // ------------------------------------------------------------------------------------------

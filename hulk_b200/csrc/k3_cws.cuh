@@ -85,11 +85,12 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
         // producer warp: one lane feeds the ring
         if (lane == 0) {
             uint32_t it = 0;
+            uint32_t seg = (uint32_t)(t_begin / rows), slot = (uint32_t)(t_begin % rows);   // one division per CTA
             for (uint64_t t = t_begin; t < t_end; t++, it++) {
                 const int s = it % K3_STAGES;
                 const uint32_t round = it / K3_STAGES;
                 if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-                const uint32_t seg = (uint32_t)(t / rows), slot = (uint32_t)(t % rows);
+                if (t != t_begin && ++slot == rows) { slot = 0; seg++; }
                 const uint64_t col0 = (uint64_t)seg * K3_SEG;
                 const uint32_t ncols = (uint32_t)((Dp - col0 < (uint64_t)K3_SEG) ? (Dp - col0) : K3_SEG);
                 mbar_arrive_expect_tx(&full[s], ncols * 4u);
@@ -99,10 +100,11 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
         }
     } else {
         uint32_t it = 0;
+        uint32_t seg = (uint32_t)(t_begin / rows), slot = (uint32_t)(t_begin % rows);
         for (uint64_t t = t_begin; t < t_end; t++, it++) {
             const int s = it % K3_STAGES;
             const uint32_t round = it / K3_STAGES;
-            const uint32_t seg = (uint32_t)(t / rows), slot = (uint32_t)(t % rows);
+            if (t != t_begin && ++slot == rows) { slot = 0; seg++; }
             const uint64_t col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
             double thr = 0.0;
             if (lane == 0) thr = weights[slot];     // issued ahead of the wait: its latency hides behind the stage

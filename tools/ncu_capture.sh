@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 echo "launch list rc=$?"
 # one full capture of each hot kernel (second step of the timed region)
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k1_minimizer_histogram|k2_cms_update|k3_filter|k3_resolve' -s 16 -c 4 \
+    -k regex:'k1_minimizer_histogram|k1_jump_queue|k2_cms_update|k3_filter|k3_resolve' -s 20 -c 5 \
     -f -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/
