@@ -12,8 +12,9 @@ LIB_PATH = os.path.join(HERE, "libhulk_b200.so")
 EXPORTS = [
     "hulk_b200_version", "hulk_b200_strerror", "hulk_b200_last_error", "hulk_b200_create",
     "hulk_b200_destroy", "hulk_b200_set_cws_tables", "hulk_b200_generate_cws_tables",
+    "hulk_b200_generate_cws_tables_async",
     "hulk_b200_set_cws_tables_device", "hulk_b200_reset", "hulk_b200_profile_enable", "hulk_b200_profile_read", "hulk_b200_profile_timeline", "hulk_b200_set_overlap",
-    "hulk_b200_new_cws", "hulk_b200_push_reads", "hulk_b200_push_reads_fixed",
+    "hulk_b200_new_cws", "hulk_b200_new_cws_parallel", "hulk_b200_push_reads", "hulk_b200_push_reads_fixed",
     "hulk_b200_push_reads_device", "hulk_b200_sync_inputs", "hulk_b200_flush", "hulk_b200_sync",
     "hulk_b200_finish", "hulk_b200_snapshot_async", "hulk_b200_get_stats", "hulk_b200_histogram_device_ptr", "hulk_b200_stream",
     "hulk_b200_merge_histogram", "hulk_b200_add_minimizer_count", "hulk_b200_get_histogram", "hulk_b200_get_estimates",
@@ -72,6 +73,7 @@ def load():
         "hulk_b200_destroy": (None, [vp]),
         "hulk_b200_set_cws_tables": (C.c_int, [vp, vp, vp, vp]),
         "hulk_b200_generate_cws_tables": (C.c_int, [vp]),
+        "hulk_b200_generate_cws_tables_async": (C.c_int, [vp]),
         "hulk_b200_set_cws_tables_device": (C.c_int, [vp, vp, vp, vp]),
         "hulk_b200_reset": (C.c_int, [vp]),
         "hulk_b200_profile_enable": (C.c_int, [vp, C.c_int]),
@@ -79,6 +81,7 @@ def load():
         "hulk_b200_profile_timeline": (C.c_int, [vp, vp, u64, C.POINTER(u64)]),
         "hulk_b200_profile_read": (C.c_int, [vp, C.POINTER(Profile)]),
         "hulk_b200_new_cws": (C.c_int, [u32, i32, u32, u32, vp, vp, vp]),
+        "hulk_b200_new_cws_parallel": (C.c_int, [u32, i32, u32, u32, vp, vp, vp, u32, u64]),
         "hulk_b200_push_reads": (C.c_int, [vp, vp, vp, u64]),
         "hulk_b200_push_reads_fixed": (C.c_int, [vp, vp, u64, u32]),
         "hulk_b200_push_reads_device": (C.c_int, [vp, vp, vp, u64, u32]),

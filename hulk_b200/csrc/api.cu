@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hulk_b200.h"
@@ -95,6 +96,11 @@ struct hulk_b200_ctx {
     unsigned long long *d_sketch = nullptr;
     double *d_weights = nullptr;
     bool tables_set = false;
+    // generate_cws_tables_async: the host draw runs on its own thread; the first flush (or set/finish) joins it
+    std::thread gen_thread;
+    std::vector<double> gen_r, gen_c, gen_b;
+    int gen_rc = 0;
+    bool gen_pending = false;
 
     hulk_b200_stats st{};
     uint64_t extra_minimizers = 0;
@@ -204,6 +210,7 @@ static cudaError_t dmalloc(T **p, uint64_t n) {
 
 void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->gen_thread.joinable()) ctx->gen_thread.join();
     cudaSetDevice(ctx->P.device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < NBUF; i++)
@@ -586,6 +593,36 @@ int hulk_b200_profile_timeline(hulk_b200_ctx *ctx, double *rows, uint64_t cap, u
     return HULK_B200_OK;
 }
 
+int hulk_b200_generate_cws_tables_async(hulk_b200_ctx *ctx) {
+    if (!ctx) return HULK_B200_EARG;
+    if (ctx->gen_pending) return fail(ctx, HULK_B200_ESTATE, "table generation already running");
+    const uint64_t n = (uint64_t)ctx->rows * (uint64_t)ctx->D;
+    try {
+        ctx->gen_r.resize(n ? n : 1); ctx->gen_c.resize(n ? n : 1); ctx->gen_b.resize(n ? n : 1);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, HULK_B200_ENOMEM, "host memory for the CWS tables");
+    }
+    ctx->gen_pending = true;
+    ctx->gen_thread = std::thread([ctx] {
+        ctx->gen_rc = hulk_b200_new_cws(ctx->s, ctx->D, ctx->P.slot_begin, ctx->P.slot_end, ctx->gen_r.data(),
+                                        ctx->gen_c.data(), ctx->gen_b.data());
+    });
+    return HULK_B200_OK;
+}
+// join the generator thread (if any) and upload its tables
+static int finish_async_tables(hulk_b200_ctx *ctx) {
+    if (!ctx->gen_pending) return HULK_B200_OK;
+    if (ctx->gen_thread.joinable()) ctx->gen_thread.join();
+    ctx->gen_pending = false;
+    int rc = ctx->gen_rc;
+    if (rc == HULK_B200_OK) rc = upload_tables(ctx, ctx->gen_r.data(), ctx->gen_c.data(), ctx->gen_b.data());
+    else fail(ctx, rc);
+    std::vector<double>().swap(ctx->gen_r);
+    std::vector<double>().swap(ctx->gen_c);
+    std::vector<double>().swap(ctx->gen_b);
+    return rc;
+}
+
 int hulk_b200_generate_cws_tables(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
@@ -870,6 +907,11 @@ int hulk_b200_sync_inputs(hulk_b200_ctx *ctx) {
 // ------------------------------------------------------------------------------------------
 int hulk_b200_flush(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
+    if (ctx->gen_pending) {
+        CU(cudaSetDevice(ctx->P.device));
+        const int rc = finish_async_tables(ctx);
+        if (rc) return rc;
+    }
     if (!ctx->tables_set) return fail(ctx, HULK_B200_ESTATE, "CWS tables not set (set_cws_tables / generate_cws_tables)");
     CU(cudaSetDevice(ctx->P.device));
     cudaStream_t st = ctx->stream;

@@ -38,11 +38,15 @@ void logf(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(msg, sizeof msg, fmt, ap);
     va_end(ap);
-    const time_t t = time(nullptr);
+    struct timespec now;
+    clock_gettime(CLOCK_REALTIME, &now);
+    const time_t t = now.tv_sec;
     struct tm tmv;
     localtime_r(&t, &tmv);
-    char ts[32];
-    strftime(ts, sizeof ts, "%Y/%m/%d %H:%M:%S", &tmv);
+    char ts[48];
+    size_t tl = strftime(ts, sizeof ts, "%Y/%m/%d %H:%M:%S", &tmv);
+    static const bool micros = getenv("HULK_LOG_MICROSECONDS") != nullptr;     // Go's log.Lmicroseconds, for timing runs
+    if (micros) snprintf(ts + tl, sizeof ts - tl, ".%06ld", now.tv_nsec / 1000);
     size_t n = strlen(msg);
     while (n && msg[n - 1] == '\n') msg[--n] = 0;
     fprintf(g_log, "%s %s\n", ts, msg);
@@ -376,7 +380,7 @@ int run_sketch(int argc, char **argv) {
     hulk_b200_ctx *ctx = nullptr;
     rc = hulk_b200_create(&P, &ctx);                        // findMinimizers + NewHistoSketch parameter checks
     if (rc) fatal(hulk_b200_last_error(nullptr));
-    rc = hulk_b200_generate_cws_tables(ctx);                // NewHistoSketch -> newCWS
+    rc = hulk_b200_generate_cws_tables_async(ctx);          // NewHistoSketch -> newCWS, drawn while the reads are counted
     if (rc) fatal(hulk_b200_last_error(ctx));
 
     rc = hulk_b200_sketch_reader(ctx, rd, o.interval, log_line, nullptr);

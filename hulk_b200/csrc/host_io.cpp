@@ -5,11 +5,14 @@
 //   * the HULKdata JSON exactly as encoding/json.MarshalIndent(..., "", "    ") emits it
 //     (src/sketchio/sketchio.go:20-34,78-97; src/histosketch/histosketch.go:36-47).
 // No CUDA in this file.
+#include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hulk_b200.h"
@@ -58,6 +61,68 @@ struct GoSource {
         const uint64_t x = vec[feed] + vec[tap];
         vec[feed] = x;
         return x;
+    }
+    // ---- jump-ahead.  The recurrence s[n] = s[n-607] + s[n-273] (mod 2^64) is linear, so the state N
+    // outputs further on is x^N mod (x^607 - x^334 - 1) applied to the current window (the same algebra
+    // tools/gen_rng_cooked.py uses to rebuild rngCooked).  vec[(334 - m) mod 607] holds s[m].
+    static int pmod(long v) { v %= kRngLen; return (int)(v < 0 ? v + kRngLen : v); }
+    // out = a * b mod (x^607 - x^334 - 1), coefficients mod 2^64
+    static void polymul(const uint64_t *a, const uint64_t *b, uint64_t *out) {
+        std::vector<uint64_t> res(2 * kRngLen - 1, 0);
+        for (int i = 0; i < kRngLen; i++) {
+            const uint64_t ai = a[i];
+            if (!ai) continue;
+            for (int j = 0; j < kRngLen; j++) res[i + j] += ai * b[j];
+        }
+        for (int d = 2 * kRngLen - 2; d >= kRngLen; d--) {       // x^607 = x^334 + 1
+            const uint64_t c = res[d];
+            res[d - kRngLen + (kRngLen - kRngTap)] += c;
+            res[d - kRngLen] += c;
+        }
+        std::copy(res.begin(), res.begin() + kRngLen, out);
+    }
+    static void xpow(uint64_t n, uint64_t *out) {                 // x^n mod P
+        std::vector<uint64_t> result(kRngLen, 0), base(kRngLen, 0);
+        result[0] = 1;
+        base[1] = 1;
+        while (n) {
+            if (n & 1) polymul(result.data(), base.data(), result.data());
+            n >>= 1;
+            if (n) polymul(base.data(), base.data(), base.data());
+        }
+        std::copy(result.begin(), result.end(), out);
+    }
+    // advance by n outputs given xn = x^n mod P
+    void jump(const uint64_t *xn, uint64_t n) {
+        const int ph = pmod(-(long)tap);                          // outputs so far, mod 607
+        uint64_t init[kRngLen], res[kRngLen], outv[kRngLen];
+        for (int j = 0; j < kRngLen; j++) init[j] = vec[pmod(334L - ph + 606 - j)];   // s[n0 - 606 + j]
+        std::copy(xn, xn + kRngLen, res);
+        for (int t = 0; t < kRngLen; t++) {                       // s[n0 + n - 606 + t]
+            uint64_t acc = 0;
+            for (int j = 0; j < kRngLen; j++) acc += res[j] * init[j];
+            outv[t] = acc;
+            const uint64_t c = res[kRngLen - 1];                  // res *= x
+            for (int j = kRngLen - 1; j > 0; j--) res[j] = res[j - 1];
+            res[0] = c;
+            res[kRngLen - kRngTap] += c;
+        }
+        const int ph2 = (int)((ph + n % kRngLen) % kRngLen);
+        for (int t = 0; t < kRngLen; t++) vec[pmod(334L - ph2 + 606 - t)] = outv[t];
+        tap = pmod(-(long)ph2);
+        feed = pmod(334L - ph2);
+    }
+    void skip(uint64_t n) {
+        if (n < 4096) { for (uint64_t i = 0; i < n; i++) next(); return; }
+        std::vector<uint64_t> xn(kRngLen);
+        xpow(n, xn.data());
+        jump(xn.data(), n);
+    }
+    // Float64() of one raw output; *is_one: it rounded to 1.0 (rand.Float64 draws again)
+    static inline double to_float64(uint64_t raw, bool *is_one) {
+        const double f = (double)(int64_t)(raw & 0x7fffffffffffffffULL) / 9223372036854775808.0;
+        *is_one = (f == 1.0);
+        return f;
     }
     // rand.Float64(): float64(Int63()) / (1 << 63), resampled when it rounds to 1.0
     inline double float64() {
@@ -234,14 +299,187 @@ std::string go_string(const char *s) {
     return out;
 }
 
+// ------------------------------------------------------------------------------------------
+// newCWS on all host cores, bit-identical to the sequential draw.
+//
+// The gamma stream is one generator consumed in order by a rejection sampler, so draw #m sits at a
+// data-dependent position.  What makes it splittable: (1) the raw generator can jump ahead; (2) an
+// attempt consumes two uniforms except when u1 falls outside (1e-7, 0.9999999), which consumes one --
+// those rare positions (~2e-7 of all) are found by a scan of the raw stream and resolved sequentially,
+// which fixes the attempt phase at every chunk boundary; (3) every thread then runs the sampler over its
+// chunk of the RAW stream into a local buffer, a prefix sum over the accepted counts gives each chunk
+// its first draw index, and the draws are scattered to r (even draws) and c = ln (odd draws).
+// The uniform stream of b has a fixed position per element.  A raw output that converts to exactly 1.0
+// (Float64 redraws; probability 2^-53 per output) shifts every later position: the parallel draw gives up
+// and the caller falls back to the sequential loop.
+// ------------------------------------------------------------------------------------------
+struct GammaChunk {
+    uint64_t begin = 0, end = 0;              // raw positions [begin, end)
+    uint64_t start = 0;                       // first attempt start >= begin
+    std::vector<uint64_t> extremes;           // raw positions in [begin, end) whose uniform is outside (1e-7, .9999999)
+    std::vector<double> draws;                // accepted x, in order
+    bool saw_one = false;
+};
+
+bool new_cws_parallel(uint32_t slot_begin, uint32_t slot_end, int32_t num_bins, double *r, double *c, double *b,
+                      unsigned n_threads, uint64_t chunk_raw) {
+    const uint64_t D = (uint64_t)num_bins;
+    const uint64_t E = (uint64_t)slot_end * D;                    // elements drawn (rows below slot_begin are discarded)
+    const uint64_t skip_elems = (uint64_t)slot_begin * D;
+    const uint64_t need = 2 * E;                                  // gamma draws: r, c, r, c, ...
+    if (E == 0) return true;
+    const unsigned T = std::max(1u, n_threads);
+    static const double kMagic = 1.0 + std::log(4.5);
+    const double alpha = 2.0, ainv = std::sqrt(2.0 * alpha - 1.0), bbb = alpha - std::log(4.0), ccc = alpha + ainv;
+
+    // per-thread generator positioned at its first chunk; the stride between a thread's chunks is fixed
+    std::vector<GoSource> src(T, GoSource(1));
+    std::vector<uint64_t> stride_poly(kRngLen);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++)
+            th.emplace_back([&, t] {
+                if (t == 0) GoSource::xpow((uint64_t)T * chunk_raw, stride_poly.data());
+                else src[t].skip((uint64_t)t * chunk_raw);
+            });
+        for (auto &x : th) x.join();
+    }
+    std::vector<GammaChunk> ch(T);
+    std::vector<std::vector<uint64_t>> raw(T);
+    uint64_t produced = 0;                                        // gamma draws placed so far
+    uint64_t next_start = 0;                                      // first attempt start of the next chunk
+    std::atomic<bool> failed(false);
+    for (uint64_t round = 0; produced < need && !failed; round++) {
+        // pass 1: raw outputs of every chunk (+2 look-ahead) and their extreme positions
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; t++)
+                th.emplace_back([&, t] {
+                    GammaChunk &k = ch[t];
+                    k.begin = (round * T + t) * chunk_raw;
+                    k.end = k.begin + chunk_raw;
+                    k.extremes.clear();
+                    k.saw_one = false;
+                    GoSource g = src[t];                          // copy: src[t] stays at the chunk start for the jump
+                    std::vector<uint64_t> &v = raw[t];
+                    v.resize(chunk_raw + 2);
+                    for (uint64_t i = 0; i < chunk_raw + 2; i++) {
+                        const uint64_t x = g.next();
+                        v[i] = x;
+                        bool one;
+                        const double u = GoSource::to_float64(x, &one);
+                        if (one) k.saw_one = true;
+                        if (i < chunk_raw && !(1e-7 < u && u < .9999999)) k.extremes.push_back(k.begin + i);
+                    }
+                    src[t].jump(stride_poly.data(), (uint64_t)T * chunk_raw);
+                });
+            for (auto &x : th) x.join();
+        }
+        // resolve the attempt phase at every chunk boundary (sequential, a handful of events)
+        for (unsigned t = 0; t < T; t++) {
+            GammaChunk &k = ch[t];
+            if (k.saw_one) { failed = true; break; }
+            uint64_t pos = next_start;                            // an attempt starts here (begin or begin + 1)
+            k.start = pos;
+            for (uint64_t e : k.extremes) {
+                if (e < pos) continue;
+                if (((e - pos) & 1) == 0) pos = e + 1;            // it is a u1: the attempt consumed one uniform
+            }
+            next_start = ((k.end > pos) && ((k.end - pos) & 1)) ? k.end + 1 : std::max(k.end, pos);
+        }
+        if (failed) break;
+        // pass 2: the sampler over every chunk
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; t++)
+                th.emplace_back([&, t] {
+                    GammaChunk &k = ch[t];
+                    const std::vector<uint64_t> &v = raw[t];
+                    k.draws.clear();
+                    k.draws.reserve(chunk_raw / 2 + 16);
+                    bool one;
+                    uint64_t p = k.start;
+                    while (p < k.end) {
+                        const double u1 = GoSource::to_float64(v[p - k.begin], &one);
+                        if (!(1e-7 < u1 && u1 < .9999999)) { p += 1; continue; }
+                        const double u2 = 1.0 - GoSource::to_float64(v[p + 1 - k.begin], &one);
+                        p += 2;
+                        const double vv = std::log(u1 / (1.0 - u1)) / ainv;
+                        const double x = alpha * std::exp(vv);
+                        const double z = u1 * u1 * u2;
+                        const double rr = bbb + ccc * vv - x;
+                        if (rr + kMagic - 4.5 * z >= 0.0 || rr >= std::log(z)) k.draws.push_back(x * 1.0);
+                    }
+                });
+            for (auto &x : th) x.join();
+        }
+        // scatter: draw m -> element m / 2, r when m is even, c = ln when odd
+        {
+            std::vector<uint64_t> first(T);
+            for (unsigned t = 0; t < T; t++) {
+                first[t] = produced;
+                produced += ch[t].draws.size();
+            }
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; t++)
+                th.emplace_back([&, t] {
+                    const GammaChunk &k = ch[t];
+                    uint64_t m = first[t];
+                    for (size_t i = 0; i < k.draws.size() && m < need; i++, m++) {
+                        const uint64_t elem = m >> 1;
+                        if (elem < skip_elems) continue;
+                        const uint64_t at = elem - skip_elems;
+                        if (m & 1) c[at] = std::log(k.draws[i]);
+                        else r[at] = k.draws[i];
+                    }
+                });
+            for (auto &x : th) x.join();
+        }
+    }
+    if (failed) return false;
+    // b = U * r, element e uses uniform #e of its own generator (histosketch.go:104,116)
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++)
+            th.emplace_back([&, t] {
+                const uint64_t e0 = E * t / T, e1 = E * (t + 1) / T;
+                GoSource g(1);
+                g.skip(e0);
+                for (uint64_t e = e0; e < e1; e++) {
+                    bool one;
+                    const double u = GoSource::to_float64(g.next(), &one);
+                    if (one) { failed = true; return; }
+                    if (e >= skip_elems) b[e - skip_elems] = (0.0 + u * (1.0 - 0.0)) * r[e - skip_elems];
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    return !failed;
+}
+
 }  // namespace
 
 extern "C" {
+
+// test hook: the parallel draw with an explicit thread count and raw-chunk length; returns 1 when it had to give up
+int hulk_b200_new_cws_parallel(uint32_t s, int32_t num_bins, uint32_t slot_begin, uint32_t slot_end, double *r,
+                               double *c, double *b, uint32_t n_threads, uint64_t chunk_raw) {
+    if (!r || !c || !b || num_bins < 0 || slot_begin > slot_end || chunk_raw < 16) return HULK_B200_EARG;
+    if (slot_end > s) slot_end = s;
+    return new_cws_parallel(slot_begin, slot_end, num_bins, r, c, b, n_threads, chunk_raw) ? 0 : 1;
+}
 
 int hulk_b200_new_cws(uint32_t s, int32_t num_bins, uint32_t slot_begin, uint32_t slot_end, double *r, double *c,
                       double *b) {
     if (!r || !c || !b || num_bins < 0 || slot_begin > slot_end) return HULK_B200_EARG;
     if (slot_end > s) slot_end = s;
+    // large tables: all host cores (bit-identical to the loop below, see new_cws_parallel)
+    const uint64_t elems = (uint64_t)slot_end * (uint64_t)num_bins;
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (elems >= (1u << 20) && hw > 1) {
+        const unsigned T = std::min(hw, 32u);
+        if (new_cws_parallel(slot_begin, slot_end, num_bins, r, c, b, T, 1u << 21)) return HULK_B200_OK;
+    }
     GoSource gamma_src(1), unif_src(1);                       // DISTRIBUTION_SEED  histosketch.go:20,103-104
     for (uint32_t i = 0; i < slot_end; i++) {
         for (int32_t j = 0; j < num_bins; j++) {

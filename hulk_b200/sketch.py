@@ -174,9 +174,11 @@ class HistoSketch:
         names = ("k1_minimizer_histogram", "k2_countmin", "k3_filter", "k3_resolve")
         return {n: {"ms": pr.ms[i], "launches": int(pr.launches[i])} for i, n in enumerate(names)}
 
-    def generate_tables(self):
-        """newCWS with the reference's seeded streams (histosketch.go:95-126)."""
-        self._check(self._L.hulk_b200_generate_cws_tables(self._ctx))
+    def generate_tables(self, background: bool = False):
+        """newCWS with the reference's seeded streams (histosketch.go:95-126).  background=True draws on a
+        host thread while reads are pushed; the first flush waits for it."""
+        fn = self._L.hulk_b200_generate_cws_tables_async if background else self._L.hulk_b200_generate_cws_tables
+        self._check(fn(self._ctx))
 
     # -- stage 1+2 ---------------------------------------------------------------------------
     def add_reads(self, bases: np.ndarray, offsets: np.ndarray):

@@ -213,12 +213,22 @@ def test_sketch_with_concept_drift(hb, oracle, decay):
     _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=(0.0 if decay == 0.0 else 1e-9))
 
 
+def test_c3_shape_k31_drift(hb, oracle):
+    # BASELINE config C3 at reduced size: k=31 (D = 923 521, integer-compare scan path), concept drift on
+    k, s, decay = 31, 12, 0.02
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 23)
+    batches = [[bytes(r) for r in hb.synthetic_reads(15000, 150, seed=31, first_read=15000 * i)] for i in range(3)]
+    st = _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=1e-9)
+    assert st["n_flushes"] == 3
+
+
 def test_c1_golden_json(hb, fixture_reads):
     # BASELINE config C1: hulk sketch -f testing/test-reads-small.fq.gz -k 21 -s 50, Go-compatible tables
     for name, decay, interval in (("c1_k21_s50.json", 1.0, 0), ("c1_k21_s50_x02_i250.json", 0.2, 250)):
         want = open(os.path.join(GOLDEN, name)).read()
         with hb.HistoSketch(21, 9, 50, decay) as hs:
-            hs.generate_tables()
+            hs.generate_tables(background=(interval != 0))     # the drawn-while-counting path gives the same tables
             mins, weights, st = hb.sketch_reads(hs, [hb.pack_reads(fixture_reads)], interval=interval)
         doc = hb.sketch_json("testing/test-reads-small.fq.gz,", 21, mins, weights, 194481, decay != 1.0)
         wj, gj = json.loads(want), json.loads(doc)

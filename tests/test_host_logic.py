@@ -70,6 +70,22 @@ def test_new_cws_equals_oracle(oracle):
     np.testing.assert_array_equal(b2, bo[2:4])
 
 
+@pytest.mark.parametrize("s,D,sb,se,T,chunk", [(3, 1000, 0, 3, 4, 64), (5, 777, 2, 5, 3, 100), (2, 50000, 0, 2, 7, 4096),
+                                               (4, 14641, 1, 3, 8, 1 << 14), (6, 14641, 0, 6, 5, 1000)])
+def test_parallel_cws_draw_is_bit_identical(oracle, s, D, sb, se, T, chunk):
+    # jump-ahead of Go's ALFG + sequential resolution of the rejection sampler's phase: same tables as the
+    # one-generator loop of histosketch.go:95-126, whatever the thread count and chunk length
+    L = hulk_b200.load()
+    rows = se - sb
+    r, c, b = (np.full((rows, D), np.nan) for _ in range(3))
+    rc = L.hulk_b200_new_cws_parallel(s, D, sb, se, r.ctypes.data, c.ctypes.data, b.ctypes.data, T, chunk)
+    assert rc == 0
+    ro, co, bo = oracle.new_cws(s, D)
+    np.testing.assert_array_equal(r, ro[sb:se])
+    np.testing.assert_array_equal(c, co[sb:se])
+    np.testing.assert_array_equal(b, bo[sb:se])
+
+
 def test_md5_and_json_equal_oracle_side():
     rng = np.random.default_rng(0)
     mins = rng.integers(0, 923521, 64).astype(np.uint64)
