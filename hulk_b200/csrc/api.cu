@@ -72,6 +72,7 @@ struct hulk_b200_ctx {
     uint64_t queue_cap[NBUF] = {};
     int k1_ctas_per_sm = 4;                    // scan CTAs per SM in queue mode (tasks are handed out dynamically):
                                                // one short of what fits, so the flush chain always finds SM room
+    uint64_t max_launch_reads = 1ull << 22;    // reads per k1 launch (HULK_B200_MAX_LAUNCH_READS)
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
     bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
@@ -389,6 +390,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         ctx->force_tile_path = e && *e == '1';
         e = getenv("HULK_B200_K1_CTAS");
         if (e && *e >= '1' && *e <= '0' + K1_W9_CTAS_PER_SM) ctx->k1_ctas_per_sm = *e - '0';
+        e = getenv("HULK_B200_MAX_LAUNCH_READS");
+        if (e && atoll(e) >= 32) ctx->max_launch_reads = (uint64_t)atoll(e);
         e = getenv("HULK_B200_JUMP_BATCH");
         if (e && (*e == '2' || *e == '4')) ctx->jump_batch = *e - '0';
         e = getenv("HULK_B200_K1_FUSED");
@@ -659,9 +662,46 @@ static void k1_geometry(const hulk_b200_ctx *ctx, uint64_t n_reads, uint64_t tot
 // enqueue the minimizer/histogram kernels over one device-resident batch
 // hs: which spectrum buffer / overflow set to use; st: the stream to enqueue on
 template <bool DUMP>
+static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t *d_bases, uint64_t bases_bytes,
+                         const uint64_t *d_offsets, uint64_t off_base, uint32_t fixed_len, uint64_t n_reads,
+                         uint64_t total_bytes, uint64_t *d_dump, uint32_t dump_cap, uint32_t *d_dump_counts,
+                         uint64_t first_read);
+
+// A batch of any size: launches of at most max_launch_reads reads each (bounds the minimizer queue and keeps
+// its indices in 32 bits), back to back on the same stream.
+template <bool DUMP>
 static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t *d_bases, uint64_t bases_bytes,
                      const uint64_t *d_offsets, uint64_t off_base, uint32_t fixed_len, uint64_t n_reads,
                      uint64_t total_bytes, uint64_t *d_dump, uint32_t dump_cap, uint32_t *d_dump_counts) {
+    const uint64_t step = ctx->max_launch_reads;
+    if (n_reads <= step)
+        return launch_k1_one<DUMP>(ctx, hs, st, d_bases, bases_bytes, d_offsets, off_base, fixed_len, n_reads,
+                                   total_bytes, d_dump, dump_cap, d_dump_counts, 0);
+    const uint64_t avg = total_bytes / n_reads + 1;
+    for (uint64_t r0 = 0; r0 < n_reads; r0 += step) {
+        const uint64_t nr = std::min(step, n_reads - r0);
+        int rc;
+        if (fixed_len) {      // the sub-batch is its own byte range
+            const uint64_t skip = r0 * (uint64_t)fixed_len;
+            rc = launch_k1_one<DUMP>(ctx, hs, st, d_bases + skip, bases_bytes > skip ? bases_bytes - skip : 0, nullptr,
+                                     off_base, fixed_len, nr, nr * (uint64_t)fixed_len,
+                                     d_dump ? d_dump + r0 * dump_cap : nullptr, dump_cap,
+                                     d_dump_counts ? d_dump_counts + r0 : nullptr, r0);
+        } else {              // same byte range, the offsets array is entered further in
+            rc = launch_k1_one<DUMP>(ctx, hs, st, d_bases, bases_bytes, d_offsets + r0, off_base, 0, nr, nr * avg,
+                                     d_dump ? d_dump + r0 * dump_cap : nullptr, dump_cap,
+                                     d_dump_counts ? d_dump_counts + r0 : nullptr, r0);
+        }
+        if (rc) return rc;
+    }
+    return HULK_B200_OK;
+}
+
+template <bool DUMP>
+static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t *d_bases, uint64_t bases_bytes,
+                         const uint64_t *d_offsets, uint64_t off_base, uint32_t fixed_len, uint64_t n_reads,
+                         uint64_t total_bytes, uint64_t *d_dump, uint32_t dump_cap, uint32_t *d_dump_counts,
+                         uint64_t first_read) {
     if (n_reads == 0) return HULK_B200_OK;
     K1Params p{};
     p.bases = d_bases;
@@ -669,7 +709,7 @@ static int launch_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint8_t 
     p.offsets = d_offsets;
     p.fixed_len = fixed_len;
     p.n_reads = n_reads;
-    p.read_base = ctx->st.n_reads;
+    p.read_base = ctx->st.n_reads + first_read;
     p.off_base = off_base;
     p.k = ctx->P.k;
     p.w = ctx->P.w;

@@ -161,6 +161,41 @@ def test_device_resident_input_equals_host_input(hb):
         np.testing.assert_array_equal(2 * a.histogram(), b.histogram())
 
 
+def test_large_batches_are_split_into_bounded_launches(hb, monkeypatch):
+    # a push of any size becomes k1 launches of bounded size (here forced down to 1000 reads): same spectrum,
+    # same per-read error reporting, for fixed-length, offset-addressed and device-resident input
+    import torch
+    n, L = 12345, 150
+    reads = hb.synthetic_reads(n, L, seed=9)
+    ragged = random_reads(3000, 100, seed=10, n_frac=0.01, ragged=80)
+    with hb.HistoSketch(21, 9, 4) as ref:
+        ref.add_reads_fixed(reads.reshape(-1), n, L)
+        ref.add_seqs(ragged)
+        want, want_n = ref.histogram(), ref.stats()["n_minimizers"]
+    monkeypatch.setenv("HULK_B200_MAX_LAUNCH_READS", "1000")
+    with hb.HistoSketch(21, 9, 4) as a:
+        a.add_reads_fixed(reads.reshape(-1), n, L)
+        a.add_seqs(ragged)
+        np.testing.assert_array_equal(a.histogram(), want)
+        assert a.stats()["n_minimizers"] == want_n
+        sets, counts = a.minimizers(ragged[:2500])
+        assert int(counts.sum()) > 0 and len(sets) == 2500
+    with hb.HistoSketch(21, 9, 4) as b:
+        t = torch.from_numpy(reads.reshape(-1).copy()).cuda()
+        bases, offs = hb.pack_reads(ragged)
+        tb, to = torch.from_numpy(bases).cuda(), torch.from_numpy(offs.astype(np.int64)).cuda()
+        torch.cuda.synchronize()
+        b.add_reads_device(t.data_ptr(), None, n, L)
+        b.add_reads_device(tb.data_ptr(), to.data_ptr(), len(ragged), 0)
+        np.testing.assert_array_equal(b.histogram(), want)
+    with hb.HistoSketch(21, 9, 4) as c:
+        bad = ragged[:1500] + [b"ACGT"] + ragged[1500:]
+        with pytest.raises(hb.HulkError) as e:
+            c.add_seqs(bad)
+            c.sync()
+        assert e.value.code == -4 and "read 1500" in str(e.value)
+
+
 # ---- stage 3: count-min + CWS ---------------------------------------------------------------------
 def _run_both(hb, oracle, k, w, s, decay, reads_batches, tables, check_estimates=True, rtol_f=0.0):
     D = hb.spectrum_size(k)
