@@ -86,8 +86,14 @@ struct hulk_b200_ctx {
     int32_t *d_csr_bins = nullptr;
     uint32_t *d_words = nullptr, *d_word_prefix = nullptr, *d_block_count = nullptr, *d_block_prefix = nullptr;
     double *d_q = nullptr;
-    unsigned long long *d_fbits = nullptr;
-    float *d_invf = nullptr;
+    // estimate vectors, double-buffered: the count-min update of flush i+1 (k2 stream) overlaps the CWS
+    // sweep of flush i (main stream)
+    unsigned long long *d_fbits[2] = {nullptr, nullptr};
+    float *d_invf[2] = {nullptr, nullptr};
+    int flush_idx = 0, last_flush_idx = 0;     // parity of the next / the latest flush
+    cudaStream_t k2_stream = nullptr;
+    cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k3_done[2] = {nullptr, nullptr};
+    bool k3_pending[2] = {false, false};
 
     // stage 3b
     double *d_r = nullptr, *d_c = nullptr, *d_b = nullptr;
@@ -216,6 +222,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < NBUF; i++)
         if (ctx->k1_stream[i]) cudaStreamSynchronize(ctx->k1_stream[i]);
+    if (ctx->k2_stream) cudaStreamSynchronize(ctx->k2_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < NBUF; i++) {
         void *per[] = {ctx->d_hist[i], ctx->d_ovf_count[i], ctx->d_ovf_list[i], ctx->d_arena[i], ctx->d_arena_cursor[i],
@@ -229,7 +236,8 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     }
     void *ptrs[] = {ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
-                    ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits, ctx->d_invf, ctx->d_r, ctx->d_c,
+                    ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits[0], ctx->d_fbits[1], ctx->d_invf[0],
+                    ctx->d_invf[1], ctx->d_r, ctx->d_c,
                     ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights, ctx->d_cand};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -243,6 +251,11 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
         if (ctx->k1_stream[i]) cudaStreamDestroy(ctx->k1_stream[i]);
     }
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_k2_done[i]) cudaEventDestroy(ctx->ev_k2_done[i]);
+        if (ctx->ev_k3_done[i]) cudaEventDestroy(ctx->ev_k3_done[i]);
+    }
+    if (ctx->k2_stream) cudaStreamDestroy(ctx->k2_stream);
     for (int c = 0; c < 4; c++)
         for (auto &pr : ctx->prof_events[c]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -255,6 +268,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
 static int sync_all(hulk_b200_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->copy_stream));
     for (int i = 0; i < NBUF; i++) CU(cudaStreamSynchronize(ctx->k1_stream[i]));
+    CU(cudaStreamSynchronize(ctx->k2_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return HULK_B200_OK;
 }
@@ -286,6 +300,11 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(cudaStreamCreateWithPriority(&ctx->k1_stream[i], cudaStreamNonBlocking, prio_least));
     }
     CU(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithPriority(&ctx->k2_stream, cudaStreamNonBlocking, prio_greatest));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_k2_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_k3_done[i], cudaEventDisableTiming));
+    }
     const int32_t D = ctx->D;
     const uint32_t rows = ctx->rows;
     ctx->Dp = ((uint64_t)D + K3_SUB - 1) / K3_SUB * K3_SUB;
@@ -312,8 +331,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(dmalloc(&ctx->d_block_count, ctx->nblk));
     CU(dmalloc(&ctx->d_block_prefix, ctx->nblk));
     CU(dmalloc(&ctx->d_q, CMS_CELLS));
-    CU(dmalloc(&ctx->d_fbits, D));
-    CU(dmalloc(&ctx->d_invf, ctx->Dp));
+    for (int i = 0; i < 2; i++) {
+        CU(dmalloc(&ctx->d_fbits[i], D));
+        CU(dmalloc(&ctx->d_invf[i], ctx->Dp));
+    }
     CU(dmalloc(&ctx->d_m32, (uint64_t)rows * ctx->nsub_row));
     CU(dmalloc(&ctx->d_sketch, rows));
     CU(dmalloc(&ctx->d_cand, rows));
@@ -329,7 +350,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->d_errword, 0xff, 8, st));
     CU(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(FlushCtl), st));
     CU(cudaMemsetAsync(ctx->d_q, 0, sizeof(double) * CMS_CELLS, st));
-    CU(cudaMemsetAsync(ctx->d_invf, 0xff, sizeof(float) * ctx->Dp, st));            // NaN padding
+    for (int i = 0; i < 2; i++) CU(cudaMemsetAsync(ctx->d_invf[i], 0xff, sizeof(float) * ctx->Dp, st));   // NaN padding
     CU(cudaMemsetAsync(ctx->d_sketch, 0, sizeof(unsigned long long) * (rows ? rows : 1), st));   // histosketch.go:84-87
     CU(cudaMemsetAsync(ctx->d_cand, 0, sizeof(unsigned int) * (rows ? rows : 1), st));
     {
@@ -384,6 +405,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, false, false>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, true, false>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true, 21>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false, true, 31>, attr, big));
     }
     {
         const char *e = getenv("HULK_B200_K1_TILE");
@@ -518,6 +541,8 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
         ctx->k1_pending[i] = false;
     }
     ctx->cur_hist = 0;
+    ctx->flush_idx = ctx->last_flush_idx = 0;
+    ctx->k3_pending[0] = ctx->k3_pending[1] = false;
     CU(cudaMemsetAsync(ctx->d_nmin, 0, 8, st));
     CU(cudaMemsetAsync(ctx->d_errword, 0xff, 8, st));
     CU(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(FlushCtl), st));
@@ -784,7 +809,13 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
             const uint64_t nctas = (n_reads + K1_TPB - 1) / K1_TPB;
             const int per_sm9 = use_queue ? ctx->k1_ctas_per_sm : K1_W9_CTAS_PER_SM;
             const unsigned grid9 = (unsigned)std::min<uint64_t>(nctas, (uint64_t)ctx->sm_count * per_sm9);
-            K1_DISPATCH(k1_minimizer_histogram_w9, grid9, smem9);
+            // the k values of the BASELINE configs get the scan with k folded in at compile time
+            if (use_queue && fp && ctx->P.k == 21)
+                k1_minimizer_histogram_w9<false, true, true, 21><<<grid9, K1_TPB, smem9, st>>>(p);
+            else if (use_queue && !fp && ctx->P.k == 31)
+                k1_minimizer_histogram_w9<false, false, true, 31><<<grid9, K1_TPB, smem9, st>>>(p);
+            else
+                K1_DISPATCH(k1_minimizer_histogram_w9, grid9, smem9);
         } else {
             K1_DISPATCH(k1_minimizer_histogram, grid, smem);
         }
@@ -954,53 +985,71 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
     }
     if (!ctx->tables_set) return fail(ctx, HULK_B200_ESTATE, "CWS tables not set (set_cws_tables / generate_cws_tables)");
     CU(cudaSetDevice(ctx->P.device));
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->stream;                                     // CWS sweep
+    cudaStream_t k2s = ctx->overlap ? ctx->k2_stream : ctx->stream;    // count-min update
     const int32_t D = ctx->D;
     const int hs = ctx->cur_hist;
+    const int fi = ctx->flush_idx;
     uint32_t *const hist = ctx->d_hist[hs];
-    if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(st, ctx->ev_k1_last[hs], 0));   // every read of the interval is counted
-    CU(cudaMemsetAsync(&ctx->d_ctl->nnz, 0, 4, st));
+    unsigned long long *const fbits = ctx->d_fbits[fi];
+    float *const invf = ctx->d_invf[fi];
+    if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k1_last[hs], 0));  // every read of the interval is counted
+    if (ctx->k3_pending[fi]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k3_done[fi], 0));  // the sweep two flushes back read this f
+    CU(cudaMemsetAsync(&ctx->d_ctl->nnz[fi], 0, 4, k2s));
     {
-    ProfScope prof_scope(ctx, 1);
-    k2_mask_count<<<ctx->nblk, 1024, 0, st>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count,
-                                              ctx->d_fbits, ctx->d_ctl);
+    ProfScope prof_scope(ctx, 1, k2s);
+    k2_mask_count<<<ctx->nblk, 1024, 0, k2s>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count, fbits,
+                                               ctx->d_ctl, fi);
     LAUNCH_CHECK("k2_mask_count");
-    k2_flush_decide<<<1, 1024, 0, st>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl);
+    k2_flush_decide<<<1, 1024, 0, k2s>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl, fi);
     LAUNCH_CHECK("k2_flush_decide");
-    k2_cms_update<<<(CMS_CELLS * 32 + 255) / 256, 256, 0, st>>>(hist, ctx->d_csr_start, ctx->d_csr_bins,
-                                                                ctx->d_words, ctx->d_word_prefix, ctx->d_block_prefix,
-                                                                ctx->d_q, ctx->d_fbits, ctx->d_ctl,
-                                                                ctx->apply_scaling ? 1 : 0, ctx->decay_weight);
+    k2_cms_update<<<(CMS_CELLS * 32 + 255) / 256, 256, 0, k2s>>>(hist, ctx->d_csr_start, ctx->d_csr_bins,
+                                                                 ctx->d_words, ctx->d_word_prefix, ctx->d_block_prefix,
+                                                                 ctx->d_q, fbits, ctx->d_ctl, fi,
+                                                                 ctx->apply_scaling ? 1 : 0, ctx->decay_weight);
     LAUNCH_CHECK("k2_cms_update");
-    k2_finalize<<<(unsigned)(((uint64_t)D + 255) / 256), 256, 0, st>>>(hist, D, ctx->d_fbits, ctx->d_invf,
-                                                                       ctx->d_ctl);
+    k2_finalize<<<(unsigned)(((uint64_t)D + 255) / 256), 256, 0, k2s>>>(hist, D, fbits, invf, ctx->d_ctl, fi);
     LAUNCH_CHECK("k2_finalize");
     }
     // the buffer is wiped: the next interval but one may count into it while the CWS sweep below runs
-    CU(cudaEventRecord(ctx->ev_hist_free[hs], st));
+    CU(cudaEventRecord(ctx->ev_hist_free[hs], k2s));
     ctx->k1_pending[hs] = false;
     ctx->cur_hist = (hs + 1) % ctx->nbuf;
+    ctx->last_flush_idx = fi;
+    ctx->flush_idx = fi ^ 1;
     if (ctx->rows) {
+        if (k2s != st) {
+            CU(cudaEventRecord(ctx->ev_k2_done[fi], k2s));
+            CU(cudaStreamWaitEvent(st, ctx->ev_k2_done[fi], 0));
+        }
         const int stages = ctx->k3_stages;
         const size_t smem = (size_t)stages * K3_SEG * 4 + 2 * stages * 8;
         const uint64_t T = (uint64_t)ctx->rows * ctx->nseg;
         const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)ctx->sm_count * ctx->k3_ctas_per_sm);
         {
             ProfScope prof_scope(ctx, 2);
-#define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, ctx->d_invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_weights, ctx->d_cand, \
-                       ctx->drift ? 1 : 0, ctx->d_ctl
+#define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_weights, ctx->d_cand, \
+                       ctx->drift ? 1 : 0, ctx->d_ctl, fi
             if (stages == 4) k3_filter<4><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
             else if (stages == 6) k3_filter<6><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
             else k3_filter<8><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
 #undef K3_FILTER_ARGS
             LAUNCH_CHECK("k3_filter");
         }
-        ProfScope prof_scope(ctx, 3);
-        k3_resolve<<<(ctx->rows * 32 + 127) / 128, 128, 0, st>>>(ctx->d_m32, ctx->nsub_row, ctx->d_r, ctx->d_c, ctx->d_b,
-                                                                 D, ctx->d_fbits, ctx->rows, ctx->d_sketch,
-                                                                 ctx->d_weights, ctx->drift ? 1 : 0, ctx->decay_weight,
-                                                                 ctx->d_cand, ctx->d_ctl);
-        LAUNCH_CHECK("k3_resolve");
+        {
+            ProfScope prof_scope(ctx, 3);
+            k3_resolve<<<(ctx->rows * 32 + 127) / 128, 128, 0, st>>>(ctx->d_m32, ctx->nsub_row, ctx->d_r, ctx->d_c,
+                                                                     ctx->d_b, D, fbits, ctx->rows, ctx->d_sketch,
+                                                                     ctx->d_weights, ctx->drift ? 1 : 0,
+                                                                     ctx->decay_weight, ctx->d_cand, ctx->d_ctl, fi);
+            LAUNCH_CHECK("k3_resolve");
+        }
+        CU(cudaEventRecord(ctx->ev_k3_done[fi], st));
+        ctx->k3_pending[fi] = true;
+    } else if (k2s != st) {
+        // no slots owned (a pure counting rank): keep the main stream ordered behind the flush all the same
+        CU(cudaEventRecord(ctx->ev_k2_done[fi], k2s));
+        CU(cudaStreamWaitEvent(st, ctx->ev_k2_done[fi], 0));
     }
     return HULK_B200_OK;
 }
@@ -1106,14 +1155,15 @@ int hulk_b200_histogram_device_ptr(hulk_b200_ctx *ctx, void **d_hist_u32, int32_
     // the spectrum of the interval being counted; work enqueued on the context's stream after this
     // call (e.g. the all-reduce across GPUs) sees every read pushed so far
     const int hs = ctx->cur_hist;
-    if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_k1_last[hs], 0));
+    cudaStream_t k2s = ctx->overlap ? ctx->k2_stream : ctx->stream;
+    if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k1_last[hs], 0));
     *d_hist_u32 = ctx->d_hist[hs];
     if (num_bins) *num_bins = ctx->D;
     return HULK_B200_OK;
 }
 int hulk_b200_stream(hulk_b200_ctx *ctx, void **cuda_stream) {
     if (!ctx || !cuda_stream) return HULK_B200_EARG;
-    *cuda_stream = ctx->stream;
+    *cuda_stream = ctx->overlap ? ctx->k2_stream : ctx->stream;    // where the flush starts: the spectrum's stream
     return HULK_B200_OK;
 }
 __global__ void k_merge_hist(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int32_t D) {
@@ -1154,8 +1204,8 @@ int hulk_b200_get_histogram(hulk_b200_ctx *ctx, uint32_t *hist) {
 int hulk_b200_get_estimates(hulk_b200_ctx *ctx, double *f) {
     if (!ctx || !f) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpy(f, ctx->d_fbits, sizeof(double) * (size_t)ctx->D, cudaMemcpyDeviceToHost));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    CU(cudaMemcpy(f, ctx->d_fbits[ctx->last_flush_idx], sizeof(double) * (size_t)ctx->D, cudaMemcpyDeviceToHost));
     for (int32_t i = 0; i < ctx->D; i++)
         if (std::isinf(f[i])) f[i] = NAN;
     return HULK_B200_OK;
@@ -1163,7 +1213,7 @@ int hulk_b200_get_estimates(hulk_b200_ctx *ctx, double *f) {
 int hulk_b200_get_cms(hulk_b200_ctx *ctx, double *q) {
     if (!ctx || !q) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
     CU(cudaMemcpy(q, ctx->d_q, sizeof(double) * CMS_CELLS, cudaMemcpyDeviceToHost));
     return HULK_B200_OK;
 }

@@ -189,20 +189,42 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
                                                 const uint32_t list_cap, uint32_t n, const bool valid,
                                                 const bool overflow, const uint64_t r, const uint32_t nb,
                                                 unsigned long long &local_minimizers) {
-    // ---- exact per-read set: drop values already present earlier in the list (minimizer.go:189-198)
+    // ---- exact per-read set: drop values already present earlier in the list (minimizer.go:189-198).
+    // Four candidates at a time: every entry of the accepted prefix is loaded once and compared with all
+    // four (independent compares, no load waits on a compare), then the four are compared with each
+    // other; survivors are appended in order (in place: m_out never passes the read cursor).
+    constexpr uint64_t NONE = Sentinel<FP>::value;           // never a list value
     uint32_t m_out = 0;
-    for (uint32_t a = 0; a < n; a++) {
-        const uint64_t x = my_list[a * 32];
-        bool dup = false;
-        uint32_t b = 0;
-        for (; b + 4 <= m_out; b += 4) {
-            const bool e0 = ueq64<FP>(my_list[b * 32], x), e1 = ueq64<FP>(my_list[(b + 1) * 32], x);
-            const bool e2 = ueq64<FP>(my_list[(b + 2) * 32], x), e3 = ueq64<FP>(my_list[(b + 3) * 32], x);
-            if (e0 | e1 | e2 | e3) dup = true;
+    for (uint32_t a = 0; a < n; a += 4) {
+        uint64_t x[4];
+        bool dup[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool have = a + u < n;
+            x[u] = have ? my_list[(a + u) * 32] : NONE;
+            dup[u] = !have;
         }
-        for (; b < m_out; b++)
-            if (ueq64<FP>(my_list[b * 32], x)) dup = true;
-        if (!dup) { my_list[m_out * 32] = x; m_out++; }
+        uint32_t b = 0;
+        for (; b + 2 <= m_out; b += 2) {
+            const uint64_t y0 = my_list[b * 32], y1 = my_list[(b + 1) * 32];
+#pragma unroll
+            for (int u = 0; u < 4; u++) dup[u] |= ueq64<FP>(y0, x[u]) | ueq64<FP>(y1, x[u]);
+        }
+        if (b < m_out) {
+            const uint64_t y0 = my_list[b * 32];
+#pragma unroll
+            for (int u = 0; u < 4; u++) dup[u] |= ueq64<FP>(y0, x[u]);
+        }
+        dup[1] |= ueq64<FP>(x[1], x[0]);
+        dup[2] |= ueq64<FP>(x[2], x[0]) | ueq64<FP>(x[2], x[1]);
+        dup[3] |= ueq64<FP>(x[3], x[0]) | ueq64<FP>(x[3], x[1]) | ueq64<FP>(x[3], x[2]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (!dup[u]) {
+                if (m_out != a + u) my_list[m_out * 32] = x[u];
+                m_out++;
+            }
+        }
     }
     if (DUMP) {
         if (valid) {
@@ -388,7 +410,7 @@ struct GlobalSrc8 {
     }
 };
 
-template <bool DUMP, bool FP, bool QUEUE>
+template <bool DUMP, bool FP, bool QUEUE, int KC = 0>
 __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histogram_w9(const K1Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *list_all = reinterpret_cast<uint64_t *>(smem);                       // [warps][list_cap][32]
@@ -430,7 +452,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
                     n += fresh ? 1u : 0u;                                        // n still counts them (overflow test)
                     last = fresh ? m : last;
                 };
-                k1_scan_read_w9<FP>(GlobalSrc8(p.bases + b0, len64, lim), (int32_t)len64, (int32_t)p.k, emit);
+                k1_scan_read_w9<FP, KC>(GlobalSrc8(p.bases + b0, len64, lim), (int32_t)len64, (int32_t)p.k, emit);
             }
         }
         const bool overflow = valid && n > list_cap;

@@ -167,9 +167,12 @@ HULK_UNROLL
     }
 };
 
-template <bool FP, class Src8, class Emit>
-HULK_HD void k1_scan_read_w9(Src8 src, int32_t len, int32_t k, Emit emit) {
+// KC: compile-time k (0 = use the run-time argument): with k fixed the 2k-bit mask, the shifts and the
+// xor-shift steps of hash64 on words that are known to be zero fold away.
+template <bool FP, int KC = 0, class Src8, class Emit>
+HULK_HD void k1_scan_read_w9(Src8 src, int32_t len, int32_t k_arg, Emit emit) {
     constexpr int32_t W = 9, B = 8;
+    const int32_t k = KC ? KC : k_arg;
     constexpr uint64_t SENT = Sentinel<FP>::value;
     const uint64_t mask = (1ull << (2 * k)) - 1ull;       // minimizer.go:103  (k <= 31)
     const int shift = 2 * (k - 1);                        // minimizer.go:104

@@ -33,8 +33,10 @@ constexpr unsigned long long F_EMPTY_BITS = 0x7FF0000000000000ull;   // +inf: bi
 
 // per-flush control block in device memory
 struct FlushCtl {
-    unsigned int nnz;              // used bins of the histogram being flushed
-    unsigned int go;               // 1: this flush runs; 0: histogram empty (no-op) or error
+    // two flushes can be in flight (count-min of flush i+1 while the CWS sweep of flush i runs): the
+    // per-flush words are indexed by the flush's parity `fi`
+    unsigned int nnz[2];           // used bins of the histogram being flushed
+    unsigned int go[2];            // 1: this flush runs; 0: histogram empty (no-op) or error
     int err;                       // sticky: HULK_B200_ESPARSE once a flush was < 1% used
     unsigned int pad;
     unsigned long long t0;         // AddElement calls before this flush
@@ -115,7 +117,8 @@ __global__ void k2_sort_csr(const unsigned int *start, int32_t *csr_bins) {
 __global__ void __launch_bounds__(1024) k2_mask_count(const uint32_t *__restrict__ hist, int32_t D,
                                                       uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
                                                       uint32_t *__restrict__ block_count,
-                                                      unsigned long long *__restrict__ fbits, FlushCtl *ctl) {
+                                                      unsigned long long *__restrict__ fbits, FlushCtl *ctl,
+                                                      const int fi) {
     __shared__ uint32_t pc[32];
     const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
     const bool nz = (i < D) && (hist[i] != 0u);
@@ -137,13 +140,14 @@ __global__ void __launch_bounds__(1024) k2_mask_count(const uint32_t *__restrict
         word_prefix[(size_t)blockIdx.x * 32 + lane] = s - v;   // used bins before this word, inside the block
         if (lane == 31) {
             block_count[blockIdx.x] = s;
-            if (s) atomicAdd(&ctl->nnz, s);
+            if (s) atomicAdd(&ctl->nnz[fi], s);
         }
     }
 }
 // (b) single block: exclusive scan of the per-block counts + the flush decision
 __global__ void __launch_bounds__(1024) k2_flush_decide(const uint32_t *__restrict__ block_count, uint32_t nblocks,
-                                                        uint32_t *__restrict__ block_prefix, int32_t D, FlushCtl *ctl) {
+                                                        uint32_t *__restrict__ block_prefix, int32_t D, FlushCtl *ctl,
+                                                        const int fi) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(1024) k2_flush_decide(const uint32_t *__restri
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const unsigned int nnz = ctl->nnz;
+        const unsigned int nnz = ctl->nnz[fi];
         unsigned int go = 0;
         if (nnz != 0) {                                                   // boss.go:117
             const double prop = (double)nnz / (double)D;                  // kmerspectrum.go:92
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(1024) k2_flush_decide(const uint32_t *__restri
                 go = 1;
             }
         }
-        ctl->go = go;
+        ctl->go[fi] = go;
         ctl->t0 = ctl->n_adds;
         if (go) {
             ctl->n_adds += nnz;
@@ -208,9 +212,9 @@ __global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict_
                                                      const uint32_t *__restrict__ word_prefix,
                                                      const uint32_t *__restrict__ block_prefix,
                                                      double *__restrict__ q, unsigned long long *__restrict__ fbits,
-                                                     const FlushCtl *__restrict__ ctl, const int apply_scaling,
-                                                     const double decay_weight) {
-    if (!ctl->go) return;
+                                                     const FlushCtl *__restrict__ ctl, const int fi,
+                                                     const int apply_scaling, const double decay_weight) {
+    if (!ctl->go[fi]) return;
     const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (cell >= CMS_CELLS) return;
     const int lane = threadIdx.x & 31;
@@ -269,17 +273,17 @@ __global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict_
                 ct = __shfl_sync(0xffffffffu, t, 31);
             }
         }
-        const unsigned long long t1 = t0 + ctl->nnz;
+        const unsigned long long t1 = t0 + ctl->nnz[fi];
         if (lane == 0) q[cell] = cval * pow(decay_weight, (double)(t1 - ct));
     }
 }
 
 // (d) estimate -> fp32 reciprocal for the streaming filter; wipe the histogram (kmerspectrum.go:58-64)
 __global__ void k2_finalize(uint32_t *__restrict__ hist, int32_t D, const unsigned long long *__restrict__ fbits,
-                            float *__restrict__ invf, const FlushCtl *__restrict__ ctl) {
+                            float *__restrict__ invf, const FlushCtl *__restrict__ ctl, const int fi) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D) return;
-    const unsigned int go = ctl->go;
+    const unsigned int go = ctl->go[fi];
     if (go) {
         const bool used = hist[i] != 0u;
         const double f = __longlong_as_double((long long)fbits[i]);

@@ -59,8 +59,8 @@ template <int K3_STAGES>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restrict__ invf, float *__restrict__ m32,
           const uint32_t rows, const uint32_t nseg, const double *__restrict__ weights, unsigned int *__restrict__ cand,
-          const int drift, const FlushCtl *__restrict__ ctl) {
-    if (!ctl->go) return;
+          const int drift, const FlushCtl *__restrict__ ctl, const int fi) {
+    if (!ctl->go[fi]) return;
     extern __shared__ __align__(128) uint8_t smem[];
     float *stage = reinterpret_cast<float *>(smem);                                    // [STAGES][SEG]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)K3_STAGES * K3_SEG * 4);
@@ -150,8 +150,8 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
            const double *__restrict__ c, const double *__restrict__ b, const int32_t D,
            const unsigned long long *__restrict__ fbits, const uint32_t rows, unsigned long long *__restrict__ sketch,
            double *__restrict__ weights, const int drift, const double decay_weight, unsigned int *__restrict__ cand,
-           FlushCtl *ctl) {
-    if (!ctl->go) return;
+           FlushCtl *ctl, const int fi) {
+    if (!ctl->go[fi]) return;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= rows) return;
     const int lane = threadIdx.x & 31;
