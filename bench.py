@@ -406,6 +406,24 @@ def run_b200(a):
                 "k3_filter_GBps": (alg_bytes["k3_filter"] / (prof["k3_filter"]["ms"] / max(1, prof["k3_filter"]["launches"]) * 1e-3) / 1e9)
                 if prof["k3_filter"]["ms"] > 0 else None}
 
+    # K1 is issue-bound, not HBM-bound: next to the contract's HBM figure, report its
+    # warp-instruction rate against the SM sub-partitions' issue rate.  Instruction counts per read are the
+    # ncu-measured ones of profiles/traffic.json (they depend on k, w and the read length only).
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        wipr = sum(tj.get("warp_inst_per_read", {}).values())
+        if wipr and k == 21 and w == 9 and RL == 150 and prof["k1_minimizer_histogram"]["ms"] > 0:
+            k1_ms = prof["k1_minimizer_histogram"]["ms"] / max(1, prof["k1_minimizer_histogram"]["launches"])
+            sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+            mhz = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+            peak_ips = sm_count * 4 * mhz * 1e6
+            ach = wipr * I / (k1_ms * 1e-3)
+            roofline["k1_issue"] = {"bound": "issue", "achieved": ach / 1e9, "peak": peak_ips / 1e9, "unit": "G warp-inst/s",
+                                    "frac": ach / peak_ips, "warp_inst_per_launch": wipr * I,
+                                    "source": "profiles/traffic.json (ncu smsp__inst_executed.sum), 4 issue slots per SM per clock"}
+    except Exception:
+        pass
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

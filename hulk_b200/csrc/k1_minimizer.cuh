@@ -93,6 +93,10 @@ constexpr int K1_WARPS = K1_TPB / 32;
 
 // keeps a loop-invariant double in registers (the compiler would otherwise re-materialise the
 // 64-bit immediate with two moves in front of every use)
+// Loop-invariant doubles of the jump step live in the constant bank: DFMA/DMUL take a c[bank][offset]
+// operand directly, so no instruction is spent re-materialising a 64-bit immediate in front of each use.
+__constant__ double k1_jump_consts[2] = {1.0 - JUMP_EPS, 1.0 + JUMP_EPS};
+
 __device__ __forceinline__ double k1_pin(double x) {
     asm volatile("" : "+d"(x));
     return x;
@@ -114,7 +118,7 @@ __device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32
     double jd1[2] = {1.0, 1.0};
     uint32_t bkt[2] = {0, 0};
     bool busy[2] = {false, false}, loaded[2] = {false, false};
-    const double c_lo = k1_pin(1.0 - JUMP_EPS), c_hi = k1_pin(1.0 + JUMP_EPS);
+    const double c_lo = k1_jump_consts[0], c_hi = k1_jump_consts[1];
     const double two52 = k1_pin(JUMP_TWO52), two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0);
     for (;;) {
 #pragma unroll
