@@ -21,7 +21,8 @@ EXPORTS = [
     "hulk_b200_get_cms", "hulk_b200_minimizers", "hulk_b200_jump_hash", "hulk_b200_get_folded_table",
     "hulk_b200_md5_mins", "hulk_b200_sketch_json", "hulk_b200_write_json", "hulk_b200_alloc_pinned",
     "hulk_b200_free_pinned", "hulk_b200_reader_open", "hulk_b200_reader_next", "hulk_b200_reader_error",
-    "hulk_b200_reader_close", "hulk_b200_sketch_reader",
+    "hulk_b200_reader_close", "hulk_b200_sketch_reader", "hulk_b200_sketch_load", "hulk_b200_sketch_find",
+    "hulk_b200_sketch_banner", "hulk_b200_sketch_free", "hulk_b200_smash",
 ]
 
 OK, EW, EK, EEMPTYSEQ, ESHORTSEQ, ESPARSE = 0, -1, -2, -3, -4, -6
@@ -111,6 +112,11 @@ def load():
         "hulk_b200_reader_error": (C.c_char_p, [vp]),
         "hulk_b200_reader_close": (None, [vp]),
         "hulk_b200_sketch_reader": (C.c_int, [vp, vp, u64, LOG_FN, vp]),
+        "hulk_b200_sketch_load": (C.c_int, [C.c_char_p, C.POINTER(vp), C.c_char_p, u64]),
+        "hulk_b200_sketch_find": (C.c_int, [vp, u32, C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32), C.c_char_p, u64]),
+        "hulk_b200_sketch_banner": (C.c_char_p, [vp]),
+        "hulk_b200_sketch_free": (None, [vp]),
+        "hulk_b200_smash": (C.c_int, [vp, vp, u32, u32, C.c_int, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -8,8 +8,10 @@
 //   cmd/sketch.go:64-179     runSketch: log lines, parameter checks, pipeline wiring
 //   cmd/sketch.go:185-214    sketchParamCheck
 //   src/pipeline/sketch.go:182-301  SeqMinimizer.Run / Sketcher.Run log lines and the output file
-// Not here (out of scope): `hulk smash`, --profiling (pprof), KMV/KHF side sketches
+//   cmd/smash.go             `hulk smash`: flags, checks, the similarity matrix CSV
+// Not here (out of scope): --profiling (pprof), KMV/KHF side sketches
 // (unwired in the reference, src/pipeline/boss.go:18-19: the flags are accepted and logged, like there).
+#include <dirent.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -85,8 +87,9 @@ struct FlagDef {
     const char *usage;
 };
 
+const char *g_usage_cmd = "sketch";
 void usage_sketch(const std::vector<FlagDef> &defs, FILE *out) {
-    fprintf(out, "Usage:\n  hulk sketch [flags]\n\nFlags:\n");
+    fprintf(out, "Usage:\n  hulk %s [flags]\n\nFlags:\n", g_usage_cmd);
     for (const FlagDef &d : defs) {
         if (d.shorthand) fprintf(out, "  -%c, --%-14s %s\n", d.shorthand, d.name, d.usage);
         else fprintf(out, "      --%-14s %s\n", d.name, d.usage);
@@ -422,6 +425,176 @@ int run_sketch(int argc, char **argv) {
     return 0;
 }
 
+// ---- hulk smash (cmd/smash.go) ------------------------------------------------------------------------
+// encoding/csv field quoting: a field is quoted when it is empty-looking-special, or contains the delimiter,
+// a quote, CR or LF, or starts with a space
+std::string csv_field(const std::string &f) {
+    bool q = f.empty() ? false : (f[0] == ' ' || f == "\\.");
+    for (char c : f)
+        if (c == ',' || c == '"' || c == '\r' || c == '\n') q = true;
+    if (!q) return f;
+    std::string o = "\"";
+    for (char c : f) {
+        if (c == '"') o += "\"\"";
+        else o += c;
+    }
+    return o + "\"";
+}
+void csv_write(FILE *fh, const std::vector<std::string> &row) {
+    for (size_t i = 0; i < row.size(); i++) fprintf(fh, "%s%s", i ? "," : "", csv_field(row[i]).c_str());
+    fputc('\n', fh);
+}
+bool ends_with_json(const std::string &name) {          // filepath.Match("*.json", name)
+    return name.size() >= 5 && name.compare(name.size() - 5, 5, ".json") == 0;
+}
+void collect_jsons(const std::string &dir, bool recursive, std::vector<std::string> &out) {   // helpers.CollectJSONs
+    DIR *d = opendir(dir.c_str());
+    if (!d) return;
+    std::vector<std::string> names;
+    while (struct dirent *e = readdir(d)) names.push_back(e->d_name);
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    for (const std::string &nm : names) {
+        if (nm == "." || nm == "..") continue;
+        const std::string path = dir + nm;
+        struct stat st;
+        if (stat(path.c_str(), &st) != 0) continue;
+        if (S_ISDIR(st.st_mode)) {
+            if (recursive) collect_jsons(path + "/", true, out);
+        } else if (ends_with_json(nm)) {
+            out.push_back(path);
+        }
+    }
+}
+
+int run_smash(int argc, char **argv) {
+    unsigned long kmer_size = 21;
+    long proc = 1, device = 0;
+    bool profiling = false, recursive = false, banner_matrix = false;
+    std::string out_file, log_file, sketch_dir = "./", algo = "histosketch", metric = "jaccard";
+    char stamp[32];
+    const time_t t0 = time(nullptr);
+    struct tm tmv;
+    localtime_r(&t0, &tmv);
+    strftime(stamp, sizeof stamp, "%Y%m%d%H%M%S", &tmv);
+    out_file = std::string("./hulk-") + stamp;
+    g_usage_cmd = "smash";
+    const std::vector<FlagDef> defs = {
+        {"sketchDir", 'd', FlagDef::STRING, &sketch_dir, "the directory containing the sketches to smash (compare)... (default \"./\")"},
+        {"recursive", 0, FlagDef::BOOL, &recursive, "recursively search the supplied sketch directory (-d)"},
+        {"algorithm", 'a', FlagDef::STRING, &algo, "tells HULK which sketching algorithm to use [histosketch kmv khf] (default \"histosketch\")"},
+        {"metric", 'm', FlagDef::STRING, &metric, "tells HULK which distance metric to use [jaccard weightedjaccard] (default \"jaccard\")"},
+        {"bannerMatrix", 0, FlagDef::BOOL, &banner_matrix, "write a matrix file for banner"},
+        {"kmerSize", 'k', FlagDef::UINT, &kmer_size, "minimizer k-mer length (default 21)"},
+        {"outFile", 'o', FlagDef::STRING, &out_file, "directory and basename for saving the outfile(s)"},
+        {"log", 0, FlagDef::STRING, &log_file, "filename for log file, if omitted then STDOUT used by default"},
+        {"processors", 'p', FlagDef::INT, &proc, "number of processors to use (default 1)"},
+        {"profiling", 0, FlagDef::BOOL, &profiling, "create the files needed to profile HULK using the go tool pprof"},
+        {"device", 0, FlagDef::INT, &device, "CUDA device ordinal (this build; default 0)"},
+    };
+    parse_flags(defs, argc, argv, 2);
+    if (!log_file.empty()) {
+        g_log = fopen(log_file.c_str(), "a");
+        if (!g_log) { perror(log_file.c_str()); return 1; }
+    }
+    logf("this is hulk (version %s)", hulk_b200_version());
+    logf("starting the smash subcommand");
+
+    // smashParamCheck (cmd/smash.go:100-180)
+    if (metric != "jaccard" && metric != "weightedjaccard")
+        fatal("supplied distance metric is not available: " + metric + "\nplease select one of the following: [jaccard weightedjaccard]");
+    if (algo != "histosketch" && algo != "kmv" && algo != "khf")
+        fatal("supplied algorithm not available: " + algo + "\nplease select one of the following: [histosketch kmv khf]");
+    const std::string out_dir = dir_of(out_file);
+    if (out_dir != "." && is_not_exist(out_dir) && !mkdir_all(out_dir, 0700))
+        fatal(std::string("can't create specified output directory: mkdir ") + out_dir + ": " + strerror(errno));
+    if (sketch_dir.empty()) fatal("no directory specified");
+    {
+        struct stat st;
+        if (stat(sketch_dir.c_str(), &st) != 0) {
+            if (errno == ENOENT) fatal("directory does not exist: " + sketch_dir);
+            fatal("can't access adirectory (check permissions): " + sketch_dir);
+        }
+    }
+    if (sketch_dir.back() != '/') sketch_dir += '/';
+    std::vector<std::string> files;
+    collect_jsons(sketch_dir, recursive, files);
+    if (files.empty()) fatal("no JSON files found in supplied directory: " + sketch_dir + "\n");
+    std::vector<hulk_b200_sketch_file *> loaded;
+    char err[1024];
+    for (const std::string &f : files) {
+        hulk_b200_sketch_file *sf = nullptr;
+        if (hulk_b200_sketch_load(f.c_str(), &sf, err, sizeof err)) fatal(err);
+        loaded.push_back(sf);
+    }
+    if (loaded.size() < 2)
+        fatal(std::to_string(loaded.size()) + " sketches found in the supplied directory, HULK needs at least 2 to smash!\n");
+    logf("checking parameters and collecting sketches...");
+    logf("\talgorithm: %s", algo.c_str());
+    logf("\tk-mer size: %lu", kmer_size);
+    logf("\tcreate matrix for banner: %s", banner_matrix ? "true" : "false");
+    logf("\tnumber of sketch objects: %zu", loaded.size());
+    logf("HULK SMASH!");
+
+    // makeMatrix (cmd/smash.go:183-226); `files` is already in sort.Strings order
+    std::vector<size_t> order(files.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return files[a] < files[b]; });
+    const size_t n = files.size();
+    uint32_t s = 0;
+    std::vector<uint64_t> mins;
+    std::vector<double> weights;
+    for (size_t r = 0; r < n; r++) {
+        const uint64_t *m = nullptr;
+        const double *w = nullptr;
+        uint32_t sz = 0;
+        if (hulk_b200_sketch_find(loaded[order[r]], (uint32_t)kmer_size, algo.c_str(), &m, &w, &sz, err, sizeof err)) fatal(err);
+        if (r == 0) s = sz;
+        if (sz != s) fatal("sketch length mismatch: " + std::to_string(s) + " vs " + std::to_string(sz) + "\n");
+        if (metric == "weightedjaccard" && (algo != "histosketch" || !w))
+            fatal("weighted jaccard is only supported for histosketches");
+        mins.insert(mins.end(), m, m + sz);
+        if (w) weights.insert(weights.end(), w, w + sz);
+        else weights.insert(weights.end(), sz, 0.0);
+    }
+    std::vector<double> sim(n * n);
+    const int rc = hulk_b200_smash(mins.data(), weights.data(), (uint32_t)n, s, metric == "weightedjaccard" ? 1 : 0,
+                                   (int32_t)device, sim.data());
+    if (rc) fatal(std::string(hulk_b200_strerror(rc)) + (rc == HULK_B200_ECUDA ? ": no CUDA device (no CPU fallback exists)" : ""));
+    const std::string matrix_path = out_file + ".hulk-matrix.csv";
+    FILE *fh = fopen(matrix_path.c_str(), "wb");
+    if (!fh) fatal("open " + matrix_path + ": " + strerror(errno));
+    std::vector<std::string> row(n);
+    for (size_t c = 0; c < n; c++) row[c] = files[order[c]];
+    csv_write(fh, row);
+    for (size_t r = 0; r < n; r++) {
+        for (size_t c = 0; c < n; c++) {
+            char buf[64];
+            snprintf(buf, sizeof buf, "%.2f", sim[r * n + c]);            // strconv.FormatFloat(v, 'f', 2, 64)
+            row[c] = buf;
+        }
+        csv_write(fh, row);
+    }
+    fclose(fh);
+    logf("\twritten similarity matrix to disk: %s", matrix_path.c_str());
+    if (banner_matrix) {                                                  // makeBannerMatrix (cmd/smash.go:229-262)
+        const std::string banner_path = out_file + ".banner-matrix.csv";  // (the reference ranges over a map: its
+        fh = fopen(banner_path.c_str(), "wb");                            //  row order is random; ours is sorted)
+        if (!fh) fatal("open " + banner_path + ": " + strerror(errno));
+        for (size_t r = 0; r < n; r++) {
+            std::vector<std::string> line;
+            for (uint32_t t = 0; t < s; t++) line.push_back(std::to_string(mins[r * s + t]));
+            line.push_back(hulk_b200_sketch_banner(loaded[order[r]]));
+            csv_write(fh, line);
+        }
+        fclose(fh);
+        logf("\twritten banner matrix to disk: %s", banner_path.c_str());
+    }
+    for (auto *sf : loaded) hulk_b200_sketch_free(sf);
+    logf("finished");
+    return 0;
+}
+
 void usage_root() {
     printf("\n\tHULK is a tool that creates small, fixed-size sketches from streaming microbiome sequencing data,\n"
            "\tenabling rapid metagenomic dissimilarity analysis. HULK generates an approximate k-mer spectrum from\n"
@@ -429,6 +602,7 @@ void usage_root() {
            "Usage:\n  hulk [command]\n\nAvailable Commands:\n"
            "  help        Help about any command\n"
            "  sketch      Create a sketch from a set of reads\n"
+           "  smash       Smash a bunch of sketches and return a distance matrix\n"
            "  version     Prints the current version and exits\n\n"
            "Use \"hulk [command] --help\" for more information about a command.\n");
 }
@@ -445,10 +619,7 @@ int main(int argc, char **argv) {
         return 0;
     }
     if (!strcmp(argv[1], "sketch")) return run_sketch(argc, argv);
-    if (!strcmp(argv[1], "smash")) {
-        printf("Error: `hulk smash` is not part of the B200 build (only the sketch hot path is; see DESIGN.md)\n");
-        return 1;
-    }
+    if (!strcmp(argv[1], "smash")) return run_smash(argc, argv);
     printf("Error: unknown command \"%s\" for \"hulk\"\nRun 'hulk --help' for usage.\n", argv[1]);
     return 1;
 }

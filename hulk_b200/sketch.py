@@ -321,3 +321,41 @@ def sketch_reads(hs: HistoSketch, batches: Iterable[Tuple[np.ndarray, np.ndarray
     if seq_count == 0:
         raise HulkError(N.EARG, "no sequences received")     # sketch.go:237-239
     return mins, weights, hs.stats()
+
+
+def load_sketch(path: str, k: int = 21, algo: str = "histosketch"):
+    """sketchio.LoadHULKdata + HULKdata.FindSketch (src/sketchio/sketchio.go:98-260): (mins, weights, banner)."""
+    L = N.load()
+    f = C.c_void_p()
+    err = C.create_string_buffer(1024)
+    rc = L.hulk_b200_sketch_load(path.encode(), C.byref(f), err, 1024)
+    if rc:
+        raise HulkError(rc, err.value.decode(errors="replace"))
+    try:
+        mins, weights, s = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        rc = L.hulk_b200_sketch_find(f, k, algo.encode(), C.byref(mins), C.byref(weights), C.byref(s), err, 1024)
+        if rc:
+            raise HulkError(rc, err.value.decode(errors="replace"))
+        m = np.ctypeslib.as_array(C.cast(mins, C.POINTER(C.c_uint64)), shape=(s.value,)).copy()
+        w = (np.ctypeslib.as_array(C.cast(weights, C.POINTER(C.c_double)), shape=(s.value,)).copy()
+             if weights.value else np.zeros(0))
+        return m, w, L.hulk_b200_sketch_banner(f).decode()
+    finally:
+        L.hulk_b200_sketch_free(f)
+
+
+def smash(mins: np.ndarray, weights: Optional[np.ndarray] = None, metric: str = "jaccard", device: int = 0) -> np.ndarray:
+    """All-pairs similarity (100 - 100 * distance, cmd/smash.go:183-226) of n sketches: mins uint64[n, s],
+    weights float64[n, s] (needed for "weightedjaccard").  Returns float64[n, n], computed on the GPU."""
+    L = N.load()
+    m = np.ascontiguousarray(mins, dtype=np.uint64)
+    n, s = m.shape
+    weighted = {"jaccard": 0, "weightedjaccard": 1}.get(metric)
+    if weighted is None:
+        raise HulkError(N.EARG, "supplied distance metric is not available: %s" % metric)
+    w = np.ascontiguousarray(weights, dtype=np.float64) if weights is not None else None
+    out = np.zeros((n, n), dtype=np.float64)
+    rc = L.hulk_b200_smash(_ptr(m), _ptr(w), n, s, weighted, device, _ptr(out))
+    if rc:
+        raise HulkError(rc, L.hulk_b200_strerror(rc).decode())
+    return out

@@ -279,3 +279,44 @@ def sketch_json(filename, k, mins, weights, D, drift, banner="blank") -> str:
     L.append(f'{I}"banner_label": {go_json_string(banner)}')
     L.append("}")
     return "\n".join(L)
+
+
+# ---- `hulk smash` (test infrastructure, like everything in oracle/) ----------------------------------
+def get_distance(mins_a, mins_b, weights_a, metric: str) -> float:
+    """HULKdata.GetDistance (src/sketchio/sketchio.go:262-306) + distances.GetDistance / GetWJD
+    (src/distances/distances.go:12-72).  For "weightedjaccard" the reference takes BOTH weight vectors from the
+    subject (sketchio.go:293-299 asserts hsB from subjectSketchObj), so only weights_a is used."""
+    set_a = [float(int(x)) for x in mins_a]
+    set_b = [float(int(x)) for x in mins_b]
+    if len(set_a) != len(set_b):
+        raise ValueError("sketch length mismatch: %d vs %d" % (len(set_a), len(set_b)))
+    if metric == "jaccard":
+        intersect = 0.0
+        for a, b in zip(set_a, set_b):
+            if a == b:
+                intersect += 1
+        return 1.0 - (intersect / float(len(set_a)))
+    if metric == "weightedjaccard":
+        intersect, union = 0.0, 0.0
+        for i in range(len(set_a)):
+            w = float(weights_a[i])
+            wa = max(max(w, 0.0), max(-w, 0.0))
+            wb = wa
+            if set_a[i] == set_b[i]:
+                if wa < wb:
+                    intersect += wa
+                    union += wb
+                else:
+                    intersect += wb
+                    union += wa
+            else:
+                union += wa if wa > wb else wb
+        return 1 - (intersect / union)
+    raise ValueError("unknown distance metric: %s" % metric)
+
+
+def smash_matrix(mins, weights, metric: str):
+    """makeMatrix (cmd/smash.go:183-226): similarity = 100 - distance * 100, formatted 'f', 2."""
+    n = len(mins)
+    sim = [[100 - (get_distance(mins[i], mins[j], weights[i], metric) * 100) for j in range(n)] for i in range(n)]
+    return sim, [["%.2f" % v for v in row] for row in sim]
