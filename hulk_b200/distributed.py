@@ -50,12 +50,19 @@ class ShardedSketch:
         self._dist = dist
         self.slots = slot_range(sketch_size, world, rank)
         self._hist = engine.histogram_tensor() if world > 1 else None
-        # the collective must be ordered with the engine's kernels: issue it on the engine's own CUDA stream
-        self._stream = None
-        if world > 1 and self._hist.is_cuda and hasattr(engine, "stream_handle"):
-            import torch
-            self._stream = torch.cuda.ExternalStream(engine.stream_handle(), device=self._hist.device)
+        self._streams = {}          # CUDA stream handle -> torch ExternalStream
         self.seq_count = 0          # global seqCount (src/pipeline/sketch.go:203)
+
+    def _collective_stream(self, hist):
+        """The stream the engine orders its spectrum on (asked every flush: it depends on the engine's mode).
+        The collective must be enqueued there: behind the counting kernels, ahead of the flush."""
+        if not hist.is_cuda or not hasattr(self.engine, "stream_handle"):
+            return None
+        import torch
+        h = self.engine.stream_handle()
+        if h not in self._streams:
+            self._streams[h] = torch.cuda.ExternalStream(h, device=hist.device)
+        return self._streams[h]
 
     # stage 1-2 on this rank's chunk of a segment that lies inside one interval
     def add_segment(self, bases: np.ndarray, offsets: np.ndarray):
@@ -68,10 +75,11 @@ class ShardedSketch:
     def flush(self):
         """theBoss.Flush (src/pipeline/boss.go:112-128) over the spectrum summed across ranks."""
         if self.world > 1:
-            hist = self.engine.histogram_tensor()      # the engine double-buffers its spectrum: ask every flush
-            if self._stream is not None:
+            hist = self.engine.histogram_tensor()      # the engine multi-buffers its spectrum: ask every flush
+            stream = self._collective_stream(hist)
+            if stream is not None:
                 import torch
-                with torch.cuda.stream(self._stream):
+                with torch.cuda.stream(stream):
                     self._dist.all_reduce(hist, op=self._dist.ReduceOp.SUM, group=self.group)
             else:
                 self._dist.all_reduce(hist, op=self._dist.ReduceOp.SUM, group=self.group)

@@ -157,6 +157,14 @@ def _gpu_worker(rank, world, port, case, out_dir):
             cuts = [0, n // 3, n // 3 + 1, n]
             batches = [(bases, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
             mins, weights, nmin = sketch_reads_sharded(sh, batches, interval)
+            # the same job with the engine's internal pipelining switched off and back on: the collective has
+            # to follow the engine to whichever stream orders its spectrum
+            for overlap in (False, True):
+                hs.reset()
+                hs.set_overlap(overlap)
+                sh.seq_count = 0
+                m2, w2, n2 = sketch_reads_sharded(sh, batches, interval)
+                assert (m2 == mins).all() and (w2 == weights).all() and n2 == nmin, "overlap=%s differs" % overlap
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mins=mins, weights=weights, nmin=nmin)
     finally:
         dist.destroy_process_group()
