@@ -231,6 +231,20 @@ def run_b200(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; hulk_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    # NUMA: run this rank (and first-touch its pinned input buffers) on the CPUs next to its GPU
+    affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 1)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            affinity = len(cpus)
+    except Exception:
+        pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -433,6 +447,7 @@ def run_b200(a):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
+        "host_cpus_per_rank": affinity,
         "clocks": clocks,
         "roofline": roofline,
         "n_minimizers": st_value["n_minimizers"], "n_rescans": st_value["n_rescans"],

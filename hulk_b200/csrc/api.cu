@@ -51,7 +51,7 @@ struct hulk_b200_ctx {
     // their own stream) while interval i is still being flushed on the main stream.
     uint32_t *d_hist[NBUF] = {};
     int cur_hist = 0;                          // buffer (and k1 stream) of the interval being counted
-    int nbuf = 3;
+    int nbuf = 4;
     cudaStream_t k1_stream[NBUF] = {};
     cudaEvent_t ev_k1_last[NBUF] = {};         // last k1 launch into buffer b
     cudaEvent_t ev_hist_free[NBUF] = {};       // buffer b consumed and wiped by its flush
@@ -753,12 +753,17 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     // only reserve the large arena when the generic path will take whole batches
     if (ctx->P.w <= (uint32_t)K1_W_FAST) want = std::min<uint64_t>(want, 1ull << 26);
     if (want > ctx->arena_entries[hs]) {
-        CU(cudaStreamSynchronize(st));
-        if (ctx->d_arena[hs]) cudaFree(ctx->d_arena[hs]);
-        ctx->d_arena[hs] = nullptr;
-        ctx->arena_entries[hs] = 0;
-        CU(dmalloc(&ctx->d_arena[hs], want));
-        ctx->arena_entries[hs] = want;
+        // grow the scratch of EVERY spectrum buffer at once: the next intervals will need the same, and an
+        // allocation (a device-wide synchronisation) belongs in front of the pipeline, not inside it
+        { const int rc = sync_all(ctx); if (rc) return rc; }
+        for (int i = 0; i < ctx->nbuf; i++) {
+            if (want <= ctx->arena_entries[i]) continue;
+            if (ctx->d_arena[i]) cudaFree(ctx->d_arena[i]);
+            ctx->d_arena[i] = nullptr;
+            ctx->arena_entries[i] = 0;
+            CU(dmalloc(&ctx->d_arena[i], want));
+            ctx->arena_entries[i] = want;
+        }
     }
     // minimizer queue of the batch: at most list_cap keys per read (longer lists go to k1_generic)
     const bool fast = ctx->P.w <= (uint32_t)K1_W_FAST;
@@ -769,12 +774,15 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         const uint64_t need = n_reads * (uint64_t)p.list_cap;
         if (need >= (1ull << 31)) return fail(ctx, HULK_B200_EARG, "batch too large for one minimizer queue");
         if (need > ctx->queue_cap[hs]) {
-            CU(cudaStreamSynchronize(st));
-            if (ctx->d_queue[hs]) cudaFree(ctx->d_queue[hs]);
-            ctx->d_queue[hs] = nullptr;
-            ctx->queue_cap[hs] = 0;
-            CU(dmalloc(&ctx->d_queue[hs], need));
-            ctx->queue_cap[hs] = need;
+            { const int rc = sync_all(ctx); if (rc) return rc; }
+            for (int i = 0; i < ctx->nbuf; i++) {
+                if (need <= ctx->queue_cap[i]) continue;
+                if (ctx->d_queue[i]) cudaFree(ctx->d_queue[i]);
+                ctx->d_queue[i] = nullptr;
+                ctx->queue_cap[i] = 0;
+                CU(dmalloc(&ctx->d_queue[i], need));
+                ctx->queue_cap[i] = need;
+            }
         }
         p.queue = ctx->d_queue[hs];
         p.queue_cursor = ctx->d_queue_cursor[hs];
