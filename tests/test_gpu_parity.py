@@ -248,6 +248,31 @@ def test_sketch_with_concept_drift(hb, oracle, decay):
     _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=(0.0 if decay == 0.0 else 1e-9))
 
 
+@pytest.mark.parametrize("decay", [1.0, 0.3])
+def test_pipelined_and_serial_runs_are_identical(hb, decay):
+    # many short intervals back to back keep several intervals in flight (counting i+1, i+2 while i is flushed,
+    # count-min of i+1 under the CWS sweep of i); switching the overlap off must not change a bit
+    k, s, n_int, per = 11, 40, 14, 6000
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 31)
+    reads = hb.synthetic_reads(n_int * per, 150, seed=12)
+    out = []
+    for overlap in (True, False, True):
+        with hb.HistoSketch(k, 9, s, decay, tables=tables, async_input=True) as hs:
+            hs.set_overlap(overlap)
+            for i in range(n_int):
+                hs.add_reads_fixed(reads[i * per:(i + 1) * per].reshape(-1), per, 150)
+                hs.flush()
+            mins, weights = hs.finish()
+            out.append((mins, weights, hs.cms(), hs.estimates(), hs.stats()))
+    for mins, weights, q, f, st in out[1:]:
+        np.testing.assert_array_equal(mins, out[0][0])
+        np.testing.assert_array_equal(weights, out[0][1])
+        np.testing.assert_array_equal(q, out[0][2])
+        np.testing.assert_array_equal(f, out[0][3])
+        assert st["n_flushes"] == n_int and st["n_minimizers"] == out[0][4]["n_minimizers"]
+
+
 def test_c3_shape_k31_drift(hb, oracle):
     # BASELINE config C3 at reduced size: k=31 (D = 923 521, integer-compare scan path), concept drift on
     k, s, decay = 31, 12, 0.02
