@@ -93,19 +93,30 @@ def synthetic_reads_torch(torch, n_reads, read_len, seed, first_read, device):
     return lut[codes].contiguous()
 
 
-def synthetic_tables_torch(torch, rows, D, seed, device):
-    """Random CWS tables with the reference's distributions (r, exp(c) ~ Gamma(2,1); b = U(0,1)*r)."""
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
+def synthetic_tables_torch(torch, s, D, seed, device, slots=None, chunk=32):
+    """Random CWS tables with the reference's distributions (r, exp(c) ~ Gamma(2,1); b = U(0,1)*r), rows
+    [slots[0], slots[1]) of the s x D tables.  Row chunk j is drawn from its own generator (seed + j), so any
+    rank can produce exactly its rows without materialising the rest (k=31, s=2048 is 45 GB in float64)."""
+    a, b_ = slots if slots is not None else (0, s)
+    r = torch.empty((b_ - a, D), dtype=torch.float64, device=device)
+    c = torch.empty_like(r)
+    b = torch.empty_like(r)
 
-    def gamma2(shape):   # Gamma(2,1) = -ln(U1*U2)
+    def gamma2(shape, g):   # Gamma(2,1) = -ln(U1*U2)
         u = torch.rand(shape, dtype=torch.float64, device=device, generator=g).clamp_min(1e-300)
         v = torch.rand(shape, dtype=torch.float64, device=device, generator=g).clamp_min(1e-300)
         return -(torch.log(u) + torch.log(v))
 
-    r = gamma2((rows, D))
-    c = torch.log(gamma2((rows, D)))
-    b = torch.rand((rows, D), dtype=torch.float64, device=device, generator=g) * r
+    for j in range(a // chunk, (b_ + chunk - 1) // chunk):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed + j)
+        rr = gamma2((chunk, D), g)
+        cc = torch.log(gamma2((chunk, D), g))
+        bb = torch.rand((chunk, D), dtype=torch.float64, device=device, generator=g) * rr
+        lo, hi = max(a, j * chunk), min(b_, (j + 1) * chunk)
+        r[lo - a:hi - a] = rr[lo - j * chunk:hi - j * chunk]
+        c[lo - a:hi - a] = cc[lo - j * chunk:hi - j * chunk]
+        b[lo - a:hi - a] = bb[lo - j * chunk:hi - j * chunk]
     return r, c, b
 
 
@@ -267,8 +278,7 @@ def run_b200(a):
         for st in range(n_steps_data):
             first = (st * world + rank) * I
             reads_dev[st] = synthetic_reads_torch(torch, I, RL, 1, first, dev)
-        r_t, c_t, b_t = synthetic_tables_torch(torch, s, D, 1234, dev)
-        r_t, c_t, b_t = (t[slots[0]:slots[1]].contiguous() for t in (r_t, c_t, b_t))
+        r_t, c_t, b_t = synthetic_tables_torch(torch, s, D, 1234, dev, slots)
     stream.synchronize()
 
     hs = hulk_b200.HistoSketch(k, w, s, a.decay, device=local, slots=slots, stream=stream.cuda_stream,

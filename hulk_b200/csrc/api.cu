@@ -406,6 +406,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, false, false>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<true, true, false>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true, 21>, attr, big));
+        CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true, 11>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false, true, 31>, attr, big));
     }
     {
@@ -820,6 +821,8 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
             // the k values of the BASELINE configs get the scan with k folded in at compile time
             if (use_queue && fp && ctx->P.k == 21)
                 k1_minimizer_histogram_w9<false, true, true, 21><<<grid9, K1_TPB, smem9, st>>>(p);
+            else if (use_queue && fp && ctx->P.k == 11)
+                k1_minimizer_histogram_w9<false, true, true, 11><<<grid9, K1_TPB, smem9, st>>>(p);
             else if (use_queue && !fp && ctx->P.k == 31)
                 k1_minimizer_histogram_w9<false, false, true, 31><<<grid9, K1_TPB, smem9, st>>>(p);
             else
