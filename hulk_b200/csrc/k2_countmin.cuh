@@ -16,7 +16,7 @@
 // context; per flush one warp per counter scans its list.  Without decay the sums are integers
 // in float64 (exact, order independent).  With decay, counter value after the hit at global add
 // index t is Q(t) = Q(t_prev) * w^(t - t_prev) + v, scanned with the associative operator
-// (t1,B1) o (t2,B2) = (t2, B1 * w^(t2 - t1) + B2); w^n is pow(w, n) instead of n roundings of a
+// (t1,B1) o (t2,B2) = (t2, B1 * w^(t2 - t1) + B2); w^n is exp(n ln w) instead of n roundings of a
 // repeated product (differs from the reference by <= ~n * 2^-53 relative).
 #pragma once
 #include <math.h>
@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict_
                                                      const FlushCtl *__restrict__ ctl, const int fi,
                                                      const int apply_scaling, const double decay_weight) {
     if (!ctl->go[fi]) return;
+    // w^n as exp(n ln w): ~5x fewer instructions than pow(); n |ln w| 2^-53 relative, the same order as the
+    // rounding drift of the reference's n repeated multiplications (tolerance 1e-9)
+    const double lnw = apply_scaling ? log(decay_weight) : 0.0;
     const uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (cell >= CMS_CELLS) return;
     const int lane = threadIdx.x & 31;
@@ -259,13 +262,13 @@ __global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict_
                 const unsigned long long tl = __shfl_up_sync(0xffffffffu, t, o);
                 const int vl = __shfl_up_sync(0xffffffffu, (int)valid, o);
                 if (lane >= o && vl) {
-                    if (valid) B = Bl * pow(decay_weight, (double)(t - tl)) + B;
+                    if (valid) B = Bl * exp(lnw * (double)(t - tl)) + B;
                     else { B = Bl; t = tl; valid = true; }
                 }
             }
             // B: contribution of this chunk's hits up to and including this lane, as of time t
             double est = 0.0;
-            if (valid) est = cval * pow(decay_weight, (double)(t - ct)) + B;
+            if (valid) est = cval * exp(lnw * (double)(t - ct)) + B;
             if (e < end && bin >= 0 && hist[bin] != 0u) atomicMin(&fbits[bin], (unsigned long long)__double_as_longlong(est));
             const int lastv = __shfl_sync(0xffffffffu, (int)valid, 31);
             if (lastv) {
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict_
             }
         }
         const unsigned long long t1 = t0 + ctl->nnz[fi];
-        if (lane == 0) q[cell] = cval * pow(decay_weight, (double)(t1 - ct));
+        if (lane == 0) q[cell] = cval * exp(lnw * (double)(t1 - ct));
     }
 }
 
