@@ -70,13 +70,15 @@ __device__ __forceinline__ float2 k3_mul2(float ax, float ay, float bx, float by
 // tile = (segment, slot); tiles are enumerated segment-major so a CTA's consecutive tiles share
 // the segment's (1/f) values (L1-resident); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G).
 // cand[slot] is raised when a chunk minimum could pass the slot's test as it stands at the start of the
-// flush; without concept drift W only decreases during a flush, so a slot whose flag stays down cannot
-// change and k3_resolve skips it (with drift the flag is raised unconditionally).
+// flush.  Without concept drift W only decreases during a flush, so a slot whose flag stays down cannot
+// change and k3_resolve skips it.  With drift the test is A < W / decayWeight: for W < 0 a replacement
+// gives W' = A < W / decayWeight < W, so the threshold still only decreases and the same shortcut holds;
+// for W >= 0 (or NaN) the threshold may grow during the flush and the flag is raised unconditionally.
 template <int K3_STAGES>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restrict__ invf, float *__restrict__ m32,
           const uint32_t rows, const uint32_t nseg, const double *__restrict__ weights, unsigned int *__restrict__ cand,
-          const int drift, const FlushCtl *__restrict__ ctl, const int fi) {
+          const int drift, const double decay_weight, const FlushCtl *__restrict__ ctl, const int fi) {
     if (!ctl->go[fi]) return;
     extern __shared__ __align__(128) uint8_t smem[];
     float *stage = reinterpret_cast<float *>(smem);                                    // [STAGES][SEG]
@@ -124,7 +126,12 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
             if (t != t_begin && ++slot == rows) { slot = 0; seg++; }
             const uint64_t col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
             double thr = 0.0;
-            if (lane == 0) thr = weights[slot];     // issued ahead of the wait: its latency hides behind the stage
+            bool always = false;
+            if (lane == 0) {                        // issued ahead of the wait: its latency hides behind the stage
+                const double W = weights[slot];
+                always = drift && !(W < 0.0);
+                thr = drift ? W / decay_weight : W; // histosketch.go:141-146
+            }
             mbar_wait(&full[s], round & 1);
             float m = __int_as_float(0x7f800000);
             if (col0 < Dp) {
@@ -146,7 +153,7 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
                 for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
                 if (lane == 0) {
                     m32[(uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG + warp] = m;
-                    const bool c = drift || ((double)m < thr + K3_EPS * fabs(thr) + 1e-37);   // same test as k3_resolve
+                    const bool c = always || ((double)m < thr + K3_EPS * fabs(thr) + 1e-37);  // same test as k3_resolve
                     if (c && m < __int_as_float(0x7f800000)) atomicOr(&cand[slot], 1u);
                 }
             }
