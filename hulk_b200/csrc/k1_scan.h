@@ -167,6 +167,48 @@ HULK_UNROLL
     }
 };
 
+// One group of four positions (base indices i0h .. i0h + 3, block offsets 4 H .. 4 H + 3).
+// INTERIOR: every position of the block holds a k-mer with the full span and lies inside the read
+// (i >= k + w - 2 and i < len), so the range tests and the span arithmetic drop out.
+template <bool FP, bool INTERIOR, int H, class Emit>
+HULK_HD void k1_w9_group(const uint32_t codes, const int32_t i0h, const int32_t len, const int32_t k,
+                         const uint64_t mask, const int shift, const bool warm, uint64_t &fwd, uint64_t &rev,
+                         uint64_t &pref, uint64_t (&A)[8], Emit &emit) {
+    constexpr int32_t W = 9;
+    constexpr uint64_t SENT = Sentinel<FP>::value;
+    uint64_t X[4], canon[4];
+    bool skip[4];
+HULK_UNROLL
+    for (int u = 0; u < 4; u++) {
+        const uint32_t c = (codes >> (8 * u)) & 0xffu;                    // 0..4
+        fwd = ((fwd << 2) | (uint64_t)c) & mask;                          // :134
+        rev = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);                 // :137 (not masked)
+        skip[u] = ueq64<FP>(fwd, rev);                                    // :145-147
+        canon[u] = umin64<FP>(fwd, rev);                                  // :150-153
+    }
+    if (warm) return;                                                     // :140-142
+HULK_UNROLL
+    for (int u = 0; u < 4; u++) {
+        int32_t span = k;
+        if (!INTERIOR) {
+            const int32_t wi = i0h + u - W + 1;                           // windowIndex :112
+            span = (wi + 1 < k) ? (wi + 1) : k;                           // :127-131
+        }
+        X[u] = (hash64(canon[u], mask) << 8) | (uint64_t)(int64_t)span;   // :156-159
+    }
+HULK_UNROLL
+    for (int u = 0; u < 4; u++) {
+        const int t = 4 * H + u;
+        const int32_t i = i0h + u;
+        const bool real = INTERIOR ? !skip[u] : ((i >= k - 1) && (i < len) && !skip[u]);
+        const uint64_t Xe = real ? X[u] : SENT;
+        pref = umin64<FP>(pref, Xe);
+        const uint64_t m = umin64<FP>(pref, A[t]);                        // prefix of this block, suffix of the previous one
+        A[t] = Xe;
+        emit(m, INTERIOR ? real : (real && i >= W - 1));                  // minimizer.go:186-199
+    }
+}
+
 // KC: compile-time k (0 = use the run-time argument): with k fixed the 2k-bit mask, the shifts and the
 // xor-shift steps of hash64 on words that are known to be zero fold away.
 template <bool FP, int KC = 0, class Src8, class Emit>
@@ -195,38 +237,14 @@ HULK_UNROLL
             }
         }
         const bool warm = i0 + (B - 1) < k - 1;                           // whole block in front of the first k-mer
-HULK_UNROLL
-        for (int h = 0; h < 2; h++) {                                     // two groups of four independent hash chains
-            uint64_t X[4], canon[4];
-            bool skip[4];
-HULK_UNROLL
-            for (int u = 0; u < 4; u++) {
-                const uint32_t c = (codes[h] >> (8 * u)) & 0xffu;         // 0..4
-                fwd = ((fwd << 2) | (uint64_t)c) & mask;                  // :134
-                rev = (rev >> 2) | ((uint64_t)(3u ^ c) << shift);         // :137 (not masked)
-                skip[u] = ueq64<FP>(fwd, rev);                            // :145-147
-                canon[u] = umin64<FP>(fwd, rev);                          // :150-153
-            }
-            if (warm) continue;                                           // :140-142
-HULK_UNROLL
-            for (int u = 0; u < 4; u++) {
-                const int32_t wi = i0 + 4 * h + u - W + 1;                // windowIndex :112
-                const int32_t span = (wi + 1 < k) ? (wi + 1) : k;         // :127-131
-                X[u] = (hash64(canon[u], mask) << 8) | (uint64_t)(int64_t)span;   // :156-159
-            }
-HULK_UNROLL
-            for (int u = 0; u < 4; u++) {
-                const int t = 4 * h + u;
-                const int32_t i = i0 + t;
-                const bool real = (i >= k - 1) && (i < len) && !skip[u];
-                const uint64_t Xe = real ? X[u] : SENT;
-                pref = umin64<FP>(pref, Xe);
-                const uint64_t m = umin64<FP>(pref, A[t]);                // prefix of this block, suffix of the previous one
-                A[t] = Xe;
-                emit(m, real && i >= W - 1);                              // minimizer.go:186-199
-            }
+        if (i0 >= k + W - 2 && i0 + B <= len) {                           // the bulk of every read
+            k1_w9_group<FP, true, 0>(codes[0], i0, len, k, mask, shift, false, fwd, rev, pref, A, emit);
+            k1_w9_group<FP, true, 1>(codes[1], i0 + 4, len, k, mask, shift, false, fwd, rev, pref, A, emit);
+        } else {
+            k1_w9_group<FP, false, 0>(codes[0], i0, len, k, mask, shift, warm, fwd, rev, pref, A, emit);
+            k1_w9_group<FP, false, 1>(codes[1], i0 + 4, len, k, mask, shift, warm, fwd, rev, pref, A, emit);
+            if (warm) continue;
         }
-        if (warm) continue;
         uint64_t run = SENT;
 HULK_UNROLL
         for (int x = B - 1; x >= 0; x--) {                                // suffix minima in place
