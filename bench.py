@@ -63,7 +63,7 @@ def workload_config(a, n_gpus):
                        if n_gpus > 1 else "single GPU",
         "l2_policy": "inputs larger than L2: each step reads fresh reads and streams the %.0f MB CWS table"
                      % (4.0 * a.s * a.k ** 4 / n_gpus / 1e6),
-        "pipelining": "the spectrum is double-buffered: interval i+1 is counted (k1) while interval i is flushed (k2, k3)",
+        "pipelining": "the spectrum is multi-buffered: intervals i+1.. are counted (k1) while interval i is flushed (k2, k3)",
     }
 
 

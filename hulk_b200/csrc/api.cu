@@ -1040,7 +1040,7 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
         {
             ProfScope prof_scope(ctx, 2);
 #define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_weights, ctx->d_cand, \
-                       ctx->drift ? 1 : 0, ctx->decay_weight, ctx->d_ctl, fi
+                       ctx->drift ? 1 : 0, ctx->drift ? 1.0 / ctx->decay_weight : 1.0, ctx->d_ctl, fi
             if (stages == 4) k3_filter<4><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
             else if (stages == 6) k3_filter<6><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
             else k3_filter<8><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);

@@ -78,7 +78,7 @@ template <int K3_STAGES>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restrict__ invf, float *__restrict__ m32,
           const uint32_t rows, const uint32_t nseg, const double *__restrict__ weights, unsigned int *__restrict__ cand,
-          const int drift, const double decay_weight, const FlushCtl *__restrict__ ctl, const int fi) {
+          const int drift, const double thr_scale, const FlushCtl *__restrict__ ctl, const int fi) {
     if (!ctl->go[fi]) return;
     extern __shared__ __align__(128) uint8_t smem[];
     float *stage = reinterpret_cast<float *>(smem);                                    // [STAGES][SEG]
@@ -130,7 +130,10 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
             if (lane == 0) {                        // issued ahead of the wait: its latency hides behind the stage
                 const double W = weights[slot];
                 always = drift && !(W < 0.0);
-                thr = drift ? W / decay_weight : W; // histosketch.go:141-146
+                thr = W * thr_scale;                // W / decayWeight under drift (histosketch.go:141-146), else W:
+                                                    // the scale is 1/decayWeight or 1, a reciprocal is fine for a
+                                                    // screen that carries a 1e-6 guard band (a division here costs
+                                                    // ~40 issue slots per tile)
             }
             mbar_wait(&full[s], round & 1);
             float m = __int_as_float(0x7f800000);
