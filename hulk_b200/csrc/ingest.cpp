@@ -16,6 +16,7 @@
 // here; the only CUDA dependency is the pinned allocation (plain memory when no device exists, so the
 // reader itself can be tested on a CPU-only box -- it computes nothing).
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -27,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -39,6 +41,8 @@ namespace {
 constexpr size_t kBlock = 4u << 20;             // bytes per read()/gzread()
 constexpr size_t kMaxToken = 64 * 1024;         // bufio.MaxScanTokenSize
 constexpr int kRing = 4;                        // batches in flight
+constexpr size_t kParChunk = 8u << 20;          // parallel FASTQ parse: bytes of file per worker task
+constexpr uint64_t kParMinBytes = 256ull << 20; // ... used for plain files from this total size on
 
 struct HostBuf {                                // page-locked when a device exists
     void *p = nullptr;
@@ -79,6 +83,9 @@ struct hulk_b200_reader {
     uint64_t batch_bytes = 0;
 
     Batch ring[kRing];
+    std::vector<std::unique_ptr<Batch>> pring;  // parallel mode: 2 x workers batches of kParChunk bytes
+    unsigned par_workers = 0;                   // > 0: parallel FASTQ parse of plain files (see produce_parallel)
+    size_t par_chunk = kParChunk;               // bytes of file per worker task (HULK_B200_PARALLEL_CHUNK: tests)
     std::deque<Batch *> free_q, full_q;
     Batch *held = nullptr;                      // batch currently lent to the consumer
     std::mutex mu;
@@ -262,8 +269,217 @@ struct hulk_b200_reader {
         return fasta_stop ? true : end_of_file(carry);
     }
 
+    // ---- parallel parse of plain FASTQ files ---------------------------------------------------------
+    // FastqHandler groups the NON-EMPTY lines of the stream in fours and never resynchronises
+    // (sketch.go:139-159), so the slot a line fills is (number of non-empty lines before it) mod 4.  That
+    // makes the framing splittable without guessing: pass 1 counts non-empty lines per chunk in parallel, a
+    // prefix sum gives every chunk its starting slot, pass 2 frames the chunks in parallel (a chunk that
+    // starts inside a record looks back for the lines it needs), and the batches are delivered in file
+    // order.  The result is byte-identical to the one-thread reader, errors included.
+    struct ParJob {
+        const uint8_t *d = nullptr;      // the mapped file
+        size_t size = 0, begin = 0, end = 0;   // [begin, end): whole lines, the last may lack its newline
+        uint64_t nonempty = 0;
+        int phase = 0;
+        Batch *out = nullptr;
+        int err = 0;
+        std::string err_text;
+    };
+    std::vector<std::string> carry_lines;       // pending lines (l1.. of the open record) at the end of the previous file
+
+    template <class F>
+    static void par_lines(const ParJob &j, F f) {      // f(ptr, len) for every line of the job, CR dropped; false stops
+        size_t pos = j.begin;
+        while (pos < j.end) {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(j.d + pos, '\n', j.end - pos));
+            const size_t stop = nl ? (size_t)(nl - j.d) : j.end;
+            size_t len = stop - pos;
+            const bool too_long = len >= kMaxToken;
+            if (len && j.d[pos + len - 1] == '\r') len--;
+            if (!f(j.d + pos, len, too_long)) return;
+            pos = stop + 1;
+        }
+    }
+    static void par_count(ParJob &j) {
+        uint64_t n = 0;
+        par_lines(j, [&](const uint8_t *, size_t len, bool) { n += len != 0; return true; });
+        j.nonempty = n;
+    }
+    void par_parse(ParJob &j) const {
+        Batch &b = *j.out;
+        b.n_reads = b.n_bytes = 0;
+        b.o()[0] = 0;
+        int slot = j.phase;
+        uint8_t l1_first = '@';
+        std::string l1_text;
+        const uint8_t *seq = nullptr;
+        size_t seq_len = 0;
+        std::string seq_copy;
+        if (slot) {                                         // the record in progress: find its lines so far
+            std::vector<std::pair<const uint8_t *, size_t>> prev;          // newest first
+            size_t pos = j.begin;
+            while ((int)prev.size() < slot && pos > 0) {
+                const size_t line_end = pos - 1;                          // the newline that ends the previous line
+                const void *q = line_end ? memrchr(j.d, '\n', line_end) : nullptr;
+                const size_t start = q ? (size_t)(static_cast<const uint8_t *>(q) - j.d) + 1 : 0;
+                size_t len = line_end - start;
+                if (len && j.d[start + len - 1] == '\r') len--;
+                if (len) prev.emplace_back(j.d + start, len);
+                pos = start;
+            }
+            // lines still missing were the tail of the previous file
+            const int missing = slot - (int)prev.size();
+            auto line_at = [&](int idx, const uint8_t **p, size_t *len) {    // idx 0 = l1
+                if (idx < missing) {
+                    const std::string &c = carry_lines[carry_lines.size() - missing + idx];
+                    *p = reinterpret_cast<const uint8_t *>(c.data());
+                    *len = c.size();
+                } else {
+                    const auto &pr = prev[prev.size() - 1 - (idx - missing)];
+                    *p = pr.first;
+                    *len = pr.second;
+                }
+            };
+            const uint8_t *p1;
+            size_t n1;
+            line_at(0, &p1, &n1);
+            l1_first = p1[0];
+            if (l1_first != '@') l1_text.assign(reinterpret_cast<const char *>(p1), n1);
+            if (slot >= 2) line_at(1, &seq, &seq_len);
+        }
+        par_lines(j, [&](const uint8_t *p, size_t len, bool too_long) {
+            if (too_long) {
+                j.err = HULK_B200_ETOOLONG;
+                j.err_text = "bufio.Scanner: token too long";
+                return false;
+            }
+            if (len == 0) return true;
+            switch (slot) {
+                case 0:
+                    l1_first = p[0];
+                    if (l1_first != '@') l1_text.assign(reinterpret_cast<const char *>(p), len);
+                    slot = 1;
+                    break;
+                case 1: seq = p; seq_len = len; slot = 2; break;
+                case 2: slot = 3; break;
+                default:
+                    if (l1_first != '@') {
+                        j.err = HULK_B200_EFASTQ;
+                        j.err_text = "read ID in fastq file does not begin with @: " + l1_text;
+                        return false;
+                    }
+                    memcpy(b.b() + b.n_bytes, seq, seq_len);
+                    b.n_bytes += seq_len;
+                    b.n_reads += 1;
+                    b.o()[b.n_reads] = b.n_bytes;
+                    slot = 0;
+                    break;
+            }
+            return true;
+        });
+    }
+
+    bool produce_parallel() {
+        uint64_t nonempty_total = 0;                        // non-empty lines of the stream so far
+        const unsigned W = par_workers;
+        for (size_t fi = 0; fi < paths.size(); fi++) {
+            const std::string &name = paths[fi];
+            const int fd = ::open(name.c_str(), O_RDONLY);
+            if (fd < 0) return fail(HULK_B200_EIO, "open " + name + ": " + strerror(errno));
+            struct stat st;
+            if (fstat(fd, &st) != 0) { ::close(fd); return fail(HULK_B200_EIO, "stat " + name); }
+            const size_t size = (size_t)st.st_size;
+            if (size == 0) { ::close(fd); continue; }
+            void *map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            ::close(fd);
+            if (map == MAP_FAILED) return fail(HULK_B200_EIO, "mmap " + name + ": " + strerror(errno));
+            madvise(map, size, MADV_SEQUENTIAL);
+            const uint8_t *d = static_cast<const uint8_t *>(map);
+            auto line_start_at_or_after = [&](size_t off) -> size_t {      // first line start >= off
+                if (off == 0) return 0;
+                if (off >= size) return size;
+                const void *q = memchr(d + off - 1, '\n', size - (off - 1));
+                return q ? (size_t)(static_cast<const uint8_t *>(q) - d) + 1 : size;
+            };
+            const size_t n_chunks = (size + par_chunk - 1) / par_chunk;
+            bool ok = true;
+            for (size_t c0 = 0; ok && c0 < n_chunks; c0 += W) {
+                const unsigned nj = (unsigned)std::min<size_t>(W, n_chunks - c0);
+                std::vector<ParJob> jobs(nj);
+                for (unsigned t = 0; t < nj; t++) {
+                    jobs[t].d = d;
+                    jobs[t].size = size;
+                    jobs[t].begin = line_start_at_or_after((c0 + t) * par_chunk);
+                    jobs[t].end = line_start_at_or_after((c0 + t + 1) * par_chunk);
+                }
+                {
+                    std::vector<std::thread> th;
+                    for (unsigned t = 0; t < nj; t++) th.emplace_back([&, t] { par_count(jobs[t]); });
+                    for (auto &x : th) x.join();
+                }
+                for (unsigned t = 0; t < nj; t++) {
+                    jobs[t].phase = (int)(nonempty_total & 3);
+                    nonempty_total += jobs[t].nonempty;
+                    if (!(jobs[t].out = take_free())) { munmap(map, size); return false; }     // stopped
+                }
+                {
+                    std::vector<std::thread> th;
+                    for (unsigned t = 0; t < nj; t++) th.emplace_back([&, t] { par_parse(jobs[t]); });
+                    for (auto &x : th) x.join();
+                }
+                for (unsigned t = 0; t < nj; t++) {
+                    if (!ok) {                               // behind an error: hand the batch back unused
+                        std::lock_guard<std::mutex> lk(mu);
+                        free_q.push_back(jobs[t].out);
+                        continue;
+                    }
+                    if (jobs[t].out->n_reads > 0) publish(jobs[t].out);
+                    else { std::lock_guard<std::mutex> lk(mu); free_q.push_back(jobs[t].out); }
+                    if (jobs[t].err) ok = fail(jobs[t].err, jobs[t].err_text);
+                }
+            }
+            if (ok) {                                        // lines of a record left open at the end of this file
+                const int open_lines = (int)(nonempty_total & 3);
+                std::vector<std::string> tail;               // newest first
+                size_t pos = size;
+                if (pos > 0 && d[pos - 1] != '\n') {         // final line without a newline
+                    const void *q = memrchr(d, '\n', pos);
+                    const size_t start = q ? (size_t)(static_cast<const uint8_t *>(q) - d) + 1 : 0;
+                    size_t len = pos - start;
+                    if (len && d[start + len - 1] == '\r') len--;
+                    if (len && (int)tail.size() < open_lines) tail.emplace_back(reinterpret_cast<const char *>(d + start), len);
+                    pos = start;
+                }
+                while ((int)tail.size() < open_lines && pos > 0) {
+                    const size_t line_end = pos - 1;
+                    const void *q = line_end ? memrchr(d, '\n', line_end) : nullptr;
+                    const size_t start = q ? (size_t)(static_cast<const uint8_t *>(q) - d) + 1 : 0;
+                    size_t len = line_end - start;
+                    if (len && d[start + len - 1] == '\r') len--;
+                    if (len) tail.emplace_back(reinterpret_cast<const char *>(d + start), len);
+                    pos = start;
+                }
+                std::vector<std::string> next_carry;
+                const int missing = open_lines - (int)tail.size();          // still older: from the previous carry
+                for (int i = 0; i < missing; i++) next_carry.push_back(carry_lines[carry_lines.size() - missing + i]);
+                for (size_t i = tail.size(); i-- > 0;) next_carry.push_back(tail[i]);
+                carry_lines.swap(next_carry);
+            }
+            munmap(map, size);
+            if (!ok) return false;
+        }
+        return true;
+    }
+
     void produce() {
         bool ok = true;
+        if (par_workers) {
+            ok = produce_parallel();
+            std::lock_guard<std::mutex> lk(mu);
+            done = true;
+            cv_full.notify_all();
+            return;
+        }
         if (paths.empty()) {
             ok = read_plain(0, "STDIN");
         } else {
@@ -313,6 +529,41 @@ int hulk_b200_reader_open(const char *const *paths, uint32_t n_paths, int fasta,
     rd->fasta = fasta != 0;
     rd->batch_bytes = batch_bytes ? batch_bytes : (32ull << 20);
     if (rd->batch_bytes < 4096) rd->batch_bytes = 4096;
+    // plain FASTQ files of some size: parse them on several threads (produce_parallel); everything else
+    // (gzip, STDIN, FASTA, small inputs) goes through the one-thread line reader
+    if (!rd->fasta && n_paths > 0 && batch_bytes == 0) {
+        uint64_t total = 0;
+        bool eligible = true;
+        for (const std::string &nm : rd->paths) {
+            struct stat st;
+            const size_t dot = nm.rfind('.');
+            const bool gz = dot != std::string::npos && nm.compare(dot + 1, std::string::npos, "gz") == 0;
+            if (gz || stat(nm.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) { eligible = false; break; }
+            total += (uint64_t)st.st_size;
+        }
+        const char *force = getenv("HULK_B200_PARALLEL_READER");           // "1": also for small inputs, "0": never
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (eligible && hw >= 4 && !(force && *force == '0') && (total >= kParMinBytes || (force && *force == '1')))
+            rd->par_workers = std::min(8u, hw / 2);
+        const char *pc = getenv("HULK_B200_PARALLEL_CHUNK");
+        if (pc && atoll(pc) >= 16) rd->par_chunk = (size_t)atoll(pc);
+    }
+    if (rd->par_workers) {
+        for (unsigned i = 0; i < 2 * rd->par_workers; i++) {
+            std::unique_ptr<Batch> b(new Batch());
+            // a chunk's sequences plus one record carried in from the chunk before; records of >= 8 bytes
+            // (a chunk ends at the first line start at or after its nominal end, so one more line may ride along)
+            if (!b->bases.alloc(rd->par_chunk + 2 * kMaxToken) || !b->offsets.alloc((rd->par_chunk / 8 + 8) * 8)) {
+                delete rd;
+                return HULK_B200_ENOMEM;
+            }
+            rd->free_q.push_back(b.get());
+            rd->pring.push_back(std::move(b));
+        }
+        rd->th = std::thread([rd] { rd->produce(); });
+        *out = rd;
+        return HULK_B200_OK;
+    }
     // offsets: room for reads as short as 32 bases on average (shorter reads just close the batch earlier)
     const uint64_t cap_reads = std::max<uint64_t>(1024, rd->batch_bytes / 32);
     for (int i = 0; i < kRing; i++) {
@@ -367,6 +618,7 @@ void hulk_b200_reader_close(hulk_b200_reader *rd) {
     }
     if (rd->th.joinable()) rd->th.join();
     for (int i = 0; i < kRing; i++) { rd->ring[i].bases.release(); rd->ring[i].offsets.release(); }
+    for (auto &b : rd->pring) { b->bases.release(); b->offsets.release(); }
     delete rd;
 }
 

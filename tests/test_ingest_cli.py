@@ -201,3 +201,66 @@ def test_cli_reference_fatals(tmp_path):
     r = _hulk("sketch", "-f", str(empty), "-o", str(tmp_path / "s"))
     assert r.returncode == 1 and "ERROR---> no sequences received" in r.stdout
     assert not os.path.exists(str(tmp_path / "s.json"))
+
+
+# ---- the parallel parse of plain FASTQ files (csrc/ingest.cpp produce_parallel) -----------------------
+def _native_env(paths, env):
+    """Read through the native reader in a subprocess (the mode switches are read from the environment at open)."""
+    code = ("import sys, hashlib; sys.path.insert(0, %r); import hulk_b200\n"
+            "try:\n"
+            "    with hulk_b200.NativeReader(sys.argv[1:]) as rd:\n"
+            "        n = 0; h = hashlib.md5(); hl = hashlib.md5()      # independent of how reads are batched\n"
+            "        for b, offs in rd:\n"
+            "            n += len(offs) - 1; h.update(b.tobytes()); hl.update((offs[1:] - offs[:-1]).tobytes())\n"
+            "    print('OK', n, h.hexdigest(), hl.hexdigest())\n"
+            "except ValueError as e:\n"
+            "    print('ERR', n, h.hexdigest(), hl.hexdigest(), str(e))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([os.sys.executable, "-c", code, *[str(p) for p in paths]], capture_output=True, text=True, env=e, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.strip()
+
+
+@pytest.mark.parametrize("chunk", ["16", "61", "257", "4096", "100000"])
+def test_parallel_reader_equals_sequential(tmp_path, chunk):
+    # every chunk size puts the task boundaries somewhere else: inside headers, sequences, quality lines,
+    # runs of empty lines, CRLF pairs; records straddle tasks and files
+    rng = np.random.default_rng(int(chunk))
+    reads = random_reads(3000, 40, seed=5, ragged=120)
+    parts = []
+    for i, r in enumerate(reads):
+        nl = b"\r\n" if rng.random() < 0.1 else b"\n"
+        rec = b"@r%d" % i + nl + r + nl + b"+" + nl + bytes(rng.integers(33, 74, len(r)).astype(np.uint8)) + nl
+        if rng.random() < 0.05:
+            rec = rec.replace(nl, nl + b"\n" * int(rng.integers(1, 4)), 1)       # empty lines inside a record
+        parts.append(rec)
+    blob = b"".join(parts)
+    cut1 = blob.index(b"\n", len(blob) // 3) + 1                 # file 1 ends inside a record (after some line)
+    cut2 = 2 * len(blob) // 3                                     # file 2 ends in the middle of a line: no final newline
+    cut2 = blob.index(b"\n", cut2)                                # ... exactly in front of a newline, which opens file 3
+    files = [tmp_path / "a.fq", tmp_path / "b.fastq", tmp_path / "c.fq"]
+    files[0].write_bytes(blob[:cut1])
+    files[1].write_bytes(blob[cut1:cut2])
+    files[2].write_bytes(blob[cut2 + 1:])
+    seq = _native_env(files, {"HULK_B200_PARALLEL_READER": "0"})
+    par = _native_env(files, {"HULK_B200_PARALLEL_READER": "1", "HULK_B200_PARALLEL_CHUNK": chunk})
+    assert seq.startswith("OK 3000 ") and par == seq
+
+
+def test_parallel_reader_errors_equal_sequential(tmp_path):
+    reads = random_reads(400, 60, seed=8)
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads)]
+    bad = list(recs)
+    bad[250] = bad[250].replace(b"@r250", b"r250")                # read ID without '@' in record 250
+    f1 = tmp_path / "bad.fq"
+    f1.write_bytes(b"".join(bad))
+    long_ = list(recs)
+    long_[300] = b"@r300\n" + b"A" * 70000 + b"\n+\n" + b"I" * 10 + b"\n"        # bufio.Scanner: token too long
+    f2 = tmp_path / "long.fq"
+    f2.write_bytes(b"".join(long_))
+    for f, msg in ((f1, "read ID in fastq file does not begin with @: r250"), (f2, "token too long")):
+        seq = _native_env([f], {"HULK_B200_PARALLEL_READER": "0"})
+        for chunk in ("64", "1000", "50000"):
+            par = _native_env([f], {"HULK_B200_PARALLEL_READER": "1", "HULK_B200_PARALLEL_CHUNK": chunk})
+            assert par == seq and msg in par and par.startswith("ERR")
