@@ -418,11 +418,12 @@ int run_sketch(int argc, char **argv) {
     if (rc == HULK_B200_EARG) fatal("json: unsupported value: a sketch weight is not finite");
     if (rc) fatal("open " + out_json + ": " + strerror(errno));
     logf("\twritten sketch to disk: %s", out_json.c_str());
-    hulk_b200_reader_close(rd);
-    hulk_b200_destroy(ctx);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     logf("finished in %s", go_duration(secs).c_str());
-    return 0;
+    // the process ends here: unmapping gigabytes of device and pinned memory one buffer at a time
+    // (hulk_b200_destroy / reader_close) would only delay the exit -- the driver reclaims it all at once
+    fflush(nullptr);
+    _exit(0);
 }
 
 // ---- hulk smash (cmd/smash.go) ------------------------------------------------------------------------
