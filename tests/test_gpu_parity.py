@@ -321,6 +321,45 @@ def test_flush_semantics(hb):
         assert e.value.code == -21
 
 
+def test_context_reuse_snapshot_and_async_input(hb, oracle):
+    # one context, several samples: reset() returns it to the freshly-created state; snapshot_async works into
+    # pageable memory (copy engine) and pinned memory (kernel write); ASYNC_INPUT + sync_inputs
+    import ctypes as C
+    k, s = 9, 24
+    D = k ** 4
+    tables = _tables(s, D, 41)
+    samples = [random_reads(2500, 90, seed=300 + i, ragged=30) for i in range(3)]
+    want = []
+    for reads in samples:
+        ref = oracle.HistoSketch(k, s, D, 1.0, *tables)
+        ref.run(9, *oracle.pack_reads(reads), interval=1000)
+        want.append(ref.get())
+    L = hb.load()
+    pin = C.c_void_p()
+    assert L.hulk_b200_alloc_pinned(C.byref(pin), 16 * s) == 0
+    with hb.HistoSketch(k, 9, s, tables=tables, async_input=True) as hs:
+        for reads, (mo, wo) in zip(samples, want):
+            hs.reset()
+            bases, offs = hb.pack_reads(reads)
+            for a in range(0, len(reads), 1000):
+                hs.add_reads(bases, offs[a:a + 1001])
+                hs.flush()
+            assert L.hulk_b200_sync_inputs(hs._ctx) == 0
+            page_m, page_w = np.zeros(s, np.uint64), np.zeros(s)
+            assert L.hulk_b200_snapshot_async(hs._ctx, page_m.ctypes.data, page_w.ctypes.data) == 0
+            assert L.hulk_b200_snapshot_async(hs._ctx, pin.value, pin.value + 8 * s) == 0
+            hs.sync()
+            pin_m = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint64)), shape=(s,)).copy()
+            pin_w = np.ctypeslib.as_array(C.cast(C.c_void_p(pin.value + 8 * s), C.POINTER(C.c_double)), shape=(s,)).copy()
+            mins, weights = hs.finish()
+            for m, w in ((mins, weights), (page_m, page_w), (pin_m, pin_w)):
+                np.testing.assert_array_equal(m, mo)
+                np.testing.assert_allclose(w, wo, rtol=W_RTOL, atol=0)
+            st = hs.stats()
+            assert st["n_reads"] == len(reads) and st["n_flushes"] == 3
+    L.hulk_b200_free_pinned(pin)
+
+
 def test_intervals_match_oracle_run(hb, oracle):
     k, w, s = 11, 9, 40
     D = hb.spectrum_size(k)
