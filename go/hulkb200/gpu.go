@@ -50,7 +50,7 @@ func (proc *GPUSketcher) Run() {
 	}
 	check(C.hulk_b200_create(&p, &ctx))
 	defer C.hulk_b200_destroy(ctx)
-	check(C.hulk_b200_generate_cws_tables(ctx)) // newCWS, histosketch.go:95-126
+	check(C.hulk_b200_generate_cws_tables_async(ctx)) // newCWS (histosketch.go:95-126), drawn on all cores while reads are counted
 
 	bases := make([]byte, 0, batchBytes+1<<20)
 	offsets := []C.uint64_t{0}
