@@ -99,6 +99,7 @@ struct hulk_b200_ctx {
     double *d_r = nullptr, *d_c = nullptr, *d_b = nullptr;
     float *d_K32 = nullptr, *d_m32 = nullptr;
     unsigned int *d_cand = nullptr;            // per slot: some chunk of the current flush may change it
+    float *d_thr32 = nullptr;                  // per slot: the fp32 screen bound (k3_thr32), kept by k3_resolve
     int k3_stages = 4, k3_ctas_per_sm = 2;     // 2 x (4 x 16 KB) per SM: 5.7 TB/s alone, and k1 CTAs still fit next to it
     unsigned long long *d_sketch = nullptr;
     double *d_weights = nullptr;
@@ -238,7 +239,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits[0], ctx->d_fbits[1], ctx->d_invf[0],
                     ctx->d_invf[1], ctx->d_r, ctx->d_c,
-                    ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights, ctx->d_cand};
+                    ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights, ctx->d_cand, ctx->d_thr32};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < NSTAGE; i++) {
@@ -338,6 +339,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(dmalloc(&ctx->d_m32, (uint64_t)rows * ctx->nsub_row));
     CU(dmalloc(&ctx->d_sketch, rows));
     CU(dmalloc(&ctx->d_cand, rows));
+    CU(dmalloc(&ctx->d_thr32, rows));
     CU(dmalloc(&ctx->d_weights, rows));
 
     cudaStream_t st = ctx->stream;
@@ -353,6 +355,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     for (int i = 0; i < 2; i++) CU(cudaMemsetAsync(ctx->d_invf[i], 0xff, sizeof(float) * ctx->Dp, st));   // NaN padding
     CU(cudaMemsetAsync(ctx->d_sketch, 0, sizeof(unsigned long long) * (rows ? rows : 1), st));   // histosketch.go:84-87
     CU(cudaMemsetAsync(ctx->d_cand, 0, sizeof(unsigned int) * (rows ? rows : 1), st));
+    if (rows) k3_fill_f32<<<(rows + 255) / 256, 256, 0, st>>>(ctx->d_thr32, rows, INFINITY);   // W = MaxFloat64
     {
         std::vector<double> w(rows ? rows : 1, 1.7976931348623157e308);             // math.MaxFloat64
         CU(cudaMemcpyAsync(ctx->d_weights, w.data(), sizeof(double) * rows, cudaMemcpyHostToDevice, st));
@@ -550,6 +553,7 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->d_q, 0, sizeof(double) * CMS_CELLS, st));
     CU(cudaMemsetAsync(ctx->d_sketch, 0, sizeof(unsigned long long) * (ctx->rows ? ctx->rows : 1), st));
     CU(cudaMemsetAsync(ctx->d_cand, 0, sizeof(unsigned int) * (ctx->rows ? ctx->rows : 1), st));
+    if (ctx->rows) k3_fill_f32<<<(ctx->rows + 255) / 256, 256, 0, st>>>(ctx->d_thr32, ctx->rows, INFINITY);
     std::vector<double> w(ctx->rows ? ctx->rows : 1, 1.7976931348623157e308);
     CU(cudaMemcpyAsync(ctx->d_weights, w.data(), sizeof(double) * ctx->rows, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
@@ -1039,8 +1043,7 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
         const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)ctx->sm_count * ctx->k3_ctas_per_sm);
         {
             ProfScope prof_scope(ctx, 2);
-#define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_weights, ctx->d_cand, \
-                       ctx->drift ? 1 : 0, ctx->drift ? 1.0 / ctx->decay_weight : 1.0, ctx->d_ctl, fi
+#define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_thr32, ctx->d_cand, ctx->d_ctl, fi
             if (stages == 4) k3_filter<4><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
             else if (stages == 6) k3_filter<6><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
             else k3_filter<8><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
@@ -1052,7 +1055,9 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
             k3_resolve<<<(ctx->rows * 32 + 127) / 128, 128, 0, st>>>(ctx->d_m32, ctx->nsub_row, ctx->d_r, ctx->d_c,
                                                                      ctx->d_b, D, fbits, ctx->rows, ctx->d_sketch,
                                                                      ctx->d_weights, ctx->drift ? 1 : 0,
-                                                                     ctx->decay_weight, ctx->d_cand, ctx->d_ctl, fi);
+                                                                     ctx->decay_weight, ctx->d_cand, ctx->d_thr32,
+                                                                     ctx->drift ? 1.0 / ctx->decay_weight : 1.0,
+                                                                     ctx->d_ctl, fi);
             LAUNCH_CHECK("k3_resolve");
         }
         CU(cudaEventRecord(ctx->ev_k3_done[fi], st));

@@ -69,16 +69,32 @@ __device__ __forceinline__ float2 k3_mul2(float ax, float ay, float bx, float by
 // ---- per flush: streaming filter ----
 // tile = (segment, slot); tiles are enumerated segment-major so a CTA's consecutive tiles share
 // the segment's (1/f) values (L1-resident); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G).
-// cand[slot] is raised when a chunk minimum could pass the slot's test as it stands at the start of the
-// flush.  Without concept drift W only decreases during a flush, so a slot whose flag stays down cannot
-// change and k3_resolve skips it.  With drift the test is A < W / decayWeight: for W < 0 a replacement
-// gives W' = A < W / decayWeight < W, so the threshold still only decreases and the same shortcut holds;
-// for W >= 0 (or NaN) the threshold may grow during the flush and the flag is raised unconditionally.
+// The screen.  thr32[slot] is the slot's test bound as it stands at the start of the flush, rounded UP to
+// float: a chunk whose fp32 minimum is not below it cannot pass k3_resolve's own test
+// (m < thr + eps |thr|, thr = W or W / decayWeight), so cand[slot] stays down and k3_resolve skips the slot.
+// This is exact because the bound only decreases during a flush: without concept drift W only decreases;
+// with drift a replacement gives W' = A < W / decayWeight < W when W < 0, and for W >= 0 (or NaN), where the
+// bound may grow, thr32 is +inf (every non-empty chunk is a candidate).  k3_resolve maintains thr32.
+__device__ __forceinline__ float k3_thr32(const double W, const int drift, const double thr_scale) {
+    if (drift && !(W < 0.0)) return __int_as_float(0x7f800000);
+    const double thr = W * thr_scale;            // thr_scale = 1 / decayWeight under drift (a reciprocal is fine
+                                                 // for a screen with a 1e-6 guard band), else 1
+    const double lim = thr + K3_EPS * fabs(thr) + 1e-37;
+    if (lim != lim) return __int_as_float(0xff800000);       // -inf + inf: nothing can pass
+    return __double2float_ru(lim);
+}
+__global__ void k3_fill_f32(float *p, uint32_t n, float v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// tile = (segment, slot); tiles are enumerated segment-major so a CTA's consecutive tiles share the
+// segment's (1/f) values (L1-resident); CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G).
 template <int K3_STAGES>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restrict__ invf, float *__restrict__ m32,
-          const uint32_t rows, const uint32_t nseg, const double *__restrict__ weights, unsigned int *__restrict__ cand,
-          const int drift, const double thr_scale, const FlushCtl *__restrict__ ctl, const int fi) {
+          const uint32_t rows, const uint32_t nseg, const float *__restrict__ thr32, unsigned int *__restrict__ cand,
+          const FlushCtl *__restrict__ ctl, const int fi) {
     if (!ctl->go[fi]) return;
     extern __shared__ __align__(128) uint8_t smem[];
     float *stage = reinterpret_cast<float *>(smem);                                    // [STAGES][SEG]
@@ -97,49 +113,40 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
 
     const uint64_t T = (uint64_t)rows * nseg;
     const uint64_t t_begin = T * blockIdx.x / gridDim.x;
-    const uint64_t t_end = T * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t n_tiles = (uint32_t)(T * (blockIdx.x + 1) / gridDim.x - t_begin);
     const uint32_t nsub_row = (uint32_t)(Dp / K3_SUB);
+    uint32_t seg = (uint32_t)(t_begin / rows), slot = (uint32_t)(t_begin % rows);       // one division per CTA
 
     if (warp == K3_CONSUMER_WARPS) {
         // producer warp: one lane feeds the ring
         if (lane == 0) {
-            uint32_t it = 0;
-            uint32_t seg = (uint32_t)(t_begin / rows), slot = (uint32_t)(t_begin % rows);   // one division per CTA
-            for (uint64_t t = t_begin; t < t_end; t++, it++) {
-                const int s = it % K3_STAGES;
-                const uint32_t round = it / K3_STAGES;
+            uint32_t s = 0, round = 0;
+            for (uint32_t it = 0; it < n_tiles; it++) {
                 if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-                if (t != t_begin && ++slot == rows) { slot = 0; seg++; }
                 const uint64_t col0 = (uint64_t)seg * K3_SEG;
                 const uint32_t ncols = (uint32_t)((Dp - col0 < (uint64_t)K3_SEG) ? (Dp - col0) : K3_SEG);
                 mbar_arrive_expect_tx(&full[s], ncols * 4u);
                 bulk_g2s_evict_first(stage + (size_t)s * K3_SEG, K32 + (uint64_t)slot * Dp + col0, ncols * 4u,
                                      &full[s]);
+                if (++slot == rows) { slot = 0; seg++; }
+                if (++s == K3_STAGES) { s = 0; round++; }
             }
         }
     } else {
-        uint32_t it = 0;
-        uint32_t seg = (uint32_t)(t_begin / rows), slot = (uint32_t)(t_begin % rows);
-        for (uint64_t t = t_begin; t < t_end; t++, it++) {
-            const int s = it % K3_STAGES;
-            const uint32_t round = it / K3_STAGES;
-            if (t != t_begin && ++slot == rows) { slot = 0; seg++; }
-            const uint64_t col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
-            double thr = 0.0;
-            bool always = false;
-            if (lane == 0) {                        // issued ahead of the wait: its latency hides behind the stage
-                const double W = weights[slot];
-                always = drift && !(W < 0.0);
-                thr = W * thr_scale;                // W / decayWeight under drift (histosketch.go:141-146), else W:
-                                                    // the scale is 1/decayWeight or 1, a reciprocal is fine for a
-                                                    // screen that carries a 1e-6 guard band (a division here costs
-                                                    // ~40 issue slots per tile)
-            }
-            mbar_wait(&full[s], round & 1);
+        // consumer warps: everything that depends on the segment only is recomputed when the segment changes
+        const float *my_stage = stage + warp * K3_SUB;
+        uint32_t s = 0, parity = 0;
+        uint64_t col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
+        bool live = col0 < Dp;
+        const float4 *fs = reinterpret_cast<const float4 *>(invf + (live ? col0 : 0));
+        float *mout = m32 + (uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG + warp;
+        for (uint32_t it = 0; it < n_tiles; it++) {
+            float thr = 0.f;
+            if (lane == 0) thr = thr32[slot];       // issued ahead of the wait: its latency hides behind the stage
+            mbar_wait(&full[s], parity);
             float m = __int_as_float(0x7f800000);
-            if (col0 < Dp) {
-                const float4 *ks = reinterpret_cast<const float4 *>(stage + (size_t)s * K3_SEG + warp * K3_SUB);
-                const float4 *fs = reinterpret_cast<const float4 *>(invf + col0);
+            if (live) {
+                const float4 *ks = reinterpret_cast<const float4 *>(my_stage + (size_t)s * K3_SEG);
 #pragma unroll
                 for (int u = 0; u < K3_SUB / 128; u++) {
                     const float4 kv = ks[u * 32 + lane];
@@ -151,15 +158,24 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);  // the stage is free before the (global) epilogue
-            if (col0 < Dp) {
+            if (live) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
                 if (lane == 0) {
-                    m32[(uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG + warp] = m;
-                    const bool c = always || ((double)m < thr + K3_EPS * fabs(thr) + 1e-37);  // same test as k3_resolve
-                    if (c && m < __int_as_float(0x7f800000)) atomicOr(&cand[slot], 1u);
+                    *mout = m;
+                    if (m < thr) atomicOr(&cand[slot], 1u);
                 }
             }
+            mout += nsub_row;
+            if (++slot == rows) {
+                slot = 0;
+                seg++;
+                col0 = (uint64_t)seg * K3_SEG + (uint64_t)warp * K3_SUB;
+                live = col0 < Dp;
+                fs = reinterpret_cast<const float4 *>(invf + (live ? col0 : 0));
+                mout = m32 + (uint64_t)seg * K3_SUBS_PER_SEG + warp;
+            }
+            if (++s == K3_STAGES) { s = 0; parity ^= 1; }
         }
     }
 }
@@ -176,7 +192,7 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
            const double *__restrict__ c, const double *__restrict__ b, const int32_t D,
            const unsigned long long *__restrict__ fbits, const uint32_t rows, unsigned long long *__restrict__ sketch,
            double *__restrict__ weights, const int drift, const double decay_weight, unsigned int *__restrict__ cand,
-           FlushCtl *ctl, const int fi) {
+           float *__restrict__ thr32, const double thr_scale, FlushCtl *ctl, const int fi) {
     if (!ctl->go[fi]) return;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= rows) return;
@@ -246,6 +262,7 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
     if (lane == 0) {
         weights[slot] = W;
         sketch[slot] = S;
+        thr32[slot] = k3_thr32(W, drift, thr_scale);    // the next flush's screen
         if (rescans) atomicAdd(&ctl->n_rescans, (unsigned long long)rescans);
     }
 }
