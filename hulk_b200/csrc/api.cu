@@ -73,6 +73,7 @@ struct hulk_b200_ctx {
     int k1_ctas_per_sm = 4;                    // scan CTAs per SM in queue mode (tasks are handed out dynamically):
                                                // one short of what fits, so the flush chain always finds SM room
     uint64_t max_launch_reads = 1ull << 22;    // reads per k1 launch (HULK_B200_MAX_LAUNCH_READS)
+    int jump_ctas_per_sm = K1_JUMP_CTAS_PER_SM;
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
     bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
@@ -419,6 +420,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e >= '1' && *e <= '0' + K1_W9_CTAS_PER_SM) ctx->k1_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_MAX_LAUNCH_READS");
         if (e && atoll(e) >= 32) ctx->max_launch_reads = (uint64_t)atoll(e);
+        e = getenv("HULK_B200_JUMP_CTAS");
+        if (e && *e >= '1' && *e <= '8') ctx->jump_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_JUMP_BATCH");
         if (e && (*e == '2' || *e == '4')) ctx->jump_batch = *e - '0';
         e = getenv("HULK_B200_K1_FUSED");
@@ -837,7 +840,7 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
 #undef K1_DISPATCH
         LAUNCH_CHECK("k1_minimizer_histogram");
         if (use_queue) {
-            const unsigned gridj = (unsigned)(ctx->sm_count * K1_JUMP_CTAS_PER_SM);
+            const unsigned gridj = (unsigned)(ctx->sm_count * ctx->jump_ctas_per_sm);
             if (ctx->jump_batch == 2) k1_jump_queue<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             else k1_jump_queue<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             LAUNCH_CHECK("k1_jump_queue");

@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
 // across the whole grid whatever the per-read set sizes were.
 // ------------------------------------------------------------------------------------------
 constexpr int K1_JUMP_TPB = 256;
-constexpr int K1_JUMP_CTAS_PER_SM = 4;      // 32 warps per SM, one wave: every warp walks one contiguous segment
+constexpr int K1_JUMP_CTAS_PER_SM = 3;      // 24 warps per SM, one wave: every warp walks one contiguous segment
 template <int BATCH>
 __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue(const K1Params p) {
     const unsigned long long filled = *p.queue_cursor;
