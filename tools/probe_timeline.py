@@ -8,7 +8,7 @@ import hulk_b200
 from bench import synthetic_reads_torch, synthetic_tables_torch
 L = hulk_b200.load()
 dev = torch.device("cuda", 0)
-k, w, s, I, RL, K = 21, 9, 512, 100_000, 150, 12
+k, w, s, I, RL, K = 21, 9, 512, 100_000, 150, int(os.environ.get("TIMELINE_STEPS", "12"))
 D = k ** 4
 stream = torch.cuda.Stream(priority=-1)
 with torch.cuda.stream(stream):
