@@ -99,6 +99,11 @@ struct hulk_b200_ctx {
     // stage 3b
     double *d_r = nullptr, *d_c = nullptr, *d_b = nullptr;
     float *d_K32 = nullptr, *d_m32 = nullptr;
+    // bf16 screen (default; HULK_B200_K3_FP32=1 keeps the fp32 one): K16 replaces K32, (1/f)16 replaces (1/f)32
+    bool filter16 = true;
+    __nv_bfloat16 *d_K16 = nullptr;
+    __nv_bfloat16 *d_invf16[2] = {nullptr, nullptr};
+    double k3_eps = K3_EPS16;
     unsigned int *d_cand = nullptr;            // per slot: some chunk of the current flush may change it
     float *d_thr32 = nullptr;                  // per slot: the fp32 screen bound (k3_thr32), kept by k3_resolve
     int k3_stages = 4, k3_ctas_per_sm = 2;     // 2 x (4 x 16 KB) per SM: 5.7 TB/s alone, and k1 CTAs still fit next to it
@@ -240,7 +245,8 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits[0], ctx->d_fbits[1], ctx->d_invf[0],
                     ctx->d_invf[1], ctx->d_r, ctx->d_c,
-                    ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights, ctx->d_cand, ctx->d_thr32};
+                    ctx->d_b, ctx->d_K32, ctx->d_m32, ctx->d_sketch, ctx->d_weights, ctx->d_cand, ctx->d_thr32,
+                    ctx->d_K16, ctx->d_invf16[0], ctx->d_invf16[1]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < NSTAGE; i++) {
@@ -311,7 +317,13 @@ static int create_impl(hulk_b200_ctx *ctx) {
     const uint32_t rows = ctx->rows;
     ctx->Dp = ((uint64_t)D + K3_SUB - 1) / K3_SUB * K3_SUB;
     ctx->nsub_row = (uint32_t)(ctx->Dp / K3_SUB);
-    ctx->nseg = (uint32_t)((ctx->Dp + K3_SEG - 1) / K3_SEG);
+    {
+        const char *e = getenv("HULK_B200_K3_FP32");
+        if (e && *e == '1') ctx->filter16 = false;
+    }
+    ctx->k3_eps = ctx->filter16 ? K3_EPS16 : K3_EPS;
+    const uint64_t seg_bins = ctx->filter16 ? K3_SEG16 : K3_SEG;
+    ctx->nseg = (uint32_t)((ctx->Dp + seg_bins - 1) / seg_bins);
     ctx->nblk = (uint32_t)(((uint64_t)D + 1023) / 1024);
 
     for (int i = 0; i < NBUF; i++) CU(dmalloc(&ctx->d_hist[i], D));
@@ -336,6 +348,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     for (int i = 0; i < 2; i++) {
         CU(dmalloc(&ctx->d_fbits[i], D));
         CU(dmalloc(&ctx->d_invf[i], ctx->Dp));
+        if (ctx->filter16) CU(dmalloc(&ctx->d_invf16[i], ctx->Dp));
     }
     CU(dmalloc(&ctx->d_m32, (uint64_t)rows * ctx->nsub_row));
     CU(dmalloc(&ctx->d_sketch, rows));
@@ -353,7 +366,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->d_errword, 0xff, 8, st));
     CU(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(FlushCtl), st));
     CU(cudaMemsetAsync(ctx->d_q, 0, sizeof(double) * CMS_CELLS, st));
-    for (int i = 0; i < 2; i++) CU(cudaMemsetAsync(ctx->d_invf[i], 0xff, sizeof(float) * ctx->Dp, st));   // NaN padding
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMemsetAsync(ctx->d_invf[i], 0xff, sizeof(float) * ctx->Dp, st));                 // NaN padding
+        if (ctx->filter16) CU(cudaMemsetAsync(ctx->d_invf16[i], 0xff, 2 * ctx->Dp, st));        // bf16 0xffff = NaN
+    }
     CU(cudaMemsetAsync(ctx->d_sketch, 0, sizeof(unsigned long long) * (rows ? rows : 1), st));   // histosketch.go:84-87
     CU(cudaMemsetAsync(ctx->d_cand, 0, sizeof(unsigned int) * (rows ? rows : 1), st));
     if (rows) k3_fill_f32<<<(rows + 255) / 256, 256, 0, st>>>(ctx->d_thr32, rows, INFINITY);   // W = MaxFloat64
@@ -386,6 +402,9 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(cudaFuncSetAttribute(k3_filter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * K3_SEG * 4 + 2 * 4 * 8));
     CU(cudaFuncSetAttribute(k3_filter<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * K3_SEG * 4 + 2 * 6 * 8));
     CU(cudaFuncSetAttribute(k3_filter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * K3_SEG * 4 + 2 * 8 * 8));
+    CU(cudaFuncSetAttribute(k3_filter16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * K3_SEG16 * 2 + 2 * 4 * 8));
+    CU(cudaFuncSetAttribute(k3_filter16<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * K3_SEG16 * 2 + 2 * 6 * 8));
+    CU(cudaFuncSetAttribute(k3_filter16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * K3_SEG16 * 2 + 2 * 8 * 8));
     {
         const char *e = getenv("HULK_B200_K3_STAGES");
         if (e && (*e == '4' || *e == '6' || *e == '8')) ctx->k3_stages = *e - '0';
@@ -487,7 +506,8 @@ static int upload_tables(hulk_b200_ctx *ctx, const double *r, const double *c, c
         CU(dmalloc(&ctx->d_r, n));
         CU(dmalloc(&ctx->d_c, n));
         CU(dmalloc(&ctx->d_b, n));
-        CU(dmalloc(&ctx->d_K32, (uint64_t)ctx->rows * ctx->Dp));
+        if (ctx->filter16) CU(dmalloc(&ctx->d_K16, (uint64_t)ctx->rows * ctx->Dp));
+        else CU(dmalloc(&ctx->d_K32, (uint64_t)ctx->rows * ctx->Dp));
     }
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(ctx->d_r, r, sizeof(double) * n, cudaMemcpyHostToDevice, st));
@@ -496,8 +516,12 @@ static int upload_tables(hulk_b200_ctx *ctx, const double *r, const double *c, c
     ctx->st.h2d_bytes += 3 * sizeof(double) * n;
     const uint64_t total = (uint64_t)ctx->rows * ctx->Dp;
     if (total) {
-        k3_fold<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
-                                                                 ctx->Dp, ctx->d_K32);
+        if (ctx->filter16)
+            k3_fold16<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
+                                                                       ctx->Dp, ctx->d_K16);
+        else
+            k3_fold<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
+                                                                     ctx->Dp, ctx->d_K32);
         LAUNCH_CHECK("k3_fold");
     }
     CU(cudaStreamSynchronize(st));
@@ -521,7 +545,8 @@ int hulk_b200_set_cws_tables_device(hulk_b200_ctx *ctx, const double *d_r, const
         CU(dmalloc(&ctx->d_r, n));
         CU(dmalloc(&ctx->d_c, n));
         CU(dmalloc(&ctx->d_b, n));
-        CU(dmalloc(&ctx->d_K32, (uint64_t)ctx->rows * ctx->Dp));
+        if (ctx->filter16) CU(dmalloc(&ctx->d_K16, (uint64_t)ctx->rows * ctx->Dp));
+        else CU(dmalloc(&ctx->d_K32, (uint64_t)ctx->rows * ctx->Dp));
     }
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(ctx->d_r, d_r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
@@ -529,8 +554,12 @@ int hulk_b200_set_cws_tables_device(hulk_b200_ctx *ctx, const double *d_r, const
     CU(cudaMemcpyAsync(ctx->d_b, d_b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     const uint64_t total = (uint64_t)ctx->rows * ctx->Dp;
     if (total) {
-        k3_fold<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
-                                                                 ctx->Dp, ctx->d_K32);
+        if (ctx->filter16)
+            k3_fold16<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
+                                                                       ctx->Dp, ctx->d_K16);
+        else
+            k3_fold<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
+                                                                     ctx->Dp, ctx->d_K32);
         LAUNCH_CHECK("k3_fold");
     }
     CU(cudaStreamSynchronize(st));
@@ -1026,7 +1055,8 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
                                                                  ctx->d_q, fbits, ctx->d_ctl, fi,
                                                                  ctx->apply_scaling ? 1 : 0, ctx->decay_weight);
     LAUNCH_CHECK("k2_cms_update");
-    k2_finalize<<<(unsigned)(((uint64_t)D + 255) / 256), 256, 0, k2s>>>(hist, D, fbits, invf, ctx->d_ctl, fi);
+    k2_finalize<<<(unsigned)(((uint64_t)D + 255) / 256), 256, 0, k2s>>>(hist, D, fbits, invf, ctx->d_invf16[fi],
+                                                                        ctx->d_ctl, fi);
     LAUNCH_CHECK("k2_finalize");
     }
     // the buffer is wiped: the next interval but one may count into it while the CWS sweep below runs
@@ -1046,11 +1076,19 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
         const unsigned grid = (unsigned)std::min<uint64_t>(T, (uint64_t)ctx->sm_count * ctx->k3_ctas_per_sm);
         {
             ProfScope prof_scope(ctx, 2);
-#define K3_FILTER_ARGS ctx->d_K32, ctx->Dp, invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_thr32, ctx->d_cand, ctx->d_ctl, fi
-            if (stages == 4) k3_filter<4><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
-            else if (stages == 6) k3_filter<6><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
-            else k3_filter<8><<<grid, K3_THREADS, smem, st>>>(K3_FILTER_ARGS);
+#define K3_FILTER_ARGS ctx->Dp, invf, ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_thr32, ctx->d_cand, ctx->d_ctl, fi
+#define K3_FILTER16_ARGS ctx->Dp, ctx->d_invf16[fi], ctx->d_m32, ctx->rows, ctx->nseg, ctx->d_thr32, ctx->d_cand, ctx->d_ctl, fi
+            if (ctx->filter16) {
+                if (stages == 4) k3_filter16<4><<<grid, K3_THREADS, smem, st>>>(ctx->d_K16, K3_FILTER16_ARGS);
+                else if (stages == 6) k3_filter16<6><<<grid, K3_THREADS, smem, st>>>(ctx->d_K16, K3_FILTER16_ARGS);
+                else k3_filter16<8><<<grid, K3_THREADS, smem, st>>>(ctx->d_K16, K3_FILTER16_ARGS);
+            } else {
+                if (stages == 4) k3_filter<4><<<grid, K3_THREADS, smem, st>>>(ctx->d_K32, K3_FILTER_ARGS);
+                else if (stages == 6) k3_filter<6><<<grid, K3_THREADS, smem, st>>>(ctx->d_K32, K3_FILTER_ARGS);
+                else k3_filter<8><<<grid, K3_THREADS, smem, st>>>(ctx->d_K32, K3_FILTER_ARGS);
+            }
 #undef K3_FILTER_ARGS
+#undef K3_FILTER16_ARGS
             LAUNCH_CHECK("k3_filter");
         }
         {
@@ -1060,7 +1098,7 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
                                                                      ctx->d_weights, ctx->drift ? 1 : 0,
                                                                      ctx->decay_weight, ctx->d_cand, ctx->d_thr32,
                                                                      ctx->drift ? 1.0 / ctx->decay_weight : 1.0,
-                                                                     ctx->d_ctl, fi);
+                                                                     ctx->k3_eps, ctx->d_ctl, fi);
             LAUNCH_CHECK("k3_resolve");
         }
         CU(cudaEventRecord(ctx->ev_k3_done[fi], st));
@@ -1304,7 +1342,17 @@ int hulk_b200_get_folded_table(hulk_b200_ctx *ctx, float *out, uint64_t *row_str
     if (!ctx->tables_set) return fail(ctx, HULK_B200_ESTATE, "CWS tables not set");
     CU(cudaSetDevice(ctx->P.device));
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpy(out, ctx->d_K32, sizeof(float) * (size_t)ctx->rows * ctx->Dp, cudaMemcpyDeviceToHost));
+    const size_t ne = (size_t)ctx->rows * ctx->Dp;
+    if (ctx->filter16) {                      // widen the stored bf16 values (exact)
+        std::vector<uint16_t> h(ne ? ne : 1);
+        CU(cudaMemcpy(h.data(), ctx->d_K16, 2 * ne, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < ne; i++) {
+            const uint32_t bits = (uint32_t)h[i] << 16;
+            memcpy(&out[i], &bits, 4);
+        }
+        return HULK_B200_OK;
+    }
+    CU(cudaMemcpy(out, ctx->d_K32, sizeof(float) * ne, cudaMemcpyDeviceToHost));
     return HULK_B200_OK;
 }
 

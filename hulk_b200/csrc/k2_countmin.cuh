@@ -19,6 +19,7 @@
 // (t1,B1) o (t2,B2) = (t2, B1 * w^(t2 - t1) + B2); w^n is exp(n ln w) instead of n roundings of a
 // repeated product (differs from the reference by <= ~n * 2^-53 relative).
 #pragma once
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -283,14 +284,16 @@ __global__ void __launch_bounds__(256) k2_cms_update(const uint32_t *__restrict_
 
 // (d) estimate -> fp32 reciprocal for the streaming filter; wipe the histogram (kmerspectrum.go:58-64)
 __global__ void k2_finalize(uint32_t *__restrict__ hist, int32_t D, const unsigned long long *__restrict__ fbits,
-                            float *__restrict__ invf, const FlushCtl *__restrict__ ctl, const int fi) {
+                            float *__restrict__ invf, __nv_bfloat16 *__restrict__ invf16,
+                            const FlushCtl *__restrict__ ctl, const int fi) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D) return;
     const unsigned int go = ctl->go[fi];
     if (go) {
         const bool used = hist[i] != 0u;
         const double f = __longlong_as_double((long long)fbits[i]);
-        invf[i] = used ? (float)(1.0 / f) : __int_as_float(0x7fc00000);
+        if (invf16) invf16[i] = used ? __double2bfloat16(1.0 / f) : __float2bfloat16(__int_as_float(0x7fc00000));
+        else invf[i] = used ? (float)(1.0 / f) : __int_as_float(0x7fc00000);
     }
     // boss.go:117-128: the spectrum is wiped only when a dump happened (cardinality != 0 and no error)
     if (go) hist[i] = 0u;

@@ -18,6 +18,7 @@
 //              float64 r, c, b tables.  Every value that reaches Sketch/Weights therefore comes
 //              from the float64 formula; fp32 only decides which chunks cannot matter.
 #pragma once
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -33,6 +34,13 @@ constexpr int K3_STAGES_MAX = 8;                    // ring depth (template para
 constexpr int K3_CONSUMER_WARPS = K3_SUBS_PER_SEG;
 constexpr int K3_THREADS = (K3_CONSUMER_WARPS + 1) * 32;
 constexpr double K3_EPS = 1e-6;                     // >> 3 * 2^-24 (K32, (1/f)32 and product roundings)
+// bf16 screen (default): K and 1/f are stored as bfloat16 and multiplied/compared as packed pairs, so a
+// flush streams 2 bytes per (slot, bin) instead of 4 and issues half the instructions.  The guard band
+// widens accordingly: bfloat16 keeps 8 significant bits, so each of the three roundings (K, 1/f, product) is
+// off by at most 2^-8 relative; (1 + 2^-8)^3 - 1 = 0.011765 < 0.0125.
+constexpr int K3_SEG16 = 8192;                      // bins per TMA stage of the bf16 table (16 KB)
+constexpr int K3_SUBS_PER_SEG16 = K3_SEG16 / K3_SUB;
+constexpr double K3_EPS16 = 0.0125;
 
 // ---- context creation: fold the float64 tables into K32 ----
 __global__ void k3_fold(const double *__restrict__ r, const double *__restrict__ c, const double *__restrict__ b,
@@ -47,6 +55,20 @@ __global__ void k3_fold(const double *__restrict__ r, const double *__restrict__
         v = (float)(c[at] * exp(b[at] - r[at]));
     }
     K32[i] = v;
+}
+
+__global__ void k3_fold16(const double *__restrict__ r, const double *__restrict__ c, const double *__restrict__ b,
+                          uint32_t rows, int32_t D, uint64_t Dp, __nv_bfloat16 *__restrict__ K16) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)rows * Dp;
+    if (i >= total) return;
+    const uint64_t row = i / Dp, col = i % Dp;
+    __nv_bfloat16 v = __float2bfloat16(__int_as_float(0x7fc00000));
+    if (col < (uint64_t)D) {
+        const uint64_t at = row * (uint64_t)D + col;
+        v = __double2bfloat16(c[at] * exp(b[at] - r[at]));       // round to nearest
+    }
+    K16[i] = v;
 }
 
 // Blackwell packed-pair multiply (FMUL2) and three-input minimum (FMNMX3; like fminf it returns the
@@ -75,11 +97,11 @@ __device__ __forceinline__ float2 k3_mul2(float ax, float ay, float bx, float by
 // This is exact because the bound only decreases during a flush: without concept drift W only decreases;
 // with drift a replacement gives W' = A < W / decayWeight < W when W < 0, and for W >= 0 (or NaN), where the
 // bound may grow, thr32 is +inf (every non-empty chunk is a candidate).  k3_resolve maintains thr32.
-__device__ __forceinline__ float k3_thr32(const double W, const int drift, const double thr_scale) {
+__device__ __forceinline__ float k3_thr32(const double W, const int drift, const double thr_scale, const double eps) {
     if (drift && !(W < 0.0)) return __int_as_float(0x7f800000);
     const double thr = W * thr_scale;            // thr_scale = 1 / decayWeight under drift (a reciprocal is fine
                                                  // for a screen with a 1e-6 guard band), else 1
-    const double lim = thr + K3_EPS * fabs(thr) + 1e-37;
+    const double lim = thr + eps * fabs(thr) + 1e-37;
     if (lim != lim) return __int_as_float(0xff800000);       // -inf + inf: nothing can pass
     return __double2float_ru(lim);
 }
@@ -180,6 +202,111 @@ k3_filter(const float *__restrict__ K32, const uint64_t Dp, const float *__restr
     }
 }
 
+// The same screen over the bf16 table: a stage is 8192 bins, every consumer warp owns two 512-bin chunks of
+// it; K16 and (1/f)16 are multiplied and minimised as packed bf16 pairs (HMUL2.BF16 / HMNMX2.BF16, NaN = empty
+// bin or padding is ignored by the minimum), the two chunk minima are reduced and written as fp32.
+template <int K3_STAGES>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3_filter16(const __nv_bfloat16 *__restrict__ K16, const uint64_t Dp, const __nv_bfloat16 *__restrict__ invf16,
+            float *__restrict__ m32, const uint32_t rows, const uint32_t nseg, const float *__restrict__ thr32,
+            unsigned int *__restrict__ cand, const FlushCtl *__restrict__ ctl, const int fi) {
+    if (!ctl->go[fi]) return;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __nv_bfloat16 *stage = reinterpret_cast<__nv_bfloat16 *>(smem);                    // [STAGES][SEG16]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)K3_STAGES * K3_SEG16 * 2);
+    uint64_t *empty = full + K3_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K3_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], K3_CONSUMER_WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t T = (uint64_t)rows * nseg;
+    const uint64_t t_begin = T * blockIdx.x / gridDim.x;
+    const uint32_t n_tiles = (uint32_t)(T * (blockIdx.x + 1) / gridDim.x - t_begin);
+    const uint32_t nsub_row = (uint32_t)(Dp / K3_SUB);
+    uint32_t seg = (uint32_t)(t_begin / rows), slot = (uint32_t)(t_begin % rows);
+
+    if (warp == K3_CONSUMER_WARPS) {
+        if (lane == 0) {
+            uint32_t s = 0, round = 0;
+            for (uint32_t it = 0; it < n_tiles; it++) {
+                if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+                const uint64_t col0 = (uint64_t)seg * K3_SEG16;
+                const uint32_t ncols = (uint32_t)((Dp - col0 < (uint64_t)K3_SEG16) ? (Dp - col0) : K3_SEG16);
+                mbar_arrive_expect_tx(&full[s], ncols * 2u);
+                bulk_g2s_evict_first(stage + (size_t)s * K3_SEG16, K16 + (uint64_t)slot * Dp + col0, ncols * 2u,
+                                     &full[s]);
+                if (++slot == rows) { slot = 0; seg++; }
+                if (++s == K3_STAGES) { s = 0; round++; }
+            }
+        }
+    } else {
+        constexpr int PER_WARP = K3_SEG16 / K3_CONSUMER_WARPS;                         // 1024 bins = 2 chunks
+        const __nv_bfloat16 *my_stage = stage + warp * PER_WARP;
+        uint32_t s = 0, parity = 0;
+        uint64_t col0 = (uint64_t)seg * K3_SEG16 + (uint64_t)warp * PER_WARP;
+        bool live0 = col0 < Dp, live1 = col0 + K3_SUB < Dp;
+        const uint4 *fs = reinterpret_cast<const uint4 *>(invf16 + (live0 ? col0 : 0));
+        float *mout = m32 + (uint64_t)slot * nsub_row + (uint64_t)seg * K3_SUBS_PER_SEG16 + 2 * warp;
+        const __nv_bfloat162 inf2 = __floats2bfloat162_rn(INFINITY, INFINITY);
+        for (uint32_t it = 0; it < n_tiles; it++) {
+            float thr = 0.f;
+            if (lane == 0) thr = thr32[slot];
+            mbar_wait(&full[s], parity);
+            __nv_bfloat162 acc[2] = {inf2, inf2};
+            if (live0) {
+                const uint4 *ks = reinterpret_cast<const uint4 *>(my_stage + (size_t)s * K3_SEG16);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {                                          // u = 0,1: chunk 0; u = 2,3: chunk 1
+                    if (u >= 2 && !live1) break;
+                    const uint4 kv = ks[u * 32 + lane];                                // 8 bins
+                    const uint4 fv = __ldg(&fs[u * 32 + lane]);
+                    const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w}, fw[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const __nv_bfloat162 p = __hmul2(*reinterpret_cast<const __nv_bfloat162 *>(&kw[e]),
+                                                         *reinterpret_cast<const __nv_bfloat162 *>(&fw[e]));
+                        acc[u >> 1] = __hmin2(acc[u >> 1], p);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (live0) {
+                float m0 = fminf(__low2float(acc[0]), __high2float(acc[0]));
+                float m1 = fminf(__low2float(acc[1]), __high2float(acc[1]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    m0 = fminf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                    m1 = fminf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+                }
+                if (lane == 0) {
+                    mout[0] = m0;
+                    if (live1) mout[1] = m1;
+                    if (fminf(m0, m1) < thr) atomicOr(&cand[slot], 1u);
+                }
+            }
+            mout += nsub_row;
+            if (++slot == rows) {
+                slot = 0;
+                seg++;
+                col0 = (uint64_t)seg * K3_SEG16 + (uint64_t)warp * PER_WARP;
+                live0 = col0 < Dp;
+                live1 = col0 + K3_SUB < Dp;
+                fs = reinterpret_cast<const uint4 *>(invf16 + (live0 ? col0 : 0));
+                mout = m32 + (uint64_t)seg * K3_SUBS_PER_SEG16 + 2 * warp;
+            }
+            if (++s == K3_STAGES) { s = 0; parity ^= 1; }
+        }
+    }
+}
+
 // reference formula, float64 (histosketch.go:30-33)
 __device__ __forceinline__ double k3_sample(double c, double b, double r, double f) {
     const double Yka = exp(log(f) - b);
@@ -192,7 +319,7 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
            const double *__restrict__ c, const double *__restrict__ b, const int32_t D,
            const unsigned long long *__restrict__ fbits, const uint32_t rows, unsigned long long *__restrict__ sketch,
            double *__restrict__ weights, const int drift, const double decay_weight, unsigned int *__restrict__ cand,
-           float *__restrict__ thr32, const double thr_scale, FlushCtl *ctl, const int fi) {
+           float *__restrict__ thr32, const double thr_scale, const double eps, FlushCtl *ctl, const int fi) {
     if (!ctl->go[fi]) return;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= rows) return;
@@ -223,7 +350,7 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
         for (;;) {
             const double thr = drift ? W / decay_weight : W;             // histosketch.go:141-146
             // conservative: could any bin of this chunk satisfy A < thr ?  (false for NaN thr)
-            const bool cand = (m < INFINITY) && (m < thr + K3_EPS * fabs(thr) + 1e-37);
+            const bool cand = (m < INFINITY) && (m < thr + eps * fabs(thr) + 1e-37);
             const uint32_t mask = __ballot_sync(0xffffffffu, cand) & pending;
             if (mask == 0) break;
             const int first = __ffs(mask) - 1;
@@ -262,7 +389,7 @@ k3_resolve(const float *__restrict__ m32, const uint32_t nsub_row, const double 
     if (lane == 0) {
         weights[slot] = W;
         sketch[slot] = S;
-        thr32[slot] = k3_thr32(W, drift, thr_scale);    // the next flush's screen
+        thr32[slot] = k3_thr32(W, drift, thr_scale, eps);    // the next flush's screen
         if (rescans) atomicAdd(&ctl->n_rescans, (unsigned long long)rescans);
     }
 }

@@ -409,14 +409,33 @@ def test_slot_sharding_is_identical_to_single_context(hb):
     np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), weights)
 
 
-def test_folded_table_is_the_fp32_rounding_of_the_float64_coefficient(hb):
+def test_folded_table_is_the_rounding_of_the_float64_coefficient(hb, monkeypatch):
+    # the screen's coefficient table K = c * exp(b - r): bfloat16 (default) or fp32, NaN padding up to 512 bins
     k, s = 7, 5
     D = k ** 4
     r, c, b = _tables(s, D, 2)
+    want = c * np.exp(b - r)
     with hb.HistoSketch(k, 5, s, tables=(r, c, b)) as hs:
         K = hs.folded_table()
     assert K.shape[1] % 512 == 0 and np.isnan(K[:, D:]).all()
-    np.testing.assert_allclose(K[:, :D], (c * np.exp(b - r)).astype(np.float32), rtol=2e-7)
+    np.testing.assert_allclose(K[:, :D], want, rtol=2.0 ** -8)                   # bf16: 8 significant bits, round to nearest
+    assert ((np.ascontiguousarray(K[:, :D]).view(np.uint32) & 0xffff) == 0).all()
+    monkeypatch.setenv("HULK_B200_K3_FP32", "1")
+    with hb.HistoSketch(k, 5, s, tables=(r, c, b)) as hs:
+        K = hs.folded_table()
+    np.testing.assert_allclose(K[:, :D], want.astype(np.float32), rtol=2e-7)
+
+
+@pytest.mark.parametrize("fp32", ["0", "1"])
+def test_both_screens_give_the_same_sketch(hb, oracle, monkeypatch, fp32):
+    # the bf16 and the fp32 screen only decide which chunks are re-evaluated in float64: same mins, same weights
+    monkeypatch.setenv("HULK_B200_K3_FP32", fp32)
+    k, s = 11, 96
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 51)
+    batches = [random_reads(4000, 120, seed=500 + i) for i in range(6)]
+    for decay in (1.0, 0.4):
+        _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=(0.0 if decay == 1.0 else 1e-9))
 
 
 # ---- size-independent properties at a larger size -------------------------------------------------
