@@ -270,7 +270,7 @@ def run_b200(a):
     slots = (rank * rows, (rank + 1) * rows)
     K, W = a.steps, a.warmup
     stream = torch.cuda.Stream(device=dev, priority=-1)   # the flush chain runs here: ahead of the k1 streams
-    n_steps_data = K                                   # distinct intervals of reads kept resident
+    n_steps_data = min(K, 128)                         # distinct intervals of reads kept resident (cycled beyond that; >> L2)
 
     with torch.cuda.stream(stream):
         # reads of this rank: rank-th shard of every interval of the global job
