@@ -1,14 +1,20 @@
 // api.cu -- context management and the C ABI (include/hulk_b200.h) over the sm_100a kernels.
 //
 // HBM layout of one context (D bins, Dp = D padded to 512, rows = owned sketch slots):
-//   reads      2 x staging buffer (raw ASCII, + offsets), ping-pong between H2D copy and k1
-//   hist       uint32[D]              k^4-bin spectrum of the current interval (L2-resident atomics)
+//   reads      4 x staging buffer (raw ASCII, + offsets), a ring between the H2D copy stream and the k1 streams
+//   hist       4 x uint32[D]          k^4-bin spectrum, one buffer per interval in flight (L2-resident atomics)
+//   queue      4 x uint64[reads*cap]  per-batch minimizer queue: k1 scan -> k1_jump_queue
 //   cms        double[7*2000] + static CSR of bins per counter (int32[7*D]) + uint16 cols[7*D]
-//   f          uint64[D] (float64 bits; +inf = bin unused in this flush), invf float[Dp]
+//   f          2 x uint64[D] (float64 bits; +inf = bin unused in this flush), 2 x (1/f) as bfloat16[Dp] (or float)
 //   r, c, b    double[rows*D] each    reference CWS tables (exact float64 re-evaluation)
-//   K32        float[rows*Dp]         folded CWS coefficient c*exp(b-r), streamed once per flush
-//   m32        float[rows*Dp/512]     per-chunk fp32 minima of a flush
+//   K16        bfloat16[rows*Dp]      folded CWS coefficient c*exp(b-r) of the screen, streamed once per flush
+//                                     (HULK_B200_K3_FP32=1: K32 float[rows*Dp])
+//   m32        float[rows*Dp/512]     per-chunk screen minima of a flush; cand uint32[rows], thr32 float[rows]
 //   sketch     uint64[rows], weights double[rows]
+//
+// Streams: `stream` (CWS sweep, caller-visible ordering point), a count-min stream, one k1 stream per
+// spectrum buffer, a copy stream.  Events order "interval counted" -> count-min -> CWS sweep, and
+// "buffer wiped" -> next use, so interval i+1.. is counted while interval i is flushed.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -47,7 +53,7 @@ struct hulk_b200_ctx {
     bool own_stream = false;
 
     // stage 1+2
-    // The spectrum is double-buffered: the reads of interval i+1 are counted into the other buffer (on
+    // The spectrum is multi-buffered: the reads of interval i+1.. are counted into the next buffers (on
     // their own stream) while interval i is still being flushed on the main stream.
     uint32_t *d_hist[NBUF] = {};
     int cur_hist = 0;                          // buffer (and k1 stream) of the interval being counted

@@ -7,16 +7,18 @@
 //       W[j]/decayWeight under concept drift); if A < curMin { Sketch[j] = bin; W[j] = A }
 //   src/pipeline/sketch.go:281-285          called once per used bin, ascending bin order
 //
-// Design.  A = K / f with K = c * exp(b - r) fixed per (slot, bin).  K is folded once into an fp32
-// table K32[rows][Dp] (Dp = bins padded to 512); a flush streams it exactly once:
-//   k3_filter  (HBM-bound): m32[slot][chunk] = min over the chunk's 512 bins of K32 * (1/f)32,
-//              K32 row segments arriving in shared memory through a ring of 1-D bulk TMA copies;
-//   k3_resolve (tiny): per slot walks the chunks in bin order carrying W exactly like the
-//              reference's loop; a chunk whose fp32 minimum could possibly pass the test
-//              (m32 < thr + eps*|thr|, eps covering the fp32 rounding of K32 and 1/f) is
+// Design.  A = K / f with K = c * exp(b - r) fixed per (slot, bin).  K is folded once into a low-precision
+// table (bfloat16 K16[rows][Dp] by default, fp32 K32 as a switch; Dp = bins padded to 512); a flush
+// streams it exactly once:
+//   k3_filter16 / k3_filter (HBM-bound, "the screen"): m32[slot][chunk] = min over the chunk's 512 bins of
+//              K * (1/f) in that precision, row segments arriving in shared memory through a ring of 1-D
+//              bulk TMA copies; raises cand[slot] when a chunk minimum is below the slot's bound;
+//   k3_resolve (tiny): per flagged slot walks the chunks in bin order carrying W exactly like the
+//              reference's loop; a chunk whose screen minimum could possibly pass the test
+//              (m32 < thr + eps*|thr|, eps covering the roundings of K, 1/f and their product) is
 //              re-evaluated bin by bin in float64 with the reference's own formula from the
 //              float64 r, c, b tables.  Every value that reaches Sketch/Weights therefore comes
-//              from the float64 formula; fp32 only decides which chunks cannot matter.
+//              from the float64 formula; the screen only decides which chunks cannot matter.
 #pragma once
 #include <cuda_bf16.h>
 #include <math.h>
@@ -42,7 +44,7 @@ constexpr int K3_SEG16 = 8192;                      // bins per TMA stage of the
 constexpr int K3_SUBS_PER_SEG16 = K3_SEG16 / K3_SUB;
 constexpr double K3_EPS16 = 0.0125;
 
-// ---- context creation: fold the float64 tables into K32 ----
+// ---- context creation: fold the float64 tables into K32 (fp32 screen) / K16 (bf16 screen) ----
 __global__ void k3_fold(const double *__restrict__ r, const double *__restrict__ c, const double *__restrict__ b,
                         uint32_t rows, int32_t D, uint64_t Dp, float *__restrict__ K32) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -228,7 +228,7 @@ class HistoSketch:
     def histogram_tensor(self):
         """The device spectrum of the interval being counted, as a torch int32 tensor aliasing the context's
         memory (for the per-flush all-reduce of hulk_b200.distributed; uint32 sums wrap identically in two's
-        complement).  The spectrum is double-buffered, so ask again after every flush; work enqueued on the
+        complement).  The spectrum is multi-buffered, so ask again after every flush; work enqueued on the
         context's stream after this call sees every read pushed so far."""
         import torch
         ptr = self.histogram_device_ptr()
