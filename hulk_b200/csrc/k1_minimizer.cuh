@@ -5,17 +5,22 @@
 //   src/minimizer/minimizer.go:96-204  findMinimizers (see k1_scan.h for the scan itself)
 //   src/pipeline/minion.go:51-57 + boss.go:90-95 -> src/kmerspectrum/kmerspectrum.go:67-81 AddHash
 //
-// Work decomposition: one thread per read, 128 reads per CTA tile; the tile's bytes are one
-// contiguous range of the batch and are staged into shared memory with a single 1-D bulk TMA
-// copy (the other resident CTAs of the SM cover its latency).  Three phases per tile:
-//   scan    every lane walks its read four bases at a time (k1_scan.h); window minima that differ
-//           from the previous one go to the lane's private list in shared memory;
+// Work decomposition: one thread per read, in three phases:
+//   scan    every lane walks its read (k1_scan.h); window minima that differ from the previous one go to
+//           the lane's private list in shared memory;
 //   de-dup  the list is reduced in place to the exact per-read set (minimizer.go:189-198);
-//   jump    the warp's 32 lists form one work queue; every lane keeps TWO jump-hash chains in
-//           flight (ILP), runs them K1_JUMP_BATCH steps at a time with the fast step of
-//           hd_math.h, and finished chains are refilled from the queue, so lanes stay busy
-//           whatever the per-read set sizes and per-key step counts are.  Bins are counted
-//           with global (L2) atomics -- the k^4-bin histogram does not fit shared memory for k > 11.
+//   jump    every set member is binned with jump.Hash.  In the production configuration the warp's lists
+//           are compacted and appended to a per-batch queue in global memory, and a second kernel
+//           (k1_jump_queue: no shared memory, one wave of warps, keys handed out inside each warp as walks
+//           finish) bins the whole queue; two jump-hash walks per lane are in flight (ILP) and advance
+//           K1_JUMP_BATCH steps between two refill points with the bracketed fast step of hd_math.h.
+//           Bins are counted with global (L2) atomics -- the k^4-bin histogram does not fit shared memory
+//           for k > 11.
+// Two scan kernels: k1_minimizer_histogram_w9 (w = 9, the reference default: window state in registers,
+// reads streamed from global memory, warps independent, 32-read tasks handed out dynamically) and
+// k1_minimizer_histogram (any w <= 32: 128 reads per CTA tile staged by one 1-D bulk TMA copy, window
+// buffers in shared memory).  k1_generic takes what neither can (w > 32, reads whose candidate list
+// overflows).
 #pragma once
 #include <stdint.h>
 
