@@ -364,6 +364,12 @@ int run_sketch(int argc, char **argv) {
     logf("\tnumber of processes added to the sketching pipeline: %d", 4);
     logf("\tnumber of minions in the sketching pool: %ld", o.proc);
 
+    // one GPU is used: hiding the others from the CUDA runtime keeps its start-up proportional to one device
+    // (on an 8-GPU node the runtime otherwise initialises all of them before the first allocation returns)
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        setenv("CUDA_VISIBLE_DEVICES", std::to_string(o.device).c_str(), 1);
+        o.device = 0;
+    }
     // the reader starts first: reading/inflating overlaps context creation and the CWS table draw
     std::vector<const char *> paths;
     for (const std::string &f : o.fastq) paths.push_back(f.c_str());
