@@ -78,6 +78,7 @@ struct hulk_b200_ctx {
     uint64_t queue_cap[NBUF] = {};
     int k1_ctas_per_sm = 4;                    // scan CTAs per SM in queue mode (tasks are handed out dynamically):
                                                // one short of what fits, so the flush chain always finds SM room
+    uint64_t batch_max_len = 0;                // longest read of the batch being pushed (0: unknown)
     uint64_t max_launch_reads = 1ull << 22;    // reads per k1 launch (HULK_B200_MAX_LAUNCH_READS)
     int jump_ctas_per_sm = K1_JUMP_CTAS_PER_SM;
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
@@ -793,13 +794,23 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     p.dump_counts = d_dump_counts;
     // scratch arena of the generic path: 4 table slots per base of the batch, at least 4 Mi entries
     uint64_t want = std::max<uint64_t>(1ull << 22, 4 * total_bytes + (n_reads << 7));
-    // only reserve the large arena when the generic path will take whole batches
-    if (ctx->P.w <= (uint32_t)K1_W_FAST) want = std::min<uint64_t>(want, 1ull << 26);
+    // only reserve the large arena when the generic path will take whole batches ...
+    uint64_t arena_cap = 1ull << 26;
+    if (ctx->batch_max_len > (1u << 20)) {
+        // ... or a very long sequence (a chromosome in --fasta mode) is in the batch: room for its
+        // open-addressing table (two slots per k-mer, a power of two), twice over
+        uint64_t t = 64;
+        while (t < 2 * ctx->batch_max_len) t <<= 1;
+        arena_cap = std::max<uint64_t>(arena_cap, 2 * t);
+    }
+    if (ctx->P.w <= (uint32_t)K1_W_FAST) want = std::min<uint64_t>(want, arena_cap);
     if (want > ctx->arena_entries[hs]) {
         // grow the scratch of EVERY spectrum buffer at once: the next intervals will need the same, and an
         // allocation (a device-wide synchronisation) belongs in front of the pipeline, not inside it
+        // (gigabyte-sized arenas for single long sequences are grown for the buffer in use only)
         { const int rc = sync_all(ctx); if (rc) return rc; }
         for (int i = 0; i < ctx->nbuf; i++) {
+            if (want > (1ull << 26) && i != hs) continue;
             if (want <= ctx->arena_entries[i]) continue;
             if (ctx->d_arena[i]) cudaFree(ctx->d_arena[i]);
             ctx->d_arena[i] = nullptr;
@@ -935,6 +946,9 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
             b1 = upto * (uint64_t)fixed_len;
         }
         const uint64_t nb = b1 - b0, nr = upto - done;
+        ctx->batch_max_len = fixed_len;
+        if (offsets)
+            for (uint64_t i = done; i < upto; i++) ctx->batch_max_len = std::max(ctx->batch_max_len, offsets[i + 1] - offsets[i]);
         const int buf = ctx->cur_buf;
         int rc = ensure_stage(ctx, buf, nb, offsets ? nr + 1 : 0);
         if (rc) return rc;
@@ -1002,6 +1016,7 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
         total_bytes = ends[1] - ends[0];
     }
     const int hs = ctx->cur_hist;
+    ctx->batch_max_len = read_len;             // read lengths behind device offsets are not known on the host
     cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
     if (ctx->overlap && !(ctx->P.flags & HULK_B200_F_INPUT_READY)) {          // order behind whatever produced the input on the main stream
         CU(cudaEventRecord(ctx->ev_main, ctx->stream));

@@ -109,6 +109,17 @@ ORACLE_API int hulk_oracle_minimizers(uint32_t k_, uint32_t w_, const uint8_t *s
     pair_t *q = (pair_t *)malloc(sizeof(pair_t) * (size_t)(len + 1));
     int64_t qh = 0, qt = 0;                                         /* [qh, qt) */
     int64_t n = 0;
+    /* membership test of the per-read set (mapset, minimizer.go:189-198): a linear scan for read-sized
+     * inputs, an open-addressing table for chromosome-sized ones -- same set, first-insertion order kept */
+    uint64_t *tab = NULL, tab_mask = 0;
+    uint8_t *used = NULL;
+    if (len > 8192) {
+        uint64_t tcap = 64;
+        while (tcap < (uint64_t)len) tcap <<= 1;
+        tab = (uint64_t *)malloc(sizeof(uint64_t) * tcap);
+        used = (uint8_t *)calloc(tcap, 1);
+        tab_mask = tcap - 1;
+    }
 
     for (int32_t i = 0; i < len; i++) {
         int32_t windowIndex = i - w + 1;
@@ -134,14 +145,25 @@ ORACLE_API int hulk_oracle_minimizers(uint32_t k_, uint32_t w_, const uint8_t *s
         if (windowIndex >= 0) {
             uint64_t m = q[qh].X;
             int found = 0;
-            for (int64_t t = 0; t < n; t++) if (out[t] == m) { found = 1; break; }
+            if (tab) {                                               /* long read: the same set, hashed */
+                uint64_t h = (m * 0x9E3779B97F4A7C15ULL) >> 20;
+                for (;; h++) {
+                    h &= tab_mask;
+                    if (!used[h]) { used[h] = 1; tab[h] = m; break; }
+                    if (tab[h] == m) { found = 1; break; }
+                }
+            } else {
+                for (int64_t t = 0; t < n; t++) if (out[t] == m) { found = 1; break; }
+            }
             if (!found) {
-                if (n >= cap) { free(q); return ERR_CAP; }
+                if (n >= cap) { free(q); free(tab); free(used); return ERR_CAP; }
                 out[n++] = m;
             }
         }
     }
     free(q);
+    free(tab);
+    free(used);
     *n_out = n;
     return 0;
 }

@@ -73,6 +73,21 @@ def test_long_reads_take_the_generic_path(hb, oracle):
     np.testing.assert_array_equal(h, ho.astype(np.uint32))
 
 
+def test_chromosome_sized_sequence(hb, oracle):
+    # --fasta mode hands whole contigs to AddSeq: a 20 Mbp sequence needs a 2^26-entry table, more than the
+    # default scratch arena holds next to its neighbours, and must still give the reference's set
+    rng = np.random.default_rng(77)
+    big = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 20_000_000)].tobytes()
+    reads = [big, b"ACGTTGCA" * 40, big[:3_000_000]]
+    with hb.HistoSketch(21, 9, 4) as hs:
+        hs.add_seqs(reads)
+        h = hs.histogram()
+        st = hs.stats()
+    ho, nm = oracle.count_reads(21, 9, 21 ** 4, *oracle.pack_reads(reads))
+    np.testing.assert_array_equal(h, ho.astype(np.uint32))
+    assert st["n_minimizers"] == nm and st["n_bases"] == sum(len(r) for r in reads)
+
+
 def test_read_length_errors_mirror_reference(hb):
     with hb.HistoSketch(21, 9, 4) as hs:
         with pytest.raises(hb.HulkError) as e:

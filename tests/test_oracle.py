@@ -215,3 +215,14 @@ def test_run_intervals(oracle):
     assert tot == nmin
     np.testing.assert_array_equal(hs.get()[0], hs2.get()[0])
     np.testing.assert_array_equal(hs.get()[1], hs2.get()[1])
+
+
+def test_long_read_set_path_equals_python_restatement(oracle):
+    # reads longer than 8192 bases take the oracle's hashed per-read set (same set as the linear scan)
+    from oracle import pyref as P
+    rng = np.random.default_rng(5)
+    for L in (9000, 20000):
+        r = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.choice(5, L, p=[.24, .25, .25, .25, .01])].tobytes() + b"ACGT" * 300
+        a = oracle.minimizers(21, 9, r)
+        assert len(a) == len(set(int(x) for x in a))
+        assert set(int(x) for x in a) == set(P.minimizers(21, 9, r))
