@@ -577,7 +577,10 @@ int run_smash(int argc, char **argv) {
     for (size_t r = 0; r < n; r++) {
         for (size_t c = 0; c < n; c++) {
             char buf[64];
-            snprintf(buf, sizeof buf, "%.2f", sim[r * n + c]);            // strconv.FormatFloat(v, 'f', 2, 64)
+            const double v = sim[r * n + c];
+            if (v != v) snprintf(buf, sizeof buf, "NaN");                 // strconv spells the specials this way
+            else if (v - v != 0) snprintf(buf, sizeof buf, v > 0 ? "+Inf" : "-Inf");
+            else snprintf(buf, sizeof buf, "%.2f", v);                    // strconv.FormatFloat(v, 'f', 2, 64)
             row[c] = buf;
         }
         csv_write(fh, row);
