@@ -420,7 +420,7 @@ def run_b200(a):
     avg_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
     achieved = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dom], "avg_launch_ms": avg_ms,
                 "timing": "CUDA events around every launch, second pass of the same %d steps with the k1/flush "
                           "overlap disabled (serial step %.4f ms); the overlapped pass is what `value` reports" % (K, ms_serial / K),
@@ -449,6 +449,13 @@ def run_b200(a):
                                     "source": "profiles/traffic.json (ncu smsp__inst_executed.sum), 4 issue slots per SM per clock"}
     except Exception:
         pass
+
+    # whole-step figure of SURVEY 8(d): B = sum len + F (4 s D + 16 D) + 16 s bytes over the pipelined step time
+    step_bytes = float(I * RL) + 4.0 * rows * D + 16.0 * D + 16.0 * rows / max(1, K)
+    step_gbs = step_bytes / (ms_value / K * 1e-3) / 1e9
+    roofline["step_algorithmic"] = {"bytes_per_step": step_bytes, "achieved": step_gbs, "unit": "GB/s",
+                                    "frac": step_gbs / peak, "frac_of_nominal_8000": step_gbs / 8000.0,
+                                    "note": "contract bytes (dense fp32 CWS stream) over the pipelined step; per rank"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
