@@ -22,6 +22,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <condition_variable>
 #include <cstdio>
@@ -241,15 +242,122 @@ struct hulk_b200_reader {
         }
         return end_of_file(carry);
     }
+    // ---- BGZF (bgzip / htslib blocked gzip) -------------------------------------------------------------
+    // A BGZF file is a series of gzip members of at most 64 KiB whose header carries the member's size
+    // (extra subfield 'B','C'), so the members can be found without inflating and inflated independently.
+    // Go's gzip.Reader concatenates members (multistream), so the byte stream -- and everything after it --
+    // is the same as through the one-thread zlib path; only the inflating is spread over the cores.
+    static bool bgzf_block(const uint8_t *d, size_t size, size_t off, size_t *bsize, size_t *hdr) {
+        if (off + 18 > size) return false;
+        const uint8_t *h = d + off;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+        const size_t xlen = h[10] | ((size_t)h[11] << 8);
+        if (off + 12 + xlen > size) return false;
+        for (size_t x = 12; x + 4 <= 12 + xlen;) {
+            const size_t slen = h[x + 2] | ((size_t)h[x + 3] << 8);
+            if (h[x] == 'B' && h[x + 1] == 'C' && slen == 2 && x + 6 <= 12 + xlen) {
+                *bsize = (size_t)(h[x + 4] | ((size_t)h[x + 5] << 8)) + 1;
+                *hdr = 12 + xlen;
+                // no name/comment/crc fields in BGZF headers (FLG == 4)
+                return h[3] == 4 && *bsize >= *hdr + 8 && off + *bsize <= size;
+            }
+            x += 4 + slen;
+        }
+        return false;
+    }
+    // returns 1: handled (ok), 0: handled (failed, error set), -1: not a BGZF file, 2: a plain gzip member
+    // follows at *resume_off (the caller goes on with zlib from there, `carry` holds the unfinished line)
+    int read_bgzf(int fd, const std::string &name, std::vector<uint8_t> &carry, size_t *resume_off) {
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 28) return -1;
+        const size_t size = (size_t)st.st_size;
+        void *map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (map == MAP_FAILED) return -1;
+        const uint8_t *d = static_cast<const uint8_t *>(map);
+        size_t bs = 0, hd = 0;
+        if (!bgzf_block(d, size, 0, &bs, &hd)) { munmap(map, size); return -1; }
+        madvise(map, size, MADV_SEQUENTIAL);
+        const unsigned W = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+        struct Blk { size_t off, bsize, hdr, out, isize; };
+        std::vector<uint8_t> window;
+        bool ok = true, resume = false;
+        size_t off = 0;
+        while (ok && !resume && off < size && !fasta_stop) {
+            if (stop) { ok = false; break; }
+            // a window of members: ~64 MiB of output
+            std::vector<Blk> blks;
+            size_t total = 0;
+            while (off < size && total < (64u << 20)) {
+                if (!bgzf_block(d, size, off, &bs, &hd)) {
+                    if (off + 2 <= size && d[off] == 0x1f && d[off + 1] == 0x8b) resume = true;   // an ordinary member
+                    else ok = fail(HULK_B200_EIO, "gzip: invalid header");
+                    break;
+                }
+                const uint8_t *t = d + off + bs - 4;
+                const size_t isize = t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+                blks.push_back({off, bs, hd, total, isize});
+                total += isize;
+                off += bs;
+            }
+            if (!ok) break;
+            window.resize(total);
+            std::atomic<size_t> next(0);
+            std::atomic<bool> bad(false);
+            auto work = [&] {
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+                for (size_t i; (i = next.fetch_add(1)) < blks.size();) {
+                    const Blk &b = blks[i];
+                    inflateReset(&zs);
+                    zs.next_in = const_cast<Bytef *>(d + b.off + b.hdr);
+                    zs.avail_in = (uInt)(b.bsize - b.hdr - 8);
+                    zs.next_out = window.data() + b.out;
+                    zs.avail_out = (uInt)b.isize;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    const uint8_t *t = d + b.off + b.bsize - 8;
+                    const uint32_t crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+                    if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                        (uint32_t)crc32(0L, window.data() + b.out, (uInt)b.isize) != crc)
+                        bad = true;
+                }
+                inflateEnd(&zs);
+            };
+            {
+                std::vector<std::thread> th;
+                for (unsigned t = 1; t < W; t++) th.emplace_back(work);
+                work();
+                for (auto &x : th) x.join();
+            }
+            if (bad) { ok = fail(HULK_B200_EIO, "gzip: invalid checksum"); break; }
+            if (total) ok = feed(window.data(), total, carry);
+        }
+        munmap(map, size);
+        (void)name;
+        if (!ok) return 0;
+        if (resume && !fasta_stop) { *resume_off = off; return 2; }
+        return (fasta_stop ? true : end_of_file(carry)) ? 1 : 0;
+    }
+
     bool read_gz(int fd, const std::string &name) {
         uint8_t magic[2];
         const ssize_t m = ::pread(fd, magic, 2, 0);
         if (m == 0) return fail(HULK_B200_EIO, "EOF");                                    // gzip.NewReader on an empty file
         if (m != 2 || magic[0] != 0x1f || magic[1] != 0x8b) return fail(HULK_B200_EIO, "gzip: invalid header");
+        std::vector<uint8_t> carry;
+        {
+            const char *e = getenv("HULK_B200_PARALLEL_READER");
+            if (!(e && *e == '0')) {
+                size_t resume_off = 0;
+                const int rc = read_bgzf(fd, name, carry, &resume_off);
+                if (rc == 0 || rc == 1) return rc == 1;
+                if (rc == 2 && ::lseek(fd, (off_t)resume_off, SEEK_SET) < 0) return fail(HULK_B200_EIO, "seek " + name);
+            }
+        }
         gzFile gz = gzdopen(dup(fd), "rb");
         if (!gz) return fail(HULK_B200_EIO, "gzdopen " + name);
         gzbuffer(gz, 1u << 20);
-        std::vector<uint8_t> block(kBlock), carry;
+        std::vector<uint8_t> block(kBlock);
         bool ok = true;
         for (;;) {
             if (stop) { ok = false; break; }

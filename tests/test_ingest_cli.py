@@ -264,3 +264,45 @@ def test_parallel_reader_errors_equal_sequential(tmp_path):
         for chunk in ("64", "1000", "50000"):
             par = _native_env([f], {"HULK_B200_PARALLEL_READER": "1", "HULK_B200_PARALLEL_CHUNK": chunk})
             assert par == seq and msg in par and par.startswith("ERR")
+
+
+# ---- BGZF (bgzip) input: members found from their headers, inflated on several threads ----------------
+def _bgzf(data, block=0xff00, level=6):
+    """htslib's blocked gzip: one member per <= 64 KiB of input, size in the 'BC' extra subfield, EOF marker."""
+    import struct
+    import zlib
+    out = bytearray()
+    for a in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if a is None else data[a:a + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(comp) + 8
+        out += struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, 66, 67, 2, bsize - 1)
+        out += comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+    return bytes(out)
+
+
+def test_bgzf_reader_equals_plain_gzip(tmp_path):
+    reads = random_reads(20000, 150, seed=21, ragged=50)
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
+    assert gzip.decompress(_bgzf(rec)) == rec                       # the writer above makes valid multi-member gzip
+    bg = tmp_path / "b.fastq.gz"
+    bg.write_bytes(_bgzf(rec))
+    gz = tmp_path / "g.fastq.gz"
+    gz.write_bytes(gzip.compress(rec, 1))
+    want = _native_env([gz], {})
+    assert want.startswith("OK 20000 ")
+    assert _native_env([bg], {}) == want                            # parallel BGZF path
+    assert _native_env([bg], {"HULK_B200_PARALLEL_READER": "0"}) == want      # zlib path on the same file
+    # a BGZF file with an ordinary gzip member appended (cat a.gz b.gz): zlib takes over where BGZF ends,
+    # in the middle of a record and of a line
+    cut = rec.index(b"\n", len(rec) // 2) - 7
+    mixed = tmp_path / "m.fq.gz"
+    mixed.write_bytes(_bgzf(rec[:cut])[:-28] + gzip.compress(rec[cut:], 1))     # (-28: drop the EOF marker block)
+    assert _native_env([mixed], {}) == want
+    # a corrupted block is an error, not silence
+    raw = bytearray(_bgzf(rec))
+    raw[len(raw) // 2] ^= 0x55
+    bad = tmp_path / "bad.fq.gz"
+    bad.write_bytes(bytes(raw))
+    assert _native_env([bad], {}).startswith("ERR")
