@@ -204,11 +204,52 @@ def cpu_arm(a, steps, warmup):
             times.append(dt)
     total = sum(times)
     value = n_sub * len(times) / total
+    # the same step on ONE thread (one untimed + one timed step; it is ~threads x slower)
+    single = None
+    if threads > 1:
+        try:
+            O.set_threads(1)
+            reads = hulk_b200.synthetic_reads(n_sub, L, seed=1).reshape(-1)
+            for timed in (False, True):
+                t0 = time.perf_counter()
+                O.count_reads(k, w, D, reads, offs)
+                hs.flush(dense.copy(), parallel=True)
+                if timed:
+                    single = n_sub / (time.perf_counter() - t0)
+        finally:
+            O.set_threads(threads)
     sample = ("%d steps of %d reads (1/%d interval) + flush of a dense %d-bin interval histogram into %d of %d "
-              "slots; C oracle (restatement of the Go reference, gcc -O2 -fopenmp), %d threads"
-              % (len(times), n_sub, frac, D, s_sub, a.s, threads))
-    return value, total / len(times) * 1e3, {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                                             "sample": sample}
+              "slots; C oracle (restatement of the Go reference, %s), %d threads"
+              % (len(times), n_sub, frac, D, s_sub, a.s, oracle_flags(), threads))
+    base = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "single_thread_value": single if threads > 1 else value, "host": host_info()}
+    return value, total / len(times) * 1e3, base
+
+
+def oracle_flags():
+    """Compiler line of the oracle, read from its Makefile (always print the flags)."""
+    try:
+        mk = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "Makefile")).read()
+        fl = [ln.split("=", 1)[1].strip() for ln in mk.splitlines() if ln.startswith("CFLAGS")][:1]
+        return " ".join(["gcc"] + fl + ["-fopenmp"])
+    except OSError:
+        return "gcc"
+
+
+def host_info():
+    model = None
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count()
+    return {"cpu_model": model, "nproc": os.cpu_count(), "usable_cpus": usable}
 
 
 def run_reference(a):
