@@ -19,7 +19,8 @@ EXPORTS = [
     "hulk_b200_finish", "hulk_b200_snapshot_async", "hulk_b200_get_stats", "hulk_b200_histogram_device_ptr", "hulk_b200_stream",
     "hulk_b200_merge_histogram", "hulk_b200_add_minimizer_count", "hulk_b200_get_histogram", "hulk_b200_get_estimates",
     "hulk_b200_get_cms", "hulk_b200_minimizers", "hulk_b200_jump_hash", "hulk_b200_get_folded_table",
-    "hulk_b200_md5_mins", "hulk_b200_sketch_json", "hulk_b200_write_json", "hulk_b200_alloc_pinned",
+    "hulk_b200_md5_mins", "hulk_b200_sketch_json", "hulk_b200_write_json", "hulk_b200_sketch_json_minhash",
+    "hulk_b200_write_json_minhash", "hulk_b200_alloc_pinned",
     "hulk_b200_free_pinned", "hulk_b200_reader_open", "hulk_b200_reader_next", "hulk_b200_reader_error",
     "hulk_b200_reader_close", "hulk_b200_sketch_reader", "hulk_b200_sketch_load", "hulk_b200_sketch_find",
     "hulk_b200_sketch_banner", "hulk_b200_sketch_free", "hulk_b200_smash",
@@ -105,6 +106,10 @@ def load():
         "hulk_b200_md5_mins": (None, [vp, u32, C.c_char_p]),
         "hulk_b200_sketch_json": (C.c_int64, [C.c_char_p, u64, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int]),
         "hulk_b200_write_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int]),
+        "hulk_b200_sketch_json_minhash": (C.c_int64, [C.c_char_p, u64, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32,
+                                                      C.c_int, vp, u32, vp, u32]),
+        "hulk_b200_write_json_minhash": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int,
+                                                   vp, u32, vp, u32]),
         "hulk_b200_alloc_pinned": (C.c_int, [C.POINTER(vp), u64]),
         "hulk_b200_free_pinned": (None, [vp]),
         "hulk_b200_reader_open": (C.c_int, [C.POINTER(C.c_char_p), u32, C.c_int, u64, C.POINTER(vp)]),

@@ -418,8 +418,18 @@ int run_sketch(int argc, char **argv) {
     rc = hulk_b200_finish(ctx, mins.data(), weights.data());
     if (rc) fatal(hulk_b200_last_error(ctx));
     const std::string out_json = o.out_file + ".json";
-    rc = hulk_b200_write_json(out_json.c_str(), file_name.c_str(), o.banner_label.c_str(), P.k, mins.data(),
-                              weights.data(), P.sketch_size, spectrum, o.decay_ratio != 1.0);
+    // --kmv / --khf as the reference behaves today: the boss builds both MinHash sketches but nothing feeds them
+    // (src/pipeline/boss.go:18-19,70-71 "not used yet").  The KMV heap is therefore empty and HULKdata.Add refuses
+    // it (src/sketchio/sketchio.go:59-61) -- a fatal error after the histosketch was added and before the KHF one
+    // (src/pipeline/sketch.go:227-234,289-294); the KHF sketch is written with its initial MaxUint64 in every slot
+    // (src/minhash/khf.go:20-32).
+    if (P.sketch_size == 0) fatal("no sketch was generated by the histosketch algorithm");
+    if (o.add_kmv) fatal("no sketch was generated by the kmv algorithm");
+    std::vector<uint64_t> khf;
+    if (o.add_khf) khf.assign(P.sketch_size, ~0ull);
+    rc = hulk_b200_write_json_minhash(out_json.c_str(), file_name.c_str(), o.banner_label.c_str(), P.k, mins.data(),
+                                      weights.data(), P.sketch_size, spectrum, o.decay_ratio != 1.0, nullptr, 0,
+                                      o.add_khf ? khf.data() : nullptr, (uint32_t)khf.size());
     if (rc == HULK_B200_ENOSKETCH) fatal("no sketch was generated by the histosketch algorithm");
     if (rc == HULK_B200_EARG) fatal("json: unsupported value: a sketch weight is not finite");
     if (rc) fatal("open " + out_json + ": " + strerror(errno));

@@ -508,9 +508,38 @@ void hulk_b200_md5_mins(const uint64_t *mins, uint32_t n, char out_hex[33]) {
     out_hex[32] = 0;
 }
 
+// one MinHash signature (minhash.KMVsketch / minhash.KHFsketch: ksize, md5sum, mins, num -- kmv.go:12-21, khf.go:11-17)
+static void minhash_signature(std::string &o, const char *algo, uint32_t k, const uint64_t *mins, uint32_t n) {
+    const std::string I = "    ", I4 = I + I + I + I, I5 = I4 + I;
+    char md5[33];
+    hulk_b200_md5_mins(mins, n, md5);
+    o += I + I + "{\n";
+    o += I + I + I + "\"Algorithm\": \"" + algo + "\",\n";
+    o += I + I + I + "\"Sketch\": {\n";
+    o += I4 + "\"ksize\": " + std::to_string(k) + ",\n";
+    o += I4 + "\"md5sum\": \"" + md5 + "\",\n";
+    o += I4 + "\"mins\": [\n";
+    for (uint32_t i = 0; i < n; i++) o += I5 + std::to_string(mins[i]) + (i + 1 < n ? ",\n" : "\n");
+    o += I4 + "],\n";
+    o += I4 + "\"num\": " + std::to_string(n) + "\n";
+    o += I + I + I + "}\n";
+    o += I + I + "}";
+}
+
 int64_t hulk_b200_sketch_json(char *buf, uint64_t cap, const char *filename, const char *banner_label, uint32_t k,
                               const uint64_t *mins, const double *weights, uint32_t s, int32_t num_bins,
                               int concept_drift) {
+    return hulk_b200_sketch_json_minhash(buf, cap, filename, banner_label, k, mins, weights, s, num_bins,
+                                         concept_drift, nullptr, 0, nullptr, 0);
+}
+
+int64_t hulk_b200_sketch_json_minhash(char *buf, uint64_t cap, const char *filename, const char *banner_label,
+                                      uint32_t k, const uint64_t *mins, const double *weights, uint32_t s,
+                                      int32_t num_bins, int concept_drift, const uint64_t *kmv_mins, uint32_t kmv_n,
+                                      const uint64_t *khf_mins, uint32_t khf_n) {
+    // HULKdata.Add refuses a sketch without mins (sketchio.go:59-61); signatures are added in the order
+    // histosketch, kmv, khf (src/pipeline/sketch.go:227-234,289-294)
+    if ((kmv_mins && kmv_n == 0) || (khf_mins && khf_n == 0)) return HULK_B200_ENOSKETCH;
     for (uint32_t i = 0; i < s; i++)
         if (!std::isfinite(weights[i])) return HULK_B200_EARG;   // json: unsupported value
     char md5[33];
@@ -545,7 +574,10 @@ int64_t hulk_b200_sketch_json(char *buf, uint64_t cap, const char *filename, con
     o += I4 + "\"num_histogram_bins\": " + std::to_string(num_bins) + ",\n";
     o += I4 + "\"concept_drift\": " + (concept_drift ? "true" : "false") + "\n";
     o += I + I + I + "}\n";
-    o += I + I + "}\n";
+    o += I + I + "}";
+    if (kmv_mins) { o += ",\n"; minhash_signature(o, "kmv", k, kmv_mins, kmv_n); }
+    if (khf_mins) { o += ",\n"; minhash_signature(o, "khf", k, khf_mins, khf_n); }
+    o += "\n";
     o += I + "],\n";
     o += I + "\"version\": \"" HULK_B200_VERSION "\",\n";
     o += I + "\"banner_label\": " + go_string(banner_label) + "\n";
@@ -561,13 +593,21 @@ int64_t hulk_b200_sketch_json(char *buf, uint64_t cap, const char *filename, con
 int hulk_b200_write_json(const char *path, const char *filename, const char *banner_label, uint32_t k,
                          const uint64_t *mins, const double *weights, uint32_t s, int32_t num_bins,
                          int concept_drift) {
+    return hulk_b200_write_json_minhash(path, filename, banner_label, k, mins, weights, s, num_bins, concept_drift,
+                                        nullptr, 0, nullptr, 0);
+}
+
+int hulk_b200_write_json_minhash(const char *path, const char *filename, const char *banner_label, uint32_t k,
+                                 const uint64_t *mins, const double *weights, uint32_t s, int32_t num_bins,
+                                 int concept_drift, const uint64_t *kmv_mins, uint32_t kmv_n,
+                                 const uint64_t *khf_mins, uint32_t khf_n) {
     if (s == 0) return HULK_B200_ENOSKETCH;                      // sketchio.go:59-61
-    const int64_t need = hulk_b200_sketch_json(nullptr, 0, filename, banner_label, k, mins, weights, s, num_bins,
-                                               concept_drift);
+    const int64_t need = hulk_b200_sketch_json_minhash(nullptr, 0, filename, banner_label, k, mins, weights, s,
+                                                       num_bins, concept_drift, kmv_mins, kmv_n, khf_mins, khf_n);
     if (need < 0) return (int)need;
     std::vector<char> buf((size_t)need + 1);
-    hulk_b200_sketch_json(buf.data(), buf.size(), filename, banner_label, k, mins, weights, s, num_bins,
-                          concept_drift);
+    hulk_b200_sketch_json_minhash(buf.data(), buf.size(), filename, banner_label, k, mins, weights, s, num_bins,
+                                  concept_drift, kmv_mins, kmv_n, khf_mins, khf_n);
     FILE *fh = fopen(path, "wb");                                // ioutil.WriteFile(..., 0644)
     if (!fh) return HULK_B200_EIO;
     const size_t wr = fwrite(buf.data(), 1, (size_t)need, fh);

@@ -63,18 +63,36 @@ def md5_mins(mins) -> str:
 
 
 def sketch_json(filename: str, k: int, mins, weights, num_bins: int, concept_drift: bool,
-                banner_label: str = "blank") -> str:
-    """The JSON document hulk writes to <outFile>.json (src/sketchio/sketchio.go:78-97)."""
+                banner_label: str = "blank", kmv=None, khf=None) -> str:
+    """The JSON document hulk writes to <outFile>.json (src/sketchio/sketchio.go:78-97).
+
+    `kmv` / `khf`: mins of the optional MinHash signatures of `hulk sketch --kmv / --khf`, appended in that
+    order (src/pipeline/sketch.go:227-234,289-294); an EMPTY array raises the reference's "no sketch was
+    generated" error (src/sketchio/sketchio.go:59-61), None leaves the signature out."""
     L = N.load()
     m = np.ascontiguousarray(mins, dtype=np.uint64)
     w = np.ascontiguousarray(weights, dtype=np.float64)
-    args = (filename.encode(), banner_label.encode(), k, _ptr(m), _ptr(w), m.size, num_bins, int(concept_drift))
-    need = L.hulk_b200_sketch_json(None, 0, *args)
+    kv = None if kmv is None else np.ascontiguousarray(kmv, dtype=np.uint64)
+    kh = None if khf is None else np.ascontiguousarray(khf, dtype=np.uint64)
+    keep = np.zeros(1, dtype=np.uint64)              # a non-NULL address for "present but empty"
+
+    def opt(a):
+        return (None, 0) if a is None else (_ptr(a if a.size else keep), a.size)
+
+    args = (filename.encode(), banner_label.encode(), k, _ptr(m), _ptr(w), m.size, num_bins, int(concept_drift),
+            *opt(kv), *opt(kh))
+    need = L.hulk_b200_sketch_json_minhash(None, 0, *args)
     if need < 0:
         raise HulkError(int(need), L.hulk_b200_strerror(int(need)).decode())
     buf = C.create_string_buffer(need + 1)
-    L.hulk_b200_sketch_json(buf, need + 1, *args)
+    L.hulk_b200_sketch_json_minhash(buf, need + 1, *args)
     return buf.raw[:need].decode()
+
+
+def khf_unfed(s: int) -> np.ndarray:
+    """The KHF sketch `hulk sketch --khf` writes: minhash.NewKHFsketch fills s slots with MaxUint64
+    (src/minhash/khf.go:20-32) and nothing ever calls AddHash on it (src/pipeline/boss.go:18-19 "not used yet")."""
+    return np.full(s, np.iinfo(np.uint64).max, dtype=np.uint64)
 
 
 class HistoSketch:

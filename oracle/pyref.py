@@ -243,8 +243,9 @@ def go_json_string(s: str) -> str:
     return "".join(out)
 
 
-def sketch_json(filename, k, mins, weights, D, drift, banner="blank") -> str:
-    """json.MarshalIndent(HULKdata, "", "    ") -- sketchio.go:20-34,86; histosketch.go:36-47"""
+def sketch_json(filename, k, mins, weights, D, drift, banner="blank", kmv=None, khf=None) -> str:
+    """json.MarshalIndent(HULKdata, "", "    ") -- sketchio.go:20-34,86; histosketch.go:36-47;
+    optional minhash signatures (kmv.go:12-21, khf.go:11-17) in the order pipeline/sketch.go:227-234 appends them"""
     I = "    "
     L = []
     L.append("{")
@@ -273,6 +274,22 @@ def sketch_json(filename, k, mins, weights, D, drift, banner="blank") -> str:
     L.append(f'{I*4}"num_histogram_bins": {D},')
     L.append(f'{I*4}"concept_drift": {"true" if drift else "false"}')
     L.append(f"{I*3}}}")
+    for algo, mh in (("kmv", kmv), ("khf", khf)):
+        if mh is None:
+            continue
+        if len(mh) == 0:
+            raise ValueError(f"no sketch was generated by the {algo} algorithm")     # sketchio.go:59-61
+        L.append(f"{I*2}}},")
+        L.append(f"{I*2}{{")
+        L.append(f'{I*3}"Algorithm": "{algo}",')
+        L.append(f'{I*3}"Sketch": {{')
+        L.append(f'{I*4}"ksize": {k},')
+        L.append(f'{I*4}"md5sum": "{md5_of_mins(mh)}",')
+        L.append(f'{I*4}"mins": [')
+        L.extend(f"{I*5}{int(m)}" + ("," if i + 1 < len(mh) else "") for i, m in enumerate(mh))
+        L.append(f"{I*4}],")
+        L.append(f'{I*4}"num": {len(mh)}')
+        L.append(f"{I*3}}}")
     L.append(f"{I*2}}}")
     L.append(f"{I}],")
     L.append(f'{I}"version": "1.0.0",')

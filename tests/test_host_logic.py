@@ -103,6 +103,44 @@ def test_md5_and_json_equal_oracle_side():
     assert sk["weights"] == [float(x) for x in weights] and sk["mins"] == mins.tolist()
 
 
+def test_json_with_minhash_signatures(tmp_path):
+    """`hulk sketch --kmv / --khf`: extra signatures in the reference's order, fields ksize, md5sum, mins, num
+    (src/pipeline/sketch.go:227-234,289-294; src/minhash/kmv.go:12-21, khf.go:11-17); an empty sketch is refused
+    with sketchio.Add's error (src/sketchio/sketchio.go:59-61)."""
+    import json
+    rng = np.random.default_rng(3)
+    mins = rng.integers(0, 194481, 16).astype(np.uint64)
+    weights = -rng.random(16)
+    kmv = np.sort(rng.integers(0, 2 ** 63, 16).astype(np.uint64))
+    khf = hulk_b200.sketch.khf_unfed(16)
+    assert khf.tolist() == [2 ** 64 - 1] * 16
+    for kw in ({"khf": khf}, {"kmv": kmv}, {"kmv": kmv, "khf": khf}):
+        mine = hulk_b200.sketch_json("a.fq,", 21, mins, weights, 194481, False, "blank", **kw)
+        assert mine == P.sketch_json("a.fq,", 21, mins, weights, 194481, False, "blank", **kw)
+        doc = json.loads(mine)
+        assert [g["Algorithm"] for g in doc["signatures"]] == ["histosketch"] + list(kw)
+        for g in doc["signatures"][1:]:
+            assert list(g["Sketch"]) == ["ksize", "md5sum", "mins", "num"]
+            assert g["Sketch"]["md5sum"] == P.md5_of_mins(kw[g["Algorithm"]]) and g["Sketch"]["num"] == 16
+    assert (hulk_b200.sketch_json("a.fq,", 21, mins, weights, 194481, False)
+            == P.sketch_json("a.fq,", 21, mins, weights, 194481, False))
+    for kw in ({"kmv": np.zeros(0, dtype=np.uint64)}, {"khf": []}):
+        with pytest.raises(hulk_b200.HulkError) as e:
+            hulk_b200.sketch_json("a.fq,", 21, mins, weights, 194481, False, **kw)
+        assert e.value.code == N.ENOSKETCH
+        with pytest.raises(ValueError):
+            P.sketch_json("a.fq,", 21, mins, weights, 194481, False, **kw)
+    # the read side finds each signature by algorithm (sketchio.go:197-260); only histosketches carry weights
+    path = tmp_path / "multi.json"
+    path.write_text(hulk_b200.sketch_json("a.fq,", 21, mins, weights, 194481, False, kmv=kmv, khf=khf))
+    m, w, _ = hulk_b200.load_sketch(str(path), 21, "khf")
+    assert m.tolist() == khf.tolist() and w.size == 0
+    m, w, _ = hulk_b200.load_sketch(str(path), 21, "kmv")
+    assert m.tolist() == kmv.tolist() and w.size == 0
+    m, w, _ = hulk_b200.load_sketch(str(path), 21)
+    assert m.tolist() == mins.tolist() and w.tolist() == weights.tolist()
+
+
 def test_go_float_formatting_cases():
     cases = {1.7976931348623157e308: "1.7976931348623157e+308", 1e-7: "1e-7", 1.5e-9: "1.5e-9", 1e-6: "0.000001",
              9.999e-7: "9.999e-7", 1e21: "1e+21", 1e20: "100000000000000000000", -3.25: "-3.25", 100.0: "100",

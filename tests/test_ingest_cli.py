@@ -203,6 +203,32 @@ def test_cli_reference_fatals(tmp_path):
     assert not os.path.exists(str(tmp_path / "s.json"))
 
 
+@pytest.mark.gpu
+def test_cli_khf_and_kmv_flags_behave_like_the_reference(tmp_path):
+    """The reference builds both MinHash sketches but never feeds them (src/pipeline/boss.go:18-19,70-71):
+    --khf writes a signature of s MaxUint64 values behind the histosketch, --kmv dies in sketchio.Add."""
+    out = str(tmp_path / "khf")
+    r = _hulk("sketch", "-f", FIXTURE, "-k", "21", "-s", "50", "--khf", "-o", out)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "\tadding KHF sketch: true\n" in r.stdout and "\tadding KMV sketch: false\n" in r.stdout
+    doc = json.loads(open(out + ".json").read())
+    assert [g["Algorithm"] for g in doc["signatures"]] == ["histosketch", "khf"]
+    gs = doc["signatures"][0]["Sketch"]
+    ws = json.loads(open(os.path.join(GOLDEN, "c1_k21_s50.json")).read())["signatures"][0]["Sketch"]
+    assert gs["mins"] == ws["mins"] and gs["md5sum"] == ws["md5sum"] and list(gs) == list(ws)
+    np.testing.assert_allclose(gs["weights"], ws["weights"], rtol=1e-12)
+    khf = doc["signatures"][1]["Sketch"]
+    assert list(khf) == ["ksize", "md5sum", "mins", "num"] and khf["ksize"] == 21 and khf["num"] == 50
+    assert khf["mins"] == [2 ** 64 - 1] * 50 and khf["md5sum"] == hulk_b200.md5_mins(np.full(50, 2 ** 64 - 1, dtype=np.uint64))
+    m, w, _ = hulk_b200.load_sketch(out + ".json", 21, "khf")
+    assert m.tolist() == khf["mins"] and w.size == 0
+    for flags in (("--kmv",), ("--kmv", "--khf")):
+        out = str(tmp_path / "kmv")
+        r = _hulk("sketch", "-f", FIXTURE, "-k", "21", "-s", "50", *flags, "-o", out)
+        assert r.returncode == 1 and "ERROR---> no sketch was generated by the kmv algorithm" in r.stdout
+        assert "cleaning up..." in r.stdout and not os.path.exists(out + ".json")
+
+
 # ---- the parallel parse of plain FASTQ files (csrc/ingest.cpp produce_parallel) -----------------------
 def _native_env(paths, env):
     """Read through the native reader in a subprocess (the mode switches are read from the environment at open)."""
