@@ -320,6 +320,10 @@ def test_bgzf_reader_equals_plain_gzip(tmp_path):
     assert want.startswith("OK 20000 ")
     assert _native_env([bg], {}) == want                            # parallel BGZF path
     assert _native_env([bg], {"HULK_B200_PARALLEL_READER": "0"}) == want      # zlib path on the same file
+    # several windows in flight (the next one is inflated while the current one is framed): window ends fall inside
+    # lines and records, the last window can be the empty EOF marker alone
+    for win in ("1", "65280", "200000", "1000000"):
+        assert _native_env([bg], {"HULK_B200_BGZF_WINDOW": win}) == want
     # a BGZF file with an ordinary gzip member appended (cat a.gz b.gz): zlib takes over where BGZF ends,
     # in the middle of a record and of a line
     cut = rec.index(b"\n", len(rec) // 2) - 7
@@ -332,3 +336,13 @@ def test_bgzf_reader_equals_plain_gzip(tmp_path):
     bad = tmp_path / "bad.fq.gz"
     bad.write_bytes(bytes(raw))
     assert _native_env([bad], {}).startswith("ERR")
+    assert _native_env([bad], {"HULK_B200_BGZF_WINDOW": "300000"}).startswith("ERR")
+    # the mixed file again with small windows, and a member with a broken header after good blocks
+    assert _native_env([mixed], {"HULK_B200_BGZF_WINDOW": "100000"}) == want
+    good = _bgzf(rec)
+    third = good.index(b"\x1f\x8b\x08\x04", len(good) // 3)
+    hdr = tmp_path / "hdr.fq.gz"
+    hdr.write_bytes(good[:third] + b"XX" + good[third + 2:])
+    for env in ({}, {"HULK_B200_BGZF_WINDOW": "100000"}):
+        got = _native_env([hdr], env)
+        assert got.startswith("ERR") and "gzip: invalid header" in got
