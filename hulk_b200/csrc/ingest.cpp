@@ -314,7 +314,7 @@ struct hulk_b200_reader {
             }
         };
         auto inflate_window = [&](Win &w) {
-            w.data.resize(w.total);
+            w.data.resize(std::max<size_t>(w.total, 1));    // never a NULL next_out (a file that is only the EOF marker)
             std::atomic<size_t> next(0);
             auto work = [&] {
                 z_stream zs;
@@ -370,10 +370,6 @@ struct hulk_b200_reader {
     }
 
     bool read_gz(int fd, const std::string &name) {
-        uint8_t magic[2];
-        const ssize_t m = ::pread(fd, magic, 2, 0);
-        if (m == 0) return fail(HULK_B200_EIO, "EOF");                                    // gzip.NewReader on an empty file
-        if (m != 2 || magic[0] != 0x1f || magic[1] != 0x8b) return fail(HULK_B200_EIO, "gzip: invalid header");
         std::vector<uint8_t> carry;
         {
             const char *e = getenv("HULK_B200_PARALLEL_READER");
@@ -384,25 +380,79 @@ struct hulk_b200_reader {
                 if (rc == 2 && ::lseek(fd, (off_t)resume_off, SEEK_SET) < 0) return fail(HULK_B200_EIO, "seek " + name);
             }
         }
-        gzFile gz = gzdopen(dup(fd), "rb");
-        if (!gz) return fail(HULK_B200_EIO, "gzdopen " + name);
-        gzbuffer(gz, 1u << 20);
-        std::vector<uint8_t> block(kBlock);
-        bool ok = true;
-        for (;;) {
-            if (stop) { ok = false; break; }
-            const int got = gzread(gz, block.data(), (unsigned)block.size());
-            if (got < 0) {
-                int zerr = 0;
-                const char *msg = gzerror(gz, &zerr);
-                ok = fail(HULK_B200_EIO, std::string("gzip: ") + (msg ? msg : "read error"));
-                break;
+        return inflate_members(fd, name, carry);
+    }
+
+    // compress/gzip.Reader in its default multistream mode: members are concatenated; after a member the next
+    // header is read -- a clean EOF there ends the stream, fewer than 10 bytes is io.ErrUnexpectedEOF, anything
+    // that is not a gzip header is gzip.ErrHeader (trailing garbage is an ERROR in Go; zlib's gzread would
+    // silently stop), a CRC or length mismatch is gzip.ErrChecksum, a member cut short is "unexpected EOF".
+    // The file position of `fd` is where the next member starts.
+    bool inflate_members(int fd, const std::string &name, std::vector<uint8_t> &carry) {
+        std::vector<uint8_t> in(1u << 20), block(kBlock);
+        size_t in_pos = 0, in_len = 0;
+        bool eof = false;
+        auto refill = [&](size_t want) -> bool {            // keep unread input, top up to at least `want` bytes or EOF
+            if (in_pos && in_pos < in_len) memmove(in.data(), in.data() + in_pos, in_len - in_pos);
+            in_len -= in_pos;
+            in_pos = 0;
+            while (!eof && in_len < want) {
+                const ssize_t got = ::read(fd, in.data() + in_len, in.size() - in_len);
+                if (got < 0) {
+                    if (errno == EINTR) continue;
+                    return fail(HULK_B200_EIO, "read " + name + ": " + strerror(errno));
+                }
+                if (got == 0) eof = true;
+                in_len += (size_t)got;
             }
-            if (got == 0) break;
-            if (!(ok = feed(block.data(), (size_t)got, carry))) break;
-            if (fasta_stop) break;
+            return true;
+        };
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, 15 + 16) != Z_OK) return fail(HULK_B200_ENOMEM, "inflateInit2");
+        bool ok = true, first = true;
+        while (ok && !fasta_stop) {
+            // ---- member header (gzip.Reader.readHeader) ----
+            if (!(ok = refill(10))) break;
+            const size_t avail = in_len - in_pos;
+            if (avail == 0 && !first) break;                                            // io.EOF between members: done
+            if (avail < 10) { ok = fail(HULK_B200_EIO, avail == 0 ? "EOF" : "unexpected EOF"); break; }
+            const uint8_t *h = in.data() + in_pos;
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8) { ok = fail(HULK_B200_EIO, "gzip: invalid header"); break; }
+            first = false;
+            inflateReset(&zs);
+            // ---- member body ----
+            for (bool done = false; ok && !done && !fasta_stop;) {
+                if (stop) { ok = false; break; }
+                if (in_pos == in_len) {
+                    if (!(ok = refill(1))) break;
+                    if (in_len == 0) { ok = fail(HULK_B200_EIO, "unexpected EOF"); break; }
+                }
+                zs.next_in = in.data() + in_pos;
+                zs.avail_in = (uInt)(in_len - in_pos);
+                zs.next_out = block.data();
+                zs.avail_out = (uInt)block.size();
+                const int rc = inflate(&zs, Z_NO_FLUSH);
+                in_pos = in_len - zs.avail_in;
+                const size_t got = block.size() - zs.avail_out;
+                if (rc == Z_STREAM_END) done = true;
+                else if (rc == Z_DATA_ERROR || rc == Z_NEED_DICT) {
+                    const std::string m = zs.msg ? zs.msg : "";
+                    // data before the bad spot was handed on by Go's reader too
+                    if (got && !feed(block.data(), got, carry)) { ok = false; break; }
+                    ok = fail(HULK_B200_EIO, (m == "incorrect data check" || m == "incorrect length check") ? "gzip: invalid checksum"
+                                             : (m == "incorrect header check" || m == "unknown compression method" ||
+                                                m == "unknown header flags set" || m == "header crc mismatch") ? "gzip: invalid header"
+                                             : "flate: corrupt input (" + m + ")");
+                    break;
+                } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+                    ok = fail(rc == Z_MEM_ERROR ? HULK_B200_ENOMEM : HULK_B200_EIO, "inflate failed");
+                    break;
+                }
+                if (got && !(ok = feed(block.data(), got, carry))) break;
+            }
         }
-        gzclose(gz);
+        inflateEnd(&zs);
         if (!ok) return false;
         return fasta_stop ? true : end_of_file(carry);
     }

@@ -35,6 +35,7 @@ struct JValue {
 struct JParser {
     const char *p, *end;
     bool ok = true;
+    int depth = 0;                                      // a sketch document nests 5 deep; encoding/json itself stops at 10000
     void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
     bool lit(const char *s) {
         const size_t n = strlen(s);
@@ -86,6 +87,12 @@ struct JParser {
         JValue v;
         ws();
         if (p >= end) { ok = false; return v; }
+        struct Depth {
+            int &d;
+            explicit Depth(int &x) : d(x) { d++; }
+            ~Depth() { d--; }
+        } guard(depth);
+        if (depth > 256) { ok = false; return v; }
         if (*p == '{') {
             v.kind = JValue::OBJ;
             p++;

@@ -75,6 +75,40 @@ def test_native_reader_gzip_multimember_and_long_lines(tmp_path):
         hulk_b200.read_fastq(str(long))
 
 
+def test_native_reader_gzip_errors_follow_go(tmp_path):
+    """compress/gzip.Reader (multistream): garbage behind a member is gzip.ErrHeader -- zlib's gzread would stop
+    silently --, a short header or a member cut short is io.ErrUnexpectedEOF, an empty file is io.EOF from
+    gzip.NewReader, a CRC / length mismatch is gzip.ErrChecksum; log.Fatal(err) prints exactly these."""
+    reads = random_reads(300, 120, seed=9)
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
+    good = gzip.compress(rec, 1)
+
+    def run(name, data, **env):
+        f = tmp_path / name
+        f.write_bytes(data)
+        return _native_env([f], env)
+
+    assert run("ok.fq.gz", good).startswith("OK 300 ")
+    assert run("two.fq.gz", good + gzip.compress(b"", 1)).startswith("OK 300 ")          # an empty member is fine
+    for name, data, msg in (("garbage.fq.gz", good + b"trailing garbage, more than ten bytes", "gzip: invalid header"),
+                            ("zeros.fq.gz", good + b"\0" * 512, "gzip: invalid header"),     # Go does not skip padding
+                            ("short.fq.gz", good + b"\x1f\x8b\x08", "unexpected EOF"),
+                            ("cut.fq.gz", good[:len(good) // 2], "unexpected EOF"),
+                            ("cut8.fq.gz", good[:-3], "unexpected EOF"),
+                            ("empty.fq.gz", b"", "EOF"),
+                            ("one.fq.gz", b"\x1f", "unexpected EOF"),
+                            ("crc.fq.gz", good[:-8] + bytes([good[-8] ^ 1]) + good[-7:], "gzip: invalid checksum"),
+                            ("len.fq.gz", good[:-4] + bytes([good[-4] ^ 1]) + good[-3:], "gzip: invalid checksum"),
+                            ("method.fq.gz", good[:2] + b"\x07" + good[3:], "gzip: invalid header")):
+        got = run(name, data)
+        assert got.startswith("ERR") and got.endswith(" " + msg), (name, got)
+    # the reads in front of the bad spot were already handed on, like through Go's streaming reader
+    assert run("garbage2.fq.gz", good + b"x" * 64).split()[1] == "300"
+    # BGZF: a file that is only the EOF marker block holds no reads and is not an error
+    assert run("eof.fq.gz", _bgzf(b"")) == run("eof2.fq.gz", gzip.compress(b"", 1))
+    assert run("eof.fq.gz", _bgzf(b"")).startswith("OK 0 ")
+
+
 def test_native_reader_fasta(tmp_path):
     fa = tmp_path / "x.fa"
     fa.write_bytes(b"stray\n>c1 desc\nACGT\nTTAA\n>c2\n>c3\nGG\n\n>c4\nAAAA\n")

@@ -65,6 +65,14 @@ def test_load_sketch_checks_mirror_reference(tmp_path):
     for path, msg in cases:
         with pytest.raises(hulk_b200.HulkError, match=msg):
             hulk_b200.load_sketch(path)
+    # hostile documents are refused, not crashed on (tools/asan/run.sh runs the same parser under ASan/UBSan)
+    for name, data in (("deep.json", b"[" * 300000), ("deepobj.json", b'{"a":' * 200000), ("cut.json", b'{"class": "hulk_sk'),
+                       ("esc.json", b'"\\u12'), ("types.json", b'{"class": "hulk_sketch", "version": "1.0.0", "signatures": '
+                                                  b'[{"Algorithm": "histosketch", "Sketch": {"mins": 5, "weights": "x", "ksize": []}}]}')):
+        p = tmp_path / name
+        p.write_bytes(data)
+        with pytest.raises(hulk_b200.HulkError):
+            hulk_b200.load_sketch(str(p))
     with pytest.raises(hulk_b200.HulkError, match=r"specified k-mer size \(31\) not found"):
         hulk_b200.load_sketch(GOLD, k=31)
     with pytest.raises(hulk_b200.HulkError, match="no sketches were produced using the kmv algorithm"):

@@ -1,0 +1,22 @@
+#!/bin/bash
+# AddressSanitizer + UBSan pass over the host-only parsers (JSON sketches, FASTQ/FASTA/gzip/BGZF reader).
+# Runs on a CPU-only box.  usage: tools/asan/run.sh [corpus size]   -> profiles/<tag>_asan_host.txt is the caller's job
+set -u
+here="$(cd "$(dirname "$0")" && pwd)"
+root="$here/../.."
+work="${TMPDIR:-/tmp}/hulk_b200_asan"
+rm -rf "$work" && mkdir -p "$work"
+g++ -std=c++17 -O1 -g -fno-omit-frame-pointer -fsanitize=address,undefined -fno-sanitize-recover=undefined \
+    -I "$root/include" "$here/host_fuzz.cpp" "$root/hulk_b200/csrc/sketch_json.cpp" "$root/hulk_b200/csrc/ingest.cpp" \
+    "$root/hulk_b200/csrc/host_io.cpp" -o "$work/host_fuzz" -lz -lpthread || exit 1
+python "$here/make_corpus.py" "$work/corpus" "${1:-300}" || exit 1
+export ASAN_OPTIONS=detect_leaks=1:abort_on_error=0
+rc=0
+"$work/host_fuzz" json "$work"/corpus/json/* || rc=1
+for par in 0 1; do
+    HULK_B200_PARALLEL_READER=$par HULK_B200_PARALLEL_CHUNK=777 HULK_B200_BGZF_WINDOW=5000 \
+        "$work/host_fuzz" fastq "$work"/corpus/fastq/* || rc=1
+done
+"$work/host_fuzz" fasta "$work"/corpus/fasta/* || rc=1
+echo "asan/ubsan exit status: $rc"
+exit $rc
