@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--interval", type=int, default=100_000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--decay", type=float, default=1.0)
+    ap.add_argument("--reads", default="iid", choices=["iid", "genome"],
+                    help="iid: uniform i.i.d. bases (the headline workload).  genome: SURVEY section 8(d)'s realism "
+                         "variant -- reads sampled at uniform offsets and strands from a seeded 100 Mbp random genome, so "
+                         "minimizers repeat across reads (reported, never the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     return ap.parse_args()
@@ -56,7 +60,10 @@ def parse_args():
 def workload_config(a, n_gpus):
     return {
         "workload": "C2: synthetic %d bp reads, k=%d, w=%d, sketch-size %d, interval=%d reads/step, decay=%g"
-                    % (a.read_len, a.k, a.w, a.s, a.interval, a.decay),
+                    % (a.read_len, a.k, a.w, a.s, a.interval, a.decay)
+                    + (" [realism variant: reads sampled from a seeded %d Mbp random genome, both strands; not the headline]"
+                       % (GENOME_BASES // 1_000_000) if a.reads == "genome" else ""),
+        "reads": a.reads,
         "k": a.k, "w": a.w, "sketch_size": a.s, "num_bins": a.k ** 4, "interval_reads": a.interval,
         "read_len": a.read_len, "decay_ratio": a.decay, "reads_per_step_total": a.interval * n_gpus,
         "parallelism": "reads sharded over %d GPU(s); histogram all-reduce; CWS slots sharded" % n_gpus
@@ -91,6 +98,39 @@ def synthetic_reads_torch(torch, n_reads, read_len, seed, first_read, device):
     codes = ((z[:, :, None] >> shifts) & 3).reshape(n_reads, wpr * 32)[:, :read_len]
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
     return lut[codes].contiguous()
+
+
+GENOME_BASES = 100_000_000
+
+
+def genome_torch(torch, device, seed=7):
+    """The realism variant's genome: GENOME_BASES i.i.d. bases from the same counter-based generator."""
+    return synthetic_reads_torch(torch, GENOME_BASES // 100, 100, seed, 0, device).reshape(-1)
+
+
+def genome_reads_torch(torch, genome, n_reads, read_len, seed, first_read, device):
+    """Reads `first_read .. first_read + n_reads` of the realism variant: offset and strand of read i come from
+    splitmix64(seed ^ i) (so any rank can generate any read), the reverse strand is reverse-complemented."""
+    def lsr(x, n):
+        return (x >> n) & ((1 << (64 - n)) - 1)
+
+    def c64(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >> 63 else v
+
+    i = torch.arange(first_read, first_read + n_reads, dtype=torch.int64, device=device)
+    z = (i ^ seed) + c64(0x9E3779B97F4A7C15)
+    z = (z ^ lsr(z, 30)) * c64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    off = lsr(z, 1) % (genome.numel() - read_len + 1)
+    rev = (z & 1).bool()
+    pos = off[:, None] + torch.arange(read_len, dtype=torch.int64, device=device)[None, :]
+    fwd = genome[pos]
+    comp = torch.zeros(256, dtype=torch.uint8, device=device)
+    comp[torch.tensor(list(b"ACGT"), device=device).long()] = torch.tensor(list(b"TGCA"), dtype=torch.uint8, device=device)
+    rc = comp[fwd.long()].flip(1)
+    return torch.where(rev[:, None], rc, fwd).contiguous()
 
 
 def synthetic_tables_torch(torch, s, D, seed, device, slots=None, chunk=32):
@@ -316,9 +356,12 @@ def run_b200(a):
     with torch.cuda.stream(stream):
         # reads of this rank: rank-th shard of every interval of the global job
         reads_dev = torch.empty((n_steps_data, I, RL), dtype=torch.uint8, device=dev)
+        genome = genome_torch(torch, dev) if a.reads == "genome" else None
         for st in range(n_steps_data):
             first = (st * world + rank) * I
-            reads_dev[st] = synthetic_reads_torch(torch, I, RL, 1, first, dev)
+            reads_dev[st] = (synthetic_reads_torch(torch, I, RL, 1, first, dev) if genome is None
+                             else genome_reads_torch(torch, genome, I, RL, 1, first, dev))
+        del genome
         r_t, c_t, b_t = synthetic_tables_torch(torch, s, D, 1234, dev, slots)
     stream.synchronize()
 

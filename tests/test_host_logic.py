@@ -347,3 +347,25 @@ def test_kernel_scan_and_fast_jump_compiled_for_host_match_oracle(oracle, tmp_pa
             n_amb += int(amb)
     # the exact step is a rare fallback, not the common path (only buckets near 2^31 see it at all)
     assert n_amb < n_jump
+
+
+def test_bench_generators_on_cpu(monkeypatch):
+    """bench.py's device-side generators, run here on torch's CPU device: the i.i.d. reads equal the host definition
+    (hulk_b200.synthetic_reads) and the realism variant draws every read
+    from the genome, either strand, independent of how the reads are split over steps and ranks."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    got = bench.synthetic_reads_torch(torch, 300, 150, 1, 1000, "cpu").numpy()
+    np.testing.assert_array_equal(got, hulk_b200.synthetic_reads(300, 150, seed=1, first_read=1000))
+    monkeypatch.setattr(bench, "GENOME_BASES", 100_000)
+    genome = bench.genome_torch(torch, "cpu")
+    assert genome.numel() == 100_000 and set(bytes(genome.numpy())) == set(b"ACGT")
+    reads = bench.genome_reads_torch(torch, genome, 400, 150, 1, 0, "cpu")
+    text = bytes(genome.numpy())
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    fwd = sum(bytes(r) in text for r in reads.numpy())
+    rev = sum(bytes(r).translate(comp)[::-1] in text for r in reads.numpy())
+    assert fwd + rev >= 400 and fwd > 100 and rev > 100
+    again = bench.genome_reads_torch(torch, genome, 50, 150, 1, 200, "cpu")
+    assert (again == reads[200:250]).all()
