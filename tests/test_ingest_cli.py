@@ -380,3 +380,64 @@ def test_bgzf_reader_equals_plain_gzip(tmp_path):
     for env in ({}, {"HULK_B200_BGZF_WINDOW": "100000"}):
         got = _native_env([hdr], env)
         assert got.startswith("ERR") and "gzip: invalid header" in got
+
+
+# ---- randomised line soups: every reader path against the pure-Python restatement of the Go framing -----
+def _soup(rnd, fasta):
+    """A file of record-like runs with stray empty lines, CRLF, a missing final newline and -- in some files --
+    lines dropped or junk inserted, which shifts the never-resynchronising FASTQ framing."""
+    lines = []
+    damage = rnd.choice((0.0, 0.0, 0.03, 0.15))
+    for i in range(rnd.randint(0, 40)):
+        seq = [bytes(rnd.choice(b"ACGTNacgt") for _ in range(rnd.randint(1, 90))) for _ in range(rnd.randint(1, 3) if fasta else 1)]
+        rec = [b">s%d x" % i] + seq if fasta else [b"@r%d" % i, seq[0], b"+", b"I" * len(seq[0])]
+        for ln in rec:
+            if rnd.random() < 0.1 and not fasta:
+                lines.append(b"")                      # nil line: skipped by the FASTQ filler (it ends a FASTA stream)
+            t = rnd.random()
+            if t < damage / 2:
+                continue                               # line lost
+            if t < damage:
+                lines.append(bytes(rnd.choice(b"@>+!I# \tACGT") for _ in range(rnd.randint(1, 12))))
+            lines.append(ln)
+    if fasta and lines and rnd.random() < 0.3:
+        lines.insert(rnd.randrange(len(lines)), b"")
+    nl = b"\r\n" if rnd.random() < 0.2 else b"\n"
+    data = nl.join(lines)
+    if lines and rnd.random() < 0.7:
+        data += nl
+    return data
+
+
+def _outcome(fn):
+    try:
+        return ("OK", fn())
+    except ValueError as e:
+        return ("ERR", str(e))
+
+
+@pytest.mark.parametrize("fasta", [False, True])
+def test_native_reader_random_soups_equal_python_restatement(tmp_path, monkeypatch, fasta):
+    import random
+    rnd = random.Random(11 + fasta)
+    ref = hulk_b200.read_fasta if fasta else hulk_b200.read_fastq
+    n_err = n_reads = 0
+    for case in range(120):
+        data = _soup(rnd, fasta)
+        if fasta and not data.lstrip(b"\r\n").startswith(b">"):
+            data = b">first\n" + data                  # (a FASTA stream that starts without a header panics in the reference)
+        enc = rnd.choice(("plain", "gz", "bgzf"))
+        path = tmp_path / ("s%03d.%s" % (case, "fa" if fasta else "fq") + ("" if enc == "plain" else ".gz"))
+        path.write_bytes(data if enc == "plain" else gzip.compress(data, 1) if enc == "gz" else _bgzf(data, rnd.choice((64, 1000))))
+        want = _outcome(lambda: ref(str(path)))
+        modes = [{"HULK_B200_PARALLEL_READER": "0"},
+                 {"HULK_B200_PARALLEL_READER": "1", "HULK_B200_PARALLEL_CHUNK": str(rnd.choice((1, 7, 50, 300))),
+                  "HULK_B200_BGZF_WINDOW": str(rnd.choice((1, 100, 5000)))}]
+        for env in modes:
+            for key, val in env.items():
+                monkeypatch.setenv(key, val)
+            got = _outcome(lambda: _native([path], fasta=fasta, batch_bytes=rnd.choice((0, 256))))
+            assert got == want, (case, enc, env, data)
+        n_err += want[0] == "ERR"
+        n_reads += len(want[1]) if want[0] == "OK" else 0
+    assert n_reads > 500 and (fasta or n_err > 5)       # the soups exercise both outcomes
