@@ -336,21 +336,21 @@ struct hulk_b200_reader {
                 }
                 inflateEnd(&zs);
             };
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < W; t++) th.emplace_back(work);
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < W; t++) pool.emplace_back(work);
             work();
-            for (auto &x : th) x.join();
+            for (auto &x : pool) x.join();
         };
         bool ok = true, resume = false;
-        int cur = 0;
+        int wi = 0;
         plan(win[0]);
         inflate_window(win[0]);
         for (;;) {
-            Win &w = win[cur];
+            Win &w = win[wi];
             std::thread ahead;
             if (w.tail == MORE) {
-                plan(win[cur ^ 1]);
-                ahead = std::thread([&, cur] { inflate_window(win[cur ^ 1]); });
+                plan(win[wi ^ 1]);
+                ahead = std::thread([&, wi] { inflate_window(win[wi ^ 1]); });
             }
             if (stop) ok = false;
             else if (w.bad) ok = fail(HULK_B200_EIO, "gzip: invalid checksum");
@@ -360,7 +360,7 @@ struct hulk_b200_reader {
             if (w.tail == BADHDR) { ok = fail(HULK_B200_EIO, "gzip: invalid header"); break; }
             if (w.tail == RESUME) { resume = true; break; }
             if (w.tail == END) break;
-            cur ^= 1;
+            wi ^= 1;
         }
         munmap(map, size);
         (void)name;
@@ -415,14 +415,14 @@ struct hulk_b200_reader {
             // ---- member header (gzip.Reader.readHeader) ----
             if (!(ok = refill(10))) break;
             const size_t avail = in_len - in_pos;
-            if (avail == 0 && !first) break;                                            // io.EOF between members: done
+            if (avail == 0 && !first) break;                                            // io.EOF between members: the end
             if (avail < 10) { ok = fail(HULK_B200_EIO, avail == 0 ? "EOF" : "unexpected EOF"); break; }
             const uint8_t *h = in.data() + in_pos;
             if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8) { ok = fail(HULK_B200_EIO, "gzip: invalid header"); break; }
             first = false;
             inflateReset(&zs);
             // ---- member body ----
-            for (bool done = false; ok && !done && !fasta_stop;) {
+            for (bool member_done = false; ok && !member_done && !fasta_stop;) {
                 if (stop) { ok = false; break; }
                 if (in_pos == in_len) {
                     if (!(ok = refill(1))) break;
@@ -435,7 +435,7 @@ struct hulk_b200_reader {
                 const int rc = inflate(&zs, Z_NO_FLUSH);
                 in_pos = in_len - zs.avail_in;
                 const size_t got = block.size() - zs.avail_out;
-                if (rc == Z_STREAM_END) done = true;
+                if (rc == Z_STREAM_END) member_done = true;
                 else if (rc == Z_DATA_ERROR || rc == Z_NEED_DICT) {
                     const std::string m = zs.msg ? zs.msg : "";
                     // data before the bad spot was handed on by Go's reader too
@@ -497,16 +497,16 @@ struct hulk_b200_reader {
         Batch &b = *j.out;
         b.n_reads = b.n_bytes = 0;
         b.o()[0] = 0;
-        int slot = j.phase;
-        uint8_t l1_first = '@';
-        std::string l1_text;
+        int ps = j.phase;
+        uint8_t first_byte = '@';
+        std::string id_text;
         const uint8_t *seq = nullptr;
         size_t seq_len = 0;
         std::string seq_copy;
-        if (slot) {                                         // the record in progress: find its lines so far
+        if (ps) {                                           // the record in progress: find its lines so far
             std::vector<std::pair<const uint8_t *, size_t>> prev;          // newest first
             size_t pos = j.begin;
-            while ((int)prev.size() < slot && pos > 0) {
+            while ((int)prev.size() < ps && pos > 0) {
                 const size_t line_end = pos - 1;                          // the newline that ends the previous line
                 const void *q = line_end ? memrchr(j.d, '\n', line_end) : nullptr;
                 const size_t start = q ? (size_t)(static_cast<const uint8_t *>(q) - j.d) + 1 : 0;
@@ -516,7 +516,7 @@ struct hulk_b200_reader {
                 pos = start;
             }
             // lines still missing were the tail of the previous file
-            const int missing = slot - (int)prev.size();
+            const int missing = ps - (int)prev.size();
             auto line_at = [&](int idx, const uint8_t **p, size_t *len) {    // idx 0 = l1
                 if (idx < missing) {
                     const std::string &c = carry_lines[carry_lines.size() - missing + idx];
@@ -531,9 +531,9 @@ struct hulk_b200_reader {
             const uint8_t *p1;
             size_t n1;
             line_at(0, &p1, &n1);
-            l1_first = p1[0];
-            if (l1_first != '@') l1_text.assign(reinterpret_cast<const char *>(p1), n1);
-            if (slot >= 2) line_at(1, &seq, &seq_len);
+            first_byte = p1[0];
+            if (first_byte != '@') id_text.assign(reinterpret_cast<const char *>(p1), n1);
+            if (ps >= 2) line_at(1, &seq, &seq_len);
         }
         par_lines(j, [&](const uint8_t *p, size_t len, bool too_long) {
             if (too_long) {
@@ -542,25 +542,25 @@ struct hulk_b200_reader {
                 return false;
             }
             if (len == 0) return true;
-            switch (slot) {
+            switch (ps) {
                 case 0:
-                    l1_first = p[0];
-                    if (l1_first != '@') l1_text.assign(reinterpret_cast<const char *>(p), len);
-                    slot = 1;
+                    first_byte = p[0];
+                    if (first_byte != '@') id_text.assign(reinterpret_cast<const char *>(p), len);
+                    ps = 1;
                     break;
-                case 1: seq = p; seq_len = len; slot = 2; break;
-                case 2: slot = 3; break;
+                case 1: seq = p; seq_len = len; ps = 2; break;
+                case 2: ps = 3; break;
                 default:
-                    if (l1_first != '@') {
+                    if (first_byte != '@') {
                         j.err = HULK_B200_EFASTQ;
-                        j.err_text = "read ID in fastq file does not begin with @: " + l1_text;
+                        j.err_text = "read ID in fastq file does not begin with @: " + id_text;
                         return false;
                     }
                     memcpy(b.b() + b.n_bytes, seq, seq_len);
                     b.n_bytes += seq_len;
                     b.n_reads += 1;
                     b.o()[b.n_reads] = b.n_bytes;
-                    slot = 0;
+                    ps = 0;
                     break;
             }
             return true;
@@ -601,9 +601,9 @@ struct hulk_b200_reader {
                     jobs[t].end = line_start_at_or_after((c0 + t + 1) * par_chunk);
                 }
                 {
-                    std::vector<std::thread> th;
-                    for (unsigned t = 0; t < nj; t++) th.emplace_back([&, t] { par_count(jobs[t]); });
-                    for (auto &x : th) x.join();
+                    std::vector<std::thread> pool;
+                    for (unsigned t = 0; t < nj; t++) pool.emplace_back([&, t] { par_count(jobs[t]); });
+                    for (auto &x : pool) x.join();
                 }
                 for (unsigned t = 0; t < nj; t++) {
                     jobs[t].phase = (int)(nonempty_total & 3);
@@ -611,9 +611,9 @@ struct hulk_b200_reader {
                     if (!(jobs[t].out = take_free())) { munmap(map, size); return false; }     // stopped
                 }
                 {
-                    std::vector<std::thread> th;
-                    for (unsigned t = 0; t < nj; t++) th.emplace_back([&, t] { par_parse(jobs[t]); });
-                    for (auto &x : th) x.join();
+                    std::vector<std::thread> pool;
+                    for (unsigned t = 0; t < nj; t++) pool.emplace_back([&, t] { par_parse(jobs[t]); });
+                    for (auto &x : pool) x.join();
                 }
                 for (unsigned t = 0; t < nj; t++) {
                     if (!ok) {                               // behind an error: hand the batch back unused
