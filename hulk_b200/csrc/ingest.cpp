@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "../../include/hulk_b200.h"
+#include "pgzip.h"
 
 namespace {
 
@@ -371,16 +372,58 @@ struct hulk_b200_reader {
 
     bool read_gz(int fd, const std::string &name) {
         std::vector<uint8_t> carry;
-        {
-            const char *e = getenv("HULK_B200_PARALLEL_READER");
-            if (!(e && *e == '0')) {
-                size_t resume_off = 0;
-                const int rc = read_bgzf(fd, name, carry, &resume_off);
-                if (rc == 0 || rc == 1) return rc == 1;
-                if (rc == 2 && ::lseek(fd, (off_t)resume_off, SEEK_SET) < 0) return fail(HULK_B200_EIO, "seek " + name);
+        size_t resume_off = 0;
+        bool resumed = false;
+        const char *pe = getenv("HULK_B200_PARALLEL_READER");
+        const bool parallel_ok = !(pe && *pe == '0');
+        if (parallel_ok) {
+            const int rc = read_bgzf(fd, name, carry, &resume_off);
+            if (rc == 0 || rc == 1) return rc == 1;
+            if (rc == 2) {
+                resumed = true;
+                if (::lseek(fd, (off_t)resume_off, SEEK_SET) < 0) return fail(HULK_B200_EIO, "seek " + name);
             }
         }
+        if (parallel_ok) {
+            const int rc = read_gz_parallel(fd, carry, resume_off, !resumed);
+            if (rc >= 0) return rc == 1;
+        }
         return inflate_members(fd, name, carry);
+    }
+
+    // An ordinary (single-stream) gzip file of some size: inflated on several threads by pgzip.h -- block starts are
+    // guessed per chunk, every chunk is decoded against an unknown window, and a sequential pass stitches the chunks
+    // together.  Same bytes and the same errors as inflate_members.  1: ok, 0: failed, -1: not applicable.
+    int read_gz_parallel(int fd, std::vector<uint8_t> &carry, size_t start, bool first) {
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return -1;
+        size_t min_bytes = 16u << 20;
+        if (const char *e = getenv("HULK_B200_PGZ_MIN")) min_bytes = strtoull(e, nullptr, 10);
+        const size_t size = (size_t)st.st_size;
+        if (size < min_bytes || size <= start) return -1;
+        void *map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (map == MAP_FAILED) return -1;
+        madvise(map, size, MADV_SEQUENTIAL);
+        pgz::Options opt;
+        const unsigned hw = std::thread::hardware_concurrency();
+        opt.threads = std::max(1u, std::min(16u, hw > 2 ? hw - 2 : 1u));
+        opt.chunk_bytes = 2u << 20;
+        if (const char *e = getenv("HULK_B200_PGZ_CHUNK")) opt.chunk_bytes = std::max<size_t>(64, strtoull(e, nullptr, 10));
+        if (const char *e = getenv("HULK_B200_PGZ_THREADS")) opt.threads = (unsigned)std::max(1, atoi(e));
+        bool stopped = false, sink_failed = false;
+        const std::string text = pgz::inflate_parallel(
+            static_cast<const uint8_t *>(map), size, start, first, opt, nullptr,
+            [&](const uint8_t *p, size_t n) {
+                if (stop) return false;
+                if (!feed(p, n, carry)) { sink_failed = true; return false; }
+                return !fasta_stop;
+            },
+            &stopped);
+        munmap(map, size);
+        if (sink_failed) return 0;
+        if (!text.empty()) return fail(HULK_B200_EIO, text) ? 1 : 0;
+        if (stopped) return fasta_stop ? 1 : 0;
+        return end_of_file(carry) ? 1 : 0;
     }
 
     // compress/gzip.Reader in its default multistream mode: members are concatenated; after a member the next

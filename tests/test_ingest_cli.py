@@ -441,3 +441,54 @@ def test_native_reader_random_soups_equal_python_restatement(tmp_path, monkeypat
         n_err += want[0] == "ERR"
         n_reads += len(want[1]) if want[0] == "OK" else 0
     assert n_reads > 500 and (fasta or n_err > 5)       # the soups exercise both outcomes
+
+
+# ---- ordinary gzip on several threads (csrc/pgzip.h): guessed block starts, marker decoding, stitching ---------
+def test_parallel_gzip_equals_zlib_path(tmp_path):
+    """One deflate stream inflated on several threads must hand on exactly the bytes of the one-thread path: compression
+    levels 1/6/9, several members (one empty), sync/full flush points, fixed-Huffman and stored blocks, a stream that is
+    almost all back-references; tiny chunks put many stitch points, member ends and false block guesses into the run."""
+    import zlib
+    reads = random_reads(30000, 150, seed=31, ragged=60)
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, bytes(33 + (7 * j + i) % 40 for j in range(len(r)))) for i, r in enumerate(reads))
+    files = {"l1": gzip.compress(rec, 1), "l6": gzip.compress(rec, 6), "l9": gzip.compress(rec[:2_000_000], 9)}
+    third = rec.index(b"\n@", len(rec) // 3) + 1
+    files["members"] = gzip.compress(rec[:third], 6) + gzip.compress(b"", 6) + gzip.compress(rec[third:], 2)
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = []
+    for i, a in enumerate(range(0, len(rec), 70_000)):
+        parts += [co.compress(rec[a:a + 70_000]), co.flush(zlib.Z_FULL_FLUSH if i % 3 == 0 else zlib.Z_SYNC_FLUSH)]
+    files["flush"] = b"".join(parts) + co.flush()
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)
+    files["fixed"] = co.compress(rec[:1_500_000]) + co.flush()
+    co = zlib.compressobj(0, zlib.DEFLATED, 31)
+    files["stored"] = co.compress(rec[:1_500_000]) + co.flush()
+    rep = b"@r\n" + b"ACGT" * 40 + b"\n+\n" + b"I" * 160 + b"\n"
+    files["repeats"] = gzip.compress(rep * 40000, 6)
+    for name, blob in files.items():
+        f = tmp_path / (name + ".fq.gz")
+        f.write_bytes(blob)
+        want = _native_env([f], {"HULK_B200_PARALLEL_READER": "0"})
+        assert want.startswith("OK "), (name, want)
+        for chunk, threads in (("100000", "4"), ("9000", "7"), ("1500", "3")):
+            got = _native_env([f], {"HULK_B200_PGZ_MIN": "0", "HULK_B200_PGZ_CHUNK": chunk, "HULK_B200_PGZ_THREADS": threads})
+            assert got == want, (name, chunk, threads)
+    # the same errors in the same words as the one-thread path (Go's)
+    good = files["l6"]
+    for name, data, msg in (("garbage", good + b"trailing garbage, more than ten bytes", "gzip: invalid header"),
+                            ("cut", good[:len(good) // 2], "unexpected EOF"),
+                            ("crc", good[:-8] + bytes([good[-8] ^ 1]) + good[-7:], "gzip: invalid checksum"),
+                            ("len", good[:-4] + bytes([good[-4] ^ 1]) + good[-3:], "gzip: invalid checksum"),
+                            ("short", good + b"\x1f\x8b", "unexpected EOF")):
+        f = tmp_path / (name + ".bad.fq.gz")
+        f.write_bytes(data)
+        for env in ({"HULK_B200_PARALLEL_READER": "0"}, {"HULK_B200_PGZ_MIN": "0", "HULK_B200_PGZ_CHUNK": "50000"}):
+            got = _native_env([f], env)
+            assert got.startswith("ERR") and got.endswith(" " + msg), (name, env, got)
+    # damage in the middle of the deflate data: both paths refuse the file
+    raw = bytearray(good)
+    raw[len(raw) // 2] ^= 0x10
+    f = tmp_path / "flip.fq.gz"
+    f.write_bytes(bytes(raw))
+    for env in ({"HULK_B200_PARALLEL_READER": "0"}, {"HULK_B200_PGZ_MIN": "0", "HULK_B200_PGZ_CHUNK": "50000"}):
+        assert _native_env([f], env).startswith("ERR")

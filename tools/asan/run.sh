@@ -14,8 +14,19 @@ export ASAN_OPTIONS=detect_leaks=1:abort_on_error=0
 rc=0
 "$work/host_fuzz" json "$work"/corpus/json/* || rc=1
 for par in 0 1; do
-    HULK_B200_PARALLEL_READER=$par HULK_B200_PARALLEL_CHUNK=777 HULK_B200_BGZF_WINDOW=5000 \
-        "$work/host_fuzz" fastq "$work"/corpus/fastq/* || rc=1
+    HULK_B200_PARALLEL_READER=$par HULK_B200_PARALLEL_CHUNK=777 HULK_B200_BGZF_WINDOW=5000 HOST_FUZZ_VERBOSE=1 \
+        "$work/host_fuzz" fastq "$work"/corpus/fastq/* > "$work/verdict$par.txt" || rc=1
+    tail -1 "$work/verdict$par.txt"
+done
+# ordinary gzip through the multi-threaded single-stream inflater (pgzip.h), forced on with tiny chunks
+HULK_B200_PARALLEL_READER=1 HULK_B200_PGZ_MIN=0 HULK_B200_PGZ_CHUNK=700 HULK_B200_PGZ_THREADS=5 HULK_B200_BGZF_WINDOW=5000 \
+    HOST_FUZZ_VERBOSE=1 "$work/host_fuzz" fastq "$work"/corpus/fastq/* > "$work/verdict2.txt" || rc=1
+tail -1 "$work/verdict2.txt"
+# every path must reach the same verdict (accepted / rejected) on every file
+for v in 1 2; do
+    if ! diff <(awk '{print $1, $3}' "$work/verdict0.txt") <(awk '{print $1, $3}' "$work/verdict$v.txt") > "$work/diff$v.txt"; then
+        echo "verdicts differ between the one-thread reader and path $v:"; head -20 "$work/diff$v.txt"; rc=1
+    fi
 done
 "$work/host_fuzz" fasta "$work"/corpus/fasta/* || rc=1
 echo "asan/ubsan exit status: $rc"
