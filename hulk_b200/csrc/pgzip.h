@@ -352,7 +352,6 @@ struct Chunk {
     std::string corrupt_msg;
     // after stitching
     std::vector<uint8_t> window;                 // the <= 32 KiB in front of this chunk (resolved), newest last
-    uint64_t window_valid = 0;                   // how many of them belong to the current member
     Buf<uint8_t> *bytes = nullptr;               // resolved output (pool slot)
     std::vector<uint32_t> piece_crc;             // crc of [prev member end, member end) pieces + the tail piece
     bool marker_error = false;
@@ -370,7 +369,8 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
     uint64_t o = kWin;                           // write index into `out`
     int64_t member_lo;                           // absolute index in `out` of the oldest symbol a copy may reach
     size_t ti = self + 1;                        // next candidate target
-    static thread_local Table lit, dist;
+    static thread_local Table tl_lit, tl_dist;
+    Table &lit = tl_lit, &dist = tl_dist;
     if (c.at_header) {
         size_t off = (size_t)(c.start_bit >> 3);
         const Status hs = gzip_header(d, size, &off);
@@ -494,7 +494,8 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
 
 // First position in [from_bit, to_bit) that parses as a non-final dynamic block header.
 static inline bool find_block(const uint8_t *d, size_t size, uint64_t from_bit, uint64_t to_bit, uint64_t *found) {
-    static thread_local Table lit, dist;
+    static thread_local Table tl_lit, tl_dist;
+    Table &lit = tl_lit, &dist = tl_dist;
     for (uint64_t pos = from_bit; pos < to_bit; pos++) {
         // 3 + 14 header bits straight from memory
         const size_t byte = (size_t)(pos >> 3);
@@ -570,6 +571,13 @@ struct Options {
 // Inflates the gzip members of the file image [d, d + size) from byte offset `start` and hands the bytes to
 // sink(ptr, len) in order; sink returns false to stop early.  Returns "" or Go's error text; *stopped is set when the
 // sink asked to stop.  `first`: no member has been read from this file yet (an empty input is then io.EOF).
+// One group of chunks after the parallel stages: everything the sequential hand-over needs.
+struct Group {
+    std::vector<Chunk> ch;
+    std::vector<size_t> live;                    // the chunks that really follow each other, in order
+    bool more = false;                           // the stream goes on behind this group (at next_bit)
+};
+
 template <class Sink>
 static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t start, bool first, const Options &opt,
                                            const std::atomic<bool> *stop, Sink sink, bool *stopped) {
@@ -577,13 +585,13 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
     if (start >= size) return first ? "EOF" : "";
     const unsigned T = opt.threads ? opt.threads : 1;
     const size_t CB = opt.chunk_bytes ? opt.chunk_bytes : (4u << 20);
-    // running state of the sequential pass
+    // state of the stitching pass (advanced by prepare) ...
     std::vector<uint8_t> window;                 // last <= 32 KiB of the current member
-    uint32_t crc = 0;                            // of the current member so far
-    uint64_t member_len = 0;
     uint64_t next_bit = (uint64_t)start * 8;     // where the next chunk has to start
     bool next_is_header = true;
-    size_t group_from = start;                   // byte offset from which chunk starts are searched
+    // ... and of the hand-over (advanced by hand_over)
+    uint32_t crc = 0;                            // of the current member so far
+    uint64_t member_len = 0;
     auto run = [&](auto fn, size_t n) {
         std::atomic<size_t> next(0);
         auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); };
@@ -602,18 +610,23 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
             if (on) fprintf(stderr, "pgzip phases: search %.3f decode %.3f windows %.3f resolve %.3f sink %.3f s; chunks decoded %.0f used %.0f\n", t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
         }
     } report{timing, t_phase};
-    std::vector<Buf<uint16_t>> pool16(T);
-    std::vector<Buf<uint8_t>> pool8(T);
-    for (;;) {
-        if (stop && stop->load()) { *stopped = true; return ""; }
+    // two sets of chunk buffers: one group is handed over while the next one is decoded
+    std::vector<Buf<uint16_t>> pool16[2] = {std::vector<Buf<uint16_t>>(T), std::vector<Buf<uint16_t>>(T)};
+    std::vector<Buf<uint8_t>> pool8[2] = {std::vector<Buf<uint8_t>>(T), std::vector<Buf<uint8_t>>(T)};
+
+    // ---- stages 1-4 for the group that starts at next_bit ----
+    auto prepare = [&](Group &g, int set) {
         double t0 = now();
-        // ---- a group: chunk 0 continues exactly at next_bit, chunks 1..T start at searched block headers ----
-        std::vector<Chunk> ch(T + 1);
-        for (unsigned i = 0; i < T; i++) { ch[i].out = &pool16[i]; ch[i].bytes = &pool8[i]; }
+        // chunk 0 continues exactly at next_bit, chunks 1..T start at searched block headers
+        std::vector<Chunk> &ch = g.ch;
+        ch.clear();
+        ch.resize(T + 1);
+        g.live.clear();
+        for (unsigned i = 0; i < T; i++) { ch[i].out = &pool16[set][i]; ch[i].bytes = &pool8[set][i]; }
         ch[0].start_bit = next_bit;
         ch[0].at_header = next_is_header;
         ch[0].found = true;
-        const size_t base = std::max(group_from, (size_t)(next_bit >> 3));
+        const size_t base = (size_t)(next_bit >> 3);
         run([&](size_t i) {
             if (i == 0) return;
             const size_t from = base + i * CB;
@@ -631,8 +644,8 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
         run([&](size_t i) { if (ch[i].found) decode_chunk(d, size, ch[i], ch, i, std::max<uint64_t>(32 * (uint64_t)CB, 1u << 20), stop); }, T);
         t_phase[1] += now() - t0;
         t0 = now();
-        // ---- sequential pass: which chunks are real, windows, member ends ----
-        std::vector<size_t> live;
+        // sequential pass: which chunks are real, windows, member ends
+        std::vector<size_t> &live = g.live;
         size_t i = 0;
         for (;;) {
             live.push_back(i);
@@ -646,7 +659,6 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
         for (size_t j = 0; j < live.size(); j++) {
             Chunk &c = ch[live[j]];
             c.window = window;
-            c.window_valid = window.size();
             // resolve this chunk's tail to get the next window (only the part that reaches the end matters)
             const uint64_t last_end = c.ends.empty() ? 0 : c.ends.back().out_index;
             const uint64_t tail = c.n_out - last_end;        // symbols of the member still open at the chunk's end
@@ -656,43 +668,60 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
                 // a member started inside this chunk: its window is only what this chunk wrote behind that start
                 nw.resize(take);
                 for (uint64_t k = 0; k < take; k++) {
-                    const uint16_t s = c.out->p[kWin + c.n_out - take + k];
-                    if (s & 0x8000u) { c.marker_error = true; nw[k] = 0; }
-                    else nw[k] = (uint8_t)s;
+                    const uint16_t sy = c.out->p[kWin + c.n_out - take + k];
+                    if (sy & 0x8000u) { c.marker_error = true; nw[k] = 0; }
+                    else nw[k] = (uint8_t)sy;
                 }
             } else {
                 const uint64_t keep = std::min<uint64_t>(window.size(), kWin - take);
                 nw.assign(window.end() - (ptrdiff_t)keep, window.end());
                 nw.resize(keep + take);
                 for (uint64_t k = 0; k < take; k++) {
-                    const uint16_t s = c.out->p[kWin + c.n_out - take + k];
-                    if (s & 0x8000u) {
-                        const uint32_t back = kWin - (s & 0x7fffu);          // 1 = the byte right in front of the chunk
+                    const uint16_t sy = c.out->p[kWin + c.n_out - take + k];
+                    if (sy & 0x8000u) {
+                        const uint32_t back = kWin - (sy & 0x7fffu);         // 1 = the byte right in front of the chunk
                         if (back > window.size()) { c.marker_error = true; nw[keep + k] = 0; }
                         else nw[keep + k] = window[window.size() - back];
-                    } else nw[keep + k] = (uint8_t)s;
+                    } else nw[keep + k] = (uint8_t)sy;
                 }
             }
             window.swap(nw);
         }
         t_phase[2] += now() - t0;
         t0 = now();
-        // ---- parallel: resolve markers, narrow, crc per piece ----
+        // parallel: resolve markers, narrow, crc per piece
         run([&](size_t j) {
             Chunk &c = ch[live[j]];
-            c.bytes->reserve(c.n_out + 1, 0);
+            c.bytes->reserve(c.n_out + 64, 0);
             const uint16_t *src = c.out->p + kWin;
             const uint8_t *w = c.window.data();
             const size_t wn = c.window.size();
             uint8_t *dst = c.bytes->p;
             const uint64_t first_end = c.ends.empty() ? c.n_out : c.ends[0].out_index;
-            for (uint64_t k = 0; k < c.n_out; k++) {
-                const uint16_t s = src[k];
-                if (s & 0x8000u) {
-                    const uint32_t back = kWin - (s & 0x7fffu);
+            uint64_t k = 0;
+            for (; k + 64 <= c.n_out; k += 64) {             // 64 symbols at a time: markers die out behind the chunk's head
+                uint16_t any = 0;
+                for (int q = 0; q < 64; q++) any |= src[k + q];
+                if (!(any & 0x8000u)) {
+                    for (int q = 0; q < 64; q++) dst[k + q] = (uint8_t)src[k + q];
+                    continue;
+                }
+                for (int q = 0; q < 64; q++) {
+                    const uint16_t sy = src[k + q];
+                    if (sy & 0x8000u) {
+                        const uint32_t back = kWin - (sy & 0x7fffu);
+                        if (k + q >= first_end || back > wn) { c.marker_error = true; dst[k + q] = 0; }
+                        else dst[k + q] = w[wn - back];
+                    } else dst[k + q] = (uint8_t)sy;
+                }
+            }
+            for (; k < c.n_out; k++) {
+                const uint16_t sy = src[k];
+                if (sy & 0x8000u) {
+                    const uint32_t back = kWin - (sy & 0x7fffu);
                     if (k >= first_end || back > wn) { c.marker_error = true; dst[k] = 0; }
                     else dst[k] = w[wn - back];
-                } else dst[k] = (uint8_t)s;
+                } else dst[k] = (uint8_t)sy;
             }
             uint64_t from = 0;
             for (size_t m = 0; m <= c.ends.size(); m++) {
@@ -705,10 +734,19 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
             }
         }, live.size());
         t_phase[3] += now() - t0;
-        t0 = now();
-        // ---- sequential: hand the bytes on, close members, report the first problem in stream order ----
-        for (size_t j = 0; j < live.size(); j++) {
-            Chunk &c = ch[live[j]];
+        const Chunk &lastc = ch[live.back()];
+        g.more = lastc.status == ST_TARGET;
+        if (g.more) {
+            next_bit = lastc.end_bit;
+            next_is_header = false;
+        }
+    };
+
+    // ---- stage 5: hand the bytes on, close members, report the first problem in stream order ----
+    auto hand_over = [&](Group &g, bool *done) -> std::string {
+        *done = true;
+        for (size_t j = 0; j < g.live.size(); j++) {
+            Chunk &c = g.ch[g.live[j]];
             uint64_t from = 0;
             // a copy reached in front of the member's first byte
             if (c.marker_error) return std::string("flate: corrupt input (invalid distance too far back)");
@@ -725,20 +763,31 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
                 from = to;
             }
         }
-        t_phase[4] += now() - t0;
-        Chunk &lastc = ch[live.back()];
+        const Chunk &lastc = g.ch[g.live.back()];
         switch (lastc.status) {
-            case ST_TARGET:
-                next_bit = lastc.end_bit;
-                next_is_header = false;
-                group_from = (size_t)(next_bit >> 3);
-                continue;
+            case ST_TARGET: *done = false; return "";
             case ST_END: return "";
             case ST_EOF: return "unexpected EOF";
             case ST_HEADER: return "gzip: invalid header";
             case ST_STOPPED: *stopped = true; return "";
             default: return "flate: corrupt input (" + lastc.corrupt_msg + ")";
         }
+    };
+
+    Group grp[2];
+    int cur = 0;
+    prepare(grp[0], 0);
+    for (;;) {
+        if (stop && stop->load()) { *stopped = true; return ""; }
+        std::thread ahead;
+        if (grp[cur].more) ahead = std::thread([&, cur] { prepare(grp[cur ^ 1], cur ^ 1); });
+        bool done = true;
+        const double t0 = now();
+        const std::string text = hand_over(grp[cur], &done);
+        t_phase[4] += now() - t0;
+        if (ahead.joinable()) ahead.join();
+        if (done || !text.empty() || *stopped) return text;
+        cur ^= 1;
     }
 }
 
