@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Throughput of the native reader on a BGZF FASTQ file (written here with zlib, htslib layout) against the
-one-thread zlib path on the same file.  Usage: probe_bgzf.py [n_reads] [dir]"""
+"""Throughput of the native reader on a BGZF FASTQ file (written here with zlib, htslib layout) and on the same data as
+one ordinary gzip stream, each against the one-thread zlib path on the same file.  Usage: probe_bgzf.py [n_reads] [dir]"""
 import os, struct, sys, time, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -28,13 +28,31 @@ with open(path, "wb") as fh:
         fh.write(struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, 66, 67, 2, 12 + 6 + len(comp) + 8 - 1))
         fh.write(comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
 print("wrote %.1f MB of FASTQ as %.1f MB BGZF in %.1f s" % (len(data) / 1e6, os.path.getsize(path) / 1e6, time.time() - t0), flush=True)
-for label, env in (("bgzf parallel", "1"), ("zlib one thread", "0"), ("bgzf parallel", "1")):
+gz = os.path.join(d, "probe_plain.fq.gz")
+t0 = time.time()
+co = zlib.compressobj(4, zlib.DEFLATED, 31)
+with open(gz, "wb") as fh:
+    for a in range(0, len(data), 1 << 24):
+        fh.write(co.compress(data[a:a + (1 << 24)]))
+    fh.write(co.flush())
+print("wrote the same as %.1f MB ordinary gzip (one stream, level 4) in %.1f s" % (os.path.getsize(gz) / 1e6, time.time() - t0), flush=True)
+
+
+def run(label, file, env):
     os.environ["HULK_B200_PARALLEL_READER"] = env
     t0 = time.time()
     got = 0
-    with hulk_b200.NativeReader([path]) as rd:
+    with hulk_b200.NativeReader([file]) as rd:
         for b, offs in rd:
             got += len(offs) - 1
     dt = time.time() - t0
-    print("%-16s %d reads in %.2f s: %.2f GB/s of FASTQ, %.1f M reads/s" % (label, got, dt, len(data) / dt / 1e9, got / dt / 1e6), flush=True)
+    print("%-28s %d reads in %.2f s: %.2f GB/s of FASTQ, %.1f M reads/s" % (label, got, dt, len(data) / dt / 1e9, got / dt / 1e6), flush=True)
+
+
+for rep in range(2):
+    run("bgzf, parallel inflate", path, "1")
+    run("bgzf, zlib one thread", path, "0")
+    run("gzip, parallel (pgzip.h)", gz, "1")
+    run("gzip, zlib one thread", gz, "0")
 os.remove(path)
+os.remove(gz)
