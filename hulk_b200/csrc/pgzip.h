@@ -589,6 +589,7 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
     std::vector<uint8_t> window;                 // last <= 32 KiB of the current member
     uint64_t next_bit = (uint64_t)start * 8;     // where the next chunk has to start
     bool next_is_header = true;
+    unsigned barren = 0, quiet = 0;              // see prepare: groups without a usable guess / groups left without search
     // ... and of the hand-over (advanced by hand_over)
     uint32_t crc = 0;                            // of the current member so far
     uint64_t member_len = 0;
@@ -627,11 +628,15 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
         ch[0].at_header = next_is_header;
         ch[0].found = true;
         const size_t base = (size_t)(next_bit >> 3);
+        // input without dynamic blocks (stored or fixed-Huffman data) offers no starts: after two groups in which
+        // only chunk 0 was usable the search is skipped for a while instead of scanning every chunk in vain
+        const bool search = quiet == 0;
+        if (quiet) quiet--;
         run([&](size_t i) {
-            if (i == 0) return;
+            if (i == 0 || !search) return;
             const size_t from = base + i * CB;
             if (from >= size) return;
-            const size_t to = std::min(size, from + CB);
+            const size_t to = std::min(size, from + std::min<size_t>(CB, 512u << 10));   // blocks are tens of KB: no start in 512 KB = give up
             uint64_t pos;
             if (find_block(d, size, (uint64_t)from * 8, (uint64_t)to * 8, &pos)) {
                 ch[i].start_bit = pos;
@@ -652,6 +657,10 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
             if (ch[i].status != ST_TARGET) break;
             if (ch[i].next_live >= T) break;                 // reached the stop mark: the next group starts there
             i = ch[i].next_live;
+        }
+        if (search && T > 1) {
+            barren = live.size() == 1 ? barren + 1 : 0;
+            if (barren >= 2) { quiet = 16; barren = 0; }
         }
         for (size_t q = 0; q < T; q++) t_phase[5] += ch[q].found;
         t_phase[6] += (double)live.size();
