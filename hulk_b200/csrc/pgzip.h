@@ -344,6 +344,7 @@ struct Chunk {
     bool at_header = false, found = false, dead = false;
     Buf<uint16_t> *out = nullptr;                // kWin marker prefix + symbols (pool slot, reused across groups)
     uint64_t n_out = 0;                          // symbols behind the prefix
+    uint64_t n16 = 0;                            // the first n16 of them are 16-bit symbols in `out`, the rest bytes in `bytes`
     uint64_t first_member_lo = 0;                // symbols [0, ...) may reach into the unknown window unless at_header
     std::vector<MemberEnd> ends;
     Status status = ST_OK;                       // how decoding stopped
@@ -356,6 +357,105 @@ struct Chunk {
     std::vector<uint32_t> piece_crc;             // crc of [prev member end, member end) pieces + the tail piece
     bool marker_error = false;
 };
+
+// The symbols of one Huffman block, up to and including its end-of-block.  The bit reader lives in locals for the
+// duration (registers), `o` is the write index into out.p.  E = uint16_t while markers may be around, uint8_t after.
+template <class E>
+static inline Status huffman_block(Bits &in_, Buf<E> &out, uint64_t &o_, int64_t member_lo, const Table &lit,
+                                   const Table &dist, std::string &msg) {
+    uint64_t bb = in_.bb;
+    uint32_t bc = in_.bc;
+    const uint8_t *ip = in_.p;
+    const uint8_t *const iend = in_.end;
+    uint64_t o = o_;
+    E *op = out.p;
+    uint64_t cap = out.cap;
+    Status st = ST_OK;
+    const uint32_t PM = (1u << kPB) - 1;
+#define PGZ_REFILL()                                                  \
+    do {                                                              \
+        if (iend - ip >= 8) {                                         \
+            uint64_t w_;                                              \
+            memcpy(&w_, ip, 8);                                       \
+            bb |= w_ << bc;                                           \
+            ip += (63 - bc) >> 3;                                     \
+            bc |= 56;                                                 \
+        } else {                                                      \
+            while (bc <= 56 && ip < iend) {                           \
+                bb |= (uint64_t)(*ip++) << bc;                        \
+                bc += 8;                                              \
+            }                                                         \
+        }                                                             \
+    } while (0)
+#define PGZ_DROP(n) do { bb >>= (n); bc -= (n); } while (0)
+    for (;;) {
+        if (o + 320 > cap) {
+            out.reserve(o + 320, o);
+            op = out.p;
+            cap = out.cap;
+        }
+        PGZ_REFILL();
+        uint32_t e = lit.t[bb & PM];
+        if (e_kind(e) == SUB) {
+            PGZ_DROP(kPB);
+            e = lit.t[e_val(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1))];
+        }
+        if (e_len(e) > bc) { st = ST_EOF; break; }
+        PGZ_DROP(e_len(e));
+        const uint32_t kind = e_kind(e);
+        if (kind == LIT) {
+            op[o++] = (E)e_val(e);
+            // two more literals without a refill (>= 41 bits are left, a primary-table code takes <= 10)
+            uint32_t e2 = lit.t[bb & PM];
+            if (e_kind(e2) == LIT && e_len(e2) <= bc) {
+                PGZ_DROP(e_len(e2));
+                op[o++] = (E)e_val(e2);
+                e2 = lit.t[bb & PM];
+                if (e_kind(e2) == LIT && e_len(e2) <= bc) {
+                    PGZ_DROP(e_len(e2));
+                    op[o++] = (E)e_val(e2);
+                }
+            }
+            continue;
+        }
+        if (kind == EOB) break;
+        if (kind != LEN) { msg = "invalid literal/length code"; st = ST_CORRUPT; break; }
+        const uint32_t lx = e_extra(e);
+        if (lx > bc) { st = ST_EOF; break; }
+        const uint32_t L = e_val(e) + (uint32_t)(bb & ((1u << lx) - 1));
+        PGZ_DROP(lx);
+        if (bc < 32) PGZ_REFILL();
+        uint32_t de = dist.t[bb & PM];
+        if (e_kind(de) == SUB) {
+            PGZ_DROP(kPB);
+            de = dist.t[e_val(de) + (uint32_t)(bb & ((1u << e_extra(de)) - 1))];
+        }
+        if (e_len(de) > bc) { st = ST_EOF; break; }
+        if (e_kind(de) != LEN) { msg = "invalid distance code"; st = ST_CORRUPT; break; }
+        PGZ_DROP(e_len(de));
+        const uint32_t dx = e_extra(de);
+        if (dx > bc) { st = ST_EOF; break; }
+        const uint32_t D = e_val(de) + (uint32_t)(bb & ((1u << dx) - 1));
+        PGZ_DROP(dx);
+        if ((int64_t)o - (int64_t)D < member_lo) { msg = "invalid distance too far back"; st = ST_CORRUPT; break; }
+        const E *src = op + o - D;
+        E *dst = op + o;
+        if (D >= 8) {                                        // 8 symbols at a time; may write up to 7 symbols past the
+            for (uint32_t i = 0; i < L; i += 8)              // match, into slack that later output overwrites
+                memcpy(dst + i, src + i, 8 * sizeof(E));
+        } else {
+            for (uint32_t i = 0; i < L; i++) dst[i] = src[i];
+        }
+        o += L;
+    }
+#undef PGZ_REFILL
+#undef PGZ_DROP
+    in_.bb = bb;
+    in_.bc = bc;
+    in_.p = ip;
+    o_ = o;
+    return st;
+}
 
 // Decodes from chunk.start_bit until a block boundary equal to one of targets[ti..] is reached (ST_TARGET), the file
 // ends cleanly behind a member (ST_END), or something is wrong.  `member_lo`: index of the first symbol of the current
@@ -381,9 +481,15 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
         in.init(d, d + size, c.start_bit);
         member_lo = 0;
     }
+    // Once no copy can reach a marker any more -- the last 32 KiB (or everything since the member's first byte) are
+    // plain symbols -- the rest of the chunk is decoded straight into bytes: half the writes, nothing to resolve.
+    Buf<uint8_t> &B = *c.bytes;
+    bool byte_mode = false;
+    uint64_t next_check = kWin;
     auto finish = [&](Status s) {
         c.status = s;
         c.n_out = o - kWin;
+        if (!byte_mode) c.n16 = c.n_out;
         c.end_bit = in.pos();
     };
     for (;;) {
@@ -395,6 +501,23 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
         // (the chunks behind this one are dropped for this group)
         if (o - kWin > budget) { c.next_live = all.size(); finish(ST_TARGET); return; }
         if (stop && stop->load(std::memory_order_relaxed)) { finish(ST_STOPPED); return; }
+        if (!byte_mode && o - kWin >= next_check) {
+            const uint64_t k = o - kWin;
+            const int64_t lo_k = member_lo - (int64_t)kWin;              // < 0: the unknown window is still reachable
+            if (lo_k > 0 || k >= kWin) {
+                const uint64_t reach = lo_k > 0 ? std::min<uint64_t>(k - (uint64_t)lo_k, kWin) : kWin;
+                const uint16_t *tail = out.p + kWin + k - reach;
+                uint16_t any = 0;
+                for (uint64_t i = 0; i < reach; i++) any |= tail[i];
+                if (!(any & 0x8000u)) {
+                    c.n16 = k;
+                    B.reserve(k + (1u << 20), 0);
+                    for (uint64_t i = 0; i < reach; i++) B.p[k - reach + i] = (uint8_t)tail[i];
+                    byte_mode = true;
+                }
+            }
+            next_check = k + kWin;
+        }
         if (!in.need(3)) { finish(ST_EOF); return; }
         const uint32_t bfinal = in.peek(1), btype = (in.peek(3) >> 1);
         in.drop(3);
@@ -407,8 +530,13 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
             in.p += 4;
             const bool cut = (size_t)(in.end - in.p) < len;
             const uint32_t take = cut ? (uint32_t)(in.end - in.p) : len;
-            out.reserve(o + take + 512, o);
-            for (uint32_t i = 0; i < take; i++) out.p[o + i] = in.p[i];
+            if (byte_mode) {
+                B.reserve(o - kWin + take + 512, o - kWin);
+                memcpy(B.p + (o - kWin), in.p, take);
+            } else {
+                out.reserve(o + take + 512, o);
+                for (uint32_t i = 0; i < take; i++) out.p[o + i] = in.p[i];
+            }
             o += take;
             in.p += take;
             if (cut) { finish(ST_EOF); return; }
@@ -418,59 +546,15 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
                 const Status s = read_dynamic(in, lit, dist);
                 if (s != ST_OK) { c.corrupt_msg = "invalid code lengths"; finish(s); return; }
             }
-            uint16_t *op = out.p;
-            uint64_t cap = out.cap;
-            for (;;) {
-                if (o + 320 > cap) {
-                    out.reserve(o + 320, o);
-                    op = out.p;
-                    cap = out.cap;
-                }
-                in.refill();
-                uint32_t e = lit.t[in.bb & ((1u << kPB) - 1)];
-                if (e_kind(e) == SUB) {
-                    in.drop(kPB);
-                    e = lit.t[e_val(e) + (uint32_t)(in.bb & ((1u << e_extra(e)) - 1))];
-                }
-                if (e_len(e) > in.bc) { finish(ST_EOF); return; }
-                in.drop(e_len(e));
-                const uint32_t kind = e_kind(e);
-                if (kind == LIT) {
-                    op[o++] = (uint16_t)e_val(e);
-                    // a second literal without a refill (>= 41 bits are left)
-                    uint32_t e2 = lit.t[in.bb & ((1u << kPB) - 1)];
-                    if (e_kind(e2) == LIT && e_len(e2) <= in.bc) {
-                        in.drop(e_len(e2));
-                        op[o++] = (uint16_t)e_val(e2);
-                    }
-                    continue;
-                }
-                if (kind == EOB) break;
-                if (kind != LEN) { c.corrupt_msg = "invalid literal/length code"; finish(ST_CORRUPT); return; }
-                const uint32_t lx = e_extra(e);
-                if (lx > in.bc) { finish(ST_EOF); return; }
-                const uint32_t L = e_val(e) + in.peek(lx);
-                in.drop(lx);
-                if (in.bc < 32) in.refill();
-                uint32_t de = dist.t[in.bb & ((1u << kPB) - 1)];
-                if (e_kind(de) == SUB) {
-                    in.drop(kPB);
-                    de = dist.t[e_val(de) + (uint32_t)(in.bb & ((1u << e_extra(de)) - 1))];
-                }
-                if (e_len(de) > in.bc) { finish(ST_EOF); return; }
-                if (e_kind(de) != LEN) { c.corrupt_msg = "invalid distance code"; finish(ST_CORRUPT); return; }
-                in.drop(e_len(de));
-                const uint32_t dx = e_extra(de);
-                if (dx > in.bc) { finish(ST_EOF); return; }
-                const uint32_t D = e_val(de) + in.peek(dx);
-                in.drop(dx);
-                if ((int64_t)o - (int64_t)D < member_lo) { c.corrupt_msg = "invalid distance too far back"; finish(ST_CORRUPT); return; }
-                const uint16_t *src = op + o - D;
-                uint16_t *dst = op + o;
-                if (D >= L) memcpy(dst, src, (size_t)L * 2);
-                else for (uint32_t i = 0; i < L; i++) dst[i] = src[i];
-                o += L;
+            Status hs;
+            if (byte_mode) {
+                uint64_t k = o - kWin;
+                hs = huffman_block<uint8_t>(in, B, k, member_lo - (int64_t)kWin, lit, dist, c.corrupt_msg);
+                o = k + kWin;
+            } else {
+                hs = huffman_block<uint16_t>(in, out, o, member_lo, lit, dist, c.corrupt_msg);
             }
+            if (hs != ST_OK) { finish(hs); return; }
         }
         if (bfinal) {
             // ---- member trailer, then the next header or the end of the file (gzip.Reader.Read, multistream) ----
@@ -673,11 +757,12 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
             const uint64_t tail = c.n_out - last_end;        // symbols of the member still open at the chunk's end
             const uint64_t take = std::min<uint64_t>(tail, kWin);
             std::vector<uint8_t> nw;
+            auto sym = [&](uint64_t k) -> uint16_t { return k < c.n16 ? c.out->p[kWin + k] : (uint16_t)c.bytes->p[k]; };
             if (!c.ends.empty()) {
                 // a member started inside this chunk: its window is only what this chunk wrote behind that start
                 nw.resize(take);
                 for (uint64_t k = 0; k < take; k++) {
-                    const uint16_t sy = c.out->p[kWin + c.n_out - take + k];
+                    const uint16_t sy = sym(c.n_out - take + k);
                     if (sy & 0x8000u) { c.marker_error = true; nw[k] = 0; }
                     else nw[k] = (uint8_t)sy;
                 }
@@ -686,7 +771,7 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
                 nw.assign(window.end() - (ptrdiff_t)keep, window.end());
                 nw.resize(keep + take);
                 for (uint64_t k = 0; k < take; k++) {
-                    const uint16_t sy = c.out->p[kWin + c.n_out - take + k];
+                    const uint16_t sy = sym(c.n_out - take + k);
                     if (sy & 0x8000u) {
                         const uint32_t back = kWin - (sy & 0x7fffu);         // 1 = the byte right in front of the chunk
                         if (back > window.size()) { c.marker_error = true; nw[keep + k] = 0; }
@@ -701,14 +786,14 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
         // parallel: resolve markers, narrow, crc per piece
         run([&](size_t j) {
             Chunk &c = ch[live[j]];
-            c.bytes->reserve(c.n_out + 64, 0);
+            c.bytes->reserve(c.n_out + 64, c.n16 < c.n_out ? c.n_out : 0);     // (bytes behind n16 are already there)
             const uint16_t *src = c.out->p + kWin;
             const uint8_t *w = c.window.data();
             const size_t wn = c.window.size();
             uint8_t *dst = c.bytes->p;
             const uint64_t first_end = c.ends.empty() ? c.n_out : c.ends[0].out_index;
             uint64_t k = 0;
-            for (; k + 64 <= c.n_out; k += 64) {             // 64 symbols at a time: markers die out behind the chunk's head
+            for (; k + 64 <= c.n16; k += 64) {             // 64 symbols at a time: markers die out behind the chunk's head
                 uint16_t any = 0;
                 for (int q = 0; q < 64; q++) any |= src[k + q];
                 if (!(any & 0x8000u)) {
@@ -724,7 +809,7 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
                     } else dst[k + q] = (uint8_t)sy;
                 }
             }
-            for (; k < c.n_out; k++) {
+            for (; k < c.n16; k++) {
                 const uint16_t sy = src[k];
                 if (sy & 0x8000u) {
                     const uint32_t back = kWin - (sy & 0x7fffu);
