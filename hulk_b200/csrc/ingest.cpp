@@ -407,7 +407,7 @@ struct hulk_b200_reader {
         pgz::Options opt;
         const unsigned hw = std::thread::hardware_concurrency();
         opt.threads = std::max(1u, std::min(16u, hw > 2 ? hw - 2 : 1u));
-        opt.chunk_bytes = 2u << 20;
+        opt.chunk_bytes = 1u << 20;
         if (const char *e = getenv("HULK_B200_PGZ_CHUNK")) opt.chunk_bytes = std::max<size_t>(64, strtoull(e, nullptr, 10));
         if (const char *e = getenv("HULK_B200_PGZ_THREADS")) opt.threads = (unsigned)std::max(1, atoi(e));
         bool stopped = false, sink_failed = false;
