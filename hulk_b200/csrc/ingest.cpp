@@ -318,24 +318,24 @@ struct hulk_b200_reader {
             w.data.resize(std::max<size_t>(w.total, 1));    // never a NULL next_out (a file that is only the EOF marker)
             std::atomic<size_t> next(0);
             auto work = [&] {
-                z_stream zs;
-                memset(&zs, 0, sizeof zs);
-                if (inflateInit2(&zs, -15) != Z_OK) { w.bad = true; return; }
+                // the member payloads are raw deflate streams with an empty window: pgzip.h's byte-wide decoder
+                // (each into a scratch buffer first -- the decoder may write a few bytes past a match)
+                pgz::Buf<uint8_t> scratch;
+                std::string msg;
                 for (size_t i; (i = next.fetch_add(1)) < w.blks.size();) {
                     const Blk &b = w.blks[i];
-                    inflateReset(&zs);
-                    zs.next_in = const_cast<Bytef *>(d + b.off + b.hdr);
-                    zs.avail_in = (uInt)(b.bsize - b.hdr - 8);
-                    zs.next_out = w.data.data() + b.out;
-                    zs.avail_out = (uInt)b.isize;
-                    const int rc = inflate(&zs, Z_FINISH);
+                    uint64_t got = 0;
+                    size_t used = 0;
+                    const pgz::Status st = pgz::inflate_raw(d + b.off + b.hdr, b.bsize - b.hdr - 8, scratch, got, &used, msg);
                     const uint8_t *t = d + b.off + b.bsize - 8;
                     const uint32_t crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-                    if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                        (uint32_t)crc32(0L, w.data.data() + b.out, (uInt)b.isize) != crc)
+                    if (st != pgz::ST_OK || got != b.isize || used != b.bsize - b.hdr - 8 ||
+                        (uint32_t)crc32(0L, scratch.p, (uInt)got) != crc) {
                         w.bad = true;
+                        continue;
+                    }
+                    memcpy(w.data.data() + b.out, scratch.p, (size_t)got);
                 }
-                inflateEnd(&zs);
             };
             std::vector<std::thread> pool;
             for (unsigned t = 1; t < W; t++) pool.emplace_back(work);

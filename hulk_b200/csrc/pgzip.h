@@ -576,6 +576,48 @@ static inline void decode_chunk(const uint8_t *d, size_t size, Chunk &c, const s
     }
 }
 
+// One complete raw deflate stream with nothing in front of it (a BGZF member's payload), straight into bytes.
+// *consumed = bytes of input used, k = bytes produced.
+static inline Status inflate_raw(const uint8_t *d, size_t n, Buf<uint8_t> &B, uint64_t &k, size_t *consumed,
+                                 std::string &msg) {
+    static thread_local Table tl_lit, tl_dist;
+    Table &lit = tl_lit, &dist = tl_dist;
+    Bits in;
+    in.init(d, d + n, 0);
+    k = 0;
+    B.reserve(1u << 17, 0);
+    for (;;) {
+        if (!in.need(3)) return ST_EOF;
+        const uint32_t bfinal = in.peek(1), btype = in.peek(3) >> 1;
+        in.drop(3);
+        if (btype == 3) { msg = "invalid block type"; return ST_CORRUPT; }
+        if (btype == 0) {
+            in.align_to_byte();
+            if (in.end - in.p < 4) return ST_EOF;
+            const uint32_t len = in.p[0] | (uint32_t)in.p[1] << 8, nlen = in.p[2] | (uint32_t)in.p[3] << 8;
+            if ((len ^ 0xffffu) != nlen) { msg = "invalid stored block lengths"; return ST_CORRUPT; }
+            in.p += 4;
+            if ((size_t)(in.end - in.p) < len) return ST_EOF;
+            B.reserve(k + len + 512, k);
+            memcpy(B.p + k, in.p, len);
+            k += len;
+            in.p += len;
+        } else {
+            if (btype == 1) fixed_tables(lit, dist);
+            else {
+                const Status s = read_dynamic(in, lit, dist);
+                if (s != ST_OK) { msg = "invalid code lengths"; return s; }
+            }
+            const Status hs = huffman_block<uint8_t>(in, B, k, 0, lit, dist, msg);
+            if (hs != ST_OK) return hs;
+        }
+        if (bfinal) break;
+    }
+    in.align_to_byte();
+    *consumed = (size_t)(in.p - d);
+    return ST_OK;
+}
+
 // First position in [from_bit, to_bit) that parses as a non-final dynamic block header.
 static inline bool find_block(const uint8_t *d, size_t size, uint64_t from_bit, uint64_t to_bit, uint64_t *found) {
     static thread_local Table tl_lit, tl_dist;
