@@ -46,6 +46,15 @@ constexpr int kRing = 4;                        // batches in flight
 constexpr size_t kParChunk = 8u << 20;          // parallel FASTQ parse: bytes of file per worker task
 constexpr uint64_t kParMinBytes = 256ull << 20; // ... used for plain files from this total size on
 
+// Worker threads the reader may use next to its framing thread: all but two cores, at most `cap`;
+// HULK_B200_READER_THREADS overrides (1 = everything on the framing thread's side stays single-threaded).
+unsigned reader_threads(unsigned cap) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned n = std::max(1u, std::min(cap, hw > 2 ? hw - 2 : 1u));
+    if (const char *e = getenv("HULK_B200_READER_THREADS")) n = (unsigned)std::max(1, std::min(64, atoi(e)));
+    return n;
+}
+
 struct HostBuf {                                // page-locked when a device exists
     void *p = nullptr;
     bool pinned = false;
@@ -280,8 +289,7 @@ struct hulk_b200_reader {
         madvise(map, size, MADV_SEQUENTIAL);
         // inflating is the slow stage (~0.12 GB/s of FASTQ per core against ~3.8 GB/s for the framing thread):
         // every core but the framing thread and the caller's
-        const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned W = std::max(1u, std::min(16u, hw > 2 ? hw - 2 : 1u));
+        const unsigned W = reader_threads(16);
         struct Blk { size_t off, bsize, hdr, out, isize; };
         // Two windows of members (~64 MiB of output each): while the framing below consumes one, the next is
         // inflated on W threads.  A window ends early at a member that is not BGZF: `tail` says why.
@@ -405,8 +413,7 @@ struct hulk_b200_reader {
         if (map == MAP_FAILED) return -1;
         madvise(map, size, MADV_SEQUENTIAL);
         pgz::Options opt;
-        const unsigned hw = std::thread::hardware_concurrency();
-        opt.threads = std::max(1u, std::min(16u, hw > 2 ? hw - 2 : 1u));
+        opt.threads = reader_threads(16);
         opt.chunk_bytes = 1u << 20;
         if (const char *e = getenv("HULK_B200_PGZ_CHUNK")) opt.chunk_bytes = std::max<size_t>(64, strtoull(e, nullptr, 10));
         if (const char *e = getenv("HULK_B200_PGZ_THREADS")) opt.threads = (unsigned)std::max(1, atoi(e));
@@ -775,7 +782,7 @@ int hulk_b200_reader_open(const char *const *paths, uint32_t n_paths, int fasta,
         const char *force = getenv("HULK_B200_PARALLEL_READER");           // "1": also for small inputs, "0": never
         const unsigned hw = std::thread::hardware_concurrency();
         if (eligible && hw >= 4 && !(force && *force == '0') && (total >= kParMinBytes || (force && *force == '1')))
-            rd->par_workers = std::min(8u, hw / 2);
+            rd->par_workers = getenv("HULK_B200_READER_THREADS") ? reader_threads(8) : std::min(8u, hw / 2);
         const char *pc = getenv("HULK_B200_PARALLEL_CHUNK");
         if (pc && atoll(pc) >= 16) rd->par_chunk = (size_t)atoll(pc);
     }
