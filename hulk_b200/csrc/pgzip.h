@@ -33,7 +33,7 @@ namespace pgz {
 
 constexpr uint32_t kWin = 32768;
 constexpr int kPB = 10;                          // primary table bits (literal/length), distance uses the same
-enum Kind : uint32_t { LIT = 0, LEN = 1, EOB = 2, SUB = 3, BAD = 4 };
+enum Kind : uint32_t { LIT = 0, LEN = 1, EOB = 2, SUB = 3, BAD = 4, LIT2 = 5 };    // LIT2: two literals in one entry
 // table entry: val << 16 | extra << 8 | kind << 4 | len
 static inline uint32_t mk(uint32_t val, uint32_t extra, uint32_t kind, uint32_t len) {
     return val << 16 | extra << 8 | kind << 4 | len;
@@ -51,7 +51,7 @@ struct Table {
 // refused; an incomplete set is accepted only if it is a single code of length 1; an empty set decodes nothing.
 // `sym_entry(sym, len)` gives the entry of a symbol.  Returns false for an invalid set.
 template <class F>
-static inline bool build_table(Table &T, const uint8_t *lens, int n, F sym_entry) {
+static inline bool build_table(Table &T, const uint8_t *lens, int n, F sym_entry, bool pairs = false) {
     int count[16] = {0};
     for (int i = 0; i < n; i++) count[lens[i]]++;
     int max = 15;
@@ -112,6 +112,22 @@ static inline bool build_table(Table &T, const uint8_t *lens, int n, F sym_entry
             const uint32_t base = e_val(T.t[pre]);
             const uint32_t e = sym_entry(s, len - kPB);
             for (uint32_t i = r >> kPB; i < (1u << sb); i += 1u << (len - kPB)) T.t[base + i] = e;
+        }
+    }
+    if (pairs) {
+        // Literal-heavy data (FASTQ quality strings) is bound by the lookup -> shift -> lookup latency chain, one
+        // literal per trip.  Where the index bits behind a literal's code hold a complete second literal code, the
+        // entry yields both: val = first | second << 8, len = both lengths.  (The second lookup uses only bits the
+        // index really has: an entry of length l2 is the same for every value of the bits above l2.)
+        static thread_local uint32_t single[1 << kPB];
+        memcpy(single, T.t, sizeof single);
+        for (uint32_t i = 0; i < (1u << kPB); i++) {
+            const uint32_t e1 = single[i];
+            if (e_kind(e1) != LIT) continue;
+            const uint32_t l1 = e_len(e1);
+            const uint32_t e2 = single[i >> l1];
+            if (e_kind(e2) == LIT && l1 + e_len(e2) <= (uint32_t)kPB)
+                T.t[i] = mk(e_val(e1) | e_val(e2) << 8, 0, LIT2, l1 + e_len(e2));
         }
     }
     return true;
@@ -264,7 +280,7 @@ static inline Status read_dynamic(Bits &in, Table &lit, Table &dist) {
         while (rep--) lens[n++] = (uint8_t)val;
     }
     if (lens[256] == 0) return ST_CORRUPT;                   // zlib: "invalid code -- missing end-of-block"
-    if (!build_table(lit, lens, (int)hlit, litlen_entry)) return ST_CORRUPT;
+    if (!build_table(lit, lens, (int)hlit, litlen_entry, true)) return ST_CORRUPT;
     if (!build_table(dist, lens + hlit, (int)hdist, dist_entry)) return ST_CORRUPT;
     return ST_OK;
 }
@@ -275,7 +291,7 @@ static inline void fixed_tables(Table &lit, Table &dist) {
     for (int i = 144; i < 256; i++) lens[i] = 9;
     for (int i = 256; i < 280; i++) lens[i] = 7;
     for (int i = 280; i < 288; i++) lens[i] = 8;
-    build_table(lit, lens, 288, litlen_entry);
+    build_table(lit, lens, 288, litlen_entry, true);
     uint8_t dl[32];
     for (int i = 0; i < 32; i++) dl[i] = 5;
     build_table(dist, dl, 32, dist_entry);
@@ -403,17 +419,25 @@ static inline Status huffman_block(Bits &in_, Buf<E> &out, uint64_t &o_, int64_t
         if (e_len(e) > bc) { st = ST_EOF; break; }
         PGZ_DROP(e_len(e));
         const uint32_t kind = e_kind(e);
-        if (kind == LIT) {
-            op[o++] = (E)e_val(e);
-            // two more literals without a refill (>= 41 bits are left, a primary-table code takes <= 10)
+        if (kind == LIT || kind == LIT2) {
+            // up to three entries of literals per refill (>= 41 bits are left, a primary-table entry takes <= 10)
+            op[o] = (E)(e_val(e) & 0xffu);
+            op[o + 1] = (E)(e_val(e) >> 8);                  // (slack: overwritten when the entry held one literal)
+            o += 1 + (kind == LIT2);
             uint32_t e2 = lit.t[bb & PM];
-            if (e_kind(e2) == LIT && e_len(e2) <= bc) {
+            uint32_t k2 = e_kind(e2);
+            if ((k2 == LIT || k2 == LIT2) && e_len(e2) <= bc) {
                 PGZ_DROP(e_len(e2));
-                op[o++] = (E)e_val(e2);
+                op[o] = (E)(e_val(e2) & 0xffu);
+                op[o + 1] = (E)(e_val(e2) >> 8);
+                o += 1 + (k2 == LIT2);
                 e2 = lit.t[bb & PM];
-                if (e_kind(e2) == LIT && e_len(e2) <= bc) {
+                k2 = e_kind(e2);
+                if ((k2 == LIT || k2 == LIT2) && e_len(e2) <= bc) {
                     PGZ_DROP(e_len(e2));
-                    op[o++] = (E)e_val(e2);
+                    op[o] = (E)(e_val(e2) & 0xffu);
+                    op[o + 1] = (E)(e_val(e2) >> 8);
+                    o += 1 + (k2 == LIT2);
                 }
             }
             continue;
@@ -424,7 +448,8 @@ static inline Status huffman_block(Bits &in_, Buf<E> &out, uint64_t &o_, int64_t
         if (lx > bc) { st = ST_EOF; break; }
         const uint32_t L = e_val(e) + (uint32_t)(bb & ((1u << lx) - 1));
         PGZ_DROP(lx);
-        if (bc < 32) PGZ_REFILL();
+        // (no refill: a match is always the first entry behind one, so >= 56 - 15 - 5 = 36 bits are left and a
+        // distance takes <= 15 + 13; at the very end of the input the length checks below catch a short buffer)
         uint32_t de = dist.t[bb & PM];
         if (e_kind(de) == SUB) {
             PGZ_DROP(kPB);
@@ -440,9 +465,11 @@ static inline Status huffman_block(Bits &in_, Buf<E> &out, uint64_t &o_, int64_t
         if ((int64_t)o - (int64_t)D < member_lo) { msg = "invalid distance too far back"; st = ST_CORRUPT; break; }
         const E *src = op + o - D;
         E *dst = op + o;
-        if (D >= 8) {                                        // 8 symbols at a time; may write up to 7 symbols past the
-            for (uint32_t i = 0; i < L; i += 8)              // match, into slack that later output overwrites
-                memcpy(dst + i, src + i, 8 * sizeof(E));
+        if (D >= 16) {                                       // 16 symbols at a time; may write up to 15 symbols past the
+            memcpy(dst, src, 16 * sizeof(E));                // match, into slack that later output overwrites
+            for (uint32_t i = 16; i < L; i += 16) memcpy(dst + i, src + i, 16 * sizeof(E));
+        } else if (D >= 8) {
+            for (uint32_t i = 0; i < L; i += 8) memcpy(dst + i, src + i, 8 * sizeof(E));
         } else {
             for (uint32_t i = 0; i < L; i++) dst[i] = src[i];
         }
@@ -648,7 +675,7 @@ static inline bool find_block(const uint8_t *d, size_t size, uint64_t from_bit, 
             if (e_len(e) > in.bc) break;
             in.drop(e_len(e));
             const uint32_t kind = e_kind(e);
-            if (kind == LIT) { produced++; continue; }
+            if (kind == LIT || kind == LIT2) { produced += 1 + (kind == LIT2); continue; }
             if (kind == EOB) {
                 if (!in.need(17)) break;
                 const uint32_t h = in.peek(17), bt = (h >> 1) & 3;
