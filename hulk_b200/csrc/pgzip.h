@@ -862,11 +862,26 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
             uint8_t *dst = c.bytes->p;
             const uint64_t first_end = c.ends.empty() ? c.n_out : c.ends[0].out_index;
             uint64_t k = 0;
-            for (; k + 64 <= c.n16; k += 64) {             // 64 symbols at a time: markers die out behind the chunk's head
+            // With a full window in front of the chunk every marker is valid, and a 64 K-entry table turns symbols
+            // into bytes without a branch (FASTQ keeps markers alive in every record: the constant parts are always
+            // copied from the record before).  Blocks of 64 symbols without any marker are just narrowed.
+            static thread_local std::vector<uint8_t> lut;
+            const bool use_lut = wn == kWin && c.ends.empty();
+            if (use_lut) {
+                lut.resize(65536);
+                for (int q = 0; q < 256; q++) lut[q] = (uint8_t)q;
+                memcpy(lut.data() + 0x8000, w, kWin);        // marker 0x8000 | i  ->  window[i]
+            }
+            const uint8_t *lt = lut.data();
+            for (; k + 64 <= c.n16; k += 64) {
                 uint16_t any = 0;
                 for (int q = 0; q < 64; q++) any |= src[k + q];
                 if (!(any & 0x8000u)) {
                     for (int q = 0; q < 64; q++) dst[k + q] = (uint8_t)src[k + q];
+                    continue;
+                }
+                if (use_lut) {
+                    for (int q = 0; q < 64; q++) dst[k + q] = lt[src[k + q]];
                     continue;
                 }
                 for (int q = 0; q < 64; q++) {
