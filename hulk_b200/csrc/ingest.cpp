@@ -414,6 +414,10 @@ struct hulk_b200_reader {
         madvise(map, size, MADV_SEQUENTIAL);
         pgz::Options opt;
         opt.threads = reader_threads(16);
+        if (opt.threads < 2 && !getenv("HULK_B200_PGZ_THREADS")) {           // marker decoding costs ~1.5x zlib's work:
+            munmap(map, size);                                               // not worth it on one thread
+            return -1;
+        }
         opt.chunk_bytes = 1u << 20;
         if (const char *e = getenv("HULK_B200_PGZ_CHUNK")) opt.chunk_bytes = std::max<size_t>(64, strtoull(e, nullptr, 10));
         if (const char *e = getenv("HULK_B200_PGZ_THREADS")) opt.threads = (unsigned)std::max(1, atoi(e));
