@@ -334,10 +334,10 @@ struct hulk_b200_reader {
                     const Blk &b = w.blks[i];
                     uint64_t got = 0;
                     size_t used = 0;
-                    const pgz::Status st = pgz::inflate_raw(d + b.off + b.hdr, b.bsize - b.hdr - 8, scratch, got, &used, msg);
+                    const pgz::Status ist = pgz::inflate_raw(d + b.off + b.hdr, b.bsize - b.hdr - 8, scratch, got, &used, msg);
                     const uint8_t *t = d + b.off + b.bsize - 8;
                     const uint32_t crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-                    if (st != pgz::ST_OK || got != b.isize || used != b.bsize - b.hdr - 8 ||
+                    if (ist != pgz::ST_OK || got != b.isize || used != b.bsize - b.hdr - 8 ||
                         (uint32_t)crc32(0L, scratch.p, (uInt)got) != crc) {
                         w.bad = true;
                         continue;

@@ -361,7 +361,6 @@ struct Chunk {
     Buf<uint16_t> *out = nullptr;                // kWin marker prefix + symbols (pool slot, reused across groups)
     uint64_t n_out = 0;                          // symbols behind the prefix
     uint64_t n16 = 0;                            // the first n16 of them are 16-bit symbols in `out`, the rest bytes in `bytes`
-    uint64_t first_member_lo = 0;                // symbols [0, ...) may reach into the unknown window unless at_header
     std::vector<MemberEnd> ends;
     Status status = ST_OK;                       // how decoding stopped
     uint64_t end_bit = 0;                        // ST_TARGET: the position reached (== start of chunk `next_live`)
