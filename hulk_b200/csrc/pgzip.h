@@ -20,6 +20,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -745,14 +748,64 @@ static inline std::string inflate_parallel(const uint8_t *d, size_t size, size_t
     // ... and of the hand-over (advanced by hand_over)
     uint32_t crc = 0;                            // of the current member so far
     uint64_t member_len = 0;
-    auto run = [&](auto fn, size_t n) {
-        std::atomic<size_t> next(0);
-        auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); };
-        std::vector<std::thread> pool;
-        for (unsigned t = 1; t < T && t < n; t++) pool.emplace_back(work);
-        work();
-        for (auto &x : pool) x.join();
-    };
+    // T - 1 workers that live as long as this call (three parallel stages per group: spawning threads for each
+    // would cost a tenth of a group's time); the calling thread of run() works too
+    struct Pool {
+        std::mutex mu;
+        std::condition_variable cv_job, cv_done;
+        std::function<void(size_t)> fn;
+        size_t n = 0, next = 0, active = 0;
+        uint64_t epoch = 0;
+        bool quit = false;
+        std::vector<std::thread> th;
+        void worker() {
+            uint64_t seen = 0;
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv_job.wait(lk, [&] { return quit || epoch != seen; });
+                if (quit) return;
+                seen = epoch;
+                active++;
+                while (next < n) {
+                    const size_t i = next++;
+                    lk.unlock();
+                    fn(i);
+                    lk.lock();
+                }
+                if (--active == 0) cv_done.notify_all();
+            }
+        }
+        explicit Pool(unsigned workers) {
+            for (unsigned t = 0; t < workers; t++) th.emplace_back([this] { worker(); });
+        }
+        ~Pool() {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                quit = true;
+            }
+            cv_job.notify_all();
+            for (auto &x : th) x.join();
+        }
+        void run(std::function<void(size_t)> f, size_t count) {
+            std::unique_lock<std::mutex> lk(mu);
+            fn = std::move(f);
+            n = count;
+            next = 0;
+            epoch++;
+            active++;                                        // the caller
+            cv_job.notify_all();
+            while (next < n) {
+                const size_t i = next++;
+                lk.unlock();
+                fn(i);
+                lk.lock();
+            }
+            if (--active == 0) cv_done.notify_all();
+            cv_done.wait(lk, [&] { return active == 0 && next >= n; });
+            n = 0;
+        }
+    } pool(T > 1 ? T - 1 : 0);
+    auto run = [&](std::function<void(size_t)> fn, size_t n) { pool.run(std::move(fn), n); };
     const bool timing = getenv("HULK_B200_PGZ_TIMING") != nullptr;
     double t_phase[7] = {0, 0, 0, 0, 0, 0, 0};          // [5] chunks decoded, [6] chunks used
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
