@@ -661,6 +661,22 @@ static inline bool find_block(const uint8_t *d, size_t size, uint64_t from_bit, 
         if ((w & 7) != 4) continue;                          // BFINAL = 0, BTYPE = 10
         if (((w >> 3) & 31) > 29) continue;                  // HLIT <= 286
         if (((w >> 8) & 31) > 29) continue;                  // HDIST <= 30
+        {
+            // the code-length code must be complete (or a single 1-bit code): Kraft sum of its <= 19 three-bit
+            // lengths, straight from the next 57 bits -- rejects ~99 % of what got this far without building anything
+            const uint32_t hclen = 4 + (uint32_t)((w >> 13) & 15);
+            const uint64_t at = pos + 17;
+            if ((size_t)(at >> 3) + 8 > size) return false;
+            uint64_t v;
+            memcpy(&v, d + (at >> 3), 8);
+            v >>= (at & 7);
+            uint32_t kraft = 0, nz = 0, last = 0;
+            for (uint32_t i = 0; i < hclen; i++, v >>= 3) {
+                const uint32_t l = (uint32_t)(v & 7);
+                if (l) { kraft += 128u >> l; nz++; last = l; }
+            }
+            if (!(kraft == 128 || (nz == 1 && last == 1))) continue;
+        }
         Bits in;
         in.init(d, d + size, pos + 3);
         if (read_dynamic(in, lit, dist) != ST_OK) continue;
