@@ -18,7 +18,7 @@ EXPORTS = [
     "hulk_b200_push_reads_device", "hulk_b200_sync_inputs", "hulk_b200_flush", "hulk_b200_sync",
     "hulk_b200_finish", "hulk_b200_snapshot_async", "hulk_b200_get_stats", "hulk_b200_histogram_device_ptr", "hulk_b200_stream",
     "hulk_b200_merge_histogram", "hulk_b200_add_minimizer_count", "hulk_b200_get_histogram", "hulk_b200_get_estimates",
-    "hulk_b200_get_cms", "hulk_b200_minimizers", "hulk_b200_jump_hash", "hulk_b200_get_folded_table",
+    "hulk_b200_get_cms", "hulk_b200_minimizers", "hulk_b200_jump_hash", "hulk_b200_jump_hash_fx", "hulk_b200_rcp_selftest", "hulk_b200_get_folded_table",
     "hulk_b200_md5_mins", "hulk_b200_sketch_json", "hulk_b200_write_json", "hulk_b200_sketch_json_minhash",
     "hulk_b200_write_json_minhash", "hulk_b200_alloc_pinned",
     "hulk_b200_free_pinned", "hulk_b200_reader_open", "hulk_b200_reader_next", "hulk_b200_reader_error",
@@ -102,6 +102,8 @@ def load():
         "hulk_b200_get_cms": (C.c_int, [vp, vp]),
         "hulk_b200_minimizers": (C.c_int, [vp, vp, vp, u64, vp, u32, vp]),
         "hulk_b200_jump_hash": (C.c_int, [vp, vp, u64, i32, vp]),
+        "hulk_b200_jump_hash_fx": (C.c_int, [vp, vp, u64, i32, vp, vp]),
+        "hulk_b200_rcp_selftest": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
         "hulk_b200_get_folded_table": (C.c_int, [vp, vp, C.POINTER(u64)]),
         "hulk_b200_md5_mins": (None, [vp, u32, C.c_char_p]),
         "hulk_b200_sketch_json": (C.c_int64, [C.c_char_p, u64, C.c_char_p, C.c_char_p, u32, vp, vp, u32, i32, C.c_int]),

@@ -34,6 +34,9 @@
 
 using namespace hulk;
 
+// k values served by the second-generation w = 9 scan (k1_scan2.h: odd k with two-word k-mers)
+#define K1_V2_FOR_EACH_K(X) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31)
+
 constexpr int NBUF = 4;     // spectrum buffers allocated; ctx->nbuf of them are cycled = intervals in flight at once
 constexpr int NSTAGE = 4;   // host-input staging buffers (ring)
 
@@ -83,6 +86,8 @@ struct hulk_b200_ctx {
     int jump_ctas_per_sm = K1_JUMP_CTAS_PER_SM;
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
     bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
+    bool jump_fx = true;                       // HULK_B200_JUMP_FX=0: keep the bracketed jump step for every D (A/B measurements)
+    bool k1_v2 = true;                         // HULK_B200_K1_V2=0: keep the first-generation w = 9 scan (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
     unsigned long long *d_arena_cursor[NBUF] = {};
     uint64_t arena_entries[NBUF] = {};
@@ -438,6 +443,11 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true, 21>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, true, true, 11>, attr, big));
         CU(cudaFuncSetAttribute(k1_minimizer_histogram_w9<false, false, true, 31>, attr, big));
+#define K1_V2_ATTR(KK)                                                                   \
+        CU(cudaFuncSetAttribute(k1_scan_w9_v2<false, true, KK>, attr, big));             \
+        CU(cudaFuncSetAttribute(k1_scan_w9_v2<true, false, KK>, attr, big));
+        K1_V2_FOR_EACH_K(K1_V2_ATTR)
+#undef K1_V2_ATTR
     }
     {
         const char *e = getenv("HULK_B200_K1_TILE");
@@ -449,9 +459,13 @@ static int create_impl(hulk_b200_ctx *ctx) {
         e = getenv("HULK_B200_JUMP_CTAS");
         if (e && *e >= '1' && *e <= '8') ctx->jump_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_JUMP_BATCH");
-        if (e && (*e == '2' || *e == '4')) ctx->jump_batch = *e - '0';
+        if (e && (*e == '2' || *e == '3' || *e == '4')) ctx->jump_batch = *e - '0';
+        e = getenv("HULK_B200_JUMP_FX");
+        if (e && *e == '0') ctx->jump_fx = false;
         e = getenv("HULK_B200_K1_FUSED");
         ctx->fused_jump = e && *e == '1';
+        e = getenv("HULK_B200_K1_V2");
+        if (e && *e == '0') ctx->k1_v2 = false;
         e = getenv("HULK_B200_SERIAL");
         if (e && *e == '1') ctx->overlap = false;
     }
@@ -871,8 +885,24 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
             const uint64_t nctas = (n_reads + K1_TPB - 1) / K1_TPB;
             const int per_sm9 = use_queue ? ctx->k1_ctas_per_sm : K1_W9_CTAS_PER_SM;
             const unsigned grid9 = (unsigned)std::min<uint64_t>(nctas, (uint64_t)ctx->sm_count * per_sm9);
+            // odd k >= 17: the second-generation scan, k folded in at compile time
+            bool done = false;
+            if (ctx->k1_v2 && (use_queue || DUMP)) {
+                switch (ctx->P.k) {
+#define K1_V2_CASE(KK)                                                                              \
+                    case KK:                                                                        \
+                        if (use_queue) k1_scan_w9_v2<false, true, KK><<<grid9, K1_TPB, smem9, st>>>(p); \
+                        else k1_scan_w9_v2<true, false, KK><<<grid9, K1_TPB, smem9, st>>>(p);       \
+                        done = true;                                                                \
+                        break;
+                    K1_V2_FOR_EACH_K(K1_V2_CASE)
+#undef K1_V2_CASE
+                    default: break;
+                }
+            }
             // the k values of the BASELINE configs get the scan with k folded in at compile time
-            if (use_queue && fp && ctx->P.k == 21)
+            if (done) {
+            } else if (use_queue && fp && ctx->P.k == 21)
                 k1_minimizer_histogram_w9<false, true, true, 21><<<grid9, K1_TPB, smem9, st>>>(p);
             else if (use_queue && fp && ctx->P.k == 11)
                 k1_minimizer_histogram_w9<false, true, true, 11><<<grid9, K1_TPB, smem9, st>>>(p);
@@ -887,7 +917,11 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         LAUNCH_CHECK("k1_minimizer_histogram");
         if (use_queue) {
             const unsigned gridj = (unsigned)(ctx->sm_count * ctx->jump_ctas_per_sm);
-            if (ctx->jump_batch == 2) k1_jump_queue<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+            if (ctx->jump_fx && (uint32_t)ctx->D <= JUMP_FX_MAX_BUCKETS) {          // every k^4-bin spectrum
+                if (ctx->jump_batch == 2) k1_jump_queue_fx<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                else if (ctx->jump_batch == 3) k1_jump_queue_fx<3><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                else k1_jump_queue_fx<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+            } else if (ctx->jump_batch == 2) k1_jump_queue<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             else k1_jump_queue<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             LAUNCH_CHECK("k1_jump_queue");
         }
@@ -1353,6 +1387,48 @@ int hulk_b200_jump_hash(hulk_b200_ctx *ctx, const uint64_t *keys, uint64_t n, in
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpy(out, d_out, 4 * n, cudaMemcpyDeviceToHost));
     cudaFree(d_keys);
+    cudaFree(d_out);
+    return HULK_B200_OK;
+}
+int hulk_b200_jump_hash_fx(hulk_b200_ctx *ctx, const uint64_t *keys, uint64_t n, int32_t num_buckets, int32_t *out,
+                           uint64_t *n_ambiguous) {
+    if (!ctx || !keys || !out) return HULK_B200_EARG;
+    if (num_buckets < 1 || (uint32_t)num_buckets > JUMP_FX_MAX_BUCKETS)
+        return fail(ctx, HULK_B200_EARG, "the fixed-point step serves 1 <= num_buckets <= 2^20");
+    if (n == 0) return HULK_B200_OK;
+    CU(cudaSetDevice(ctx->P.device));
+    uint64_t *d_keys = nullptr;
+    int32_t *d_out = nullptr;
+    unsigned long long *d_amb = nullptr;
+    CU(dmalloc(&d_keys, n));
+    CU(dmalloc(&d_out, n));
+    CU(dmalloc(&d_amb, 1));
+    CU(cudaMemcpyAsync(d_keys, keys, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_amb, 0, 8, ctx->stream));
+    k_jump_fx_tap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_keys, n, num_buckets, d_out, d_amb);
+    LAUNCH_CHECK("k_jump_fx_tap");
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, d_out, 4 * n, cudaMemcpyDeviceToHost));
+    unsigned long long amb = 0;
+    CU(cudaMemcpy(&amb, d_amb, 8, cudaMemcpyDeviceToHost));
+    if (n_ambiguous) *n_ambiguous = amb;
+    cudaFree(d_keys);
+    cudaFree(d_out);
+    cudaFree(d_amb);
+    return HULK_B200_OK;
+}
+int hulk_b200_rcp_selftest(hulk_b200_ctx *ctx, uint32_t q_begin, uint32_t n, double out[2]) {
+    if (!ctx || !out) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    unsigned long long *d_out = nullptr;
+    CU(dmalloc(&d_out, 2));
+    CU(cudaMemsetAsync(d_out, 0, 16, ctx->stream));
+    if (n) {
+        k_rcp_selftest<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(q_begin, n, d_out);
+        LAUNCH_CHECK("k_rcp_selftest");
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, d_out, 16, cudaMemcpyDeviceToHost));
     cudaFree(d_out);
     return HULK_B200_OK;
 }

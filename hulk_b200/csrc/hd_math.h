@@ -155,6 +155,45 @@ HULK_HD int32_t jump_hash_fast(uint64_t key, int32_t num_buckets, uint32_t *n_am
     }
 }
 
+// ---- fixed-point form of the fast step, for num_buckets <= 2^20 (every k^4-bin spectrum: 31^4 < 2^20) ----
+// x = (b + 1) 2^31 / q is evaluated as above (seed, one Newton step folded into the product) and added to
+// 2^32 in one FMA: y = 2^32 + x carries 20 fraction bits in the low word of its mantissa, floor(x) in the 32
+// bits above them.  While x < 2^20 the value of y is within 2 units of 2^-20 of the real quotient
+// (x 2^-40 from the reciprocal, 2^-21 from rounding y; the reference's own double rounding moves its product
+// by less than 2^-30), so unless the fraction lies in {0xFFFFE, 0xFFFFF, 0, 1} the integer part IS the
+// reference's trunc(); otherwise (2^-18 per step) the caller recomputes the step with the true division.
+// x >= 2^20 means "finished" whatever the error is (num_buckets <= 2^20).  One FMA replaces the two directed
+// roundings of the bracket, and the state between steps is the 32-bit bucket alone.
+constexpr double JUMP_TWO32 = 4294967296.0;               // 2^32
+constexpr uint32_t JUMP_FX_MAX_BUCKETS = 1u << 20;
+// returns 0: stepped (b updated), 1: finished (b is the answer), 2: ambiguous -> use jump_step_exact
+HULK_HD int jump_step_fx(uint64_t &key, uint32_t &b, const uint32_t num_buckets) {
+    key = key * 2862933555777941757ull + 1ull;
+    const double qd = dbl_make(0x43300000u, (uint32_t)(key >> 33)) - (JUMP_TWO52 - 1.0);   // (double)q, q = (key >> 33) + 1
+    const double jd1 = dbl_make(0x43300000u, b) - (JUMP_TWO52 - 1.0);                      // (double)(b + 1)
+    const double r0 = rcp_seed(qd);
+    const double e = fma(-qd, r0, 1.0);
+    const double jr = jd1 * r0;
+    const double xq = fma(jr, e, jr);                                                      // ~ (b + 1) / q
+    const double y = fma(xq, 2147483648.0, JUMP_TWO32);
+    if ((uint32_t)((dbl_lo(y) + 2u) << 12) < (4u << 12)) return 2;
+    if (y >= JUMP_TWO32 + (double)num_buckets) return 1;
+    b = (dbl_hi(y) << 12) | (dbl_lo(y) >> 20);                                             // floor(x): the exponent bits shift out
+    return 0;
+}
+HULK_HD int32_t jump_hash_fx(uint64_t key, int32_t num_buckets, uint32_t *n_ambiguous = nullptr) {
+    uint32_t b = 0;
+    for (;;) {
+        int rc = jump_step_fx(key, b, (uint32_t)num_buckets);
+        if (rc == 2) {
+            if (n_ambiguous) ++*n_ambiguous;
+            double jd1;
+            rc = jump_step_exact(key, b, jd1, (uint32_t)num_buckets);
+        }
+        if (rc) return (int32_t)b;
+    }
+}
+
 // ---- word-wise base encoding ---------------------------------------------------------------
 // Four ASCII bases in one little-endian word -> four 2-bit codes (byte j of the result = code of
 // base j) and a flag telling whether every byte was one of ACGTUacgtu.  (b >> 1 ^ b >> 2) & 3

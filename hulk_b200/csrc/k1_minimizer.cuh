@@ -26,6 +26,7 @@
 
 #include "hd_math.h"
 #include "k1_scan.h"
+#include "k1_scan2.h"
 #include "ptx_util.cuh"
 
 namespace hulk {
@@ -190,10 +191,90 @@ __device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32
     }
 }
 
+// ---- the same walks with the fixed-point step (hd_math.h jump_step_fx), for num_buckets <= 2^20 ----------
+// State per walk: the LCG key and the 32-bit bucket.  Per step: LCG (IMAD.WIDE + 2 IMAD), (double)q and
+// (double)(b + 1) by the 2^52 trick (one DADD each, the constant high words stay in their registers), the
+// reciprocal seed (MUFU.RCP64H), residual, product and folded Newton step (DFMA, DMUL, DFMA), y = 2^32 + x
+// (DFMA), "finished" as one DSETP against 2^32 + n, the ambiguity band as one IMAD + ISETP on the fraction bits,
+// floor(x) by one funnel shift.  About 20 instructions against 33 for the bracketed step, 7 of them on the FP64 pipe.
+template <int BATCH, class Load>
+__device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t g, const uint32_t total, uint32_t *const hist,
+                                                const uint32_t nb) {
+    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
+    uint64_t key[2] = {0, 0};
+    uint32_t bkt[2] = {0, 0};
+    bool busy[2] = {false, false}, loaded[2] = {false, false};
+    const double two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0), two31 = k1_pin(2147483648.0),
+                 two32 = k1_pin(JUMP_TWO32);
+    const double ynb = k1_pin(JUMP_TWO32 + (double)nb);
+    for (;;) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (!busy[c] && loaded[c]) {                                 // its walk ended in the last batch
+                atomicAdd(&hist[bkt[c]], 1u);
+                loaded[c] = false;
+            }
+            const uint32_t need = __ballot_sync(0xffffffffu, !busy[c]);
+            const uint32_t mine = g + __popc(need & lane_lt);
+            g = min(g + (uint32_t)__popc(need), total);
+            if (!busy[c] && mine < total) {
+                key[c] = load(mine);
+                bkt[c] = 0;                                              // first step of jump.Hash: b = 0
+                busy[c] = loaded[c] = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
+#pragma unroll
+        for (int it = 0; it < BATCH; it++) {
+            uint32_t nbk[2];
+            bool fin[2], amb[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
+                key[c] = key[c] * 2862933555777941757ull + 1ull;
+                const double qd = dbl_make(0x43300000u, (uint32_t)(key[c] >> 33)) - two52m1;   // (double)q
+                const double jd1 = dbl_make(0x43300000u, bkt[c]) - two52m1;                    // (double)(b + 1)
+                const double r0 = rcp_seed(qd);
+                const double e = fma(-qd, r0, one);
+                const double jr = jd1 * r0;
+                const double xq = fma(jr, e, jr);                                              // ~ (b + 1) / q
+                const double y = fma(xq, two31, two32);                                        // 2^32 + x
+                amb[c] = (uint32_t)(dbl_lo(y) * 4096u + 8192u) < 16384u;                       // fraction in {-2, -1, 0, 1} 2^-20
+                fin[c] = y >= ynb;
+                nbk[c] = __funnelshift_l(dbl_lo(y), dbl_hi(y), 12);                            // floor(x)
+            }
+            if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // 2^-18 per step: the true division
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (amb[c] && busy[c]) {
+                        uint32_t b = bkt[c];
+                        double j1;
+                        fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
+                        nbk[c] = b;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {                                // commit
+                const bool adv = busy[c] && !fin[c];
+                bkt[c] = adv ? nbk[c] : bkt[c];
+                busy[c] = adv;
+            }
+        }
+    }
+}
+
 // ---- the part of a warp's work behind the scan: exact per-read sets, then jump-hash binning -------
 // wl: the warp's list block [list_cap][32] (entry e of lane l at wl[e * 32 + l]); n: this lane's number
 // of adjacent-distinct window minima (0 when the read is invalid or was queued for k1_generic).
-template <bool DUMP, bool FP, bool QUEUE>
+// KREP: 0 = the lists hold the reference's X; k = they hold the stored form of K1Repr<k> (k1_scan2.h), converted
+// back when a value leaves the list block.
+template <int KREP>
+__device__ __forceinline__ uint64_t k1_list_value(uint64_t stored) {
+    if constexpr (KREP != 0) return K1Repr<KREP>::to_x(stored);
+    else return stored;
+}
+
+template <bool DUMP, bool FP, bool QUEUE, int KREP = 0>
 __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl, uint64_t *my_list, const int lane,
                                                 const uint32_t list_cap, uint32_t n, const bool valid,
                                                 const bool overflow, const uint64_t r, const uint32_t nb,
@@ -237,7 +318,8 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
     }
     if (DUMP) {
         if (valid) {
-            for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++) p.dump[r * p.dump_cap + e] = my_list[e * 32];
+            for (uint32_t e = 0; e < m_out && e < p.dump_cap; e++)
+                p.dump[r * p.dump_cap + e] = k1_list_value<KREP>(my_list[e * 32]);
             p.dump_counts[r] = m_out;
         } else if (r < p.n_reads && !overflow) {
             p.dump_counts[r] = 0;
@@ -272,10 +354,11 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
             if (base + total > p.queue_cap) {
                 if (lane == 0) k1_report(p, r, K1_ERR_OVF);
             } else {
-                for (uint32_t j = lane; j < total; j += 32) p.queue[base + j] = wl[j];
+                for (uint32_t j = lane; j < total; j += 32) p.queue[base + j] = k1_list_value<KREP>(wl[j]);
             }
         } else {
-            k1_jump_walk<false, K1_JUMP_BATCH>([&](uint32_t g) { return wl[g]; }, (uint32_t)lane, 32u, total, p.hist, nb);
+            k1_jump_walk<false, K1_JUMP_BATCH>([&](uint32_t g) { return k1_list_value<KREP>(wl[g]); }, (uint32_t)lane, 32u,
+                                               total, p.hist, nb);
         }
     }
 }
@@ -484,6 +567,106 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
 }
 
 // ------------------------------------------------------------------------------------------
+// Second-generation w = 9 scan (k1_scan2.h), k folded in at compile time.  Same work decomposition as
+// k1_minimizer_histogram_w9 (one lane per read, independent warps, dynamic 32-read tasks, lists in shared
+// memory); the per-position work is about 45 instructions instead of 77 and spread over the ALU, FMA and FP64
+// pipes.
+// ------------------------------------------------------------------------------------------
+// Bases of one read, eight at a time, from aligned 8-byte global loads issued one block ahead.  The byte
+// offset inside a word is undone by one PRMT per word (selector fixed per read), the word offset inside the
+// 8-byte unit by three selects on a per-read predicate.
+struct GlobalSrcW {
+    const uint2 *p;          // aligned unit that holds the next unread base
+    uint2 cur, nxt;
+    uint32_t sel;            // 0x3210 + 0x1111 * (address & 3)
+    bool hiw;                // the read starts in the high word of its first unit
+    uintptr_t lim;           // no 8-byte load may touch this address or beyond
+    uintptr_t end;           // end of this read: bytes at or past it are never interpreted
+    __device__ __forceinline__ uint2 ld(const uint2 *q) const {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        if (a + 8 <= lim) return __ldg(q);
+        uint2 v = make_uint2(0u, 0u);                      // the last few bytes of the batch
+        for (int j = 0; j < 8; j++)
+            if (a + j < end) (j < 4 ? v.x : v.y) |= (uint32_t) reinterpret_cast<const uint8_t *>(q)[j] << (8 * (j & 3));
+        return v;
+    }
+    __device__ __forceinline__ GlobalSrcW(const uint8_t *read, uint64_t len, uintptr_t lim_)
+        : lim(lim_), end(reinterpret_cast<uintptr_t>(read) + len) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(read);
+        p = reinterpret_cast<const uint2 *>(a & ~(uintptr_t)7);
+        sel = 0x3210u + 0x1111u * (uint32_t)(a & 3);
+        hiw = (a & 4) != 0;
+        cur = ld(p);
+        nxt = ld(p + 1);
+    }
+    __device__ __forceinline__ void next(uint32_t &w0, uint32_t &w1) {
+        const uint32_t t0 = hiw ? cur.y : cur.x, t1 = hiw ? nxt.x : cur.y, t2 = hiw ? nxt.y : nxt.x;
+        w0 = __byte_perm(t0, t1, sel);
+        w1 = __byte_perm(t1, t2, sel);
+        cur = nxt;
+        p++;
+        nxt = ld(p + 1);
+    }
+};
+
+template <bool DUMP, bool QUEUE, int K>
+__global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_scan_w9_v2(const K1Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *list_all = reinterpret_cast<uint64_t *>(smem);                       // [warps][list_cap][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t list_cap = p.list_cap;
+    uint64_t *wl = list_all + (size_t)warp * list_cap * 32;
+    uint64_t *my_list = wl + lane;
+    unsigned long long local_minimizers = 0;
+    const uint32_t nb = (uint32_t)p.D;
+    const uint64_t ntasks = (p.n_reads + 31) / 32;
+    const uintptr_t lim = reinterpret_cast<uintptr_t>(p.bases) + p.bases_bytes;
+
+    unsigned long long *const task_counter = QUEUE ? p.queue_cursor + 1 : nullptr;
+    for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp;;) {
+        if (task_counter) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(task_counter, 1ull);
+            task = __shfl_sync(0xffffffffu, t, 0);
+        }
+        if (task >= ntasks) break;
+        const uint64_t r = task * 32 + lane;
+        uint32_t n = 0;
+        bool valid = false;
+        if (r < p.n_reads) {
+            const uint64_t b0 = k1_read_off(p, r), b1 = k1_read_off(p, r + 1);
+            const uint64_t len64 = b1 - b0;
+            if (len64 < 1) {
+                k1_report(p, r, K1_ERR_EMPTY);                                   // minimizer.go:71-73
+            } else if (len64 < (uint64_t)(9 + K - 1)) {
+                k1_report(p, r, K1_ERR_SHORT);                                   // minimizer.go:74-76
+            } else {
+                valid = true;
+                K1List<32> L{my_list, list_cap, 0u, 0.0};
+                k1_scan_read_w9_v2<K, 32>(GlobalSrcW(p.bases + b0, len64, lim), (int32_t)len64, L);
+                n = L.n;
+            }
+        }
+        const bool overflow = valid && n > list_cap;
+        if (overflow) {
+            const unsigned int slot = atomicAdd(p.ovf_count, 1u);
+            if (slot < p.ovf_cap) p.ovf_list[slot] = r;
+            else k1_report(p, r, K1_ERR_OVF);
+            n = 0;
+            valid = false;
+        }
+        __syncwarp();
+        k1_finish_lists<DUMP, true, QUEUE, K>(p, wl, my_list, lane, list_cap, n, valid, overflow, r, nb, local_minimizers);
+        __syncwarp();                                                            // the queue is drained before the lists refill
+        if (!task_counter) task += (uint64_t)gridDim.x * K1_WARPS;
+    }
+    if (!DUMP) {
+        for (int o = 16; o > 0; o >>= 1) local_minimizers += __shfl_down_sync(0xffffffffu, local_minimizers, o);
+        if (lane == 0 && local_minimizers) atomicAdd(p.n_minimizers, local_minimizers);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Second half of stage 1+2 when the scan kernels run in QUEUE mode: bin every key of the batch queue.
 // No shared memory and few registers, so it runs at full occupancy and shares an SM with the CWS
 // filter's TMA ring or the next interval's scan CTAs; the queue is dense, so the walks are balanced
@@ -500,6 +683,42 @@ __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue(const K1Params p) {
     const uint32_t seg_begin = (uint32_t)(total * gw / nwarps), seg_end = (uint32_t)(total * (gw + 1) / nwarps);
     const uint64_t *const q = p.queue;
     k1_jump_walk<true, BATCH>([&](uint32_t i) { return q[i]; }, seg_begin, 0u, seg_end, p.hist, (uint32_t)p.D);
+}
+// the same kernel with the fixed-point step (num_buckets <= 2^20)
+template <int BATCH>
+__global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue_fx(const K1Params p) {
+    const unsigned long long filled = *p.queue_cursor;
+    const uint64_t total = filled < p.queue_cap ? filled : p.queue_cap;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (K1_JUMP_TPB / 32);
+    const uint64_t gw = (uint64_t)blockIdx.x * (K1_JUMP_TPB / 32) + (threadIdx.x >> 5);
+    const uint32_t seg_begin = (uint32_t)(total * gw / nwarps), seg_end = (uint32_t)(total * (gw + 1) / nwarps);
+    const uint64_t *const q = p.queue;
+    k1_jump_walk_fx<BATCH>([&](uint32_t i) { return q[i]; }, seg_begin, seg_end, p.hist, (uint32_t)p.D);
+}
+
+// reciprocal self-test (parity tap): for q = q0 + i the seed's and the refined reciprocal's relative errors,
+// as residuals 1 - q r evaluated with one FMA; out[0] = max |1 - q r0|, out[1] = max |1 - q R| over the grid's range
+__global__ void k_rcp_selftest(uint32_t q0, uint32_t n, unsigned long long *out) {
+    double m0 = 0.0, m1 = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double qd = (double)(q0 + (uint32_t)i);
+        const double r0 = rcp_seed(qd);
+        const double e = fma(-qd, r0, 1.0);
+        const double R = fma(r0, e, r0);
+        const double e2 = fma(-qd, R, 1.0);
+        m0 = fmax(m0, fabs(e));
+        m1 = fmax(m1, fabs(e2));
+    }
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(m0));    // non-negative doubles order like integers
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(m1));
+}
+// fixed-point jump hash tap (parity tests): out[i] = jump_hash_fx(keys[i]), n_amb += ambiguous steps
+__global__ void k_jump_fx_tap(const uint64_t *keys, uint64_t n, int32_t buckets, int32_t *out, unsigned long long *n_amb) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t amb = 0;
+    out[i] = jump_hash_fx(keys[i], buckets, &amb);
+    if (amb) atomicAdd(n_amb, (unsigned long long)amb);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -307,6 +307,20 @@ class HistoSketch:
         self._check(self._L.hulk_b200_jump_hash(self._ctx, _ptr(keys), keys.size, num_buckets, _ptr(out)))
         return out
 
+    def jump_hash_fx(self, keys, num_buckets: int):
+        """jump.Hash through the kernel's fixed-point step; returns (bins, number of exact-division fallbacks)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(keys.size, dtype=np.int32)
+        amb = C.c_uint64(0)
+        self._check(self._L.hulk_b200_jump_hash_fx(self._ctx, _ptr(keys), keys.size, num_buckets, _ptr(out), C.byref(amb)))
+        return out, int(amb.value)
+
+    def rcp_selftest(self, q_begin: int, n: int):
+        """Largest relative error of the reciprocal seed and of the refined reciprocal over q in [q_begin, q_begin + n)."""
+        out = np.zeros(2, dtype=np.float64)
+        self._check(self._L.hulk_b200_rcp_selftest(self._ctx, q_begin, n, _ptr(out)))
+        return float(out[0]), float(out[1])
+
     def folded_table(self) -> np.ndarray:
         stride = C.c_uint64()
         self._check(self._L.hulk_b200_get_folded_table(self._ctx, None, C.byref(stride)))

@@ -150,6 +150,39 @@ def test_histogram_bit_exact_synthetic(hb, oracle, k, w, L):
         np.testing.assert_array_equal(hs.histogram(), h1)
 
 
+def test_jump_hash_fixed_point_step_bit_exact(hb, oracle):
+    """The binning kernel's step for num_buckets <= 2^20 (hd_math.h jump_step_fx) against the oracle, and on two million
+    keys against the device's literal jump.Hash (itself pinned above); the true-division fallback must stay rare."""
+    rng = np.random.default_rng(6)
+    keys = np.concatenate([rng.integers(0, 2 ** 64, 20000, dtype=np.uint64),
+                           np.array([0, 1, 42, 256, 0xDEAD10CC, 2 ** 64 - 1, 2 ** 63, 2 ** 33, 2 ** 33 - 1], dtype=np.uint64)])
+    big = rng.integers(0, 2 ** 64, 2_000_000, dtype=np.uint64)
+    with hb.HistoSketch(21, 9, 4) as hs:
+        for n in (1, 2, 10, 57, 666, 1024, 2000, 14641, 194481, 923521, 2 ** 20):
+            got, amb = hs.jump_hash_fx(keys, n)
+            want = np.array([oracle.jump(int(x), n) for x in keys], dtype=np.int32)
+            np.testing.assert_array_equal(got, want)
+        for n in (194481, 923521, 2 ** 20, 4 ** 10 - 1):
+            got, amb = hs.jump_hash_fx(big, n)
+            np.testing.assert_array_equal(got, hs.jump_hash(big, n))
+            assert amb < big.size * 20 * 2.0 ** -15, amb        # ~2^-18 per step expected
+        with pytest.raises(hb.HulkError):
+            hs.jump_hash_fx(keys, 2 ** 20 + 1)
+
+
+def test_reciprocal_error_budget_of_the_jump_step(hb):
+    """EVERY divisor the Lamping-Veach step can meet (q = 1 .. 2^31): the hardware seed refined by one Newton step must be
+    within 2^-41 relative, half of the 2^-40 the step's ambiguity band (and the bracket's epsilon) allow for."""
+    with hb.HistoSketch(21, 9, 4) as hs:
+        worst_seed = worst = 0.0
+        for q0 in range(1, 2 ** 31, 2 ** 29):
+            a, b = hs.rcp_selftest(q0, min(2 ** 29, 2 ** 31 - q0 + 1))
+            worst_seed, worst = max(worst_seed, a), max(worst, b)
+        print("reciprocal seed error 2^%.2f, refined 2^%.2f" % (np.log2(worst_seed), np.log2(worst)))
+        assert worst_seed < 2.0 ** -20
+        assert worst < 2.0 ** -41
+
+
 def test_histogram_with_n_and_ragged_reads(hb, oracle):
     reads = random_reads(5000, 60, seed=3, n_frac=0.01, lower_frac=0.3, ragged=200)
     bases, offs = oracle.pack_reads(reads)
@@ -212,7 +245,7 @@ def test_large_batches_are_split_into_bounded_launches(hb, monkeypatch):
 
 
 # ---- stage 3: count-min + CWS ---------------------------------------------------------------------
-def _run_both(hb, oracle, k, w, s, decay, reads_batches, tables, check_estimates=True, rtol_f=0.0):
+def _run_both(hb, oracle, k, w, s, decay, reads_batches, tables, check_estimates=True, rtol_f=0.0, parallel=False):
     D = hb.spectrum_size(k)
     r, c, b = tables
     ref = oracle.HistoSketch(k, s, D, decay, r, c, b)
@@ -220,7 +253,7 @@ def _run_both(hb, oracle, k, w, s, decay, reads_batches, tables, check_estimates
         for reads in reads_batches:
             bases, offs = oracle.pack_reads(reads)
             hist, _ = oracle.count_reads(k, w, D, bases, offs)
-            f_ref = ref.flush(hist)
+            f_ref = ref.flush(hist, parallel=parallel)      # parallel: same per-slot order, slots over host threads
             hs.add_reads(bases, offs)
             hs.flush()
             if check_estimates:
@@ -296,6 +329,36 @@ def test_c3_shape_k31_drift(hb, oracle):
     batches = [[bytes(r) for r in hb.synthetic_reads(15000, 150, seed=31, first_read=15000 * i)] for i in range(3)]
     st = _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=1e-9)
     assert st["n_flushes"] == 3
+
+
+def _dense_batches(hb, n_flushes, per, seed):
+    return [[bytes(r) for r in hb.synthetic_reads(per, 150, seed=seed, first_read=per * i)] for i in range(n_flushes)]
+
+
+@pytest.mark.parametrize("fp32", [False, True])
+def test_c2_shape_dense_spectrum_three_flushes(hb, oracle, monkeypatch, fp32):
+    """BASELINE config C2 at its own shape: k=21, w=9, s=512, three intervals of 100 000 synthetic 150 bp reads each.  Every
+    bin of the 194 481-bin spectrum is non-zero in every flush (the steady state the bench times: all screen chunks
+    populated, W converged after the first flush), against the oracle's AddElement loop, with either screen."""
+    monkeypatch.setenv("HULK_B200_K3_FP32", "1" if fp32 else "0")
+    k, s = 21, 512
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 41)
+    batches = _dense_batches(hb, 3, 100_000, seed=1)
+    st = _run_both(hb, oracle, k, 9, s, 1.0, batches, tables, parallel=True)
+    assert st["n_flushes"] == 3 and st["n_adds"] == 3 * D            # dense: every bin in every flush
+
+
+def test_c3_shape_dense_spectrum_drift(hb, oracle):
+    """BASELINE config C3's regime: k=31 (D = 923 521), concept drift 0.02, a dense spectrum (350 000 reads per flush put
+    ~9 minimizers into the average bin) over two flushes.  256 of C3's 1024 slots: the float64 tables of all 1024
+    would be 22.7 GB of host memory for the oracle; the slots are independent (histosketch.go:135-153)."""
+    k, s, decay = 31, 256, 0.02
+    D = hb.spectrum_size(k)
+    tables = _tables(s, D, 43)
+    batches = _dense_batches(hb, 2, 350_000, seed=3)
+    st = _run_both(hb, oracle, k, 9, s, decay, batches, tables, rtol_f=1e-9, parallel=True)
+    assert st["n_flushes"] == 2 and st["n_adds"] > 1.99 * D
 
 
 def test_c1_golden_json(hb, fixture_reads):

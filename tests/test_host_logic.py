@@ -241,7 +241,25 @@ SCAN_TEST_SRC = r"""
 #include <string>
 #include <vector>
 #include "k1_scan.h"
+#include "k1_scan2.h"
 struct VH { uint64_t* b; uint64_t& operator()(int t) const { return b[t]; } };
+// second-generation w = 9 scan (k1_scan2.h): the candidate list, converted back to the reference's X
+template <int K>
+static std::vector<uint64_t> scan_v2(const char* buf, int len, uint32_t cap) {
+    std::vector<uint64_t> store(cap + 1);
+    hulk::K1List<1> L{store.data(), cap, 0u, 0.0};
+    hulk::k1_scan_read_w9_v2<K, 1>(hulk::ByteSrcW{(const uint8_t*)buf, len, 0}, len, L);
+    std::vector<uint64_t> out;
+    if (L.n > cap) { out.push_back(~0ull); return out; }                 // overflow: the kernel hands the read on
+    for (uint32_t e = 0; e < L.n; e++) out.push_back(hulk::K1Repr<K>::to_x(store[e]));
+    return out;
+}
+template <int K>
+static std::vector<uint64_t> scan_v2_k(int k, const char* buf, int len, uint32_t cap) {
+    if (k == K) return scan_v2<K>(buf, len, cap);
+    if constexpr (K < 31) return scan_v2_k<K + 1>(k, buf, len, cap);
+    return {};
+}
 // same role as the kernel's SmemWordSrc: aligned word loads + funnel shift
 struct WordSrc {
     const uint32_t* words; uint32_t sh;
@@ -285,6 +303,13 @@ int main() {
                     else hulk::k1_scan_read_w9<false>(hulk::ByteSrc8{(const uint8_t*)buf, len, 0}, len, k, em);
                     if (d != a) { printf("MISMATCH_W9\n"); return 2; }
                 }
+                if (k >= 8) {                         // k1_scan2.h: same minima with adjacent repeats dropped
+                    std::vector<uint64_t> want;
+                    for (uint64_t x : a) if (want.empty() || want.back() != x) want.push_back(x);
+                    if (scan_v2_k<8>(k, buf, len, 1u << 20) != want) { printf("MISMATCH_V2\n"); return 2; }
+                    // a list that is too short reports the overflow and never writes past its capacity
+                    if (want.size() > 12 && scan_v2_k<8>(k, buf, len, 12).at(0) != ~0ull) { printf("MISMATCH_V2_OVF\n"); return 2; }
+                }
             }
             std::sort(a.begin(), a.end());
             a.erase(std::unique(a.begin(), a.end()), a.end());
@@ -317,7 +342,8 @@ def test_kernel_scan_and_fast_jump_compiled_for_host_match_oracle(oracle, tmp_pa
     lines, want = [], []
     cases = [(21, 9, 150), (31, 9, 151), (11, 9, 149), (4, 4, 60), (21, 1, 80), (15, 32, 200), (5, 9, 40),
              (3, 7, 30), (7, 40, 120), (21, 200, 400), (2, 2, 5), (27, 9, 35), (28, 9, 100), (1, 9, 9), (8, 9, 16),
-             (9, 9, 17), (21, 9, 29), (21, 9, 33)]
+             (9, 9, 17), (21, 9, 29), (21, 9, 33), (17, 9, 150), (19, 9, 101), (23, 9, 150), (25, 9, 97), (29, 9, 150),
+             (31, 9, 64), (12, 9, 150), (13, 9, 77), (16, 9, 150), (22, 9, 150), (30, 9, 99), (10, 9, 41)]
     for k, w, L in cases:
         reads = (random_reads(6, L, seed=k * 100 + w) + random_reads(4, L, seed=k + w, n_frac=0.05, lower_frac=0.3)
                  + [b"A" * L, (b"ACGTU" * L)[:L], (b"acgn0123RYKM" * L)[:L], (b"AC" * L)[:L]])
