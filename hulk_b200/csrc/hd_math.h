@@ -69,13 +69,14 @@ HULK_HD int32_t jump_hash(uint64_t key, int32_t num_buckets) {
 // One step is j' = trunc(fl(fl(2^31 / q) * (j + 1))) with q = (key >> 33) + 1.  The exact IEEE
 // quotient is only needed when the product lies within a few ulps of an integer, so the hot
 // loop evaluates x ~= (j + 1) * 2^31 / q from the hardware reciprocal seed plus one Newton
-// step (relative error <= JUMP_RCP_ERR, measured on the device by the self-test tap) and
+// step (relative error <= JUMP_RCP_ERR = 2^-39.88: the seed is good to 2^-19.94, measured over every
+// q in [1, 2^31] by hulk_b200_rcp_selftest, tests/test_gpu_parity.py) and
 // brackets the reference value: with EPS >= JUMP_RCP_ERR + 2^-50 the reference product lies
 // in [x(1-EPS), x(1+EPS)], so when both ends truncate to the same integer that integer IS the
 // reference's result.  Otherwise (probability ~ 2 EPS x per step) the caller recomputes the
 // step with the true division.  No rounding-mode or fast-math assumptions leak out: the
 // result is bit-identical to jump_hash() above by construction.
-constexpr double JUMP_EPS = 9.094947017729282e-13;        // 2^-40
+constexpr double JUMP_EPS = 1.8189894035458565e-12;       // 2^-39
 constexpr double JUMP_TWO52 = 4503599627370496.0;         // 2^52
 
 #if defined(__CUDA_ARCH__)
@@ -157,26 +158,28 @@ HULK_HD int32_t jump_hash_fast(uint64_t key, int32_t num_buckets, uint32_t *n_am
 
 // ---- fixed-point form of the fast step, for num_buckets <= 2^20 (every k^4-bin spectrum: 31^4 < 2^20) ----
 // x = (b + 1) 2^31 / q is evaluated as above (seed, one Newton step folded into the product) and added to
-// 2^32 in one FMA: y = 2^32 + x carries 20 fraction bits in the low word of its mantissa, floor(x) in the 32
-// bits above them.  While x < 2^20 the value of y is within 2 units of 2^-20 of the real quotient
-// (x 2^-40 from the reciprocal, 2^-21 from rounding y; the reference's own double rounding moves its product
-// by less than 2^-30), so unless the fraction lies in {0xFFFFE, 0xFFFFF, 0, 1} the integer part IS the
-// reference's trunc(); otherwise (2^-18 per step) the caller recomputes the step with the true division.
+// 2^32: y = 2^32 + x carries 20 fraction bits in the low word of its mantissa, floor(x) in the 32
+// bits above them.  While x < 2^20 the value of y is within 1.6 units of 2^-20 of the real quotient
+// (x 2^-39.88 from the reciprocal, 2^-21 from rounding y; the reference's own double rounding moves its product
+// by less than 2^-30), so unless the fraction lies within 3 units of an integer (0xFFFFD .. 0xFFFFF, 0 .. 2) the
+// integer part IS the reference's trunc(); otherwise (2^-17 per step) the caller recomputes the step with the
+// true division.
 // x >= 2^20 means "finished" whatever the error is (num_buckets <= 2^20).  One FMA replaces the two directed
 // roundings of the bracket, and the state between steps is the 32-bit bucket alone.
 constexpr double JUMP_TWO32 = 4294967296.0;               // 2^32
+constexpr double JUMP_TWO83M = 9671406556917033397649408.0 - 2147483648.0;   // 2^83 - 2^31 = (2^52 - 1) 2^31, exact
 constexpr uint32_t JUMP_FX_MAX_BUCKETS = 1u << 20;
 // returns 0: stepped (b updated), 1: finished (b is the answer), 2: ambiguous -> use jump_step_exact
 HULK_HD int jump_step_fx(uint64_t &key, uint32_t &b, const uint32_t num_buckets) {
     key = key * 2862933555777941757ull + 1ull;
     const double qd = dbl_make(0x43300000u, (uint32_t)(key >> 33)) - (JUMP_TWO52 - 1.0);   // (double)q, q = (key >> 33) + 1
-    const double jd1 = dbl_make(0x43300000u, b) - (JUMP_TWO52 - 1.0);                      // (double)(b + 1)
+    const double jd1 = dbl_make(0x45200000u, b) - JUMP_TWO83M;           // (2^83 + b 2^31) - (2^83 - 2^31) = (b + 1) 2^31
     const double r0 = rcp_seed(qd);
     const double e = fma(-qd, r0, 1.0);
     const double jr = jd1 * r0;
-    const double xq = fma(jr, e, jr);                                                      // ~ (b + 1) / q
-    const double y = fma(xq, 2147483648.0, JUMP_TWO32);
-    if ((uint32_t)((dbl_lo(y) + 2u) << 12) < (4u << 12)) return 2;
+    const double x = fma(jr, e, jr);                                                       // ~ (b + 1) 2^31 / q
+    const double y = x + JUMP_TWO32;
+    if ((uint32_t)((dbl_lo(y) + 3u) << 12) < (6u << 12)) return 2;
     if (y >= JUMP_TWO32 + (double)num_buckets) return 1;
     b = (dbl_hi(y) << 12) | (dbl_lo(y) >> 20);                                             // floor(x): the exponent bits shift out
     return 0;

@@ -102,6 +102,7 @@ constexpr int K1_WARPS = K1_TPB / 32;
 // Loop-invariant doubles of the jump step live in the constant bank: DFMA/DMUL take a c[bank][offset]
 // operand directly, so no instruction is spent re-materialising a 64-bit immediate in front of each use.
 __constant__ double k1_jump_consts[2] = {1.0 - JUMP_EPS, 1.0 + JUMP_EPS};
+__constant__ double k1_jump_fx_consts[3] = {JUMP_TWO52 - 1.0, JUMP_TWO83M, 1.0};
 
 __device__ __forceinline__ double k1_pin(double x) {
     asm volatile("" : "+d"(x));
@@ -201,29 +202,40 @@ template <int BATCH, class Load>
 __device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t g, const uint32_t total, uint32_t *const hist,
                                                 const uint32_t nb) {
     const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
-    uint64_t key[2] = {0, 0};
-    uint32_t bkt[2] = {0, 0};
-    bool busy[2] = {false, false}, loaded[2] = {false, false};
-    const double two52m1 = k1_pin(JUMP_TWO52 - 1.0), one = k1_pin(1.0), two31 = k1_pin(2147483648.0),
-                 two32 = k1_pin(JUMP_TWO32);
+    uint64_t key[2] = {0, 0}, spare[2] = {0, 0};
+    constexpr uint32_t NO_BIN = 0xFFFFFFFFu;                             // the walk holds no key (nothing left to count)
+    uint32_t bkt[2] = {NO_BIN, NO_BIN};
+    // busy: the walk is under way (when it ends, bkt keeps its bin until the next refill point counts it); have: a
+    // spare key is waiting (fetched one refill point ahead of its use, so no walk starts on a load still in flight)
+    bool busy[2] = {false, false}, have[2] = {false, false};
+    // loop-invariant operands come from the constant bank (an FP64 instruction takes one c[][] operand directly), so none
+    // of them is re-materialised with moves inside the loop: [0] 2^52 - 1, [1] 2^83 - 2^31, [2] 1
+    const double two52m1 = k1_jump_fx_consts[0], two83m = k1_jump_fx_consts[1], one = k1_jump_fx_consts[2];
     const double ynb = k1_pin(JUMP_TWO32 + (double)nb);
+    auto top_up = [&](int c) {                                           // hand the warp's next unclaimed keys to the empty spares
+        const uint32_t need = __ballot_sync(0xffffffffu, !have[c]);
+        const uint32_t mine = g + __popc(need & lane_lt);
+        g = min(g + (uint32_t)__popc(need), total);
+        if (!have[c] && mine < total) {
+            spare[c] = load(mine);
+            have[c] = true;
+        }
+    };
+    top_up(0);
+    top_up(1);
     for (;;) {
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            if (!busy[c] && loaded[c]) {                                 // its walk ended in the last batch
-                atomicAdd(&hist[bkt[c]], 1u);
-                loaded[c] = false;
+            if (!busy[c]) {
+                if (bkt[c] != NO_BIN) atomicAdd(&hist[bkt[c]], 1u);      // its walk ended in the last batch
+                key[c] = spare[c];
+                bkt[c] = have[c] ? 0u : NO_BIN;                          // first step of jump.Hash: b = 0
+                busy[c] = have[c];
+                have[c] = false;
             }
-            const uint32_t need = __ballot_sync(0xffffffffu, !busy[c]);
-            const uint32_t mine = g + __popc(need & lane_lt);
-            g = min(g + (uint32_t)__popc(need), total);
-            if (!busy[c] && mine < total) {
-                key[c] = load(mine);
-                bkt[c] = 0;                                              // first step of jump.Hash: b = 0
-                busy[c] = loaded[c] = true;
-            }
+            top_up(c);
         }
-        if (!__any_sync(0xffffffffu, busy[0] | busy[1])) break;
+        if (!__any_sync(0xffffffffu, busy[0] | busy[1] | have[0] | have[1])) break;
 #pragma unroll
         for (int it = 0; it < BATCH; it++) {
             uint32_t nbk[2];
@@ -232,17 +244,17 @@ __device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t g, const uin
             for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
                 key[c] = key[c] * 2862933555777941757ull + 1ull;
                 const double qd = dbl_make(0x43300000u, (uint32_t)(key[c] >> 33)) - two52m1;   // (double)q
-                const double jd1 = dbl_make(0x43300000u, bkt[c]) - two52m1;                    // (double)(b + 1)
+                const double jd1 = dbl_make(0x45200000u, bkt[c]) - two83m;                     // (b + 1) 2^31, exact
                 const double r0 = rcp_seed(qd);
                 const double e = fma(-qd, r0, one);
                 const double jr = jd1 * r0;
-                const double xq = fma(jr, e, jr);                                              // ~ (b + 1) / q
-                const double y = fma(xq, two31, two32);                                        // 2^32 + x
-                amb[c] = (uint32_t)(dbl_lo(y) * 4096u + 8192u) < 16384u;                       // fraction in {-2, -1, 0, 1} 2^-20
+                const double x = fma(jr, e, jr);                                               // ~ (b + 1) 2^31 / q
+                const double y = x + JUMP_TWO32;                                               // 2^32 + x
+                amb[c] = (uint32_t)(dbl_lo(y) * 4096u + 3u * 4096u) < 6u * 4096u;              // fraction in -3 .. 2 units of 2^-20
                 fin[c] = y >= ynb;
                 nbk[c] = __funnelshift_l(dbl_lo(y), dbl_hi(y), 12);                            // floor(x)
             }
-            if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // 2^-18 per step: the true division
+            if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-17 per step: the true division
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     if (amb[c] && busy[c]) {
@@ -284,8 +296,35 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
     // four (independent compares, no load waits on a compare), then the four are compared with each
     // other; survivors are appended in order (in place: m_out never passes the read cursor).
     constexpr uint64_t NONE = Sentinel<FP>::value;           // never a list value
-    uint32_t m_out = 0;
-    for (uint32_t a = 0; a < n; a += 4) {
+    // A value can only come back later in the list when the same k-mer occurs twice in the read with a smaller one
+    // in between: rare.  So the lists are first only TESTED -- loads and compares, four independent accumulators,
+    // nothing stored -- and the set construction below runs for a warp where the test fires (a false alarm from
+    // stale entries behind a short list only costs that pass).
+    bool maybe_dup = false;
+    {
+        const uint32_t n_max = __reduce_max_sync(0xffffffffu, n);
+        for (uint32_t a = 0; a < n_max; a += 4) {
+            uint64_t x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = (a + u < n) ? my_list[(a + u) * 32] : NONE - 1u - (uint64_t)u;   // distinct pads
+            for (uint32_t b = 0; b < a; b += 4) {                        // a is a multiple of four
+                uint64_t y[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) y[v] = my_list[(b + v) * 32];
+                bool hit = false;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) hit |= ueq64<FP>(y[v], x[u]);
+                maybe_dup |= hit;
+            }
+            maybe_dup |= ueq64<FP>(x[1], x[0]) | ueq64<FP>(x[2], x[0]) | ueq64<FP>(x[2], x[1]) | ueq64<FP>(x[3], x[0]) |
+                         ueq64<FP>(x[3], x[1]) | ueq64<FP>(x[3], x[2]);
+        }
+    }
+    const bool exact = __any_sync(0xffffffffu, maybe_dup);
+    uint32_t m_out = exact ? 0u : n;
+    for (uint32_t a = 0; exact && a < n; a += 4) {
         uint64_t x[4];
         bool dup[4];
 #pragma unroll

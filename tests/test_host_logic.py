@@ -319,8 +319,11 @@ int main() {
         } else {
             unsigned long long key; long long n;
             if (scanf("%llu %lld", &key, &n) != 2) return 1;
-            uint32_t amb = 0;
-            printf("%d %u\n", hulk::jump_hash_fast(key, (int32_t)n, &amb), amb);
+            uint32_t amb = 0, amb_fx = 0;
+            const int32_t got = hulk::jump_hash_fast(key, (int32_t)n, &amb);
+            // the fixed-point step of the binning kernel (num_buckets <= 2^20) must land in the same bucket
+            if (n <= (long long)hulk::JUMP_FX_MAX_BUCKETS && hulk::jump_hash_fx(key, (int32_t)n, &amb_fx) != got) { printf("MISMATCH_FX\n"); return 2; }
+            printf("%d %u\n", got, amb + amb_fx);
         }
     }
     return 0;
@@ -355,7 +358,7 @@ def test_kernel_scan_and_fast_jump_compiled_for_host_match_oracle(oracle, tmp_pa
             m = np.sort(oracle.minimizers(k, w, raw))
             want.append(" ".join([str(len(m))] + [str(int(x)) for x in m]))
     n_jump = 0
-    for n in (2, 10, 2000, 14641, 194481, 923521, 2 ** 31 - 1):
+    for n in (2, 10, 2000, 14641, 194481, 923521, 2 ** 20, 2 ** 31 - 1):
         for key in [0, 1, 2 ** 64 - 1] + [int(x) for x in rng.integers(0, 2 ** 64, 400, dtype=np.uint64)]:
             lines.append("J %d %d" % (key, n))
             want.append(oracle.jump(key, n))
