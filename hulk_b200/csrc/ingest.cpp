@@ -317,6 +317,10 @@ struct hulk_b200_reader {
                 }
                 const uint8_t *t = d + off + b - 4;
                 const size_t isize = t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+                if (isize > 65536) {                        // BGZF caps a member at 64 KiB of data: whatever this is, it is
+                    w.tail = RESUME;                        // not a BGZF block -- let the ordinary gzip reader judge it
+                    break;                                  // (and never size a buffer from an unchecked trailer)
+                }
                 w.blks.push_back({off, b, h, w.total, isize});
                 w.total += isize;
                 off += b;
@@ -582,6 +586,19 @@ struct hulk_b200_reader {
                     *len = pr.second;
                 }
             };
+            // A looked-back line of a token's length or more was fatal for the job (or file) it lies in; that job
+            // reports it, and the jobs of a round run side by side, so this one must not touch the line either:
+            // its batch holds par_chunk + 2 kMaxToken bytes and nothing longer than a token may be copied into it.
+            for (int idx = 0; idx < ps; idx++) {
+                const uint8_t *pl;
+                size_t nl;
+                line_at(idx, &pl, &nl);
+                if (nl >= kMaxToken) {
+                    j.err = HULK_B200_ETOOLONG;
+                    j.err_text = "bufio.Scanner: token too long";
+                    return;
+                }
+            }
             const uint8_t *p1;
             size_t n1;
             line_at(0, &p1, &n1);
@@ -608,6 +625,11 @@ struct hulk_b200_reader {
                     if (first_byte != '@') {
                         j.err = HULK_B200_EFASTQ;
                         j.err_text = "read ID in fastq file does not begin with @: " + id_text;
+                        return false;
+                    }
+                    if (b.n_bytes + seq_len > b.bases.bytes) {             // cannot happen for lines below a token's length
+                        j.err = HULK_B200_ETOOLONG;
+                        j.err_text = "bufio.Scanner: token too long";
                         return false;
                     }
                     memcpy(b.b() + b.n_bytes, seq, seq_len);

@@ -199,9 +199,8 @@ __device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32
 // (DFMA), "finished" as one DSETP against 2^32 + n, the ambiguity band as one IMAD + ISETP on the fraction bits,
 // floor(x) by one funnel shift.  About 20 instructions against 33 for the bracketed step, 7 of them on the FP64 pipe.
 template <int BATCH, class Load>
-__device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t g, const uint32_t total, uint32_t *const hist,
-                                                const uint32_t nb) {
-    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
+__device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t *const next_key, const uint32_t total,
+                                                uint32_t *const hist, const uint32_t nb) {
     uint64_t key[2] = {0, 0}, spare[2] = {0, 0};
     constexpr uint32_t NO_BIN = 0xFFFFFFFFu;                             // the walk holds no key (nothing left to count)
     uint32_t bkt[2] = {NO_BIN, NO_BIN};
@@ -212,13 +211,15 @@ __device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t g, const uin
     // of them is re-materialised with moves inside the loop: [0] 2^52 - 1, [1] 2^83 - 2^31, [2] 1
     const double two52m1 = k1_jump_fx_consts[0], two83m = k1_jump_fx_consts[1], one = k1_jump_fx_consts[2];
     const double ynb = k1_pin(JUMP_TWO32 + (double)nb);
-    auto top_up = [&](int c) {                                           // hand the warp's next unclaimed keys to the empty spares
-        const uint32_t need = __ballot_sync(0xffffffffu, !have[c]);
-        const uint32_t mine = g + __popc(need & lane_lt);
-        g = min(g + (uint32_t)__popc(need), total);
-        if (!have[c] && mine < total) {
-            spare[c] = load(mine);
-            have[c] = true;
+    // hand-out: the warp's next unclaimed key is a counter in shared memory; only lanes whose spare is empty touch it
+    // (an atomic add each, a handful per refill point), so nothing is spent on lanes that need nothing
+    auto top_up = [&](int c) {
+        if (!have[c]) {
+            const uint32_t mine = atomicAdd(next_key, 1u);
+            if (mine < total) {
+                spare[c] = load(mine);
+                have[c] = true;
+            }
         }
     };
     top_up(0);
@@ -732,7 +733,10 @@ __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue_fx(const K1Params p
     const uint64_t gw = (uint64_t)blockIdx.x * (K1_JUMP_TPB / 32) + (threadIdx.x >> 5);
     const uint32_t seg_begin = (uint32_t)(total * gw / nwarps), seg_end = (uint32_t)(total * (gw + 1) / nwarps);
     const uint64_t *const q = p.queue;
-    k1_jump_walk_fx<BATCH>([&](uint32_t i) { return q[i]; }, seg_begin, seg_end, p.hist, (uint32_t)p.D);
+    __shared__ uint32_t next_key[K1_JUMP_TPB / 32];                      // per warp: the next unclaimed key of its segment
+    if ((threadIdx.x & 31) == 0) next_key[threadIdx.x >> 5] = seg_begin;
+    __syncwarp();
+    k1_jump_walk_fx<BATCH>([&](uint32_t i) { return q[i]; }, &next_key[threadIdx.x >> 5], seg_end, p.hist, (uint32_t)p.D);
 }
 
 // reciprocal self-test (parity tap): for q = q0 + i the seed's and the refined reciprocal's relative errors,

@@ -20,9 +20,9 @@
 namespace {
 
 __global__ void k_smash(const unsigned long long *__restrict__ mins, const double *__restrict__ weights, uint32_t n,
-                        uint32_t s, int weighted, double *__restrict__ sim) {
+                        uint32_t s, int weighted, double *__restrict__ sim, uint32_t i0) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;     // query
-    const uint32_t i = blockIdx.y;                                // subject
+    const uint32_t i = i0 + blockIdx.y;                           // subject (grid.y holds at most 65535 rows per launch)
     if (j >= n) return;
     const unsigned long long *a = mins + (size_t)i * s, *b = mins + (size_t)j * s;
     double dist;
@@ -68,8 +68,10 @@ extern "C" int hulk_b200_smash(const uint64_t *mins, const double *weights, uint
     } else {
         cudaMemcpy(d_m, mins, ne * 8, cudaMemcpyHostToDevice);
         if (weighted) cudaMemcpy(d_w, weights, ne * 8, cudaMemcpyHostToDevice);
-        const dim3 grid((n + 127) / 128, n);
-        k_smash<<<grid, 128>>>(d_m, d_w, n, s, weighted, d_s);
+        for (uint32_t i0 = 0; i0 < n; i0 += 65535u) {             // the reference has no limit on the number of sketches
+            const dim3 grid((n + 127) / 128, n - i0 < 65535u ? n - i0 : 65535u);
+            k_smash<<<grid, 128>>>(d_m, d_w, n, s, weighted, d_s, i0);
+        }
         if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) rc = HULK_B200_ECUDA;
         else cudaMemcpy(similarity, d_s, (size_t)n * n * 8, cudaMemcpyDeviceToHost);
     }

@@ -326,6 +326,24 @@ def test_parallel_reader_errors_equal_sequential(tmp_path):
             assert par == seq and msg in par and par.startswith("ERR")
 
 
+def test_parallel_reader_long_line_behind_a_chunk_boundary(tmp_path):
+    """A sequence line far longer than a token (and than a worker's batch) followed by SHORT '+' and quality lines: the job
+    that starts behind it looks back for the open record's lines and must refuse the long one instead of copying it
+    (the copy used to run past the batch: 700 KB into a 384 KB buffer with the default 8 MB chunks scaled down here)."""
+    reads = random_reads(60, 50, seed=9)
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads)]
+    for big, qual in ((70000, b"I"), (716800, b"II"), (65536, b"I" * 40)):
+        body = list(recs)
+        body[30] = b"@r30\n" + b"A" * big + b"\n+\n" + qual + b"\n"
+        f = tmp_path / ("long_%d.fq" % big)
+        f.write_bytes(b"".join(body))
+        seq = _native_env([f], {"HULK_B200_PARALLEL_READER": "0"})
+        assert seq.startswith("ERR") and "token too long" in seq
+        for chunk in ("100", "777", "4096", "70000", "300000"):
+            par = _native_env([f], {"HULK_B200_PARALLEL_READER": "1", "HULK_B200_PARALLEL_CHUNK": chunk})
+            assert par == seq, (big, chunk)
+
+
 # ---- BGZF (bgzip) input: members found from their headers, inflated on several threads ----------------
 def _bgzf(data, block=0xff00, level=6):
     """htslib's blocked gzip: one member per <= 64 KiB of input, size in the 'BC' extra subfield, EOF marker."""

@@ -51,7 +51,11 @@ static void one_reads(const char *path, int fasta) {
     } report{path, reads_before, err_before};
     hulk_b200_reader *rd = nullptr;
     const char *paths[1] = {path};
-    if (hulk_b200_reader_open(paths, 1, fasta, 1 << 16, &rd) != HULK_B200_OK) { g_err++; return; }
+    // HOST_FUZZ_BATCH=0: the library's default batch size, the only setting under which reader_open takes the
+    // multi-threaded plain-FASTQ parser (produce_parallel); anything else keeps the small batches of the one-thread pass
+    const char *hb = getenv("HOST_FUZZ_BATCH");
+    const uint64_t batch = hb ? (uint64_t)atoll(hb) : (1u << 16);
+    if (hulk_b200_reader_open(paths, 1, fasta, batch, &rd) != HULK_B200_OK) { g_err++; return; }
     for (;;) {
         const uint8_t *bases = nullptr;
         const uint64_t *offs = nullptr;

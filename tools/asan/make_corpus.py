@@ -81,6 +81,20 @@ def fastq(nrec, crlf=False, blank=0.0):
 
 fq = [fastq(400), fastq(50, crlf=True), fastq(100, blank=0.3), fastq(3)[:-1], b"", b"\n\n\n", b"@only\n", b"A" * 70000 + b"\n",
       b"@r\n" + b"A" * 65535 + b"\n+\n" + b"I" * 65535 + b"\n", b"@r\n" + b"A" * 65536 + b"\n+\nI\n", b"\r\n\r\r\n", b"x\ny\nz\nw\n" * 10]
+# lines of a token's length or more in each of the four record slots, next to the chunk boundaries of the parallel
+# parser (HULK_B200_PARALLEL_CHUNK=777 in run.sh): short neighbours so that the record straddles a boundary
+def long_line_cases():
+    for slot in range(4):
+        for big in (65535, 65536, 70000, 200000):
+            for lead in (0, 3, 97):
+                rec = [b"@r", b"ACGT" * 8, b"+", b"I" * 32]
+                rec[slot] = (b"@" if slot == 0 else b"") + (b"A" if slot != 3 else b"I") * big
+                yield fastq(lead) + b"\n".join(rec) + b"\n" + fastq(4)
+    yield b"@r\n" + b"A" * 70000 + b"\n+\nII\n@s\nACGT\n+\nIIII\n"          # long sequence, short quality line
+    yield fastq(7) + b"@r\n" + b"A" * 716800 + b"\n+\nI\n" + fastq(9)
+
+
+fq += list(long_line_cases())
 n = 0
 for s in fq:
     for enc in ("plain", "gz", "bgzf"):

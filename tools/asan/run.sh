@@ -14,6 +14,8 @@ export ASAN_OPTIONS=detect_leaks=1:abort_on_error=0
 rc=0
 "$work/host_fuzz" json "$work"/corpus/json/* || rc=1
 for par in 0 1; do
+    # par=1 must reach produce_parallel: that needs the default batch size (HOST_FUZZ_BATCH=0), see host_fuzz.cpp
+    HOST_FUZZ_BATCH=$((par ? 0 : 65536)) \
     HULK_B200_PARALLEL_READER=$par HULK_B200_PARALLEL_CHUNK=777 HULK_B200_BGZF_WINDOW=5000 HOST_FUZZ_VERBOSE=1 \
         "$work/host_fuzz" fastq "$work"/corpus/fastq/* > "$work/verdict$par.txt" || rc=1
     tail -1 "$work/verdict$par.txt"
