@@ -52,6 +52,10 @@ def parse_args():
                     help="iid: uniform i.i.d. bases (the headline workload).  genome: SURVEY section 8(d)'s realism "
                          "variant -- reads sampled at uniform offsets and strands from a seeded 100 Mbp random genome, so "
                          "minimizers repeat across reads (reported, never the headline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU sketches `interval` reads per step (the default the driver's scaling run "
+                         "uses); strong = the interval is fixed at `interval` reads and split N ways (BASELINE's C2/C5 "
+                         "as written: 12 500 reads per GPU per flush at N = 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     return ap.parse_args()
@@ -65,9 +69,10 @@ def workload_config(a, n_gpus):
                        % (GENOME_BASES // 1_000_000) if a.reads == "genome" else ""),
         "reads": a.reads,
         "k": a.k, "w": a.w, "sketch_size": a.s, "num_bins": a.k ** 4, "interval_reads": a.interval,
-        "read_len": a.read_len, "decay_ratio": a.decay, "reads_per_step_total": a.interval * n_gpus,
-        "parallelism": "reads sharded over %d GPU(s); histogram all-reduce; CWS slots sharded" % n_gpus
-                       if n_gpus > 1 else "single GPU",
+        "read_len": a.read_len, "decay_ratio": a.decay,
+        "reads_per_step_total": a.interval * (n_gpus if a.scaling == "weak" else 1),
+        "parallelism": "reads sharded over %d GPU(s); spectra summed over NVLink inside the flush (peer reads, no "
+                       "collective call); CWS slots sharded" % n_gpus if n_gpus > 1 else "single GPU",
         "l2_policy": "inputs larger than L2: each step reads fresh reads and streams the %.0f MB (bf16) CWS screen table"
                      % (2.0 * a.s * a.k ** 4 / n_gpus / 1e6),
         "pipelining": "the spectrum is multi-buffered: intervals i+1.. are counted (k1) while interval i is flushed (k2, k3)",
@@ -298,6 +303,12 @@ def run_reference(a):
         return
     steps = max(1, min(a.steps, 6))
     warm = min(a.warmup, 1)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm uses every core this process may run on
+    from oracle import oracle as O
+    try:
+        O.set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        O.set_threads(os.cpu_count() or 1)
     value, ms, base = cpu_arm(a, steps, warm)
     base["value"] = value
     print(json.dumps({
@@ -312,6 +323,50 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def parity_check(hulk_b200, dist, world, rank, local):
+    """Before anything is timed: a small job (k=11, w=9, s=64, four intervals, ragged tail) sketched by the SAME
+    multi-GPU path the timed steps use -- reads split over the ranks, spectra summed in the flush, slots sharded --
+    and compared on rank 0 with the CPU oracle's single loop (the checker; src/pipeline/sketch.go:197-224,
+    src/histosketch/histosketch.go:129-155).  Returns "ok"; anything else stops the bench."""
+    k, w, s, interval, n, L = 11, 9, 64, 4000, 15000, 150
+    D = k ** 4
+    rng = np.random.default_rng(4242)
+    r = rng.gamma(2.0, 1.0, (s, D))
+    c = np.log(rng.gamma(2.0, 1.0, (s, D)))
+    b = rng.random((s, D)) * r
+    reads = hulk_b200.synthetic_reads(n, L, seed=9)
+    reads[::97, 40] = ord("N")                                        # the code-4 path too
+    bases = reads.reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    a0, a1 = hulk_b200.slot_range(s, world, rank)
+    with hulk_b200.HistoSketch(k, w, s, 1.0, device=local, slots=(a0, a1), tables=(r[a0:a1], c[a0:a1], b[a0:a1])) as hs:
+        sh = hulk_b200.ShardedSketch(hs, s, world, rank)
+        mins, weights, nmin = hulk_b200.sketch_reads_sharded(sh, [(bases, offsets)], interval)
+        mode = "peer reads over NVLink" if sh.peer_mode else ("all-reduce" if world > 1 else "single GPU")
+        if world > 1:
+            dist.barrier()                                            # nobody unmaps a buffer a peer may still read
+    verdict = "ok"
+    if rank == 0:
+        try:
+            from oracle import oracle as O
+            ref = O.HistoSketch(k, s, D, 1.0, r, c, b)
+            nmin_ref, _ = ref.run(w, bases, offsets, interval=interval, parallel=True)
+            mins_ref, weights_ref = ref.get()
+            if not ((mins == mins_ref).all() and np.allclose(weights, weights_ref, rtol=1e-12, atol=0) and nmin == nmin_ref):
+                verdict = "MISMATCH against the oracle (%s, %d ranks)" % (mode, world)
+        except OSError as e:
+            verdict = "unavailable: %r" % (e,)
+    if world > 1:
+        import torch
+        flag = torch.tensor([0 if verdict == "ok" or verdict.startswith("unavailable") else 1], device="cuda")
+        dist.broadcast(flag, 0)
+        if int(flag.item()):
+            raise SystemExit("bench.py: parity check failed: " + verdict)
+    elif not (verdict == "ok" or verdict.startswith("unavailable")):
+        raise SystemExit("bench.py: parity check failed: " + verdict)
+    return {"verdict": verdict, "job": "k=11 w=9 s=64, 15000 reads, interval 4000, %d rank(s), %s" % (world, mode)}
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -343,7 +398,10 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     L_ = hulk_b200.load()
 
-    k, w, s, I, RL = a.k, a.w, a.s, a.interval, a.read_len
+    k, w, s, RL = a.k, a.w, a.s, a.read_len
+    if a.scaling == "strong" and a.interval % world:
+        raise SystemExit("--scaling strong: the interval must divide by the number of GPUs")
+    I = a.interval if a.scaling == "weak" else a.interval // world      # reads THIS rank counts per step
     D = k ** 4
     if s % world:
         raise SystemExit("sketch size must divide by the number of GPUs")
@@ -364,6 +422,8 @@ def run_b200(a):
         del genome
         r_t, c_t, b_t = synthetic_tables_torch(torch, s, D, 1234, dev, slots)
     stream.synchronize()
+
+    parity = parity_check(hulk_b200, dist, world, rank, local)
 
     hs = hulk_b200.HistoSketch(k, w, s, a.decay, device=local, slots=slots, stream=stream.cuda_stream,
                                async_input=True, input_ready=True)
@@ -511,10 +571,22 @@ def run_b200(a):
                 "kernel_ms_per_step": {n: prof[n]["ms"] / K for n in prof},
                 "kernel_share_of_step": {n: prof[n]["ms"] / ms_serial for n in prof},
                 "serial_ms_per_step": ms_serial / K,
-                "k3_filter_GBps": (alg_bytes["k3_filter"] / (prof["k3_filter"]["ms"] / max(1, prof["k3_filter"]["launches"]) * 1e-3) / 1e9)
-                if prof["k3_filter"]["ms"] > 0 else None,
-                "k3_filter_note": "k3_filter_GBps is against the contract's dense fp32 stream (4 B per slot and bin, SURVEY 8d); "
-                                  "the screen table is stored as bfloat16 (2 B), so the bytes actually streamed are half of that"}
+                }
+    # the CWS screen: bytes it really streams (the stored table: 2 B per slot and bin as bfloat16, 4 B with
+    # HULK_B200_K3_FP32=1, plus the (1/f) vector once per slot row from L2) against the measured HBM peak FIRST; the contract's
+    # dense fp32 stream is given beside it as what the screen stands in for
+    if prof["k3_filter"]["ms"] > 0:
+        k3_ms = prof["k3_filter"]["ms"] / max(1, prof["k3_filter"]["launches"])
+        elem = 4.0 if os.environ.get("HULK_B200_K3_FP32") == "1" else 2.0
+        Dp = (D + 511) // 512 * 512
+        streamed = elem * rows * Dp
+        roofline["k3_filter"] = {"bound": "hbm", "streamed_bytes_per_launch": streamed, "avg_launch_ms": k3_ms,
+                                 "achieved": streamed / (k3_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": streamed / (k3_ms * 1e-3) / 1e9 / peak,
+                                 "contract_bytes_per_launch": alg_bytes["k3_filter"],
+                                 "contract_GBps": alg_bytes["k3_filter"] / (k3_ms * 1e-3) / 1e9,
+                                 "note": "frac = bytes streamed from HBM / time / measured peak; contract_GBps divides the "
+                                         "contract's dense fp32 bytes (which are never streamed) by the same time"}
 
     # K1 is issue-bound, not HBM-bound: next to the contract's HBM figure, report its
     # warp-instruction rate against the SM sub-partitions' issue rate.  Instruction counts per read are the
@@ -537,19 +609,26 @@ def run_b200(a):
     # whole-step figure of SURVEY 8(d): B = sum len + F (4 s D + 16 D) + 16 s bytes over the pipelined step time
     step_bytes = float(I * RL) + 4.0 * rows * D + 16.0 * D + 16.0 * rows / max(1, K)
     step_gbs = step_bytes / (ms_value / K * 1e-3) / 1e9
+    elem = 4.0 if os.environ.get("HULK_B200_K3_FP32") == "1" else 2.0
+    moved = float(I * RL) + elem * rows * ((D + 511) // 512 * 512) + 40.0 * D      # reads, stored screen table, spectrum + f + 1/f
+    moved_gbs = moved / (ms_value / K * 1e-3) / 1e9
+    roofline["step"] = {"bytes_moved_per_step": moved, "achieved": moved_gbs, "unit": "GB/s", "frac": moved_gbs / peak,
+                        "note": "bytes the pipelined step really moves through HBM over its time; per rank"}
     roofline["step_algorithmic"] = {"bytes_per_step": step_bytes, "achieved": step_gbs, "unit": "GB/s",
                                     "frac": step_gbs / peak, "frac_of_nominal_8000": step_gbs / 8000.0,
-                                    "note": "contract bytes (dense fp32 CWS stream) over the pipelined step; per rank"}
+                                    "note": "contract bytes of SURVEY 8(d) (dense fp32 CWS stream, never streamed as such: the "
+                                            "screen table is stored at half that) over the pipelined step; per rank"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "u64 minimizer/jump-hash, u32 histogram, bf16 CWS screen + f64 CWS resolve", "data": "synthetic",
         "config": workload_config(a, world),
         "gbases_per_s": value * RL / 1e9,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
+        "parity_check": parity["verdict"], "parity_job": parity["job"],
         "host_cpus_per_rank": affinity,
         "clocks": clocks,
         "roofline": roofline,

@@ -24,7 +24,14 @@ EXPORTS = [
     "hulk_b200_free_pinned", "hulk_b200_reader_open", "hulk_b200_reader_next", "hulk_b200_reader_error",
     "hulk_b200_reader_close", "hulk_b200_sketch_reader", "hulk_b200_sketch_load", "hulk_b200_sketch_find",
     "hulk_b200_sketch_banner", "hulk_b200_sketch_free", "hulk_b200_smash",
+    "hulk_b200_peer_export", "hulk_b200_peer_connect", "hulk_b200_peer_connect_local",
+    "hulk_b200_group_create", "hulk_b200_group_destroy", "hulk_b200_group_last_error", "hulk_b200_group_size",
+    "hulk_b200_group_member", "hulk_b200_group_set_cws_tables", "hulk_b200_group_generate_cws_tables",
+    "hulk_b200_group_push_reads", "hulk_b200_group_push_reads_fixed", "hulk_b200_group_sync_inputs",
+    "hulk_b200_group_flush", "hulk_b200_group_sync", "hulk_b200_group_finish", "hulk_b200_group_reset",
+    "hulk_b200_group_get_stats", "hulk_b200_group_sketch_reader",
 ]
+PEER_HANDLE_BYTES = 64
 
 OK, EW, EK, EEMPTYSEQ, ESHORTSEQ, ESPARSE = 0, -1, -2, -3, -4, -6
 EHSK, EDECAY, EBINS, ENEGBINS, ENOSKETCH = -10, -11, -12, -13, -14
@@ -124,6 +131,25 @@ def load():
         "hulk_b200_sketch_banner": (C.c_char_p, [vp]),
         "hulk_b200_sketch_free": (None, [vp]),
         "hulk_b200_smash": (C.c_int, [vp, vp, u32, u32, C.c_int, i32, vp]),
+        "hulk_b200_peer_export": (C.c_int, [vp, vp]),
+        "hulk_b200_peer_connect": (C.c_int, [vp, u32, u32, vp]),
+        "hulk_b200_peer_connect_local": (C.c_int, [vp, u32, u32, C.POINTER(vp)]),
+        "hulk_b200_group_create": (C.c_int, [C.POINTER(Params), C.POINTER(i32), u32, C.POINTER(vp)]),
+        "hulk_b200_group_destroy": (None, [vp]),
+        "hulk_b200_group_last_error": (C.c_char_p, [vp]),
+        "hulk_b200_group_size": (u32, [vp]),
+        "hulk_b200_group_member": (vp, [vp, u32]),
+        "hulk_b200_group_set_cws_tables": (C.c_int, [vp, vp, vp, vp]),
+        "hulk_b200_group_generate_cws_tables": (C.c_int, [vp, C.c_int]),
+        "hulk_b200_group_push_reads": (C.c_int, [vp, vp, vp, u64]),
+        "hulk_b200_group_push_reads_fixed": (C.c_int, [vp, vp, u64, u32]),
+        "hulk_b200_group_sync_inputs": (C.c_int, [vp]),
+        "hulk_b200_group_flush": (C.c_int, [vp]),
+        "hulk_b200_group_sync": (C.c_int, [vp]),
+        "hulk_b200_group_finish": (C.c_int, [vp, vp, vp]),
+        "hulk_b200_group_reset": (C.c_int, [vp]),
+        "hulk_b200_group_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+        "hulk_b200_group_sketch_reader": (C.c_int, [vp, vp, u64, LOG_FN, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

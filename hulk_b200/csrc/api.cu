@@ -128,6 +128,17 @@ struct hulk_b200_ctx {
     int gen_rc = 0;
     bool gen_pending = false;
 
+    // multi-GPU (k2_countmin.cuh, "the spectrum of a flush is the sum of every GPU's counting buffer")
+    uint32_t world = 1, rank = 0;
+    uint8_t *arena = nullptr;                  // the NBUF spectrum buffers + the two flag arrays: one allocation, one IPC handle
+    size_t arena_bytes = 0, hist_stride = 0, off_counted = 0, off_gathered = 0;
+    uint8_t *peer_arena[PEER_MAX] = {};        // every rank's arena as this device reaches it (own at [rank])
+    bool peer_ipc[PEER_MAX] = {};              // opened with cudaIpcOpenMemHandle (another process)
+    uint32_t use_seq[NBUF] = {};               // how many flushes buffer b has been through (never reset: the flags only grow)
+    uint32_t peer_dirty[NBUF] = {};            // use of buffer b that every peer must have gathered before it is wiped
+    uint32_t *d_hist_sum = nullptr;            // the summed spectrum of the flush under way
+    unsigned int *d_ticket = nullptr;
+
     hulk_b200_stats st{};
     uint64_t extra_minimizers = 0;
     std::string err;
@@ -244,7 +255,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (ctx->k2_stream) cudaStreamSynchronize(ctx->k2_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < NBUF; i++) {
-        void *per[] = {ctx->d_hist[i], ctx->d_ovf_count[i], ctx->d_ovf_list[i], ctx->d_arena[i], ctx->d_arena_cursor[i],
+        void *per[] = {ctx->d_ovf_count[i], ctx->d_ovf_list[i], ctx->d_arena[i], ctx->d_arena_cursor[i],
                        ctx->d_queue[i], ctx->d_queue_cursor[i]};
         for (void *p : per)
             if (p) cudaFree(p);
@@ -253,7 +264,9 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
         if (ctx->d_off[i]) cudaFree(ctx->d_off[i]);
     }
-    void *ptrs[] = {ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
+    for (uint32_t p = 0; p < PEER_MAX; p++)
+        if (ctx->peer_ipc[p] && ctx->peer_arena[p]) cudaIpcCloseMemHandle(ctx->peer_arena[p]);
+    void *ptrs[] = {ctx->arena, ctx->d_hist_sum, ctx->d_ticket, ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits[0], ctx->d_fbits[1], ctx->d_invf[0],
                     ctx->d_invf[1], ctx->d_r, ctx->d_c,
@@ -338,7 +351,13 @@ static int create_impl(hulk_b200_ctx *ctx) {
     ctx->nseg = (uint32_t)((ctx->Dp + seg_bins - 1) / seg_bins);
     ctx->nblk = (uint32_t)(((uint64_t)D + 1023) / 1024);
 
-    for (int i = 0; i < NBUF; i++) CU(dmalloc(&ctx->d_hist[i], D));
+    ctx->hist_stride = ((size_t)D * 4 + 255) & ~(size_t)255;
+    ctx->off_counted = (size_t)NBUF * ctx->hist_stride;
+    ctx->off_gathered = ctx->off_counted + sizeof(uint32_t) * NBUF * PEER_MAX;
+    ctx->arena_bytes = ctx->off_gathered + sizeof(uint32_t) * NBUF * PEER_MAX;
+    CU(dmalloc(&ctx->arena, ctx->arena_bytes));
+    for (int i = 0; i < NBUF; i++) ctx->d_hist[i] = reinterpret_cast<uint32_t *>(ctx->arena + (size_t)i * ctx->hist_stride);
+    ctx->peer_arena[0] = ctx->arena;
     CU(dmalloc(&ctx->d_nmin, 1));
     CU(dmalloc(&ctx->d_errword, 1));
     ctx->ovf_cap = 1u << 20;
@@ -369,8 +388,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(dmalloc(&ctx->d_weights, rows));
 
     cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(ctx->arena, 0, ctx->arena_bytes, st));
     for (int i = 0; i < NBUF; i++) {
-        CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)D, st));
         CU(cudaMemsetAsync(ctx->d_ovf_count[i], 0, 4, st));
         CU(cudaMemsetAsync(ctx->d_arena_cursor[i], 0, 8, st));
     }
@@ -594,6 +613,11 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     { const int rc = sync_all(ctx); if (rc) return rc; }
     for (int i = 0; i < NBUF; i++) {
+        if (ctx->world > 1 && ctx->peer_dirty[i]) {      // a peer may still be reading this buffer
+            const uint32_t *flags = reinterpret_cast<const uint32_t *>(ctx->arena + ctx->off_gathered) + (size_t)i * PEER_MAX;
+            k_peer_wait<<<1, 32, 0, st>>>(flags, ctx->world, ctx->peer_dirty[i], ctx->d_ctl);
+            ctx->peer_dirty[i] = 0;
+        }
         CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)ctx->D, st));
         ctx->k1_pending[i] = false;
     }
@@ -956,6 +980,25 @@ static int ensure_stage(hulk_b200_ctx *ctx, int buf, uint64_t bytes, uint64_t n_
     return HULK_B200_OK;
 }
 
+// The first counting kernel into spectrum buffer hs since its last flush: the buffer must be clean.  One GPU: the flush
+// chain wiped it (k2_finalize) -- wait for that.  Several GPUs: the flush chain worked on the SUM; the buffer itself is
+// wiped here, once every peer has gathered it.
+static int before_first_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t ks) {
+    if (ctx->k1_pending[hs]) return HULK_B200_OK;
+    if (ctx->world == 1) {
+        CU(cudaStreamWaitEvent(ks, ctx->ev_hist_free[hs], 0));
+        return HULK_B200_OK;
+    }
+    if (ctx->peer_dirty[hs]) {
+        const uint32_t *flags = reinterpret_cast<const uint32_t *>(ctx->arena + ctx->off_gathered) + (size_t)hs * PEER_MAX;
+        k_peer_wait<<<1, 32, 0, ks>>>(flags, ctx->world, ctx->peer_dirty[hs], ctx->d_ctl);
+        LAUNCH_CHECK("k_peer_wait");
+        CU(cudaMemsetAsync(ctx->d_hist[hs], 0, sizeof(uint32_t) * (size_t)ctx->D, ks));
+        ctx->peer_dirty[hs] = 0;
+    }
+    return HULK_B200_OK;
+}
+
 static const uint64_t kMaxBatchBytes = 256ull << 20;   // staging granularity of one H2D copy + k1 launch
 
 static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
@@ -995,7 +1038,7 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
         const int hs = ctx->cur_hist;
         cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
         CU(cudaStreamWaitEvent(ks, ctx->ev_copy[buf], 0));
-        if (!ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ks, ctx->ev_hist_free[hs], 0));   // its last flush wiped it
+        { const int rcw = before_first_k1(ctx, hs, ks); if (rcw) return rcw; }              // its last flush left it clean
         ctx->st.h2d_bytes += nb + (offsets ? sizeof(uint64_t) * (nr + 1) : 0);
         rc = launch_k1<false>(ctx, hs, ks, ctx->d_stage[buf], (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr,
                               b0, fixed_len, nr, nb, nullptr, 0, nullptr);
@@ -1056,7 +1099,7 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
         CU(cudaEventRecord(ctx->ev_main, ctx->stream));
         CU(cudaStreamWaitEvent(ks, ctx->ev_main, 0));
     }
-    if (!ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(ks, ctx->ev_hist_free[hs], 0));
+    { const int rcw = before_first_k1(ctx, hs, ks); if (rcw) return rcw; }
     // bytes that may be touched: the batch itself, rounded DOWN to 16 so wide loads never overrun it
     const int rc = launch_k1<false>(ctx, hs, ks, d_bases, extent & ~15ull, d_offsets, off_base, read_len, n_reads,
                                     total_bytes, nullptr, 0, nullptr);
@@ -1092,16 +1135,50 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
     const int32_t D = ctx->D;
     const int hs = ctx->cur_hist;
     const int fi = ctx->flush_idx;
-    uint32_t *const hist = ctx->d_hist[hs];
+    const bool peers = ctx->world > 1;
+    uint32_t *const hist = peers ? ctx->d_hist_sum : ctx->d_hist[hs];
     unsigned long long *const fbits = ctx->d_fbits[fi];
     float *const invf = ctx->d_invf[fi];
+    uint32_t seq = 0;
+    if (peers) {
+        // tell every GPU (this one included) that this GPU's share of the interval is counted
+        cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
+        { const int rcw = before_first_k1(ctx, hs, ks); if (rcw) return rcw; }      // nothing pushed here: still a clean buffer
+        seq = ++ctx->use_seq[hs];
+        PeerTargets t{};
+        t.n = ctx->world;
+        t.seq = seq;
+        for (uint32_t p = 0; p < ctx->world; p++)
+            t.flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_arena[p] + ctx->off_counted) + (size_t)hs * PEER_MAX + ctx->rank;
+        k_peer_signal<<<1, 32, 0, ks>>>(t);
+        LAUNCH_CHECK("k_peer_signal");
+        CU(cudaEventRecord(ctx->ev_k1_last[hs], ks));
+        ctx->k1_pending[hs] = true;
+    }
     if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k1_last[hs], 0));  // every read of the interval is counted
     if (ctx->k3_pending[fi]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k3_done[fi], 0));  // the sweep two flushes back read this f
     CU(cudaMemsetAsync(&ctx->d_ctl->nnz[fi], 0, 4, k2s));
     {
     ProfScope prof_scope(ctx, 1, k2s);
-    k2_mask_count<<<ctx->nblk, 1024, 0, k2s>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count, fbits,
-                                               ctx->d_ctl, fi);
+    if (peers) {
+        const uint32_t *flags = reinterpret_cast<const uint32_t *>(ctx->arena + ctx->off_counted) + (size_t)hs * PEER_MAX;
+        k_peer_wait<<<1, 32, 0, k2s>>>(flags, ctx->world, seq, ctx->d_ctl);         // ... on every GPU
+        LAUNCH_CHECK("k_peer_wait");
+        PeerSources src{};
+        PeerTargets done{};
+        src.n = done.n = ctx->world;
+        done.seq = seq;
+        for (uint32_t p = 0; p < ctx->world; p++) {
+            src.hist[p] = reinterpret_cast<const uint32_t *>(ctx->peer_arena[p] + (size_t)hs * ctx->hist_stride);
+            done.flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_arena[p] + ctx->off_gathered) + (size_t)hs * PEER_MAX + ctx->rank;
+        }
+        k2_mask_count_peers<<<ctx->nblk, 1024, 0, k2s>>>(src, D, hist, ctx->d_words, ctx->d_word_prefix,
+                                                         ctx->d_block_count, fbits, ctx->d_ctl, fi, done, ctx->d_ticket);
+        ctx->peer_dirty[hs] = seq;
+    } else {
+        k2_mask_count<<<ctx->nblk, 1024, 0, k2s>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count, fbits,
+                                                   ctx->d_ctl, fi);
+    }
     LAUNCH_CHECK("k2_mask_count");
     k2_flush_decide<<<1, 1024, 0, k2s>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl, fi);
     LAUNCH_CHECK("k2_flush_decide");
@@ -1301,6 +1378,68 @@ int hulk_b200_add_minimizer_count(hulk_b200_ctx *ctx, uint64_t n) {
     if (!ctx) return HULK_B200_EARG;
     ctx->extra_minimizers += n;
     return HULK_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: peers
+// ------------------------------------------------------------------------------------------
+static int peer_finish_connect(hulk_b200_ctx *ctx, uint32_t world, uint32_t rank) {
+    if (!ctx->d_hist_sum) {
+        CU(dmalloc(&ctx->d_hist_sum, ctx->D));
+        CU(dmalloc(&ctx->d_ticket, 1));
+        CU(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
+    }
+    ctx->world = world;
+    ctx->rank = rank;
+    return HULK_B200_OK;
+}
+int hulk_b200_peer_export(hulk_b200_ctx *ctx, void *handle) {
+    if (!ctx || !handle) return HULK_B200_EARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= HULK_B200_PEER_HANDLE_BYTES, "handle size");
+    CU(cudaSetDevice(ctx->P.device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->arena));
+    memset(handle, 0, HULK_B200_PEER_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    return HULK_B200_OK;
+}
+int hulk_b200_peer_connect(hulk_b200_ctx *ctx, uint32_t world, uint32_t rank, const void *handles) {
+    if (!ctx || !handles || world < 1 || world > PEER_MAX || rank >= world) return fail(ctx, HULK_B200_EARG, "peer world/rank");
+    if (ctx->world != 1) return fail(ctx, HULK_B200_ESTATE, "peers already connected");
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    for (uint32_t p = 0; p < world; p++) {
+        if (p == rank) { ctx->peer_arena[p] = ctx->arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const uint8_t *>(handles) + (size_t)p * HULK_B200_PEER_HANDLE_BYTES, sizeof h);
+        void *ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_arena[p] = static_cast<uint8_t *>(ptr);
+        ctx->peer_ipc[p] = true;
+    }
+    return peer_finish_connect(ctx, world, rank);
+}
+int hulk_b200_peer_connect_local(hulk_b200_ctx *ctx, uint32_t world, uint32_t rank, hulk_b200_ctx *const *peers) {
+    if (!ctx || !peers || world < 1 || world > PEER_MAX || rank >= world || peers[rank] != ctx)
+        return fail(ctx, HULK_B200_EARG, "peer world/rank");
+    if (ctx->world != 1) return fail(ctx, HULK_B200_ESTATE, "peers already connected");
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    for (uint32_t p = 0; p < world; p++) {
+        if (!peers[p] || peers[p]->D != ctx->D) return fail(ctx, HULK_B200_EARG, "peer context");
+        if (p != rank && peers[p]->P.device != ctx->P.device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, ctx->P.device, peers[p]->P.device));
+            if (!can) return fail(ctx, HULK_B200_ECUDA, "no peer access between devices " + std::to_string(ctx->P.device) +
+                                                            " and " + std::to_string(peers[p]->P.device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(peers[p]->P.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(ctx, HULK_B200_ECUDA, std::string("cudaDeviceEnablePeerAccess -> ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        ctx->peer_arena[p] = peers[p]->arena;
+    }
+    return peer_finish_connect(ctx, world, rank);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -76,7 +76,8 @@ struct Options {
     std::string banner_label = "blank";
     bool add_khf = false, add_kmv = false;
     // this build only
-    long device = 0;
+    long device = 0;        // first CUDA device ordinal
+    long gpus = 1;          // GPUs to spread the sketch over (devices device .. device + gpus - 1)
 };
 
 struct FlagDef {
@@ -295,6 +296,7 @@ int run_sketch(int argc, char **argv) {
         {"processors", 'p', FlagDef::INT, &o.proc, "number of processors to use (default 1)"},
         {"profiling", 0, FlagDef::BOOL, &o.profiling, "create the files needed to profile HULK using the go tool pprof"},
         {"device", 0, FlagDef::INT, &o.device, "CUDA device ordinal (this build; default 0)"},
+        {"gpus", 0, FlagDef::INT, &o.gpus, "number of GPUs to spread the reads and the sketch slots over, starting at --device (this build; default 1)"},
     };
     parse_flags(defs, argc, argv, 2);
 
@@ -366,8 +368,18 @@ int run_sketch(int argc, char **argv) {
 
     // one GPU is used: hiding the others from the CUDA runtime keeps its start-up proportional to one device
     // (on an 8-GPU node the runtime otherwise initialises all of them before the first allocation returns)
-    if (!getenv("CUDA_VISIBLE_DEVICES")) {
-        setenv("CUDA_VISIBLE_DEVICES", std::to_string(o.device).c_str(), 1);
+    if (o.gpus < 1 || o.gpus > 16) fatal("--gpus must be between 1 and 16");
+    // test switch: all members of the group on --device (the multi-GPU mechanism on a single-GPU box)
+    const bool one_device = getenv("HULK_B200_GPUS_ON_ONE_DEVICE") != nullptr;
+    if (one_device) {
+        if (!getenv("CUDA_VISIBLE_DEVICES")) {
+            setenv("CUDA_VISIBLE_DEVICES", std::to_string(o.device).c_str(), 1);
+            o.device = 0;
+        }
+    } else if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string vis;
+        for (long g = 0; g < o.gpus; g++) vis += (g ? "," : "") + std::to_string(o.device + g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
         o.device = 0;
     }
     // the reader starts first: reading/inflating overlaps context creation and the CWS table draw
@@ -385,14 +397,17 @@ int run_sketch(int argc, char **argv) {
     P.sketch_size = (uint32_t)std::min<unsigned long>(o.sketch_size, 0xffffffffu);
     P.num_bins = spectrum;
     P.decay_ratio = o.decay_ratio;
-    P.device = (int32_t)o.device;
-    hulk_b200_ctx *ctx = nullptr;
-    rc = hulk_b200_create(&P, &ctx);                        // findMinimizers + NewHistoSketch parameter checks
-    if (rc) fatal(hulk_b200_last_error(nullptr));
-    rc = hulk_b200_generate_cws_tables_async(ctx);          // NewHistoSketch -> newCWS, drawn while the reads are counted
-    if (rc) fatal(hulk_b200_last_error(ctx));
+    // one handle for --gpus N (a group of one is the plain context): every interval's reads are split over the GPUs,
+    // the spectrum a flush works on is summed over NVLink, the sketch slots are sharded -- same JSON as one GPU
+    std::vector<int32_t> devs;
+    for (long g = 0; g < o.gpus; g++) devs.push_back((int32_t)(o.device + (one_device ? 0 : g)));
+    hulk_b200_group *ctx = nullptr;
+    rc = hulk_b200_group_create(&P, devs.data(), (uint32_t)devs.size(), &ctx);   // findMinimizers + NewHistoSketch parameter checks
+    if (rc) fatal(hulk_b200_group_last_error(nullptr));
+    rc = hulk_b200_group_generate_cws_tables(ctx, 1);       // NewHistoSketch -> newCWS, drawn while the reads are counted
+    if (rc) fatal(hulk_b200_group_last_error(ctx));
 
-    rc = hulk_b200_sketch_reader(ctx, rd, o.interval, log_line, nullptr);
+    rc = hulk_b200_group_sketch_reader(ctx, rd, o.interval, log_line, nullptr);
     if (rc) {
         const char *rerr = hulk_b200_reader_error(rd);
         if (rc == HULK_B200_EFASTQ || rc == HULK_B200_ETOOLONG || rc == HULK_B200_EIO) {
@@ -401,11 +416,11 @@ int run_sketch(int argc, char **argv) {
             return 1;
         }
         if (rc == HULK_B200_ENOSEQ) fatal("no sequences received");
-        fatal(hulk_b200_last_error(ctx));
+        fatal(hulk_b200_group_last_error(ctx));
     }
     hulk_b200_stats st;
-    rc = hulk_b200_get_stats(ctx, &st);
-    if (rc) fatal(hulk_b200_last_error(ctx));
+    rc = hulk_b200_group_get_stats(ctx, &st);
+    if (rc) fatal(hulk_b200_group_last_error(ctx));
     const unsigned long mean_rl = (unsigned long)((double)st.n_bases / (double)st.n_reads);
     logf("\tprocessed %llu sequences in total", (unsigned long long)st.n_reads);
     logf("\tmean sequence length: %lu", mean_rl);
@@ -415,8 +430,8 @@ int run_sketch(int argc, char **argv) {
 
     std::vector<uint64_t> mins(P.sketch_size);
     std::vector<double> weights(P.sketch_size);
-    rc = hulk_b200_finish(ctx, mins.data(), weights.data());
-    if (rc) fatal(hulk_b200_last_error(ctx));
+    rc = hulk_b200_group_finish(ctx, mins.data(), weights.data());
+    if (rc) fatal(hulk_b200_group_last_error(ctx));
     const std::string out_json = o.out_file + ".json";
     // --kmv / --khf as the reference behaves today: the boss builds both MinHash sketches but nothing feeds them
     // (src/pipeline/boss.go:18-19,70-71 "not used yet").  The KMV heap is therefore empty and HULKdata.Add refuses

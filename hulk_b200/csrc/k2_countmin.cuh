@@ -198,6 +198,99 @@ __global__ void __launch_bounds__(1024) k2_flush_decide(const uint32_t *__restri
     }
 }
 
+// ---- multi-GPU: the spectrum of a flush is the sum of every GPU's counting buffer --------
+// The GPUs of a node reach each other's memory over NVLink (peer access inside one process, CUDA IPC across processes),
+// so the all-reduce is not a collective call: every GPU reads the other buffers straight from their owners while it
+// builds its used-bin bitmap (k2_mask_count_peers).  0.78 MB per peer at k = 21: latency, not bandwidth.
+// Ordering is by sequence numbers in device memory: the owner of a buffer PUSHES "counted up to use n" into every
+// reader's flag array when its counting kernels are done (k_peer_signal), a reader waits on its LOCAL copy (k_peer_wait,
+// one warp), and the reader's last block pushes "gathered use n" back to the owner, who waits for all of them before
+// the buffer is wiped and counted into again.  Integer sums: the result is bit-identical to one GPU whatever the
+// arrival order is.
+constexpr uint32_t PEER_MAX = 16;                   // GPUs of one node
+struct PeerTargets {                                // by value: up to PEER_MAX remote words to set to `seq`
+    uint32_t *flag[PEER_MAX];
+    uint32_t n;
+    uint32_t seq;
+};
+struct PeerSources {                                // by value: the same spectrum buffer on every GPU
+    const uint32_t *hist[PEER_MAX];
+    uint32_t n;
+};
+__global__ void k_peer_signal(const PeerTargets t) {
+    __threadfence_system();                         // everything this stream did before is visible system-wide first
+    if (threadIdx.x < t.n) *reinterpret_cast<volatile uint32_t *>(t.flag[threadIdx.x]) = t.seq;
+    __threadfence_system();
+}
+// one warp; flags: this GPU's array [n] for the buffer in question; gives up after ~30 s (a peer died) with ctl->err set
+__global__ void k_peer_wait(const uint32_t *flags, const uint32_t n, const uint32_t seq, FlushCtl *ctl) {
+    if (threadIdx.x < n) {
+        const volatile uint32_t *f = flags + threadIdx.x;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int32_t)(*f - seq) < 0) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 30000000000ull) {
+                if (ctl->err == 0) ctl->err = -30;  // HULK_B200_ECUDA: peer timeout
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+// k2_mask_count over the SUM of the peers' buffers; the sum is kept (hist_sum) for the kernels behind it
+__global__ void __launch_bounds__(1024) k2_mask_count_peers(const PeerSources src, int32_t D,
+                                                            uint32_t *__restrict__ hist_sum,
+                                                            uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
+                                                            uint32_t *__restrict__ block_count,
+                                                            unsigned long long *__restrict__ fbits, FlushCtl *ctl,
+                                                            const int fi, const PeerTargets done, unsigned int *ticket) {
+    __shared__ uint32_t pc[32];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    uint32_t sum = 0;
+    if (i < D) {
+#pragma unroll 4
+        for (uint32_t p = 0; p < src.n; p++) sum += __ldcv(src.hist[p] + i);   // never a stale cached copy
+        hist_sum[i] = sum;
+        fbits[i] = F_EMPTY_BITS;
+    }
+    const bool nz = sum != 0u;
+    const uint32_t word = __ballot_sync(0xffffffffu, nz);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        words[(size_t)blockIdx.x * 32 + wid] = word;
+        pc[wid] = __popc(word);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = pc[lane];
+        uint32_t s = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        word_prefix[(size_t)blockIdx.x * 32 + lane] = s - v;
+        if (lane == 31) {
+            block_count[blockIdx.x] = s;
+            if (s) atomicAdd(&ctl->nnz[fi], s);
+        }
+    }
+    // the last block to finish tells every owner that this GPU is done with its buffer
+    __syncthreads();
+    __shared__ unsigned int last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *ticket = 0;
+        __threadfence_system();
+        if (threadIdx.x < done.n) *reinterpret_cast<volatile uint32_t *>(done.flag[threadIdx.x]) = done.seq;
+    }
+}
+
 __device__ __forceinline__ uint32_t k2_rank(int32_t bin, const uint32_t *words, const uint32_t *word_prefix,
                                             const uint32_t *block_prefix) {
     // number of used bins <= bin (1-based position of `bin` among this flush's AddElement calls)

@@ -6,8 +6,11 @@ SURVEY.md section 8(e):
 
   * every interval's reads [(f-1)*I, f*I) are split into `world` contiguous chunks, rank g counts chunk g
     into its own uint32 spectrum (stage 1-2 is a commutative integer sum over reads);
-  * ONE integer all-reduce of the k^4-bin spectrum per flush (order independent => the summed spectrum is
-    bit-identical to the single-GPU one);
+  * ONE integer sum of the k^4-bin spectrum per flush (order independent => the summed spectrum is bit-identical
+    to the single-GPU one).  With the CUDA engine every rank READS its peers' counting buffers over NVLink inside
+    the flush (hulk_b200_peer_connect: CUDA IPC handles exchanged once through the process group, sequence flags in
+    device memory, no collective call and no host synchronisation per flush); any other engine (the CPU checker
+    of the gloo tests) gets a torch.distributed all-reduce;
   * the count-min update is replicated (tiny), the CWS sweep is sharded by sketch slot: rank g owns slots
     [g*s/world, (g+1)*s/world) and only those rows of the CWS tables;
   * `finish` all-gathers the (min, weight) pairs, so every rank returns the complete s-slot sketch.
@@ -41,7 +44,7 @@ class ShardedSketch:
             on the device the process group communicates on.
     """
 
-    def __init__(self, engine, sketch_size: int, world: int, rank: int, group=None):
+    def __init__(self, engine, sketch_size: int, world: int, rank: int, group=None, peers: bool = True):
         import torch.distributed as dist
         self.engine = engine
         self.sketch_size = sketch_size
@@ -49,9 +52,23 @@ class ShardedSketch:
         self.group = group
         self._dist = dist
         self.slots = slot_range(sketch_size, world, rank)
-        self._hist = engine.histogram_tensor() if world > 1 else None
         self._streams = {}          # CUDA stream handle -> torch ExternalStream
         self.seq_count = 0          # global seqCount (src/pipeline/sketch.go:203)
+        # peers: the engine sums the spectra itself; the process group only carries the IPC handles, once
+        self.peer_mode = False
+        if world > 1 and peers and hasattr(engine, "peer_export") and hasattr(engine, "peer_connect"):
+            handles = [None] * world
+            dist.all_gather_object(handles, engine.peer_export(), group=group)
+            engine.peer_connect(world, rank, handles)
+            dist.barrier(group=group)                       # every rank is connected before anyone flushes
+            self.peer_mode = True
+        self._hist = engine.histogram_tensor() if world > 1 and not self.peer_mode else None
+
+    def _device(self):
+        if self._hist is not None:
+            return self._hist.device
+        import torch
+        return torch.device("cuda", self.engine.device) if self.peer_mode else torch.device("cpu")
 
     def _collective_stream(self, hist):
         """The stream the engine orders its spectrum on (asked every flush: it depends on the engine's mode).
@@ -74,7 +91,7 @@ class ShardedSketch:
 
     def flush(self):
         """theBoss.Flush (src/pipeline/boss.go:112-128) over the spectrum summed across ranks."""
-        if self.world > 1:
+        if self.world > 1 and not self.peer_mode:
             hist = self.engine.histogram_tensor()      # the engine multi-buffers its spectrum: ask every flush
             stream = self._collective_stream(hist)
             if stream is not None:
@@ -92,7 +109,7 @@ class ShardedSketch:
         if self.world == 1:
             return mins, weights
         # (min, weight) pairs as int64 bit patterns: one object-free all_gather on the group's device
-        dev = self._hist.device
+        dev = self._device()
         rows_max = max(b - a for a, b in (slot_range(self.sketch_size, self.world, r) for r in range(self.world)))
         mine = np.zeros((2, rows_max), dtype=np.int64)
         mine[0, :mins.size] = mins.view(np.int64)
@@ -115,7 +132,7 @@ class ShardedSketch:
         n = int(self.engine.stats()["n_minimizers"])
         if self.world == 1:
             return n
-        t = torch.tensor([n], dtype=torch.int64, device=self._hist.device)
+        t = torch.tensor([n], dtype=torch.int64, device=self._device())
         self._dist.all_reduce(t, group=self.group)
         return int(t.item())
 

@@ -274,6 +274,21 @@ class HistoSketch:
     def add_minimizer_count(self, n: int):
         self._check(self._L.hulk_b200_add_minimizer_count(self._ctx, int(n)))
 
+    def peer_export(self) -> bytes:
+        """This context's handle for hulk_b200_peer_connect in ANOTHER process (CUDA IPC, one process per GPU)."""
+        buf = C.create_string_buffer(N.PEER_HANDLE_BYTES)
+        self._check(self._L.hulk_b200_peer_export(self._ctx, buf))
+        return buf.raw
+
+    def peer_connect(self, world: int, rank: int, handles: Sequence[bytes]):
+        """Join `world` contexts (one per GPU, one per process): from now on a flush works on the SUM of their spectra,
+        read from the peers over NVLink inside the flush -- no collective call.  flush() and reset() become collective."""
+        blob = b"".join(handles)
+        if len(blob) != world * N.PEER_HANDLE_BYTES:
+            raise HulkError(N.EARG, "one handle per rank")
+        self._check(self._L.hulk_b200_peer_connect(self._ctx, world, rank, blob))
+        self.peers = world
+
     # -- parity taps -------------------------------------------------------------------------
     def histogram(self) -> np.ndarray:
         h = np.zeros(self.num_bins, dtype=np.uint32)
@@ -327,6 +342,108 @@ class HistoSketch:
         out = np.zeros((self.rows, stride.value), dtype=np.float32)
         self._check(self._L.hulk_b200_get_folded_table(self._ctx, _ptr(out), C.byref(stride)))
         return out
+
+
+class GroupSketch:
+    """One sketch over several GPUs of THIS process (hulk_b200_group_*): the HistoSketch calls, reads split into
+    contiguous chunks per call, slots sharded, the spectrum summed over NVLink inside every flush."""
+
+    def __init__(self, k: int = 21, w: int = 9, sketch_size: int = 50, decay_ratio: float = 1.0,
+                 num_bins: Optional[int] = None, devices: Optional[Sequence[int]] = None, ngpus: Optional[int] = None,
+                 tables=None, async_input: bool = False):
+        self._L = N.load()
+        self._g = C.c_void_p()
+        self.k, self.w, self.sketch_size, self.decay_ratio = k, w, sketch_size, decay_ratio
+        self.num_bins = spectrum_size(k) if num_bins is None else num_bins
+        devs = list(devices) if devices is not None else list(range(ngpus or 1))
+        self.ngpus = len(devs)
+        p = N.Params()
+        p.k, p.w, p.sketch_size = k, w, sketch_size
+        p.num_bins = self.num_bins
+        p.decay_ratio = decay_ratio
+        p.flags = N.F_ASYNC_INPUT if async_input else 0
+        ids = (C.c_int32 * len(devs))(*devs)
+        g = C.c_void_p()
+        rc = self._L.hulk_b200_group_create(C.byref(p), ids, len(devs), C.byref(g))
+        if rc:
+            raise HulkError(rc, self._L.hulk_b200_group_last_error(None).decode())
+        self._g = g
+        self._keep = []
+        if tables is not None:
+            self.set_tables(*tables)
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._L.hulk_b200_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise HulkError(rc, self._L.hulk_b200_group_last_error(self._g).decode())
+
+    def set_tables(self, r, c, b):
+        """The FULL s x D tables; every member takes its rows."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        want = (self.sketch_size, self.num_bins)
+        for t in (r, c, b):
+            if t.shape != want:
+                raise HulkError(N.EARG, f"table shape {t.shape}, expected {want}")
+        self._check(self._L.hulk_b200_group_set_cws_tables(self._g, _ptr(r), _ptr(c), _ptr(b)))
+
+    def generate_tables(self, background: bool = False):
+        self._check(self._L.hulk_b200_group_generate_cws_tables(self._g, int(background)))
+
+    def add_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep = [bases, offsets]
+        self._check(self._L.hulk_b200_group_push_reads(self._g, _ptr(bases), _ptr(offsets), offsets.size - 1))
+
+    def add_seqs(self, reads: Sequence[bytes]):
+        self.add_reads(*pack_reads(reads))
+
+    def add_reads_fixed(self, bases: np.ndarray, n_reads: int, read_len: int):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        self._keep = [bases]
+        self._check(self._L.hulk_b200_group_push_reads_fixed(self._g, _ptr(bases), n_reads, read_len))
+
+    def flush(self):
+        self._check(self._L.hulk_b200_group_flush(self._g))
+
+    def sync(self):
+        self._check(self._L.hulk_b200_group_sync(self._g))
+
+    def reset(self):
+        self._check(self._L.hulk_b200_group_reset(self._g))
+
+    def finish(self) -> Tuple[np.ndarray, np.ndarray]:
+        mins = np.zeros(self.sketch_size, dtype=np.uint64)
+        weights = np.zeros(self.sketch_size, dtype=np.float64)
+        self._check(self._L.hulk_b200_group_finish(self._g, _ptr(mins), _ptr(weights)))
+        return mins, weights
+
+    def stats(self) -> dict:
+        st = N.Stats()
+        self._check(self._L.hulk_b200_group_get_stats(self._g, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in N.Stats._fields_}
+
+    @property
+    def concept_drift(self) -> bool:
+        return self.decay_ratio != 1.0
 
 
 def sketch_reads(hs: HistoSketch, batches: Iterable[Tuple[np.ndarray, np.ndarray]], interval: int = 0):

@@ -136,7 +136,7 @@ def test_world2_sharded_sketch_equals_single_process(oracle, tmp_path, case):
 
 
 # ---- the same sharded run on real GPUs over NCCL (needs >= 2 devices; `gpurun --gpus 2`) --------------
-def _gpu_worker(rank, world, port, case, out_dir):
+def _gpu_worker(rank, world, port, case, out_dir, peers=True):
     import torch
     import torch.distributed as dist
     import hulk_b200 as hb
@@ -153,7 +153,8 @@ def _gpu_worker(rank, world, port, case, out_dir):
         bases, offsets = _make_case(seed, n, L, ragged)
         a0, a1 = slot_range(s, world, rank)
         with hb.HistoSketch(k, w, s, decay, device=rank, slots=(a0, a1), tables=(r[a0:a1], c[a0:a1], b[a0:a1])) as hs:
-            sh = ShardedSketch(hs, s, world, rank)
+            sh = ShardedSketch(hs, s, world, rank, peers=peers)
+            assert sh.peer_mode == peers
             cuts = [0, n // 3, n // 3 + 1, n]
             batches = [(bases, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
             mins, weights, nmin = sketch_reads_sharded(sh, batches, interval)
@@ -180,15 +181,16 @@ def _n_gpus():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("peers", [True, False])      # spectra summed over NVLink inside the flush / NCCL all-reduce
 @pytest.mark.parametrize("case", [
     (11, 9, 64, 1.0, 3000, 5, 10000, 150, 0),
     (9, 5, 33, 0.3, 2500, 6, 8000, 100, 20),
 ])
-def test_nccl_sharded_sketch_equals_single_process_oracle(oracle, tmp_path, case):
+def test_nccl_sharded_sketch_equals_single_process_oracle(oracle, tmp_path, case, peers):
     import torch.multiprocessing as mp
     k, w, s, decay, interval, seed, n, L, ragged = case
-    world = 2
-    mp.spawn(_gpu_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+    world = min(_n_gpus(), 4) if peers else 2
+    mp.spawn(_gpu_worker, args=(world, _free_port(), case, str(tmp_path), peers), nprocs=world, join=True)
     D = k ** 4
     rng = np.random.default_rng(99)
     r = rng.gamma(2.0, 1.0, (s, D))
@@ -203,3 +205,95 @@ def test_nccl_sharded_sketch_equals_single_process_oracle(oracle, tmp_path, case
         assert int(z["nmin"]) == nmin_ref
         np.testing.assert_array_equal(z["mins"], mins_ref)
         np.testing.assert_allclose(z["weights"], weights_ref, rtol=1e-9)
+
+
+# ---- one process driving several GPUs through the C ABI (hulk_b200_group_*) ---------------------------------
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("case", [
+    (11, 9, 64, 1.0, 3000, 5, 10000, 150, 0),
+    (21, 9, 50, 1.0, 0, 7, 6000, 150, 30),
+    (9, 5, 33, 0.3, 2500, 6, 8000, 100, 20),
+])
+def test_group_of_gpus_equals_single_process_oracle(oracle, case):
+    """hulk_b200_group_*: one handle, the reference's call order, reads split over the GPUs of this process, the
+    spectrum summed over NVLink in every flush: same sketch as the oracle's single loop, for 2 .. all GPUs, and the same
+    bits as one GPU."""
+    import hulk_b200 as hb
+    k, w, s, decay, interval, seed, n, L, ragged = case
+    D = hb.spectrum_size(k)
+    rng = np.random.default_rng(99)
+    r = rng.gamma(2.0, 1.0, (s, D))
+    c = np.log(rng.gamma(2.0, 1.0, (s, D)))
+    b = rng.random((s, D)) * r
+    bases, offsets = _make_case(seed, n, L, ragged)
+    ref = oracle.HistoSketch(k, s, D, decay, r, c, b)
+    nmin_ref, nflush_ref = ref.run(w, bases, offsets, interval=interval)
+    mins_ref, weights_ref = ref.get()
+    cuts = [0, n // 3, n // 3 + 1, n]
+    batches = [(bases, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
+    with hb.HistoSketch(k, w, s, decay, tables=(r, c, b)) as one:
+        mins1, weights1, _ = hb.sketch_reads(one, batches, interval=interval)
+    for G in sorted({2, _n_gpus()}):
+        with hb.GroupSketch(k, w, s, decay, ngpus=G, tables=(r, c, b)) as g:
+            for rep in range(2):                       # a second sample through the same group: reset is collective
+                mins, weights, st = hb.sketch_reads(g, batches, interval=interval)
+                np.testing.assert_array_equal(mins, mins_ref)
+                np.testing.assert_allclose(weights, weights_ref, rtol=1e-9)
+                np.testing.assert_array_equal(mins, mins1)
+                np.testing.assert_array_equal(weights, weights1)
+                assert st["n_minimizers"] == nmin_ref and st["n_reads"] == n
+                g.reset()
+
+
+@pytest.mark.gpu
+def test_group_of_one_gpu_is_the_plain_context(oracle):
+    import hulk_b200 as hb
+    k, w, s = 11, 9, 40
+    D = hb.spectrum_size(k)
+    rng = np.random.default_rng(5)
+    r = rng.gamma(2.0, 1.0, (s, D))
+    c = np.log(rng.gamma(2.0, 1.0, (s, D)))
+    b = rng.random((s, D)) * r
+    bases, offsets = _make_case(3, 5000, 150, 0)
+    ref = oracle.HistoSketch(k, s, D, 1.0, r, c, b)
+    nmin_ref, _ = ref.run(w, bases, offsets, interval=2000)
+    with hb.GroupSketch(k, w, s, 1.0, ngpus=1, tables=(r, c, b)) as g:
+        mins, weights, st = hb.sketch_reads(g, [(bases, offsets)], interval=2000)
+    np.testing.assert_array_equal(mins, ref.get()[0])
+    assert st["n_minimizers"] == nmin_ref
+    with pytest.raises(hb.HulkError):
+        hb.GroupSketch(k, w, 3, 1.0, ngpus=1, devices=[0, 0, 0, 0])      # more GPUs than slots
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    (11, 9, 64, 1.0, 3000, 5, 10000, 150, 0),
+    (9, 5, 33, 0.3, 2500, 6, 8000, 100, 20),
+    (21, 9, 12, 1.0, 1000, 8, 3001, 150, 0),
+])
+def test_group_members_on_one_device_take_the_peer_path(oracle, case):
+    """The whole multi-GPU mechanism -- chunked reads, sequence flags, the spectrum summed from the peers' buffers
+    inside the flush, sharded slots, collective reset -- with three member contexts on ONE device, so it is checked
+    on a single-GPU box as well: same sketch as the oracle's single loop."""
+    import hulk_b200 as hb
+    k, w, s, decay, interval, seed, n, L, ragged = case
+    D = hb.spectrum_size(k)
+    rng = np.random.default_rng(99)
+    r = rng.gamma(2.0, 1.0, (s, D))
+    c = np.log(rng.gamma(2.0, 1.0, (s, D)))
+    b = rng.random((s, D)) * r
+    bases, offsets = _make_case(seed, n, L, ragged)
+    ref = oracle.HistoSketch(k, s, D, decay, r, c, b)
+    nmin_ref, _ = ref.run(w, bases, offsets, interval=interval)
+    mins_ref, weights_ref = ref.get()
+    cuts = [0, n // 3, n // 3 + 1, n]
+    batches = [(bases, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
+    with hb.GroupSketch(k, w, s, decay, devices=[0, 0, 0], tables=(r, c, b)) as g:
+        assert g.ngpus == 3
+        for rep in range(2):
+            mins, weights, st = hb.sketch_reads(g, batches, interval=interval)
+            np.testing.assert_array_equal(mins, mins_ref)
+            np.testing.assert_allclose(weights, weights_ref, rtol=1e-9)
+            assert st["n_minimizers"] == nmin_ref and st["n_reads"] == n
+            g.reset()

@@ -125,9 +125,10 @@ def test_native_reader_fasta(tmp_path):
         _native([none], fasta=True)
 
 
-def _hulk(*args, stdin=None):
+def _hulk(*args, stdin=None, env=None):
     assert os.path.exists(hulk_b200.CLI_PATH), "build the front end first (python -m hulk_b200.build)"
-    return subprocess.run([hulk_b200.CLI_PATH, *args], capture_output=True, text=True, timeout=600, stdin=stdin)
+    return subprocess.run([hulk_b200.CLI_PATH, *args], capture_output=True, text=True, timeout=600, stdin=stdin,
+                          env=(dict(os.environ, **env) if env else None))
 
 
 def test_cli_version_and_flag_errors(tmp_path):
@@ -217,6 +218,26 @@ def test_cli_intervals_drift_stream_and_stdin(tmp_path):
     assert p.returncode == 0, p.stdout
     assert b"\tinput file: using STDIN" in p.stdout
     _same_sketch(open(str(tmp_path / "pipe.json")).read(), open(os.path.join(GOLDEN, "c1_k21_s50.json")).read(), "STDIN")
+
+
+@pytest.mark.gpu
+def test_cli_gpus_flag_gives_the_same_json(tmp_path):
+    """`hulk sketch --gpus N` (hulk_b200_group_*: reads split per interval, spectra summed over NVLink inside the flush,
+    slots sharded) writes the golden sketches.  With the members on one device the mechanism runs on a single-GPU box;
+    with two or more GPUs present the real thing runs as well."""
+    import torch
+    runs = [("3", {"HULK_B200_GPUS_ON_ONE_DEVICE": "1"})]
+    if torch.cuda.device_count() >= 2:
+        runs.append((str(min(torch.cuda.device_count(), 4)), {}))
+    for gpus, env in runs:
+        for name, extra in (("c1_k21_s50.json", []), ("c1_k21_s50_x02_i250.json", ["-x", "0.2", "-i", "250"])):
+            out = str(tmp_path / ("g" + gpus + name))
+            r = _hulk("sketch", "-f", FIXTURE, "-k", "21", "-s", "50", "--gpus", gpus, "-o", out, *extra, env=env)
+            assert r.returncode == 0, r.stdout + r.stderr
+            assert "\tfound 17040 minimizers" in r.stdout and "\tprocessed 1000 sequences in total" in r.stdout
+            _same_sketch(open(out + ".json").read(), open(os.path.join(GOLDEN, name)).read(), FIXTURE + ",")
+    r = _hulk("sketch", "-f", FIXTURE, "--gpus", "0", "-o", str(tmp_path / "bad"))
+    assert r.returncode == 1 and "--gpus must be between 1 and 16" in r.stdout + r.stderr
 
 
 @pytest.mark.gpu
