@@ -86,6 +86,7 @@ struct hulk_b200_ctx {
     int jump_ctas_per_sm = K1_JUMP_CTAS_PER_SM;
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
     bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
+    bool jump_smem = false;                    // HULK_B200_JUMP_SMEM=1: keys handed out through a shared-memory counter (A/B measurements)
     bool jump_fx = true;                       // HULK_B200_JUMP_FX=0: keep the bracketed jump step for every D (A/B measurements)
     bool k1_v2 = true;                         // HULK_B200_K1_V2=0: keep the first-generation w = 9 scan (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
@@ -479,6 +480,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e >= '1' && *e <= '8') ctx->jump_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_JUMP_BATCH");
         if (e && (*e == '2' || *e == '3' || *e == '4')) ctx->jump_batch = *e - '0';
+        e = getenv("HULK_B200_JUMP_SMEM");
+        if (e && *e == '1') ctx->jump_smem = true;
         e = getenv("HULK_B200_JUMP_FX");
         if (e && *e == '0') ctx->jump_fx = false;
         e = getenv("HULK_B200_K1_FUSED");
@@ -942,9 +945,12 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         if (use_queue) {
             const unsigned gridj = (unsigned)(ctx->sm_count * ctx->jump_ctas_per_sm);
             if (ctx->jump_fx && (uint32_t)ctx->D <= JUMP_FX_MAX_BUCKETS) {          // every k^4-bin spectrum
-                if (ctx->jump_batch == 2) k1_jump_queue_fx<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else if (ctx->jump_batch == 3) k1_jump_queue_fx<3><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else k1_jump_queue_fx<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                if (ctx->jump_smem) {
+                    if (ctx->jump_batch == 3) k1_jump_queue_fx<3, true><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                    else k1_jump_queue_fx<4, true><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                } else if (ctx->jump_batch == 2) k1_jump_queue_fx<2, false><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                else if (ctx->jump_batch == 3) k1_jump_queue_fx<3, false><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
+                else k1_jump_queue_fx<4, false><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             } else if (ctx->jump_batch == 2) k1_jump_queue<2><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             else k1_jump_queue<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             LAUNCH_CHECK("k1_jump_queue");

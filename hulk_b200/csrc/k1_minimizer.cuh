@@ -198,9 +198,10 @@ __device__ __forceinline__ void k1_jump_walk(Load load, uint32_t g, const uint32
 // reciprocal seed (MUFU.RCP64H), residual, product and folded Newton step (DFMA, DMUL, DFMA), y = 2^32 + x
 // (DFMA), "finished" as one DSETP against 2^32 + n, the ambiguity band as one IMAD + ISETP on the fraction bits,
 // floor(x) by one funnel shift.  About 20 instructions against 33 for the bracketed step, 7 of them on the FP64 pipe.
-template <int BATCH, class Load>
-__device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t *const next_key, const uint32_t total,
+template <int BATCH, bool SMEM, class Load>
+__device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t *const next_key, uint32_t g, const uint32_t total,
                                                 uint32_t *const hist, const uint32_t nb) {
+    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     uint64_t key[2] = {0, 0}, spare[2] = {0, 0};
     constexpr uint32_t NO_BIN = 0xFFFFFFFFu;                             // the walk holds no key (nothing left to count)
     uint32_t bkt[2] = {NO_BIN, NO_BIN};
@@ -211,15 +212,22 @@ __device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t *const next_
     // of them is re-materialised with moves inside the loop: [0] 2^52 - 1, [1] 2^83 - 2^31, [2] 1
     const double two52m1 = k1_jump_fx_consts[0], two83m = k1_jump_fx_consts[1], one = k1_jump_fx_consts[2];
     const double ynb = k1_pin(JUMP_TWO32 + (double)nb);
-    // hand-out: the warp's next unclaimed key is a counter in shared memory; only lanes whose spare is empty touch it
-    // (an atomic add each, a handful per refill point), so nothing is spent on lanes that need nothing
+    // hand-out of the warp's next unclaimed keys to the empty spares.  SMEM: a counter in shared memory that only the
+    // lanes in need touch (an atomic add each); otherwise ballot + popc over the warp, no memory at all
     auto top_up = [&](int c) {
-        if (!have[c]) {
-            const uint32_t mine = atomicAdd(next_key, 1u);
-            if (mine < total) {
-                spare[c] = load(mine);
-                have[c] = true;
-            }
+        uint32_t mine;
+        if (SMEM) {
+            if (have[c]) return;
+            mine = atomicAdd(next_key, 1u);
+        } else {
+            const uint32_t need = __ballot_sync(0xffffffffu, !have[c]);
+            mine = g + __popc(need & lane_lt);
+            g = min(g + (uint32_t)__popc(need), total);
+            if (have[c]) return;
+        }
+        if (mine < total) {
+            spare[c] = load(mine);
+            have[c] = true;
         }
     };
     top_up(0);
@@ -662,12 +670,15 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_scan_w9_v2(const
     const uint64_t ntasks = (p.n_reads + 31) / 32;
     const uintptr_t lim = reinterpret_cast<uintptr_t>(p.bases) + p.bases_bytes;
 
+    // tasks (32 reads) are handed out by a counter; the NEXT task is claimed while the current one is scanned, so the
+    // atomic's round trip never sits between two tasks
     unsigned long long *const task_counter = QUEUE ? p.queue_cursor + 1 : nullptr;
+    unsigned long long claimed = 0;
+    if (task_counter && lane == 0) claimed = atomicAdd(task_counter, 1ull);
     for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp;;) {
         if (task_counter) {
-            unsigned long long t = 0;
-            if (lane == 0) t = atomicAdd(task_counter, 1ull);
-            task = __shfl_sync(0xffffffffu, t, 0);
+            task = __shfl_sync(0xffffffffu, claimed, 0);
+            if (task < ntasks && lane == 0) claimed = atomicAdd(task_counter, 1ull);
         }
         if (task >= ntasks) break;
         const uint64_t r = task * 32 + lane;
@@ -725,7 +736,7 @@ __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue(const K1Params p) {
     k1_jump_walk<true, BATCH>([&](uint32_t i) { return q[i]; }, seg_begin, 0u, seg_end, p.hist, (uint32_t)p.D);
 }
 // the same kernel with the fixed-point step (num_buckets <= 2^20)
-template <int BATCH>
+template <int BATCH, bool SMEM>
 __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue_fx(const K1Params p) {
     const unsigned long long filled = *p.queue_cursor;
     const uint64_t total = filled < p.queue_cap ? filled : p.queue_cap;
@@ -734,9 +745,12 @@ __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue_fx(const K1Params p
     const uint32_t seg_begin = (uint32_t)(total * gw / nwarps), seg_end = (uint32_t)(total * (gw + 1) / nwarps);
     const uint64_t *const q = p.queue;
     __shared__ uint32_t next_key[K1_JUMP_TPB / 32];                      // per warp: the next unclaimed key of its segment
-    if ((threadIdx.x & 31) == 0) next_key[threadIdx.x >> 5] = seg_begin;
-    __syncwarp();
-    k1_jump_walk_fx<BATCH>([&](uint32_t i) { return q[i]; }, &next_key[threadIdx.x >> 5], seg_end, p.hist, (uint32_t)p.D);
+    if (SMEM) {
+        if ((threadIdx.x & 31) == 0) next_key[threadIdx.x >> 5] = seg_begin;
+        __syncwarp();
+    }
+    k1_jump_walk_fx<BATCH, SMEM>([&](uint32_t i) { return q[i]; }, &next_key[threadIdx.x >> 5], seg_begin, seg_end, p.hist,
+                                 (uint32_t)p.D);
 }
 
 // reciprocal self-test (parity tap): for q = q0 + i the seed's and the refined reciprocal's relative errors,

@@ -266,6 +266,35 @@ def test_group_of_one_gpu_is_the_plain_context(oracle):
         hb.GroupSketch(k, w, 3, 1.0, ngpus=1, devices=[0, 0, 0, 0])      # more GPUs than slots
 
 
+ONE_DEVICE_SCRIPT = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import hulk_b200 as hb
+from oracle import oracle as O
+from test_distributed import _make_case
+k, w, s, decay, interval, seed, n, L, ragged = json.loads(sys.argv[2])
+D = hb.spectrum_size(k)
+rng = np.random.default_rng(99)
+r = rng.gamma(2.0, 1.0, (s, D)); c = np.log(rng.gamma(2.0, 1.0, (s, D))); b = rng.random((s, D)) * r
+bases, offsets = _make_case(seed, n, L, ragged)
+ref = O.HistoSketch(k, s, D, decay, r, c, b)
+nmin_ref, _ = ref.run(w, bases, offsets, interval=interval)
+mins_ref, weights_ref = ref.get()
+cuts = [0, n // 3, n // 3 + 1, n]
+batches = [(bases, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
+with hb.GroupSketch(k, w, s, decay, devices=[0, 0, 0], tables=(r, c, b)) as g:
+    assert g.ngpus == 3
+    for rep in range(2):
+        mins, weights, st = hb.sketch_reads(g, batches, interval=interval)
+        np.testing.assert_array_equal(mins, mins_ref)
+        np.testing.assert_allclose(weights, weights_ref, rtol=1e-9)
+        assert st["n_minimizers"] == nmin_ref and st["n_reads"] == n
+        g.reset()
+print("ONE_DEVICE_OK")
+"""
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [
     (11, 9, 64, 1.0, 3000, 5, 10000, 150, 0),
@@ -275,25 +304,12 @@ def test_group_of_one_gpu_is_the_plain_context(oracle):
 def test_group_members_on_one_device_take_the_peer_path(oracle, case):
     """The whole multi-GPU mechanism -- chunked reads, sequence flags, the spectrum summed from the peers' buffers
     inside the flush, sharded slots, collective reset -- with three member contexts on ONE device, so it is checked
-    on a single-GPU box as well: same sketch as the oracle's single loop."""
-    import hulk_b200 as hb
-    k, w, s, decay, interval, seed, n, L, ragged = case
-    D = hb.spectrum_size(k)
-    rng = np.random.default_rng(99)
-    r = rng.gamma(2.0, 1.0, (s, D))
-    c = np.log(rng.gamma(2.0, 1.0, (s, D)))
-    b = rng.random((s, D)) * r
-    bases, offsets = _make_case(seed, n, L, ragged)
-    ref = oracle.HistoSketch(k, s, D, decay, r, c, b)
-    nmin_ref, _ = ref.run(w, bases, offsets, interval=interval)
-    mins_ref, weights_ref = ref.get()
-    cuts = [0, n // 3, n // 3 + 1, n]
-    batches = [(bases, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
-    with hb.GroupSketch(k, w, s, decay, devices=[0, 0, 0], tables=(r, c, b)) as g:
-        assert g.ngpus == 3
-        for rep in range(2):
-            mins, weights, st = hb.sketch_reads(g, batches, interval=interval)
-            np.testing.assert_array_equal(mins, mins_ref)
-            np.testing.assert_allclose(weights, weights_ref, rtol=1e-9)
-            assert st["n_minimizers"] == nmin_ref and st["n_reads"] == n
-            g.reset()
+    on a single-GPU box as well: same sketch as the oracle's single loop.  (Own process: three contexts' streams on one
+    device need more hardware queues than the default eight, or a waiting kernel can sit in front of the very
+    signal it waits for -- on separate GPUs each device only carries its own context's streams.)"""
+    import json
+    import subprocess
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    p = subprocess.run([sys.executable, "-c", ONE_DEVICE_SCRIPT, ROOT, json.dumps(case)], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert p.returncode == 0 and "ONE_DEVICE_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]

@@ -226,7 +226,7 @@ def test_cli_gpus_flag_gives_the_same_json(tmp_path):
     slots sharded) writes the golden sketches.  With the members on one device the mechanism runs on a single-GPU box;
     with two or more GPUs present the real thing runs as well."""
     import torch
-    runs = [("3", {"HULK_B200_GPUS_ON_ONE_DEVICE": "1"})]
+    runs = [("3", {"HULK_B200_GPUS_ON_ONE_DEVICE": "1", "CUDA_DEVICE_MAX_CONNECTIONS": "32"})]
     if torch.cuda.device_count() >= 2:
         runs.append((str(min(torch.cuda.device_count(), 4)), {}))
     for gpus, env in runs:
