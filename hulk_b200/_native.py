@@ -24,7 +24,7 @@ EXPORTS = [
     "hulk_b200_free_pinned", "hulk_b200_reader_open", "hulk_b200_reader_next", "hulk_b200_reader_error",
     "hulk_b200_reader_close", "hulk_b200_sketch_reader", "hulk_b200_sketch_load", "hulk_b200_sketch_find",
     "hulk_b200_sketch_banner", "hulk_b200_sketch_free", "hulk_b200_smash",
-    "hulk_b200_peer_export", "hulk_b200_peer_connect", "hulk_b200_peer_connect_local",
+    "hulk_b200_peer_export", "hulk_b200_peer_flags", "hulk_b200_peer_connect", "hulk_b200_peer_connect_local",
     "hulk_b200_group_create", "hulk_b200_group_destroy", "hulk_b200_group_last_error", "hulk_b200_group_size",
     "hulk_b200_group_member", "hulk_b200_group_set_cws_tables", "hulk_b200_group_generate_cws_tables",
     "hulk_b200_group_push_reads", "hulk_b200_group_push_reads_fixed", "hulk_b200_group_sync_inputs",
@@ -132,6 +132,7 @@ def load():
         "hulk_b200_sketch_free": (None, [vp]),
         "hulk_b200_smash": (C.c_int, [vp, vp, u32, u32, C.c_int, i32, vp]),
         "hulk_b200_peer_export": (C.c_int, [vp, vp]),
+        "hulk_b200_peer_flags": (C.c_int, [vp, vp]),
         "hulk_b200_peer_connect": (C.c_int, [vp, u32, u32, vp]),
         "hulk_b200_peer_connect_local": (C.c_int, [vp, u32, u32, C.POINTER(vp)]),
         "hulk_b200_group_create": (C.c_int, [C.POINTER(Params), C.POINTER(i32), u32, C.POINTER(vp)]),

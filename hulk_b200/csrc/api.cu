@@ -137,6 +137,7 @@ struct hulk_b200_ctx {
     bool peer_ipc[PEER_MAX] = {};              // opened with cudaIpcOpenMemHandle (another process)
     uint32_t use_seq[NBUF] = {};               // how many flushes buffer b has been through (never reset: the flags only grow)
     uint32_t peer_dirty[NBUF] = {};            // use of buffer b that every peer must have gathered before it is wiped
+    unsigned long long peer_timeout_ns = 30000000000ull;   // a waiting GPU gives up after this long (HULK_B200_PEER_TIMEOUT_MS)
     uint32_t *d_hist_sum = nullptr;            // the summed spectrum of the flush under way
     unsigned int *d_ticket = nullptr;
 
@@ -480,6 +481,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e >= '1' && *e <= '8') ctx->jump_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_JUMP_BATCH");
         if (e && (*e == '2' || *e == '3' || *e == '4')) ctx->jump_batch = *e - '0';
+        e = getenv("HULK_B200_PEER_TIMEOUT_MS");
+        if (e && atoll(e) > 0) ctx->peer_timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
         e = getenv("HULK_B200_JUMP_SMEM");
         if (e && *e == '1') ctx->jump_smem = true;
         e = getenv("HULK_B200_JUMP_FX");
@@ -618,7 +621,7 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     for (int i = 0; i < NBUF; i++) {
         if (ctx->world > 1 && ctx->peer_dirty[i]) {      // a peer may still be reading this buffer
             const uint32_t *flags = reinterpret_cast<const uint32_t *>(ctx->arena + ctx->off_gathered) + (size_t)i * PEER_MAX;
-            k_peer_wait<<<1, 32, 0, st>>>(flags, ctx->world, ctx->peer_dirty[i], ctx->d_ctl);
+            k_peer_wait<<<1, 32, 0, st>>>(flags, ctx->world, ctx->peer_dirty[i], ctx->d_ctl, ctx->peer_timeout_ns);
             ctx->peer_dirty[i] = 0;
         }
         CU(cudaMemsetAsync(ctx->d_hist[i], 0, sizeof(uint32_t) * (size_t)ctx->D, st));
@@ -997,7 +1000,7 @@ static int before_first_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t ks) {
     }
     if (ctx->peer_dirty[hs]) {
         const uint32_t *flags = reinterpret_cast<const uint32_t *>(ctx->arena + ctx->off_gathered) + (size_t)hs * PEER_MAX;
-        k_peer_wait<<<1, 32, 0, ks>>>(flags, ctx->world, ctx->peer_dirty[hs], ctx->d_ctl);
+        k_peer_wait<<<1, 32, 0, ks>>>(flags, ctx->world, ctx->peer_dirty[hs], ctx->d_ctl, ctx->peer_timeout_ns);
         LAUNCH_CHECK("k_peer_wait");
         CU(cudaMemsetAsync(ctx->d_hist[hs], 0, sizeof(uint32_t) * (size_t)ctx->D, ks));
         ctx->peer_dirty[hs] = 0;
@@ -1168,7 +1171,7 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
     ProfScope prof_scope(ctx, 1, k2s);
     if (peers) {
         const uint32_t *flags = reinterpret_cast<const uint32_t *>(ctx->arena + ctx->off_counted) + (size_t)hs * PEER_MAX;
-        k_peer_wait<<<1, 32, 0, k2s>>>(flags, ctx->world, seq, ctx->d_ctl);         // ... on every GPU
+        k_peer_wait<<<1, 32, 0, k2s>>>(flags, ctx->world, seq, ctx->d_ctl, ctx->peer_timeout_ns);   // ... on every GPU
         LAUNCH_CHECK("k_peer_wait");
         PeerSources src{};
         PeerTargets done{};
@@ -1397,6 +1400,17 @@ static int peer_finish_connect(hulk_b200_ctx *ctx, uint32_t world, uint32_t rank
     }
     ctx->world = world;
     ctx->rank = rank;
+    return HULK_B200_OK;
+}
+// debug tap: this context's two flag arrays, [NBUF][PEER_MAX] counted then [NBUF][PEER_MAX] gathered (no synchronisation)
+int hulk_b200_peer_flags(hulk_b200_ctx *ctx, uint32_t *out) {
+    if (!ctx || !out) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    cudaStream_t tmp;
+    CU(cudaStreamCreateWithFlags(&tmp, cudaStreamNonBlocking));
+    CU(cudaMemcpyAsync(out, ctx->arena + ctx->off_counted, sizeof(uint32_t) * 2 * NBUF * PEER_MAX, cudaMemcpyDeviceToHost, tmp));
+    CU(cudaStreamSynchronize(tmp));
+    cudaStreamDestroy(tmp);
     return HULK_B200_OK;
 }
 int hulk_b200_peer_export(hulk_b200_ctx *ctx, void *handle) {

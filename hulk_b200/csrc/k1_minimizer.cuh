@@ -670,15 +670,12 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_scan_w9_v2(const
     const uint64_t ntasks = (p.n_reads + 31) / 32;
     const uintptr_t lim = reinterpret_cast<uintptr_t>(p.bases) + p.bases_bytes;
 
-    // tasks (32 reads) are handed out by a counter; the NEXT task is claimed while the current one is scanned, so the
-    // atomic's round trip never sits between two tasks
     unsigned long long *const task_counter = QUEUE ? p.queue_cursor + 1 : nullptr;
-    unsigned long long claimed = 0;
-    if (task_counter && lane == 0) claimed = atomicAdd(task_counter, 1ull);
     for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp;;) {
         if (task_counter) {
-            task = __shfl_sync(0xffffffffu, claimed, 0);
-            if (task < ntasks && lane == 0) claimed = atomicAdd(task_counter, 1ull);
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(task_counter, 1ull);
+            task = __shfl_sync(0xffffffffu, t, 0);
         }
         if (task >= ntasks) break;
         const uint64_t r = task * 32 + lane;

@@ -222,8 +222,9 @@ __global__ void k_peer_signal(const PeerTargets t) {
     if (threadIdx.x < t.n) *reinterpret_cast<volatile uint32_t *>(t.flag[threadIdx.x]) = t.seq;
     __threadfence_system();
 }
-// one warp; flags: this GPU's array [n] for the buffer in question; gives up after ~30 s (a peer died) with ctl->err set
-__global__ void k_peer_wait(const uint32_t *flags, const uint32_t n, const uint32_t seq, FlushCtl *ctl) {
+// one warp; flags: this GPU's array [n] for the buffer in question; gives up after timeout_ns (a peer died) with ctl->err set
+__global__ void k_peer_wait(const uint32_t *flags, const uint32_t n, const uint32_t seq, FlushCtl *ctl,
+                            const unsigned long long timeout_ns) {
     if (threadIdx.x < n) {
         const volatile uint32_t *f = flags + threadIdx.x;
         unsigned long long t0 = 0, now = 0;
@@ -231,7 +232,7 @@ __global__ void k_peer_wait(const uint32_t *flags, const uint32_t n, const uint3
         while ((int32_t)(*f - seq) < 0) {
             __nanosleep(200);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 30000000000ull) {
+            if (now - t0 > timeout_ns) {
                 if (ctl->err == 0) ctl->err = -30;  // HULK_B200_ECUDA: peer timeout
                 break;
             }
