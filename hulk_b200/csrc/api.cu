@@ -308,6 +308,10 @@ static int sync_all(hulk_b200_ctx *ctx) {
     return HULK_B200_OK;
 }
 
+__global__ void k_snapshot(const unsigned long long *__restrict__ sketch, const double *__restrict__ weights,
+                           unsigned long long *__restrict__ h_mins, double *__restrict__ h_weights, uint32_t rows);
+__global__ void k_merge_hist(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int32_t D);
+
 static int create_impl(hulk_b200_ctx *ctx) {
     const hulk_b200_params &P = ctx->P;
     CU(cudaSetDevice(P.device));
@@ -469,6 +473,35 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(cudaFuncSetAttribute(k1_scan_w9_v2<true, false, KK>, attr, big));
         K1_V2_FOR_EACH_K(K1_V2_ATTR)
 #undef K1_V2_ATTR
+    }
+    // CUDA loads a kernel's code the first time it is launched, and that load can wait for the device to go idle.
+    // A multi-GPU flush parks a (one-warp) kernel on the device until its peers have signalled; a first launch queued
+    // behind it from the same host thread would then wait for a signal that thread has not sent yet.  So every kernel a
+    // push or a flush can launch is loaded here, while nothing is running.
+    {
+        cudaFuncAttributes fa;
+#define HULK_PRELOAD(F) CU(cudaFuncGetAttributes(&fa, F))
+        HULK_PRELOAD(k_peer_signal);
+        HULK_PRELOAD(k_peer_wait);
+        HULK_PRELOAD(k2_mask_count_peers);
+        HULK_PRELOAD(k2_mask_count);
+        HULK_PRELOAD(k2_flush_decide);
+        HULK_PRELOAD(k2_cms_update);
+        HULK_PRELOAD(k2_finalize);
+        HULK_PRELOAD(k3_resolve);
+        HULK_PRELOAD(k3_fill_f32);
+        HULK_PRELOAD(k_snapshot);
+        HULK_PRELOAD(k_merge_hist);
+        HULK_PRELOAD(k1_generic<false>);
+        HULK_PRELOAD(k1_generic<true>);
+        HULK_PRELOAD((k1_jump_queue<2>));
+        HULK_PRELOAD((k1_jump_queue<4>));
+        HULK_PRELOAD((k1_jump_queue_fx<2, false>));
+        HULK_PRELOAD((k1_jump_queue_fx<3, false>));
+        HULK_PRELOAD((k1_jump_queue_fx<4, false>));
+        HULK_PRELOAD((k1_jump_queue_fx<3, true>));
+        HULK_PRELOAD((k1_jump_queue_fx<4, true>));
+#undef HULK_PRELOAD
     }
     {
         const char *e = getenv("HULK_B200_K1_TILE");

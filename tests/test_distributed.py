@@ -299,7 +299,7 @@ print("ONE_DEVICE_OK")
 @pytest.mark.parametrize("case", [
     (11, 9, 64, 1.0, 3000, 5, 10000, 150, 0),
     (9, 5, 33, 0.3, 2500, 6, 8000, 100, 20),
-    (21, 9, 12, 1.0, 1000, 8, 3001, 150, 0),
+    (21, 9, 12, 1.0, 1000, 8, 3000, 150, 0),
 ])
 def test_group_members_on_one_device_take_the_peer_path(oracle, case):
     """The whole multi-GPU mechanism -- chunked reads, sequence flags, the spectrum summed from the peers' buffers
