@@ -86,6 +86,7 @@ struct hulk_b200_ctx {
     int jump_ctas_per_sm = K1_JUMP_CTAS_PER_SM;
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
     bool fused_jump = false;                   // HULK_B200_K1_FUSED=1: bin inside the scan kernel (A/B measurements)
+    bool k1_persistent = false;                // HULK_B200_K1_PERSISTENT=1: scan CTAs loop over tasks handed out by a counter (A/B)
     bool jump_smem = false;                    // HULK_B200_JUMP_SMEM=1: keys handed out through a shared-memory counter (A/B measurements)
     bool jump_fx = true;                       // HULK_B200_JUMP_FX=0: keep the bracketed jump step for every D (A/B measurements)
     bool k1_v2 = true;                         // HULK_B200_K1_V2=0: keep the first-generation w = 9 scan (A/B measurements)
@@ -514,6 +515,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e >= '1' && *e <= '8') ctx->jump_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_JUMP_BATCH");
         if (e && (*e == '2' || *e == '3' || *e == '4')) ctx->jump_batch = *e - '0';
+        e = getenv("HULK_B200_K1_PERSISTENT");
+        if (e && *e == '1') ctx->k1_persistent = true;
         e = getenv("HULK_B200_PEER_TIMEOUT_MS");
         if (e && atoll(e) > 0) ctx->peer_timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
         e = getenv("HULK_B200_JUMP_SMEM");
@@ -951,11 +954,15 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
             // odd k >= 17: the second-generation scan, k folded in at compile time
             bool done = false;
             if (ctx->k1_v2 && (use_queue || DUMP)) {
+                // one 32-read task per warp, one short-lived CTA per four tasks: the block scheduler balances them, and
+                // the slots they free every few tens of microseconds go to the flush chain of the previous interval
+                // (higher stream priority) instead of staying with a persistent counting CTA for the whole interval
+                const unsigned gridv = ctx->k1_persistent ? grid9 : (unsigned)std::min<uint64_t>(nctas, 1u << 24);
                 switch (ctx->P.k) {
 #define K1_V2_CASE(KK)                                                                              \
                     case KK:                                                                        \
-                        if (use_queue) k1_scan_w9_v2<false, true, KK><<<grid9, K1_TPB, smem9, st>>>(p); \
-                        else k1_scan_w9_v2<true, false, KK><<<grid9, K1_TPB, smem9, st>>>(p);       \
+                        if (use_queue) k1_scan_w9_v2<false, true, KK><<<gridv, K1_TPB, smem9, st>>>(p); \
+                        else k1_scan_w9_v2<true, false, KK><<<gridv, K1_TPB, smem9, st>>>(p);       \
                         done = true;                                                                \
                         break;
                     K1_V2_FOR_EACH_K(K1_V2_CASE)
@@ -1214,15 +1221,15 @@ int hulk_b200_flush(hulk_b200_ctx *ctx) {
             src.hist[p] = reinterpret_cast<const uint32_t *>(ctx->peer_arena[p] + (size_t)hs * ctx->hist_stride);
             done.flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_arena[p] + ctx->off_gathered) + (size_t)hs * PEER_MAX + ctx->rank;
         }
-        k2_mask_count_peers<<<ctx->nblk, 1024, 0, k2s>>>(src, D, hist, ctx->d_words, ctx->d_word_prefix,
+        k2_mask_count_peers<<<ctx->nblk, K2_MASK_TPB, 0, k2s>>>(src, D, hist, ctx->d_words, ctx->d_word_prefix,
                                                          ctx->d_block_count, fbits, ctx->d_ctl, fi, done, ctx->d_ticket);
         ctx->peer_dirty[hs] = seq;
     } else {
-        k2_mask_count<<<ctx->nblk, 1024, 0, k2s>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count, fbits,
+        k2_mask_count<<<ctx->nblk, K2_MASK_TPB, 0, k2s>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count, fbits,
                                                    ctx->d_ctl, fi);
     }
     LAUNCH_CHECK("k2_mask_count");
-    k2_flush_decide<<<1, 1024, 0, k2s>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl, fi);
+    k2_flush_decide<<<1, 256, 0, k2s>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl, fi);
     LAUNCH_CHECK("k2_flush_decide");
     k2_cms_update<<<(CMS_CELLS * 32 + 255) / 256, 256, 0, k2s>>>(hist, ctx->d_csr_start, ctx->d_csr_bins,
                                                                  ctx->d_words, ctx->d_word_prefix, ctx->d_block_prefix,

@@ -670,7 +670,10 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_scan_w9_v2(const
     const uint64_t ntasks = (p.n_reads + 31) / 32;
     const uintptr_t lim = reinterpret_cast<uintptr_t>(p.bases) + p.bases_bytes;
 
-    unsigned long long *const task_counter = QUEUE ? p.queue_cursor + 1 : nullptr;
+    // a grid with a warp for every task runs each task once (the host's default); a smaller grid takes them from a
+    // counter (persistent CTAs)
+    unsigned long long *const task_counter =
+        (QUEUE && (uint64_t)gridDim.x * K1_WARPS < ntasks) ? p.queue_cursor + 1 : nullptr;
     for (uint64_t task = (uint64_t)blockIdx.x * K1_WARPS + warp;;) {
         if (task_counter) {
             unsigned long long t = 0;

@@ -114,21 +114,28 @@ __global__ void k2_sort_csr(const unsigned int *start, int32_t *csr_bins) {
 }
 
 // ---- per flush ----
-// (a) used-bin bitmap, per-32-bin and per-1024-bin used counts, reset of the estimate vector
-__global__ void __launch_bounds__(1024) k2_mask_count(const uint32_t *__restrict__ hist, int32_t D,
-                                                      uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
-                                                      uint32_t *__restrict__ block_count,
-                                                      unsigned long long *__restrict__ fbits, FlushCtl *ctl,
-                                                      const int fi) {
+// (a) used-bin bitmap, per-32-bin and per-1024-bin used counts, reset of the estimate vector.
+// A block covers 1024 bins with 256 threads (every warp four 32-bin words): small blocks find room next to the counting
+// kernels of the next interval, which a 1024-thread block does not.
+constexpr int K2_MASK_TPB = 256;
+__global__ void __launch_bounds__(K2_MASK_TPB) k2_mask_count(const uint32_t *__restrict__ hist, int32_t D,
+                                                             uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
+                                                             uint32_t *__restrict__ block_count,
+                                                             unsigned long long *__restrict__ fbits, FlushCtl *ctl,
+                                                             const int fi) {
     __shared__ uint32_t pc[32];
-    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-    const bool nz = (i < D) && (hist[i] != 0u);
-    if (i < D) fbits[i] = F_EMPTY_BITS;
-    const uint32_t word = __ballot_sync(0xffffffffu, nz);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        words[(size_t)blockIdx.x * 32 + wid] = word;
-        pc[wid] = __popc(word);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int wd = wid * 4 + j;                                     // word of the block
+        const int64_t i = (int64_t)blockIdx.x * 1024 + wd * 32 + lane;
+        const bool nz = (i < D) && (hist[i] != 0u);
+        if (i < D) fbits[i] = F_EMPTY_BITS;
+        const uint32_t word = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) {
+            words[(size_t)blockIdx.x * 32 + wd] = word;
+            pc[wd] = __popc(word);
+        }
     }
     __syncthreads();
     if (wid == 0) {
@@ -146,14 +153,16 @@ __global__ void __launch_bounds__(1024) k2_mask_count(const uint32_t *__restrict
     }
 }
 // (b) single block: exclusive scan of the per-block counts + the flush decision
-__global__ void __launch_bounds__(1024) k2_flush_decide(const uint32_t *__restrict__ block_count, uint32_t nblocks,
+__global__ void __launch_bounds__(256) k2_flush_decide(const uint32_t *__restrict__ block_count, uint32_t nblocks,
                                                         uint32_t *__restrict__ block_prefix, int32_t D, FlushCtl *ctl,
                                                         const int fi) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < nblocks; base += 1024) {
+    for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+        if (threadIdx.x < 32) warp_tot[threadIdx.x] = 0;                  // blocks of fewer than 32 warps
+        __syncthreads();
         const uint32_t i = base + threadIdx.x;
         const uint32_t v = (i < nblocks) ? block_count[i] : 0;
         uint32_t s = v;
@@ -241,27 +250,30 @@ __global__ void k_peer_wait(const uint32_t *flags, const uint32_t n, const uint3
     __threadfence_system();
 }
 // k2_mask_count over the SUM of the peers' buffers; the sum is kept (hist_sum) for the kernels behind it
-__global__ void __launch_bounds__(1024) k2_mask_count_peers(const PeerSources src, int32_t D,
-                                                            uint32_t *__restrict__ hist_sum,
-                                                            uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
-                                                            uint32_t *__restrict__ block_count,
-                                                            unsigned long long *__restrict__ fbits, FlushCtl *ctl,
-                                                            const int fi, const PeerTargets done, unsigned int *ticket) {
+__global__ void __launch_bounds__(K2_MASK_TPB) k2_mask_count_peers(const PeerSources src, int32_t D,
+                                                                   uint32_t *__restrict__ hist_sum,
+                                                                   uint32_t *__restrict__ words,
+                                                                   uint32_t *__restrict__ word_prefix,
+                                                                   uint32_t *__restrict__ block_count,
+                                                                   unsigned long long *__restrict__ fbits, FlushCtl *ctl,
+                                                                   const int fi, const PeerTargets done, unsigned int *ticket) {
     __shared__ uint32_t pc[32];
-    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-    uint32_t sum = 0;
-    if (i < D) {
-#pragma unroll 4
-        for (uint32_t p = 0; p < src.n; p++) sum += __ldcv(src.hist[p] + i);   // never a stale cached copy
-        hist_sum[i] = sum;
-        fbits[i] = F_EMPTY_BITS;
-    }
-    const bool nz = sum != 0u;
-    const uint32_t word = __ballot_sync(0xffffffffu, nz);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        words[(size_t)blockIdx.x * 32 + wid] = word;
-        pc[wid] = __popc(word);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int wd = wid * 4 + j;
+        const int64_t i = (int64_t)blockIdx.x * 1024 + wd * 32 + lane;
+        uint32_t sum = 0;
+        if (i < D) {
+            for (uint32_t p = 0; p < src.n; p++) sum += __ldcv(src.hist[p] + i);   // never a stale cached copy
+            hist_sum[i] = sum;
+            fbits[i] = F_EMPTY_BITS;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, sum != 0u);
+        if (lane == 0) {
+            words[(size_t)blockIdx.x * 32 + wd] = word;
+            pc[wd] = __popc(word);
+        }
     }
     __syncthreads();
     if (wid == 0) {
@@ -278,8 +290,8 @@ __global__ void __launch_bounds__(1024) k2_mask_count_peers(const PeerSources sr
         }
     }
     // the last block to finish tells every owner that this GPU is done with its buffer
-    __syncthreads();
     __shared__ unsigned int last;
+    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
