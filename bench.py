@@ -443,13 +443,18 @@ def run_b200(a):
         hs.add_reads_device(reads_dev[st % n_steps_data].data_ptr(), None, I, RL)
         sh.flush()
 
-    def timed(fn, nsteps):
+    host_enqueue = {}
+
+    def timed(fn, nsteps, tag=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
+            h0 = time.perf_counter()
             for st in range(nsteps):
                 fn(st)
+            if tag:
+                host_enqueue[tag] = (time.perf_counter() - h0) / nsteps * 1e3     # host time to issue one step (no sync)
             e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -471,7 +476,7 @@ def run_b200(a):
         time.sleep(0.35)
     launches0 = hs.stats()["n_kernel_launches"]
     t0 = time.time()
-    ms_value = timed(step_device, K)
+    ms_value = timed(step_device, K, "device")
     t1 = time.time()
     hs.sync()                                          # surfaces deferred errors (short reads, sparse flush)
     st_value = hs.stats()
@@ -512,20 +517,39 @@ def run_b200(a):
         rc = L_.hulk_b200_snapshot_async(hs._ctx, mins_p, weights_p)
         assert rc == 0
 
-    hs.reset()
-    with torch.cuda.stream(stream):
-        for st in range(min(W, n_steps_data)):
-            step_host(st)
-    hs.sync()
-    hs.reset()
-    b0 = hs.stats()
-    ms_e2e = timed(step_host, K)
-    hs.sync()
-    b1 = hs.stats()
-    e2e_value = world * I * K / (ms_e2e * 1e-3)
-    h2d = (b1["h2d_bytes"] - b0["h2d_bytes"]) / K
-    d2h = (b1["d2h_bytes"] - b0["d2h_bytes"]) / K
-    mins_e2e = np.ctypeslib.as_array(C.cast(mins_p, C.POINTER(C.c_uint64)), shape=(rows,)).copy()
+    def run_e2e(tag):
+        hs.reset()
+        with torch.cuda.stream(stream):
+            for st in range(min(W, n_steps_data)):
+                step_host(st)
+        hs.sync()
+        hs.reset()
+        b0 = hs.stats()
+        ms = timed(step_host, K, tag)
+        hs.sync()
+        b1 = hs.stats()
+        mins = np.ctypeslib.as_array(C.cast(mins_p, C.POINTER(C.c_uint64)), shape=(rows,)).copy()
+        return {"value": world * I * K / (ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) / K * world,
+                "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) / K * world,
+                "ms_per_step": ms / K, "host_pack_ms_per_step": (b1["pack_ns"] - b0["pack_ns"]) / K * 1e-6}, mins
+
+    # ASCII reads over PCIe as they are (the link is the bound: 15 MB per step) ...
+    hs.set_input_packing(0)
+    e2e_ascii, mins_ascii = run_e2e("e2e_ascii")
+    e2e_ascii["transport"] = "ASCII bases, one byte each"
+    # ... and the default host path: the same call packs the batch to 2 bits per base on the host's cores INSIDE the
+    # timed region (hulk_b200_pack_bases) and ships a quarter of the bytes; the device unpacks (k0_unpack)
+    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or (affinity or len(os.sched_getaffinity(0)))
+    if world > 1 and not affinity:
+        pack_threads = max(1, len(os.sched_getaffinity(0)) // world)
+    hs.set_input_packing(pack_threads)
+    e2e, mins_e2e = run_e2e("e2e")
+    e2e["transport"] = ("2 bits per base + positions of non-ACGTU bytes: packed from the host's ASCII buffer by %d host "
+                        "threads inside the timed region, unpacked on the device" % pack_threads)
+    e2e["pack_threads"] = pack_threads
+    hs.set_input_packing(0)
+    assert (mins_ascii == mins_e2e).all()
 
     # the runs sketched the same reads: identical sketches
     hs_mins, _ = hs.finish()
@@ -625,8 +649,9 @@ def run_b200(a):
         "dtype": "u64 minimizer/jump-hash, u32 histogram, bf16 CWS screen + f64 CWS resolve", "data": "synthetic",
         "config": workload_config(a, world),
         "gbases_per_s": value * RL / 1e9,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                "ms_per_step": ms_e2e / K},
+        "e2e": e2e,
+        "e2e_ascii": e2e_ascii,
+        "host_enqueue_ms_per_step": host_enqueue,
         "gpu_launches": int(launches),
         "parity_check": parity["verdict"], "parity_job": parity["job"],
         "host_cpus_per_rank": affinity,

@@ -6,7 +6,7 @@ pipeline interface over that ABI.  There is no CPU fallback: every numeric opera
 if the CUDA library is missing or no GPU is present.
 """
 from ._native import load, LIB_PATH, EXPORTS  # noqa: F401
-from .sketch import (GroupSketch, HistoSketch, HulkError, load_sketch, md5_mins, new_cws, pack_reads, sketch_json,  # noqa: F401
+from .sketch import (GroupSketch, HistoSketch, HulkError, load_sketch, md5_mins, new_cws, pack_bases, pack_reads, sketch_json,  # noqa: F401
                      sketch_reads, smash, spectrum_size)
 from .distributed import ShardedSketch, chunk_range, sketch_reads_sharded, slot_range  # noqa: F401
 from .seqio import NativeReader, read_fastq, read_fasta, synthetic_reads  # noqa: F401

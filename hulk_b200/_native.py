@@ -30,6 +30,7 @@ EXPORTS = [
     "hulk_b200_group_push_reads", "hulk_b200_group_push_reads_fixed", "hulk_b200_group_sync_inputs",
     "hulk_b200_group_flush", "hulk_b200_group_sync", "hulk_b200_group_finish", "hulk_b200_group_reset",
     "hulk_b200_group_get_stats", "hulk_b200_group_sketch_reader",
+    "hulk_b200_packed_bytes", "hulk_b200_pack_bases", "hulk_b200_push_reads_packed", "hulk_b200_set_input_packing",
 ]
 PEER_HANDLE_BYTES = 64
 
@@ -40,6 +41,7 @@ EFASTQ, ETOOLONG, ENOSEQ = -41, -42, -43
 LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 F_ASYNC_INPUT = 1
 F_INPUT_READY = 2
+F_PACK_INPUT = 4
 
 
 class Params(C.Structure):
@@ -53,7 +55,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_reads", "n_bases", "n_minimizers", "n_flushes", "n_adds", "n_kernel_launches", "n_rescans",
-        "h2d_bytes", "d2h_bytes")]
+        "h2d_bytes", "d2h_bytes", "pack_ns", "n_packed_batches")]
 
 
 class Profile(C.Structure):
@@ -151,6 +153,10 @@ def load():
         "hulk_b200_group_reset": (C.c_int, [vp]),
         "hulk_b200_group_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "hulk_b200_group_sketch_reader": (C.c_int, [vp, vp, u64, LOG_FN, vp]),
+        "hulk_b200_packed_bytes": (u64, [u64]),
+        "hulk_b200_pack_bases": (C.c_int, [vp, u64, vp, vp, u64, C.POINTER(u64), i32]),
+        "hulk_b200_push_reads_packed": (C.c_int, [vp, vp, vp, u64, vp, u64, u32]),
+        "hulk_b200_set_input_packing": (C.c_int, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

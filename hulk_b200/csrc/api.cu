@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +74,14 @@ struct hulk_b200_ctx {
     uint64_t off_cap[NSTAGE] = {};
     cudaEvent_t ev_copy[NSTAGE] = {}, ev_k1[NSTAGE] = {};
     int cur_buf = 0;
+    // packed transport (HULK_B200_F_PACK_INPUT / push_reads_packed): 2 bits per base + positions of the code-4 bases
+    int pack_threads = 0;                      // 0: off; > 0: host threads that pack a pushed ASCII batch; < 0: all CPUs
+    uint8_t *h_pack[NSTAGE] = {};              // pinned: the packed form of the batch in flight through stage buffer b
+    uint32_t *h_exc[NSTAGE] = {};
+    uint64_t h_pack_cap[NSTAGE] = {}, h_exc_cap[NSTAGE] = {};
+    uint8_t *d_pack[NSTAGE] = {};
+    uint32_t *d_exc[NSTAGE] = {};
+    uint64_t d_pack_cap[NSTAGE] = {}, d_exc_cap[NSTAGE] = {};
     unsigned int *d_ovf_count[NBUF] = {};      // one overflow queue + scratch arena per k1 stream
     unsigned long long *d_ovf_list[NBUF] = {};
     uint32_t ovf_cap = 0;
@@ -266,6 +275,10 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     for (int i = 0; i < NSTAGE; i++) {
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
         if (ctx->d_off[i]) cudaFree(ctx->d_off[i]);
+        if (ctx->d_pack[i]) cudaFree(ctx->d_pack[i]);
+        if (ctx->d_exc[i]) cudaFree(ctx->d_exc[i]);
+        if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
+        if (ctx->h_exc[i]) cudaFreeHost(ctx->h_exc[i]);
     }
     for (uint32_t p = 0; p < PEER_MAX; p++)
         if (ctx->peer_ipc[p] && ctx->peer_arena[p]) cudaIpcCloseMemHandle(ctx->peer_arena[p]);
@@ -312,6 +325,8 @@ static int sync_all(hulk_b200_ctx *ctx) {
 __global__ void k_snapshot(const unsigned long long *__restrict__ sketch, const double *__restrict__ weights,
                            unsigned long long *__restrict__ h_mins, double *__restrict__ h_weights, uint32_t rows);
 __global__ void k_merge_hist(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int32_t D);
+__global__ void k0_unpack(const uint32_t *__restrict__ packed, uint64_t n_words, uint4 *__restrict__ ascii);
+__global__ void k0_patch(const uint32_t *__restrict__ exc, uint64_t n, uint32_t shift, uint8_t *__restrict__ ascii);
 
 static int create_impl(hulk_b200_ctx *ctx) {
     const hulk_b200_params &P = ctx->P;
@@ -493,6 +508,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         HULK_PRELOAD(k3_fill_f32);
         HULK_PRELOAD(k_snapshot);
         HULK_PRELOAD(k_merge_hist);
+        HULK_PRELOAD(k0_unpack);
+        HULK_PRELOAD(k0_patch);
         HULK_PRELOAD(k1_generic<false>);
         HULK_PRELOAD(k1_generic<true>);
         HULK_PRELOAD((k1_jump_queue<2>));
@@ -529,6 +546,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e == '0') ctx->k1_v2 = false;
         e = getenv("HULK_B200_SERIAL");
         if (e && *e == '1') ctx->overlap = false;
+        if (P.flags & HULK_B200_F_PACK_INPUT) ctx->pack_threads = -1;
+        e = getenv("HULK_B200_PACK_INPUT");                  // A/B runs and the CLI: 1 = on, 0 = off whatever the flag says
+        if (e && *e == '1') ctx->pack_threads = -1;
+        if (e && *e == '0') ctx->pack_threads = 0;
     }
     return HULK_B200_OK;
 }
@@ -1050,9 +1071,87 @@ static int before_first_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t ks) {
 
 static const uint64_t kMaxBatchBytes = 256ull << 20;   // staging granularity of one H2D copy + k1 launch
 
-static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
-                     uint32_t fixed_len) {
+// ---- packed transport, device side: 2-bit codes -> the letters the scan kernels read ---------------------
+// One thread per packed word = 16 bases -> one 16-byte store.  Code c becomes "ACGT"[c]; k0_patch then writes 'N'
+// over the listed code-4 positions (seq_nt4_table maps every such byte to 4, minimizer.go:13-30).
+__global__ void k0_unpack(const uint32_t *__restrict__ packed, uint64_t n_words, uint4 *__restrict__ ascii) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_words) return;
+    const uint32_t x = packed[t];
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = (x >> (8 * q)) & 0xffu;
+        v = (v | (v << 4)) & 0x0F0Fu;
+        v = (v | (v << 2)) & 0x3333u;                        // nibble j = code of base j
+        o[q] = __byte_perm(0x54474341u /* "ACGT" */, 0u, v);
+    }
+    ascii[t] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void k0_patch(const uint32_t *__restrict__ exc, uint64_t n, uint32_t shift, uint8_t *__restrict__ ascii) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) ascii[exc[t] - shift] = (uint8_t)'N';
+}
+
+static int ensure_pack_stage(hulk_b200_ctx *ctx, int buf, uint64_t packed_bytes, uint64_t n_exc, bool host_side) {
+    if (packed_bytes + 16 > ctx->d_pack_cap[buf]) {
+        CU(cudaEventSynchronize(ctx->ev_k1[buf]));
+        if (ctx->d_pack[buf]) cudaFree(ctx->d_pack[buf]);
+        ctx->d_pack[buf] = nullptr;
+        ctx->d_pack_cap[buf] = 0;
+        const uint64_t cap = (packed_bytes + 16 + 4095) & ~4095ull;
+        CU(dmalloc(&ctx->d_pack[buf], cap));
+        ctx->d_pack_cap[buf] = cap;
+    }
+    if (n_exc > ctx->d_exc_cap[buf]) {
+        CU(cudaEventSynchronize(ctx->ev_k1[buf]));
+        if (ctx->d_exc[buf]) cudaFree(ctx->d_exc[buf]);
+        ctx->d_exc[buf] = nullptr;
+        ctx->d_exc_cap[buf] = 0;
+        const uint64_t cap = std::max<uint64_t>(1024, n_exc);
+        CU(dmalloc(&ctx->d_exc[buf], cap));
+        ctx->d_exc_cap[buf] = cap;
+    }
+    if (host_side) {
+        if (packed_bytes > ctx->h_pack_cap[buf]) {
+            CU(cudaEventSynchronize(ctx->ev_copy[buf]));
+            if (ctx->h_pack[buf]) cudaFreeHost(ctx->h_pack[buf]);
+            ctx->h_pack[buf] = nullptr;
+            ctx->h_pack_cap[buf] = 0;
+            const uint64_t cap = (packed_bytes + 4095) & ~4095ull;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pack[buf]), cap, cudaHostAllocDefault));
+            ctx->h_pack_cap[buf] = cap;
+        }
+        if (n_exc > ctx->h_exc_cap[buf]) {
+            CU(cudaEventSynchronize(ctx->ev_copy[buf]));
+            if (ctx->h_exc[buf]) cudaFreeHost(ctx->h_exc[buf]);
+            ctx->h_exc[buf] = nullptr;
+            ctx->h_exc_cap[buf] = 0;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_exc[buf]), n_exc * sizeof(uint32_t), cudaHostAllocDefault));
+            ctx->h_exc_cap[buf] = n_exc;
+        }
+    }
+    return HULK_B200_OK;
+}
+
+// A host batch, in one of two forms: ASCII (`bases`), or packed by the caller (`packed` + `exc`; base 0 of the stream
+// is the first base of read 0).  ASCII batches are packed here when the context's input packing is on.
+struct HostBatch {
+    const uint8_t *bases = nullptr;
+    const uint8_t *packed = nullptr;
+    const uint32_t *exc = nullptr;
+    uint64_t n_exc = 0;
+    const uint64_t *offsets = nullptr;
+    uint64_t n_reads = 0;
+    uint32_t fixed_len = 0;
+};
+
+static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
     CU(cudaSetDevice(ctx->P.device));
+    const uint64_t *offsets = hb.offsets;
+    const uint64_t n_reads = hb.n_reads;
+    const uint32_t fixed_len = hb.fixed_len;
+    const uint64_t origin = offsets ? offsets[0] : 0;      // offsets[] value of base 0 of a caller-packed stream
     uint64_t done = 0;
     while (done < n_reads) {
         // take reads [done, upto) with at most kMaxBatchBytes bytes (at least one read)
@@ -1076,10 +1175,62 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
         if (offsets)
             for (uint64_t i = done; i < upto; i++) ctx->batch_max_len = std::max(ctx->batch_max_len, offsets[i + 1] - offsets[i]);
         const int buf = ctx->cur_buf;
-        int rc = ensure_stage(ctx, buf, nb, offsets ? nr + 1 : 0);
+        int rc = ensure_stage(ctx, buf, nb + 16, offsets ? nr + 1 : 0);
         if (rc) return rc;
+
+        // ---- how the bases travel: packed by the caller, packed here, or as they are
+        const uint8_t *src_packed = nullptr;               // host bytes to copy into d_pack
+        const uint32_t *src_exc = nullptr;
+        uint64_t n_exc = 0, packed_bytes = 0, unpack_words = 0;
+        uint32_t skip = 0, exc_shift = 0;
+        if (hb.packed) {
+            const uint64_t s0 = b0 - origin, s1 = b1 - origin, a0 = s0 & ~3ull;
+            if (s1 >= (1ull << 32)) return fail(ctx, HULK_B200_EARG, "a packed batch holds fewer than 2^32 bases");
+            skip = (uint32_t)(s0 - a0);
+            exc_shift = (uint32_t)a0;
+            src_packed = hb.packed + (a0 >> 2);
+            packed_bytes = ((s1 + 3) >> 2) - (a0 >> 2);
+            unpack_words = (s1 - a0 + 15) / 16;
+            const uint32_t *e0 = std::lower_bound(hb.exc, hb.exc + hb.n_exc, (uint32_t)s0);
+            const uint32_t *e1 = std::lower_bound(e0, hb.exc + hb.n_exc, (uint32_t)s1);
+            src_exc = e0;
+            n_exc = (uint64_t)(e1 - e0);
+            rc = ensure_pack_stage(ctx, buf, packed_bytes, n_exc, false);
+            if (rc) return rc;
+        } else if (ctx->pack_threads != 0 && nb >= 4096) {
+            const uint64_t exc_cap = std::max<uint64_t>(1024, nb / 32);
+            packed_bytes = (nb + 3) / 4;
+            rc = ensure_pack_stage(ctx, buf, packed_bytes, exc_cap, true);
+            if (rc) return rc;
+            CU(cudaEventSynchronize(ctx->ev_copy[buf]));   // the copy out of this pinned buffer, NSTAGE batches ago, is done
+            const auto t_pack = std::chrono::steady_clock::now();
+            rc = hulk_b200_pack_bases(hb.bases + b0, nb, ctx->h_pack[buf], ctx->h_exc[buf], exc_cap, &n_exc,
+                                      ctx->pack_threads);
+            ctx->st.pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                   std::chrono::steady_clock::now() - t_pack).count();
+            if (rc) return fail(ctx, rc, "pack_bases");
+            if (n_exc <= exc_cap) {
+                src_packed = ctx->h_pack[buf];
+                src_exc = ctx->h_exc[buf];
+                unpack_words = (nb + 15) / 16;
+            } else {
+                n_exc = 0;                                 // too many foreign bytes to be worth it: this batch goes as ASCII
+                packed_bytes = 0;
+            }
+        }
+
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k1[buf], 0));
-        if (nb) CU(cudaMemcpyAsync(ctx->d_stage[buf], bases + b0, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+        uint64_t moved = 0;
+        if (src_packed) {
+            CU(cudaMemcpyAsync(ctx->d_pack[buf], src_packed, packed_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (n_exc)
+                CU(cudaMemcpyAsync(ctx->d_exc[buf], src_exc, sizeof(uint32_t) * n_exc, cudaMemcpyHostToDevice, ctx->copy_stream));
+            moved = packed_bytes + sizeof(uint32_t) * n_exc;
+            ctx->st.n_packed_batches++;
+        } else {
+            if (nb) CU(cudaMemcpyAsync(ctx->d_stage[buf], hb.bases + b0, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            moved = nb;
+        }
         if (offsets)
             CU(cudaMemcpyAsync(ctx->d_off[buf], offsets + done, sizeof(uint64_t) * (nr + 1), cudaMemcpyHostToDevice,
                                ctx->copy_stream));
@@ -1088,8 +1239,18 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
         cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
         CU(cudaStreamWaitEvent(ks, ctx->ev_copy[buf], 0));
         { const int rcw = before_first_k1(ctx, hs, ks); if (rcw) return rcw; }              // its last flush left it clean
-        ctx->st.h2d_bytes += nb + (offsets ? sizeof(uint64_t) * (nr + 1) : 0);
-        rc = launch_k1<false>(ctx, hs, ks, ctx->d_stage[buf], (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr,
+        ctx->st.h2d_bytes += moved + (offsets ? sizeof(uint64_t) * (nr + 1) : 0);
+        if (src_packed) {
+            k0_unpack<<<(unsigned)((unpack_words + 255) / 256), 256, 0, ks>>>(reinterpret_cast<const uint32_t *>(ctx->d_pack[buf]),
+                                                                                unpack_words,
+                                                                                reinterpret_cast<uint4 *>(ctx->d_stage[buf]));
+            LAUNCH_CHECK("k0_unpack");
+            if (n_exc) {
+                k0_patch<<<(unsigned)((n_exc + 255) / 256), 256, 0, ks>>>(ctx->d_exc[buf], n_exc, exc_shift, ctx->d_stage[buf]);
+                LAUNCH_CHECK("k0_patch");
+            }
+        }
+        rc = launch_k1<false>(ctx, hs, ks, ctx->d_stage[buf] + skip, (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr,
                               b0, fixed_len, nr, nb, nullptr, 0, nullptr);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev_k1[buf], ks));
@@ -1099,16 +1260,48 @@ static int push_host(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *o
         ctx->st.n_bases += nb;
         ctx->cur_buf = (ctx->cur_buf + 1) % NSTAGE;
         done = upto;
-        if (!(ctx->P.flags & HULK_B200_F_ASYNC_INPUT)) CU(cudaEventSynchronize(ctx->ev_copy[buf]));
+        // packed here: the caller's buffer has been read already; otherwise it is in use until the copy is done
+        if (!(ctx->P.flags & HULK_B200_F_ASYNC_INPUT) && !(src_packed && !hb.packed)) CU(cudaEventSynchronize(ctx->ev_copy[buf]));
     }
     return HULK_B200_OK;
+}
+
+int hulk_b200_set_input_packing(hulk_b200_ctx *ctx, int32_t n_threads) {
+    if (!ctx) return HULK_B200_EARG;
+    ctx->pack_threads = n_threads;
+    return HULK_B200_OK;
+}
+
+int hulk_b200_push_reads_packed(hulk_b200_ctx *ctx, const uint8_t *packed, const uint32_t *exceptions, uint64_t n_exceptions,
+                                const uint64_t *offsets, uint64_t n_reads, uint32_t read_len) {
+    if (!ctx) return HULK_B200_EARG;
+    if (n_reads == 0) return HULK_B200_OK;
+    if (!packed) return fail(ctx, HULK_B200_EARG, "packed is NULL");
+    if (n_exceptions && !exceptions) return fail(ctx, HULK_B200_EARG, "exceptions is NULL");
+    HostBatch hb;
+    hb.packed = packed;
+    hb.exc = exceptions;
+    hb.n_exc = n_exceptions;
+    hb.n_reads = n_reads;
+    if (offsets) {
+        hb.offsets = offsets;
+    } else {
+        if (read_len < 1) return fail(ctx, HULK_B200_EEMPTYSEQ);
+        if (read_len < ctx->P.w + ctx->P.k - 1) return fail(ctx, HULK_B200_ESHORTSEQ);
+        hb.fixed_len = read_len;
+    }
+    return push_host(ctx, hb);
 }
 
 int hulk_b200_push_reads(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads) {
     if (!ctx) return HULK_B200_EARG;
     if (n_reads == 0) return HULK_B200_OK;
     if (!offsets || (!bases && offsets[n_reads] != offsets[0])) return fail(ctx, HULK_B200_EARG, "bases/offsets is NULL");
-    return push_host(ctx, bases, offsets, n_reads, 0);
+    HostBatch hb;
+    hb.bases = bases;
+    hb.offsets = offsets;
+    hb.n_reads = n_reads;
+    return push_host(ctx, hb);
 }
 
 int hulk_b200_push_reads_fixed(hulk_b200_ctx *ctx, const uint8_t *bases, uint64_t n_reads, uint32_t read_len) {
@@ -1117,7 +1310,11 @@ int hulk_b200_push_reads_fixed(hulk_b200_ctx *ctx, const uint8_t *bases, uint64_
     if (read_len < 1) return fail(ctx, HULK_B200_EEMPTYSEQ);
     if (read_len < ctx->P.w + ctx->P.k - 1) return fail(ctx, HULK_B200_ESHORTSEQ);
     if (!bases) return fail(ctx, HULK_B200_EARG, "bases is NULL");
-    return push_host(ctx, bases, nullptr, n_reads, read_len);
+    HostBatch hb;
+    hb.bases = bases;
+    hb.n_reads = n_reads;
+    hb.fixed_len = read_len;
+    return push_host(ctx, hb);
 }
 
 int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,

@@ -255,6 +255,8 @@ int hulk_b200_group_get_stats(hulk_b200_group *g, hulk_b200_stats *out) {
         sum.n_rescans += st.n_rescans;
         sum.h2d_bytes += st.h2d_bytes;
         sum.d2h_bytes += st.d2h_bytes;
+        sum.pack_ns += st.pack_ns;
+        sum.n_packed_batches += st.n_packed_batches;
         if (i == 0) {                                    // every member flushes the same summed spectrum
             sum.n_flushes = st.n_flushes;
             sum.n_adds = st.n_adds;

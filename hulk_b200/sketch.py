@@ -54,6 +54,21 @@ def pack_reads(reads: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
     return bases, offsets
 
 
+def pack_bases(bases: np.ndarray, n_threads: int = 0, exceptions_cap: Optional[int] = None):
+    """hulk_b200_pack_bases: ASCII bases -> (packed uint8[ceil(n/4)], exceptions uint32[], true exception count)."""
+    L = N.load()
+    bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1)
+    n = bases.size
+    packed = np.zeros(int(L.hulk_b200_packed_bytes(n)), dtype=np.uint8)
+    cap = n if exceptions_cap is None else exceptions_cap
+    exc = np.zeros(max(1, cap), dtype=np.uint32)
+    n_exc = C.c_uint64()
+    rc = L.hulk_b200_pack_bases(_ptr(bases), n, _ptr(packed), _ptr(exc), cap, C.byref(n_exc), n_threads)
+    if rc:
+        raise HulkError(rc, L.hulk_b200_strerror(rc).decode())
+    return packed, exc[:min(cap, n_exc.value)].copy(), n_exc.value
+
+
 def md5_mins(mins) -> str:
     L = N.load()
     m = np.ascontiguousarray(mins, dtype=np.uint64)
@@ -106,7 +121,7 @@ class HistoSketch:
     def __init__(self, k: int = 21, w: int = 9, sketch_size: int = 50, decay_ratio: float = 1.0,
                  num_bins: Optional[int] = None, device: int = 0, slots: Optional[Tuple[int, int]] = None,
                  stream: Optional[int] = None, tables=None, async_input: bool = False,
-                 input_ready: bool = False):
+                 input_ready: bool = False, pack_input: bool = False):
         self._L = N.load()
         self._ctx = C.c_void_p()
         self.k, self.w, self.sketch_size, self.decay_ratio = k, w, sketch_size, decay_ratio
@@ -120,7 +135,8 @@ class HistoSketch:
         p.device = device
         p.slot_begin, p.slot_end = (slots if slots is not None else (0, 0))
         p.stream = stream
-        p.flags = (N.F_ASYNC_INPUT if async_input else 0) | (N.F_INPUT_READY if input_ready else 0)
+        p.flags = ((N.F_ASYNC_INPUT if async_input else 0) | (N.F_INPUT_READY if input_ready else 0)
+                   | (N.F_PACK_INPUT if pack_input else 0))
         ctx = C.c_void_p()
         rc = self._L.hulk_b200_create(C.byref(p), C.byref(ctx))
         if rc:
@@ -213,6 +229,20 @@ class HistoSketch:
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         self._keep = [bases]
         self._check(self._L.hulk_b200_push_reads_fixed(self._ctx, _ptr(bases), n_reads, read_len))
+
+    def set_input_packing(self, n_threads: int):
+        """Host batches travel as 2 bits per base (packed on n_threads host threads; < 0: all CPUs; 0: off)."""
+        self._check(self._L.hulk_b200_set_input_packing(self._ctx, n_threads))
+
+    def add_reads_packed(self, packed: np.ndarray, exceptions: np.ndarray, offsets: Optional[np.ndarray],
+                         n_reads: int, read_len: int = 0):
+        """theBoss.AddSeq for a batch the caller packed with pack_bases (hulk_b200_push_reads_packed)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        exceptions = np.ascontiguousarray(exceptions, dtype=np.uint32)
+        offs = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep = [packed, exceptions, offs]
+        self._check(self._L.hulk_b200_push_reads_packed(self._ctx, _ptr(packed), _ptr(exceptions), exceptions.size,
+                                                        _ptr(offs), n_reads, read_len))
 
     def add_reads_device(self, d_bases_ptr: int, d_offsets_ptr: Optional[int], n_reads: int, read_len: int = 0):
         self._check(self._L.hulk_b200_push_reads_device(self._ctx, d_bases_ptr, d_offsets_ptr, n_reads, read_len))

@@ -194,6 +194,66 @@ def test_histogram_with_n_and_ragged_reads(hb, oracle):
         assert hs.stats()["n_minimizers"] == nm
 
 
+def test_packed_transport_gives_the_same_spectrum(hb, oracle):
+    """2 bits per base + code-4 positions (HULK_B200_F_PACK_INPUT, push_reads_packed) against the oracle on the ASCII
+    reads: N, IUPAC, lower case, U, raw bytes 0..3 and every other byte value, ragged and fixed-length batches,
+    a caller-packed batch entered at a read that does not start on a byte of the packed stream."""
+    k, w = 21, 9
+    D = k ** 4
+    reads = random_reads(6000, 60, seed=5, n_frac=0.01, lower_frac=0.3, ragged=200)
+    rng = np.random.default_rng(6)
+    weird = np.frombuffer(b"ACGTacgtUuNRYKM\x00\x01\x02\x03\xff", np.uint8)
+    reads += [weird[rng.integers(0, weird.size, 151)].tobytes() for _ in range(300)]
+    reads += [bytes(range(256)), b"N" * 90, b"\x00\x01\x02\x03" * 40, b"ACGU" * 40]
+    bases, offs = oracle.pack_reads(reads)
+    ho, nm = oracle.count_reads(k, w, D, bases, offs)
+    ho = ho.astype(np.uint32)
+    # (a) the library packs a pushed ASCII batch itself
+    with hb.HistoSketch(k, w, 4, pack_input=True) as hs:
+        hs.add_reads(bases, offs)
+        np.testing.assert_array_equal(hs.histogram(), ho)
+        st = hs.stats()
+        assert st["n_minimizers"] == nm
+        assert st["h2d_bytes"] < 0.45 * bases.size + 8 * offs.size          # a quarter of the bases (+ exceptions, offsets)
+    # (b) the caller packs; the batch is pushed in two calls, the second entered mid-byte
+    packed, exc, n_exc = hb.pack_bases(bases, 3)
+    assert n_exc == exc.size > 0
+    with hb.HistoSketch(k, w, 4) as hs:
+        hs.add_reads_packed(packed, exc, offs, len(reads))
+        np.testing.assert_array_equal(hs.histogram(), ho)
+    cut = next(i for i in range(2000, len(reads)) if offs[i] % 4 == 1)
+    with hb.HistoSketch(k, w, 4) as hs:
+        hs.add_reads_packed(packed, exc, offs[:cut + 1], cut)
+        o2 = offs[cut:].copy()
+        p2, e2, _ = hb.pack_bases(bases[int(o2[0]):], 2)
+        hs.add_reads_packed(p2, e2, o2, len(reads) - cut)
+        np.testing.assert_array_equal(hs.histogram(), ho)
+    # (c) fixed-length reads, the other scan kernels (k = 11: first-generation scan; w = 5: staged tiles)
+    n, L = 20000, 150
+    fixed = hb.synthetic_reads(n, L, seed=8)
+    fixed[::53, 70] = ord("N")
+    fixed[::97, 3] = ord("c")
+    offs_f = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    for kk, ww in [(21, 9), (11, 9), (15, 5)]:
+        hf, nmf = oracle.count_reads(kk, ww, kk ** 4, fixed.reshape(-1), offs_f)
+        with hb.HistoSketch(kk, ww, 4, pack_input=True) as hs:
+            hs.add_reads_fixed(fixed.reshape(-1), n, L)
+            np.testing.assert_array_equal(hs.histogram(), hf.astype(np.uint32))
+            assert hs.stats()["n_minimizers"] == nmf
+        pf, ef, _ = hb.pack_bases(fixed.reshape(-1))
+        with hb.HistoSketch(kk, ww, 4) as hs:
+            hs.add_reads_packed(pf, ef, None, n, L)
+            np.testing.assert_array_equal(hs.histogram(), hf.astype(np.uint32))
+    # (d) a batch of mostly foreign bytes is not worth packing: it travels as ASCII, same result
+    junk = [bytes(rng.integers(0, 256, 120, dtype=np.uint8)) for _ in range(2000)]
+    jb, jo = oracle.pack_reads(junk)
+    hj, _ = oracle.count_reads(k, w, D, jb, jo)
+    with hb.HistoSketch(k, w, 4, pack_input=True) as hs:
+        hs.add_reads(jb, jo)
+        np.testing.assert_array_equal(hs.histogram(), hj.astype(np.uint32))
+        assert hs.stats()["h2d_bytes"] >= jb.size
+
+
 def test_device_resident_input_equals_host_input(hb):
     import torch
     n, L = 30000, 150

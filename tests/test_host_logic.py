@@ -398,3 +398,44 @@ def test_bench_generators_on_cpu(monkeypatch):
     assert fwd + rev >= 400 and fwd > 100 and rev > 100
     again = bench.genome_reads_torch(torch, genome, 50, 150, 1, 200, "cpu")
     assert (again == reads[200:250]).all()
+
+
+# ---- packed read transport, host side (csrc/pack.cpp) ------------------------------------------------
+def _nt4_table():
+    t = np.full(256, 4, np.uint8)
+    t[:4] = [0, 1, 2, 3]
+    for ch, c in zip("ACGTU", [0, 1, 2, 3, 3]):                     # src/minimizer/minimizer.go:13-30
+        t[ord(ch)] = c
+        t[ord(ch.lower())] = c
+    return t
+
+
+@pytest.mark.parametrize("isa", ["scalar", "avx2", "avx512"])
+def test_pack_bases_is_the_nt4_table_two_bits_per_base(isa, monkeypatch):
+    """hulk_b200_pack_bases against seq_nt4_table: codes of every non-4 base, ascending positions of the code-4 bases,
+    for every byte value, every vector path the host has, one and several threads, sizes around the vector and piece
+    boundaries."""
+    import hulk_b200 as hb
+    monkeypatch.setenv("HULK_B200_PACK_ISA", isa)        # a path the CPU lacks falls back to the next one down
+    nt4 = _nt4_table()
+    rng = np.random.default_rng(11)
+    alphabets = [np.arange(256, dtype=np.uint8), np.frombuffer(b"ACGT", np.uint8),
+                 np.frombuffer(b"ACGTacgtUuN\x00\x01\x02\x03", np.uint8)]
+    for n in [0, 1, 3, 4, 5, 63, 64, 65, 127, 1000, 65535, 65536, 65537, 200001, 1_000_003]:
+        for alpha in alphabets:
+            b = alpha[rng.integers(0, alpha.size, n)].copy()
+            codes = nt4[b]
+            want_exc = np.nonzero(codes == 4)[0].astype(np.uint32)
+            for threads in (1, 3):
+                packed, exc, n_exc = hb.pack_bases(b, threads)
+                assert packed.size == (n + 3) // 4
+                assert n_exc == want_exc.size
+                np.testing.assert_array_equal(exc, want_exc)
+                got = np.unpackbits(packed, bitorder="little").reshape(-1, 2)[:n]
+                got = got[:, 0] | (got[:, 1] << 1)
+                keep = codes != 4                                    # the code stored under an exception is a don't-care
+                np.testing.assert_array_equal(got[keep], codes[keep])
+    # a cap smaller than the exception count: the true count is still reported
+    b = np.full(5000, ord("N"), np.uint8)
+    _, exc, n_exc = hb.pack_bases(b, 2, exceptions_cap=100)
+    assert n_exc == 5000 and exc.size == 100 and (exc == np.arange(100)).all()
