@@ -540,9 +540,10 @@ def run_b200(a):
     e2e_ascii["transport"] = "ASCII bases, one byte each"
     # ... and the default host path: the same call packs the batch to 2 bits per base on the host's cores INSIDE the
     # timed region (hulk_b200_pack_bases) and ships a quarter of the bytes; the device unpacks (k0_unpack)
-    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or (affinity or len(os.sched_getaffinity(0)))
+    ncpu = len(os.sched_getaffinity(0))
+    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or max(1, min(32, ncpu - 2 if ncpu > 3 else ncpu))
     if world > 1 and not affinity:
-        pack_threads = max(1, len(os.sched_getaffinity(0)) // world)
+        pack_threads = max(1, ncpu // world - 1)
     hs.set_input_packing(pack_threads)
     e2e, mins_e2e = run_e2e("e2e")
     e2e["transport"] = ("2 bits per base + positions of non-ACGTU bytes: packed from the host's ASCII buffer by %d host "

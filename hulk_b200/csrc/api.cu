@@ -15,6 +15,7 @@
 // Streams: `stream` (CWS sweep, caller-visible ordering point), a count-min stream, one k1 stream per
 // spectrum buffer, a copy stream.  Events order "interval counted" -> count-min -> CWS sweep, and
 // "buffer wiped" -> next use, so interval i+1.. is counted while interval i is flushed.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -22,7 +23,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -72,7 +77,13 @@ struct hulk_b200_ctx {
     uint64_t stage_cap[NSTAGE] = {};
     uint64_t *d_off[NSTAGE] = {};
     uint64_t off_cap[NSTAGE] = {};
-    cudaEvent_t ev_copy[NSTAGE] = {}, ev_k1[NSTAGE] = {};
+    cudaEvent_t ev_copy[NSTAGE] = {};
+    // "the kernels that consumed stage buffer b are done": two events per buffer, used alternately, so that the event of
+    // the PREVIOUS use can still be waited on (by the feeder thread, later) after the current use has been recorded
+    cudaEvent_t ev_k1x[NSTAGE][2] = {};
+    uint32_t k1_use[NSTAGE] = {};              // uses of stage buffer b so far
+    cudaEvent_t ev_k1_prev(int b) const { return ev_k1x[b][(k1_use[b] + 1u) & 1u]; }   // last recorded (never recorded: a no-op to wait on)
+    cudaError_t ev_k1_record(int b, cudaStream_t st) { const cudaError_t e = cudaEventRecord(ev_k1x[b][k1_use[b] & 1u], st); k1_use[b]++; return e; }
     int cur_buf = 0;
     // packed transport (HULK_B200_F_PACK_INPUT / push_reads_packed): 2 bits per base + positions of the code-4 bases
     int pack_threads = 0;                      // 0: off; > 0: host threads that pack a pushed ASCII batch; < 0: all CPUs
@@ -82,6 +93,33 @@ struct hulk_b200_ctx {
     uint8_t *d_pack[NSTAGE] = {};
     uint32_t *d_exc[NSTAGE] = {};
     uint64_t d_pack_cap[NSTAGE] = {}, d_exc_cap[NSTAGE] = {};
+    // The feeder: with HULK_B200_F_ASYNC_INPUT a batch is packed and copied by this thread while the calling thread goes on
+    // enqueueing the kernels that consume it (they wait, on the device, for the batch's sequence number to appear in
+    // d_feed).  Packing a C2 interval takes about as long as counting it, so the two must not share a host thread.
+    struct FeedReq {
+        const uint8_t *src;         // ASCII bases of the batch
+        uint64_t nb;
+        const uint64_t *offsets;    // or nullptr
+        uint64_t n_off;
+        int buf;
+        uint32_t seq;
+        cudaEvent_t stage_free;     // the previous consumers of this stage buffer are done (waited for on the copy stream)
+    };
+    std::thread feeder;
+    std::mutex feed_mu;
+    std::condition_variable feed_cv;
+    std::deque<FeedReq> feed_q;
+    uint64_t feed_posted = 0, feed_done = 0;   // under feed_mu
+    bool feed_stop = false;
+    int feed_rc = 0;                           // first error of the feeder (under feed_mu)
+    std::string feed_err;
+    uint32_t feed_seq[NSTAGE] = {};            // uses of stage buffer b by the feeder path
+    uint32_t *d_feed = nullptr;                // [NSTAGE][4]: sequence flag, mode (1 = packed), exceptions, pad
+    uint32_t *h_feed = nullptr;                // pinned mirror of mode / exceptions, [NSTAGE][4]
+    std::atomic<uint64_t> feed_h2d{0}, feed_pack_ns{0}, feed_batches{0};
+    std::atomic<uint64_t> feed_t_idle{0}, feed_t_evsync{0}, feed_t_enq{0}, feed_t_backpressure{0};   // ns (HULK_B200_FEED_DEBUG)
+    CUresult (*cu_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    CUresult (*cu_write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     unsigned int *d_ovf_count[NBUF] = {};      // one overflow queue + scratch arena per k1 stream
     unsigned long long *d_ovf_list[NBUF] = {};
     uint32_t ovf_cap = 0;
@@ -193,6 +231,30 @@ struct ProfScope {
 
 static thread_local std::string g_create_err;
 
+// host-side stopwatch for HULK_B200_FEED_STATS=1 runs: where the calling thread's time goes, by label
+static const bool g_host_stats = [] { const char *e = getenv("HULK_B200_FEED_STATS"); return e && *e == '1'; }();
+struct HostStat { const char *name; uint64_t ns = 0, n = 0; };
+static HostStat g_hstat[12] = {{"push: backpressure"}, {"push: sizing"}, {"push: post"}, {"push: wait32"}, {"push: first_k1"},
+                               {"push: unpack launches"}, {"push: k1 launches"}, {"push: records"}, {"flush"}, {"snapshot"},
+                               {"push (whole call)"}, {"-"}};
+struct HostLap {
+    std::chrono::steady_clock::time_point t;
+    HostLap() { if (g_host_stats) t = std::chrono::steady_clock::now(); }
+    void lap(int i) {
+        if (!g_host_stats) return;
+        const auto now = std::chrono::steady_clock::now();
+        g_hstat[i].ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(now - t).count();
+        g_hstat[i].n++;
+        t = now;
+    }
+};
+static void host_stats_print() {
+    if (!g_host_stats) return;
+    for (auto &h : g_hstat)
+        if (h.n) fprintf(stderr, "[host] %-24s %8llu calls  %9.3f ms  %7.2f us each\n", h.name, (unsigned long long)h.n, h.ns * 1e-6,
+                         h.ns * 1e-3 / (double)h.n);
+}
+
 const char *hulk_b200_version(void) { return HULK_B200_VERSION; }
 
 const char *hulk_b200_strerror(int code) {
@@ -260,6 +322,20 @@ static cudaError_t dmalloc(T **p, uint64_t n) {
 void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (!ctx) return;
     if (ctx->gen_thread.joinable()) ctx->gen_thread.join();
+    if (ctx->feeder.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->feed_mu);
+            ctx->feed_stop = true;
+        }
+        ctx->feed_cv.notify_all();
+        ctx->feeder.join();
+        host_stats_print();
+        if (getenv("HULK_B200_FEED_STATS"))
+            fprintf(stderr, "[feed] requests %llu: feeder idle %.3f ms, waiting for its pinned buffer %.3f, packing %.3f, "
+                            "enqueueing copies %.3f; caller held back %.3f ms\n",
+                    (unsigned long long)ctx->feed_done, ctx->feed_t_idle.load() * 1e-6, ctx->feed_t_evsync.load() * 1e-6,
+                    ctx->feed_pack_ns.load() * 1e-6, ctx->feed_t_enq.load() * 1e-6, ctx->feed_t_backpressure.load() * 1e-6);
+    }
     cudaSetDevice(ctx->P.device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < NBUF; i++)
@@ -282,7 +358,8 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     }
     for (uint32_t p = 0; p < PEER_MAX; p++)
         if (ctx->peer_ipc[p] && ctx->peer_arena[p]) cudaIpcCloseMemHandle(ctx->peer_arena[p]);
-    void *ptrs[] = {ctx->arena, ctx->d_hist_sum, ctx->d_ticket, ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
+    if (ctx->h_feed) cudaFreeHost(ctx->h_feed);
+    void *ptrs[] = {ctx->d_feed, ctx->arena, ctx->d_hist_sum, ctx->d_ticket, ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits[0], ctx->d_fbits[1], ctx->d_invf[0],
                     ctx->d_invf[1], ctx->d_r, ctx->d_c,
@@ -292,7 +369,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
         if (p) cudaFree(p);
     for (int i = 0; i < NSTAGE; i++) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
-        if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]);
+        for (int q = 0; q < 2; q++) if (ctx->ev_k1x[i][q]) cudaEventDestroy(ctx->ev_k1x[i][q]);
     }
     for (int i = 0; i < NBUF; i++) {
         if (ctx->ev_k1_last[i]) cudaEventDestroy(ctx->ev_k1_last[i]);
@@ -314,7 +391,20 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
 }
 
 // every stream of the context idle (inputs copied, all k1 launches and flushes done)
+static int feed_drain(hulk_b200_ctx *ctx) {
+    if (!ctx->feeder.joinable()) return HULK_B200_OK;
+    std::unique_lock<std::mutex> lk(ctx->feed_mu);
+    ctx->feed_cv.wait(lk, [&] { return ctx->feed_done == ctx->feed_posted; });
+    if (ctx->feed_rc) {
+        const int rc = ctx->feed_rc;
+        ctx->err = ctx->feed_err;
+        ctx->feed_rc = 0;
+        return rc;
+    }
+    return HULK_B200_OK;
+}
 static int sync_all(hulk_b200_ctx *ctx) {
+    { const int rc = feed_drain(ctx); if (rc) return rc; }
     CU(cudaStreamSynchronize(ctx->copy_stream));
     for (int i = 0; i < NBUF; i++) CU(cudaStreamSynchronize(ctx->k1_stream[i]));
     CU(cudaStreamSynchronize(ctx->k2_stream));
@@ -327,6 +417,9 @@ __global__ void k_snapshot(const unsigned long long *__restrict__ sketch, const 
 __global__ void k_merge_hist(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int32_t D);
 __global__ void k0_unpack(const uint32_t *__restrict__ packed, uint64_t n_words, uint4 *__restrict__ ascii);
 __global__ void k0_patch(const uint32_t *__restrict__ exc, uint64_t n, uint32_t shift, uint8_t *__restrict__ ascii);
+__global__ void k0_unpack_fed(const uint32_t *__restrict__ packed, uint64_t n_words, uint4 *__restrict__ ascii,
+                              const uint32_t *__restrict__ meta);
+__global__ void k0_patch_fed(const uint32_t *__restrict__ exc, const uint32_t *__restrict__ meta, uint8_t *__restrict__ ascii);
 
 static int create_impl(hulk_b200_ctx *ctx) {
     const hulk_b200_params &P = ctx->P;
@@ -347,7 +440,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < NSTAGE; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->ev_k1[i], cudaEventDisableTiming));
+        for (int q = 0; q < 2; q++) CU(cudaEventCreateWithFlags(&ctx->ev_k1x[i][q], cudaEventDisableTiming));
     }
     for (int i = 0; i < NBUF; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_k1_last[i], cudaEventDisableTiming));
@@ -382,6 +475,24 @@ static int create_impl(hulk_b200_ctx *ctx) {
     ctx->peer_arena[0] = ctx->arena;
     CU(dmalloc(&ctx->d_nmin, 1));
     CU(dmalloc(&ctx->d_errword, 1));
+    CU(dmalloc(&ctx->d_feed, NSTAGE * 4));
+    CU(cudaMemset(ctx->d_feed, 0, sizeof(uint32_t) * NSTAGE * 4));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_feed), sizeof(uint32_t) * NSTAGE * 4, cudaHostAllocDefault));
+    {
+        // stream memory operations of the driver API, reached through the runtime (no link-time dependency on libcuda):
+        // "wait until the word at this device address is >= v" / "write v there" as stream-ordered operations
+        cudaDriverEntryPointQueryResult q1, q2;
+        void *f1 = nullptr, *f2 = nullptr;
+        const char *off = getenv("HULK_B200_FEEDER");
+        if (!(off && *off == '0') &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &q1) == cudaSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &q2) == cudaSuccess &&
+            q1 == cudaDriverEntryPointSuccess && q2 == cudaDriverEntryPointSuccess && f1 && f2) {
+            ctx->cu_wait32 = reinterpret_cast<decltype(ctx->cu_wait32)>(f1);
+            ctx->cu_write32 = reinterpret_cast<decltype(ctx->cu_write32)>(f2);
+        }
+        cudaGetLastError();
+    }
     ctx->ovf_cap = 1u << 20;
     for (int i = 0; i < NBUF; i++) {
         CU(dmalloc(&ctx->d_ovf_count[i], 1));
@@ -510,6 +621,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         HULK_PRELOAD(k_merge_hist);
         HULK_PRELOAD(k0_unpack);
         HULK_PRELOAD(k0_patch);
+        HULK_PRELOAD(k0_unpack_fed);
+        HULK_PRELOAD(k0_patch_fed);
         HULK_PRELOAD(k1_generic<false>);
         HULK_PRELOAD(k1_generic<true>);
         HULK_PRELOAD((k1_jump_queue<2>));
@@ -700,6 +813,9 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     const uint64_t launches = ctx->st.n_kernel_launches;
     ctx->st = hulk_b200_stats{};
     ctx->st.n_kernel_launches = launches;
+    ctx->feed_h2d = 0;
+    ctx->feed_pack_ns = 0;
+    ctx->feed_batches = 0;
     ctx->extra_minimizers = 0;
     ctx->err.clear();
     return HULK_B200_OK;
@@ -1029,9 +1145,16 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     return HULK_B200_OK;
 }
 
+static int feed_drain(hulk_b200_ctx *ctx);
+// (Re)allocations free device memory, which waits for the whole device, under a lock the feeder thread's own CUDA calls
+// need: every one of them is preceded by feed_drain -- no kernel is then waiting for a batch the feeder still owes.
 static int ensure_stage(hulk_b200_ctx *ctx, int buf, uint64_t bytes, uint64_t n_off) {
+    if (bytes + 64 > ctx->stage_cap[buf] || n_off > ctx->off_cap[buf]) {
+        const int rcd = feed_drain(ctx);
+        if (rcd) return rcd;
+    }
     if (bytes + 64 > ctx->stage_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1[buf]));
+        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
         if (ctx->d_stage[buf]) cudaFree(ctx->d_stage[buf]);
         ctx->d_stage[buf] = nullptr;
         ctx->stage_cap[buf] = 0;
@@ -1040,7 +1163,7 @@ static int ensure_stage(hulk_b200_ctx *ctx, int buf, uint64_t bytes, uint64_t n_
         ctx->stage_cap[buf] = cap;
     }
     if (n_off > ctx->off_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1[buf]));
+        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
         if (ctx->d_off[buf]) cudaFree(ctx->d_off[buf]);
         ctx->d_off[buf] = nullptr;
         ctx->off_cap[buf] = 0;
@@ -1093,9 +1216,142 @@ __global__ void k0_patch(const uint32_t *__restrict__ exc, uint64_t n, uint32_t 
     if (t < n) ascii[exc[t] - shift] = (uint8_t)'N';
 }
 
+// the same two kernels for a batch the feeder thread delivers: whether it arrived packed (meta[1]) and how many
+// exceptions it has (meta[2]) is only known on the device by the time they run
+__global__ void k0_unpack_fed(const uint32_t *__restrict__ packed, uint64_t n_words, uint4 *__restrict__ ascii,
+                              const uint32_t *__restrict__ meta) {
+    if (meta[1] == 0u) return;                               // the batch travelled as ASCII: it is in place already
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_words) return;
+    const uint32_t x = packed[t];
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = (x >> (8 * q)) & 0xffu;
+        v = (v | (v << 4)) & 0x0F0Fu;
+        v = (v | (v << 2)) & 0x3333u;
+        o[q] = __byte_perm(0x54474341u, 0u, v);
+    }
+    ascii[t] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void k0_patch_fed(const uint32_t *__restrict__ exc, const uint32_t *__restrict__ meta, uint8_t *__restrict__ ascii) {
+    if (meta[1] == 0u) return;
+    const uint32_t n = meta[2];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) ascii[exc[t]] = (uint8_t)'N';
+}
+
+static uint64_t feed_exc_cap(uint64_t nb) { return std::max<uint64_t>(1024, nb / 32); }
+static const bool g_feed_debug = [] { const char *e = getenv("HULK_B200_FEED_DEBUG"); return e && *e == '1'; }();
+#define FEED_DBG(...) do { if (g_feed_debug) { fprintf(stderr, "[feed] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+
+// body of the feeder thread: pack -> copy -> publish the batch's sequence number, request by request
+static void feeder_main(hulk_b200_ctx *ctx) {
+    cudaSetDevice(ctx->P.device);
+    for (;;) {
+        hulk_b200_ctx::FeedReq rq;
+        auto tick = std::chrono::steady_clock::now();
+        auto lap = [&](std::atomic<uint64_t> &acc) {
+            const auto now = std::chrono::steady_clock::now();
+            acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(now - tick).count();
+            tick = now;
+        };
+        {
+            std::unique_lock<std::mutex> lk(ctx->feed_mu);
+            ctx->feed_cv.wait(lk, [&] { return ctx->feed_stop || !ctx->feed_q.empty(); });
+            if (ctx->feed_q.empty()) return;                  // stop requested and nothing left
+            rq = ctx->feed_q.front();
+            ctx->feed_q.pop_front();
+        }
+        lap(ctx->feed_t_idle);
+        int rc = HULK_B200_OK;
+        std::string msg;
+        auto cu = [&](cudaError_t e, const char *what) {
+            if (e != cudaSuccess && rc == HULK_B200_OK) {
+                rc = e == cudaErrorMemoryAllocation ? HULK_B200_ENOMEM : HULK_B200_ECUDA;
+                msg = std::string(hulk_b200_strerror(rc)) + ": feeder " + what + " -> " + cudaGetErrorString(e);
+            }
+        };
+        const int buf = rq.buf;
+        const uint64_t exc_cap = feed_exc_cap(rq.nb), packed_bytes = (rq.nb + 3) / 4;
+        FEED_DBG("feeder: request buf %d seq %u, %llu bases: waiting for the pinned buffer", buf, rq.seq, (unsigned long long)rq.nb);
+        cu(cudaEventSynchronize(ctx->ev_copy[buf]), "cudaEventSynchronize");      // the pinned buffers are free again
+        lap(ctx->feed_t_evsync);
+        FEED_DBG("feeder: packing");
+        // (the pinned buffers were sized by the calling thread before it posted the request: nothing in this loop may
+        // allocate -- an allocation can wait for the device, and the device may be waiting for this loop)
+        uint64_t n_exc = 0, moved = 0;
+        bool packed = false;
+        if (rc == HULK_B200_OK) {
+            const auto t0 = std::chrono::steady_clock::now();
+            const int prc = hulk_b200_pack_bases(rq.src, rq.nb, ctx->h_pack[buf], ctx->h_exc[buf], exc_cap, &n_exc,
+                                                 ctx->pack_threads);
+            ctx->feed_pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                     std::chrono::steady_clock::now() - t0).count();
+            if (prc) { rc = prc; msg = std::string(hulk_b200_strerror(prc)) + ": pack_bases"; }
+            packed = prc == HULK_B200_OK && n_exc <= exc_cap;
+        }
+        FEED_DBG("feeder: packed (rc %d, %llu exceptions), copying", rc, (unsigned long long)n_exc);
+        tick = std::chrono::steady_clock::now();
+        // the copy stream holds nothing but this thread's copies, in request order: each waits for the kernels that last
+        // read its stage buffer and for nothing else
+        cu(cudaStreamWaitEvent(ctx->copy_stream, rq.stage_free, 0), "cudaStreamWaitEvent");
+        if (rc == HULK_B200_OK) {
+            if (packed) {
+                cu(cudaMemcpyAsync(ctx->d_pack[buf], ctx->h_pack[buf], packed_bytes, cudaMemcpyHostToDevice, ctx->copy_stream),
+                   "cudaMemcpyAsync");
+                if (n_exc)
+                    cu(cudaMemcpyAsync(ctx->d_exc[buf], ctx->h_exc[buf], sizeof(uint32_t) * n_exc, cudaMemcpyHostToDevice,
+                                       ctx->copy_stream), "cudaMemcpyAsync");
+                moved = packed_bytes + sizeof(uint32_t) * n_exc;
+                ctx->feed_batches++;
+            } else {                                          // too many foreign bytes: the letters travel as they are
+                cu(cudaMemcpyAsync(ctx->d_stage[buf], rq.src, rq.nb, cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync");
+                moved = rq.nb;
+                n_exc = 0;
+            }
+            if (rq.offsets) {
+                cu(cudaMemcpyAsync(ctx->d_off[buf], rq.offsets, sizeof(uint64_t) * rq.n_off, cudaMemcpyHostToDevice,
+                                   ctx->copy_stream), "cudaMemcpyAsync");
+                moved += sizeof(uint64_t) * rq.n_off;
+            }
+        }
+        // mode and exception count, then the sequence number that releases the kernels waiting for this batch.
+        // The number is published whatever happened: a device stream must never be left waiting for it.
+        uint32_t *hm = ctx->h_feed + 4 * buf;
+        hm[1] = (rc == HULK_B200_OK && packed) ? 1u : 0u;
+        hm[2] = (uint32_t)n_exc;
+        cu(cudaMemcpyAsync(ctx->d_feed + 4 * buf + 1, hm + 1, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream),
+           "cudaMemcpyAsync");
+        const CUresult wr = ctx->cu_write32(reinterpret_cast<CUstream>(ctx->copy_stream),
+                                            reinterpret_cast<CUdeviceptr>(ctx->d_feed + 4 * buf), rq.seq, 0);
+        if (wr != CUDA_SUCCESS && rc == HULK_B200_OK) {
+            rc = HULK_B200_ECUDA;
+            msg = std::string(hulk_b200_strerror(rc)) + ": feeder cuStreamWriteValue32 failed";
+        }
+        cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream);
+        lap(ctx->feed_t_enq);
+        FEED_DBG("feeder: published seq %u for buf %d (rc %d)", rq.seq, buf, rc);
+        ctx->feed_h2d += moved;
+        {
+            std::lock_guard<std::mutex> lk(ctx->feed_mu);
+            ctx->feed_done++;
+            if (rc != HULK_B200_OK && ctx->feed_rc == HULK_B200_OK) {
+                ctx->feed_rc = rc;
+                ctx->feed_err = msg;
+            }
+        }
+        ctx->feed_cv.notify_all();
+    }
+}
+
 static int ensure_pack_stage(hulk_b200_ctx *ctx, int buf, uint64_t packed_bytes, uint64_t n_exc, bool host_side) {
+    if (packed_bytes + 16 > ctx->d_pack_cap[buf] || n_exc > ctx->d_exc_cap[buf] ||
+        (host_side && (packed_bytes > ctx->h_pack_cap[buf] || n_exc > ctx->h_exc_cap[buf]))) {
+        const int rcd = feed_drain(ctx);
+        if (rcd) return rcd;
+    }
     if (packed_bytes + 16 > ctx->d_pack_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1[buf]));
+        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
         if (ctx->d_pack[buf]) cudaFree(ctx->d_pack[buf]);
         ctx->d_pack[buf] = nullptr;
         ctx->d_pack_cap[buf] = 0;
@@ -1104,7 +1360,7 @@ static int ensure_pack_stage(hulk_b200_ctx *ctx, int buf, uint64_t packed_bytes,
         ctx->d_pack_cap[buf] = cap;
     }
     if (n_exc > ctx->d_exc_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1[buf]));
+        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
         if (ctx->d_exc[buf]) cudaFree(ctx->d_exc[buf]);
         ctx->d_exc[buf] = nullptr;
         ctx->d_exc_cap[buf] = 0;
@@ -1197,6 +1453,71 @@ static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
             n_exc = (uint64_t)(e1 - e0);
             rc = ensure_pack_stage(ctx, buf, packed_bytes, n_exc, false);
             if (rc) return rc;
+        } else if (ctx->pack_threads != 0 && nb >= 4096 && (ctx->P.flags & HULK_B200_F_ASYNC_INPUT) && ctx->cu_wait32) {
+            // ---- the feeder thread packs and copies; this thread only enqueues the consumers behind the batch's number
+            if (!ctx->feeder.joinable()) ctx->feeder = std::thread(feeder_main, ctx);
+            FEED_DBG("push: buf %d, %llu bases", buf, (unsigned long long)nb);
+            HostLap hl;
+            {
+                // never more than NSTAGE - 1 requests ahead of the feeder: the wait enqueued on the copy stream below
+                // (for the kernels that last used this stage buffer) must find that batch's copy already enqueued
+                const auto tb = std::chrono::steady_clock::now();
+                std::unique_lock<std::mutex> lk(ctx->feed_mu);
+                ctx->feed_cv.wait(lk, [&] { return ctx->feed_posted - ctx->feed_done <= (uint64_t)(NSTAGE - 1); });
+                ctx->feed_t_backpressure += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                                std::chrono::steady_clock::now() - tb).count();
+                if (ctx->feed_rc) {
+                    const int frc = ctx->feed_rc;
+                    ctx->err = ctx->feed_err;
+                    ctx->feed_rc = 0;
+                    return frc;
+                }
+            }
+            // the feeder is done with this stage buffer's previous batch (4 requests back): size its device and pinned
+            // buffers here, before anything of this batch is enqueued
+            hl.lap(0);
+            rc = ensure_pack_stage(ctx, buf, (nb + 3) / 4, feed_exc_cap(nb), true);
+            if (rc) return rc;
+            hl.lap(1);
+            const uint32_t seq = ++ctx->feed_seq[buf];
+            {
+                std::lock_guard<std::mutex> lk(ctx->feed_mu);
+                ctx->feed_q.push_back(hulk_b200_ctx::FeedReq{hb.bases + b0, nb, offsets ? offsets + done : nullptr,
+                                                             offsets ? nr + 1 : 0, buf, seq, ctx->ev_k1_prev(buf)});
+                ctx->feed_posted++;
+            }
+            ctx->feed_cv.notify_all();
+            hl.lap(2);
+            const int hs = ctx->cur_hist;
+            cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
+            if (ctx->cu_wait32(reinterpret_cast<CUstream>(ks), reinterpret_cast<CUdeviceptr>(ctx->d_feed + 4 * buf), seq,
+                               CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail(ctx, HULK_B200_ECUDA, "cuStreamWaitValue32");
+            hl.lap(3);
+            { const int rcw = before_first_k1(ctx, hs, ks); if (rcw) return rcw; }
+            hl.lap(4);
+            const uint64_t words = (nb + 15) / 16;
+            k0_unpack_fed<<<(unsigned)((words + 255) / 256), 256, 0, ks>>>(reinterpret_cast<const uint32_t *>(ctx->d_pack[buf]),
+                                                                            words, reinterpret_cast<uint4 *>(ctx->d_stage[buf]),
+                                                                            ctx->d_feed + 4 * buf);
+            LAUNCH_CHECK("k0_unpack");
+            k0_patch_fed<<<32, 256, 0, ks>>>(ctx->d_exc[buf], ctx->d_feed + 4 * buf, ctx->d_stage[buf]);
+            LAUNCH_CHECK("k0_patch");
+            FEED_DBG("push: wait + unpack enqueued for seq %u", seq);
+            hl.lap(5);
+            rc = launch_k1<false>(ctx, hs, ks, ctx->d_stage[buf], (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr,
+                                  b0, fixed_len, nr, nb, nullptr, 0, nullptr);
+            if (rc) return rc;
+            hl.lap(6);
+            CU(ctx->ev_k1_record(buf, ks));
+            CU(cudaEventRecord(ctx->ev_k1_last[hs], ks));
+            hl.lap(7);
+            ctx->k1_pending[hs] = true;
+            ctx->st.n_reads += nr;
+            ctx->st.n_bases += nb;
+            ctx->cur_buf = (ctx->cur_buf + 1) % NSTAGE;
+            done = upto;
+            continue;
         } else if (ctx->pack_threads != 0 && nb >= 4096) {
             const uint64_t exc_cap = std::max<uint64_t>(1024, nb / 32);
             packed_bytes = (nb + 3) / 4;
@@ -1219,7 +1540,10 @@ static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
             }
         }
 
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k1[buf], 0));
+        // (a batch handled on this thread while the feeder still owes copies: let it catch up first, so that the
+        // wait below never lands on the copy stream in front of a copy the awaited kernels depend on)
+        { const int rcd = feed_drain(ctx); if (rcd) return rcd; }
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k1_prev(buf), 0));
         uint64_t moved = 0;
         if (src_packed) {
             CU(cudaMemcpyAsync(ctx->d_pack[buf], src_packed, packed_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -1253,7 +1577,7 @@ static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
         rc = launch_k1<false>(ctx, hs, ks, ctx->d_stage[buf] + skip, (nb + 15) & ~15ull, offsets ? ctx->d_off[buf] : nullptr,
                               b0, fixed_len, nr, nb, nullptr, 0, nullptr);
         if (rc) return rc;
-        CU(cudaEventRecord(ctx->ev_k1[buf], ks));
+        CU(ctx->ev_k1_record(buf, ks));
         CU(cudaEventRecord(ctx->ev_k1_last[hs], ks));
         ctx->k1_pending[hs] = true;
         ctx->st.n_reads += nr;
@@ -1314,7 +1638,10 @@ int hulk_b200_push_reads_fixed(hulk_b200_ctx *ctx, const uint8_t *bases, uint64_
     hb.bases = bases;
     hb.n_reads = n_reads;
     hb.fixed_len = read_len;
-    return push_host(ctx, hb);
+    HostLap hl;
+    const int rc = push_host(ctx, hb);
+    hl.lap(10);
+    return rc;
 }
 
 int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
@@ -1360,6 +1687,7 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
 int hulk_b200_sync_inputs(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
+    { const int rc = feed_drain(ctx); if (rc) return rc; }
     CU(cudaStreamSynchronize(ctx->copy_stream));
     return HULK_B200_OK;
 }
@@ -1367,10 +1695,18 @@ int hulk_b200_sync_inputs(hulk_b200_ctx *ctx) {
 // ------------------------------------------------------------------------------------------
 // stage 3
 // ------------------------------------------------------------------------------------------
+static int flush_impl(hulk_b200_ctx *ctx);
 int hulk_b200_flush(hulk_b200_ctx *ctx) {
+    HostLap hl;
+    const int rc = flush_impl(ctx);
+    hl.lap(8);
+    return rc;
+}
+static int flush_impl(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     if (ctx->gen_pending) {
         CU(cudaSetDevice(ctx->P.device));
+        { const int rcd = feed_drain(ctx); if (rcd) return rcd; }     // the upload allocates
         const int rc = finish_async_tables(ctx);
         if (rc) return rc;
     }
@@ -1549,7 +1885,14 @@ static bool device_can_write(const void *p) {
     return a.type == cudaMemoryTypeHost && a.devicePointer == p;
 }
 
+static int snapshot_impl(hulk_b200_ctx *ctx, uint64_t *mins, double *weights);
 int hulk_b200_snapshot_async(hulk_b200_ctx *ctx, uint64_t *mins, double *weights) {
+    HostLap hl;
+    const int rc = snapshot_impl(ctx, mins, weights);
+    hl.lap(9);
+    return rc;
+}
+static int snapshot_impl(hulk_b200_ctx *ctx, uint64_t *mins, double *weights) {
     if (!ctx) return HULK_B200_EARG;
     if (!ctx->rows) return HULK_B200_OK;
     if (!mins || !weights) return fail(ctx, HULK_B200_EARG, "mins/weights is NULL");
@@ -1581,6 +1924,9 @@ int hulk_b200_get_stats(hulk_b200_ctx *ctx, hulk_b200_stats *out) {
     ctx->st.n_adds = ctl.n_adds;
     ctx->st.n_rescans = ctl.n_rescans;
     *out = ctx->st;
+    out->h2d_bytes += ctx->feed_h2d.load();
+    out->pack_ns += ctx->feed_pack_ns.load();
+    out->n_packed_batches += ctx->feed_batches.load();
     return HULK_B200_OK;
 }
 

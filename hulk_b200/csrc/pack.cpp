@@ -20,6 +20,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -45,6 +46,10 @@ const Nt4Table kNt4;
 
 // One piece of the batch: bases [b0, b1) -> packed bytes [b0/4, ceil(b1/4)); b0 is a multiple of 64.
 // Exceptions (code 4) are appended to `exc` as positions relative to the batch.
+// The input streams from DRAM once; the hardware prefetchers stop at every 4 KiB page, so the loops ask for the line
+// this far ahead themselves (a prefetch never faults: running past the end of the batch is harmless).
+static const size_t kPrefetchAhead = []{ const char *e = getenv("HULK_B200_PACK_PREFETCH"); return e ? (size_t)atol(e) : (size_t)2048; }();
+
 typedef void (*PieceFn)(const uint8_t *bases, uint64_t b0, uint64_t b1, uint8_t *packed, std::vector<uint32_t> &exc);
 
 void piece_scalar(const uint8_t *bases, uint64_t b0, uint64_t b1, uint8_t *packed, std::vector<uint32_t> &exc) {
@@ -81,6 +86,7 @@ __attribute__((target("avx2"))) void piece_avx2(const uint8_t *bases, uint64_t b
                                             0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
     uint64_t i = b0;
     for (; i + 32 <= b1; i += 32) {
+        if ((i & 32) == 0) _mm_prefetch(reinterpret_cast<const char *>(bases + i + kPrefetchAhead), _MM_HINT_T0);
         const __m256i w = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(bases + i));
         const __m256i v = _mm256_and_si256(_mm256_xor_si256(_mm256_srli_epi16(w, 1), _mm256_srli_epi16(w, 2)), m03);
         const __m256i up = _mm256_and_si256(w, mDF);
@@ -112,6 +118,7 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) void piece_avx512(const uin
     const __m512i w14 = _mm512_set1_epi16(0x0401), w116 = _mm512_set1_epi32(0x00100001);
     uint64_t i = b0;
     for (; i + 64 <= b1; i += 64) {
+        _mm_prefetch(reinterpret_cast<const char *>(bases + i + kPrefetchAhead), _MM_HINT_T0);
         const __m512i w = _mm512_loadu_si512(bases + i);
         const __m512i v = _mm512_and_si512(_mm512_xor_si512(_mm512_srli_epi16(w, 1), _mm512_srli_epi16(w, 2)), m03);
         const __m512i up = _mm512_and_si512(w, mDF);
@@ -160,14 +167,16 @@ struct Job {
 
 struct Pool {
     std::mutex job_mu;                      // one pack call at a time
-    std::mutex mu;
+    std::mutex mu;                          // guards `job` and the sleepers
     std::condition_variable cv;
     std::vector<std::thread> workers;
     std::atomic<uint64_t> gen{0};           // bumped when a job is posted
     std::atomic<int> want{0};               // workers that should take part in the current job
     std::atomic<bool> stop{false};
-    std::atomic<Job *> job{nullptr};
-    std::atomic<int> inside{0};             // workers currently holding `job`
+    // The job is shared: a worker that wakes up late (or is descheduled between waking and looking) still holds a valid
+    // object, finds no piece left and goes back to waiting -- the caller never waits for anyone but the threads that
+    // actually took a piece.
+    std::shared_ptr<Job> job;
 
     static void run_pieces(Job *j) {
         for (;;) {
@@ -181,7 +190,7 @@ struct Pool {
     void worker(int id) {
         uint64_t seen = 0;
         for (;;) {
-            // wait for a new generation: spin first, then sleep
+            // wait for a new generation: spin first (a pipelined caller is back within ~0.1 ms), then sleep
             int spins = 0;
             while (gen.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
                 if (++spins < 20000) {
@@ -192,11 +201,13 @@ struct Pool {
                 }
             }
             if (stop.load(std::memory_order_relaxed)) return;
-            seen = gen.load(std::memory_order_acquire);
-            inside.fetch_add(1);                                     // seq_cst: pairs with the caller's job = nullptr; inside == 0
-            Job *j = job.load();
-            if (j && id < want.load(std::memory_order_relaxed) && gen.load(std::memory_order_acquire) == seen) run_pieces(j);
-            inside.fetch_sub(1);
+            std::shared_ptr<Job> j;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                seen = gen.load(std::memory_order_acquire);
+                j = job;
+            }
+            if (j && id < want.load(std::memory_order_relaxed)) run_pieces(j.get());
         }
     }
     void ensure(int n) {                    // at least n workers (called under job_mu)
@@ -230,6 +241,9 @@ int default_threads() {
 #endif
     if (!hc) hc = std::thread::hardware_concurrency();
     if (!hc) hc = 4;
+    // two CPUs stay free for the thread that issues the GPU work and whatever else the process runs: a packer that is
+    // descheduled in the middle of a piece holds the whole batch up for a scheduler quantum
+    if (hc > 3) hc -= 2;
     return (int)std::min(hc, 32u);
 }
 
@@ -248,7 +262,8 @@ int hulk_b200_pack_bases(const uint8_t *bases, uint64_t n_bases, uint8_t *packed
     const PieceFn fn = pick_piece_fn();
     Pool &P = pool();
     std::lock_guard<std::mutex> guard(P.job_mu);
-    Job j;
+    std::shared_ptr<Job> jp = std::make_shared<Job>();
+    Job &j = *jp;
     j.bases = bases;
     j.n_bases = n_bases;
     j.packed = packed;
@@ -259,10 +274,10 @@ int hulk_b200_pack_bases(const uint8_t *bases, uint64_t n_bases, uint8_t *packed
     threads = (int)std::min<uint64_t>((uint64_t)threads, j.n_pieces);
     if (threads > 1) {
         P.ensure(threads - 1);
-        P.job.store(&j);
         P.want.store(threads - 1, std::memory_order_relaxed);
         {
             std::lock_guard<std::mutex> lk(P.mu);
+            P.job = jp;
             P.gen.fetch_add(1, std::memory_order_release);
         }
         P.cv.notify_all();
@@ -270,14 +285,8 @@ int hulk_b200_pack_bases(const uint8_t *bases, uint64_t n_bases, uint8_t *packed
     Pool::run_pieces(&j);
     while (j.done.load(std::memory_order_acquire) < j.n_pieces) _mm_pause();
     if (threads > 1) {
-        // no worker may still hold a pointer to this stack frame's job
-        {
-            std::lock_guard<std::mutex> lk(P.mu);
-            P.job.store(nullptr);
-            P.gen.fetch_add(1, std::memory_order_release);
-        }
-        P.cv.notify_all();
-        while (P.inside.load() != 0) _mm_pause();
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.job.reset();
     }
     uint64_t n = 0;
     for (auto &v : j.exc) {

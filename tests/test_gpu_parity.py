@@ -254,6 +254,57 @@ def test_packed_transport_gives_the_same_spectrum(hb, oracle):
         assert hs.stats()["h2d_bytes"] >= jb.size
 
 
+def test_feeder_thread_delivers_the_same_batches(hb, oracle):
+    """HULK_B200_F_ASYNC_INPUT + HULK_B200_F_PACK_INPUT: a second host thread packs and copies each pushed batch while the
+    caller already enqueues its kernels (they wait on the device for the batch's sequence number).  Many batches in a
+    row -- more than the staging ring holds -- with flushes in between, ragged and fixed-length, a batch of mostly
+    foreign bytes (the feeder ships it as ASCII) and tiny batches (handled by the calling thread) mixed in."""
+    k, w, s = 21, 9, 16
+    D = k ** 4
+    r, c, b = _tables(s, D, 77)
+    rng = np.random.default_rng(12)
+    batches = []
+    for i in range(14):
+        if i % 5 == 3:
+            reads = [bytes(rng.integers(0, 256, 140, dtype=np.uint8)) for _ in range(1500)]      # junk
+        elif i % 5 == 4:
+            reads = random_reads(20, 60, seed=100 + i)                                             # tiny: < 4096 bases
+        else:
+            reads = random_reads(4000, 100, seed=100 + i, n_frac=0.005, lower_frac=0.1, ragged=80)
+        batches.append(oracle.pack_reads(reads))
+    fixed = hb.synthetic_reads(30000, 150, seed=3)
+    fixed[::41, 9] = ord("N")
+    ref = oracle.HistoSketch(k, s, D, 1.0, r, c, b)
+    hist = np.zeros(D)
+    n_min = 0
+    with hb.HistoSketch(k, w, s, 1.0, tables=(r, c, b), async_input=True, pack_input=True) as hs:
+        keep = []
+        for i, (bases, offs) in enumerate(batches):
+            hs.add_reads(bases, offs)
+            keep.append((bases, offs))
+            h, nm = oracle.count_reads(k, w, D, bases, offs)
+            hist += h
+            n_min += nm
+            if i % 4 == 3:
+                hs.flush()
+                ref.flush(hist)
+                hist = np.zeros(D)
+        hs.add_reads_fixed(fixed.reshape(-1), 30000, 150)
+        h, nm = oracle.count_reads(k, w, D, fixed.reshape(-1), np.arange(30001, dtype=np.uint64) * np.uint64(150))
+        hist += h
+        n_min += nm
+        np.testing.assert_array_equal(hs.histogram(), hist.astype(np.uint32))
+        hs.flush()
+        ref.flush(hist)
+        mins, weights = hs.finish()
+        st = hs.stats()
+    mins_ref, weights_ref = ref.get()
+    np.testing.assert_array_equal(mins, mins_ref)
+    np.testing.assert_allclose(weights, weights_ref, rtol=W_RTOL, atol=0)
+    assert st["n_minimizers"] == n_min
+    assert st["n_packed_batches"] >= 9
+
+
 def test_device_resident_input_equals_host_input(hb):
     import torch
     n, L = 30000, 150
