@@ -475,6 +475,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
     ctx->peer_arena[0] = ctx->arena;
     CU(dmalloc(&ctx->d_nmin, 1));
     CU(dmalloc(&ctx->d_errword, 1));
+    CU(dmalloc(&ctx->d_ticket, 1));
+    CU(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
     CU(dmalloc(&ctx->d_feed, NSTAGE * 4));
     CU(cudaMemset(ctx->d_feed, 0, sizeof(uint32_t) * NSTAGE * 4));
     CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_feed), sizeof(uint32_t) * NSTAGE * 4, cudaHostAllocDefault));
@@ -612,7 +614,6 @@ static int create_impl(hulk_b200_ctx *ctx) {
         HULK_PRELOAD(k_peer_wait);
         HULK_PRELOAD(k2_mask_count_peers);
         HULK_PRELOAD(k2_mask_count);
-        HULK_PRELOAD(k2_flush_decide);
         HULK_PRELOAD(k2_cms_update);
         HULK_PRELOAD(k2_finalize);
         HULK_PRELOAD(k3_resolve);
@@ -1149,26 +1150,28 @@ static int feed_drain(hulk_b200_ctx *ctx);
 // (Re)allocations free device memory, which waits for the whole device, under a lock the feeder thread's own CUDA calls
 // need: every one of them is preceded by feed_drain -- no kernel is then waiting for a batch the feeder still owes.
 static int ensure_stage(hulk_b200_ctx *ctx, int buf, uint64_t bytes, uint64_t n_off) {
-    if (bytes + 64 > ctx->stage_cap[buf] || n_off > ctx->off_cap[buf]) {
-        const int rcd = feed_drain(ctx);
-        if (rcd) return rcd;
-    }
-    if (bytes + 64 > ctx->stage_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
-        if (ctx->d_stage[buf]) cudaFree(ctx->d_stage[buf]);
-        ctx->d_stage[buf] = nullptr;
-        ctx->stage_cap[buf] = 0;
-        const uint64_t cap = ((bytes + 64 + 4095) & ~4095ull);
-        CU(dmalloc(&ctx->d_stage[buf], cap));
-        ctx->stage_cap[buf] = cap;
-    }
-    if (n_off > ctx->off_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
-        if (ctx->d_off[buf]) cudaFree(ctx->d_off[buf]);
-        ctx->d_off[buf] = nullptr;
-        ctx->off_cap[buf] = 0;
-        CU(dmalloc(&ctx->d_off[buf], n_off));
-        ctx->off_cap[buf] = n_off;
+    if (bytes + 64 <= ctx->stage_cap[buf] && n_off <= ctx->off_cap[buf]) return HULK_B200_OK;
+    { const int rcd = feed_drain(ctx); if (rcd) return rcd; }
+    // the next batches will be as large: grow EVERY stage buffer now -- an allocation belongs in front of the pipeline,
+    // not inside its first few steps
+    for (int i = 0; i < NSTAGE; i++) {
+        if (bytes + 64 > ctx->stage_cap[i]) {
+            CU(cudaEventSynchronize(ctx->ev_k1_prev(i)));
+            if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+            ctx->d_stage[i] = nullptr;
+            ctx->stage_cap[i] = 0;
+            const uint64_t cap = ((bytes + 64 + 4095) & ~4095ull);
+            CU(dmalloc(&ctx->d_stage[i], cap));
+            ctx->stage_cap[i] = cap;
+        }
+        if (n_off > ctx->off_cap[i]) {
+            CU(cudaEventSynchronize(ctx->ev_k1_prev(i)));
+            if (ctx->d_off[i]) cudaFree(ctx->d_off[i]);
+            ctx->d_off[i] = nullptr;
+            ctx->off_cap[i] = 0;
+            CU(dmalloc(&ctx->d_off[i], n_off));
+            ctx->off_cap[i] = n_off;
+        }
     }
     return HULK_B200_OK;
 }
@@ -1345,46 +1348,46 @@ static void feeder_main(hulk_b200_ctx *ctx) {
 }
 
 static int ensure_pack_stage(hulk_b200_ctx *ctx, int buf, uint64_t packed_bytes, uint64_t n_exc, bool host_side) {
-    if (packed_bytes + 16 > ctx->d_pack_cap[buf] || n_exc > ctx->d_exc_cap[buf] ||
-        (host_side && (packed_bytes > ctx->h_pack_cap[buf] || n_exc > ctx->h_exc_cap[buf]))) {
-        const int rcd = feed_drain(ctx);
-        if (rcd) return rcd;
-    }
-    if (packed_bytes + 16 > ctx->d_pack_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
-        if (ctx->d_pack[buf]) cudaFree(ctx->d_pack[buf]);
-        ctx->d_pack[buf] = nullptr;
-        ctx->d_pack_cap[buf] = 0;
-        const uint64_t cap = (packed_bytes + 16 + 4095) & ~4095ull;
-        CU(dmalloc(&ctx->d_pack[buf], cap));
-        ctx->d_pack_cap[buf] = cap;
-    }
-    if (n_exc > ctx->d_exc_cap[buf]) {
-        CU(cudaEventSynchronize(ctx->ev_k1_prev(buf)));
-        if (ctx->d_exc[buf]) cudaFree(ctx->d_exc[buf]);
-        ctx->d_exc[buf] = nullptr;
-        ctx->d_exc_cap[buf] = 0;
-        const uint64_t cap = std::max<uint64_t>(1024, n_exc);
-        CU(dmalloc(&ctx->d_exc[buf], cap));
-        ctx->d_exc_cap[buf] = cap;
-    }
-    if (host_side) {
-        if (packed_bytes > ctx->h_pack_cap[buf]) {
-            CU(cudaEventSynchronize(ctx->ev_copy[buf]));
-            if (ctx->h_pack[buf]) cudaFreeHost(ctx->h_pack[buf]);
-            ctx->h_pack[buf] = nullptr;
-            ctx->h_pack_cap[buf] = 0;
-            const uint64_t cap = (packed_bytes + 4095) & ~4095ull;
-            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pack[buf]), cap, cudaHostAllocDefault));
-            ctx->h_pack_cap[buf] = cap;
+    if (!(packed_bytes + 16 > ctx->d_pack_cap[buf] || n_exc > ctx->d_exc_cap[buf] ||
+          (host_side && (packed_bytes > ctx->h_pack_cap[buf] || n_exc > ctx->h_exc_cap[buf]))))
+        return HULK_B200_OK;
+    { const int rcd = feed_drain(ctx); if (rcd) return rcd; }
+    for (int i = 0; i < NSTAGE; i++) {             // every stage buffer at once, like ensure_stage
+        if (packed_bytes + 16 > ctx->d_pack_cap[i]) {
+            CU(cudaEventSynchronize(ctx->ev_k1_prev(i)));
+            if (ctx->d_pack[i]) cudaFree(ctx->d_pack[i]);
+            ctx->d_pack[i] = nullptr;
+            ctx->d_pack_cap[i] = 0;
+            const uint64_t cap = (packed_bytes + 16 + 4095) & ~4095ull;
+            CU(dmalloc(&ctx->d_pack[i], cap));
+            ctx->d_pack_cap[i] = cap;
         }
-        if (n_exc > ctx->h_exc_cap[buf]) {
-            CU(cudaEventSynchronize(ctx->ev_copy[buf]));
-            if (ctx->h_exc[buf]) cudaFreeHost(ctx->h_exc[buf]);
-            ctx->h_exc[buf] = nullptr;
-            ctx->h_exc_cap[buf] = 0;
-            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_exc[buf]), n_exc * sizeof(uint32_t), cudaHostAllocDefault));
-            ctx->h_exc_cap[buf] = n_exc;
+        if (n_exc > ctx->d_exc_cap[i]) {
+            CU(cudaEventSynchronize(ctx->ev_k1_prev(i)));
+            if (ctx->d_exc[i]) cudaFree(ctx->d_exc[i]);
+            ctx->d_exc[i] = nullptr;
+            ctx->d_exc_cap[i] = 0;
+            const uint64_t cap = std::max<uint64_t>(1024, n_exc);
+            CU(dmalloc(&ctx->d_exc[i], cap));
+            ctx->d_exc_cap[i] = cap;
+        }
+        if (!host_side) continue;
+        if (packed_bytes > ctx->h_pack_cap[i]) {
+            CU(cudaEventSynchronize(ctx->ev_copy[i]));
+            if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
+            ctx->h_pack[i] = nullptr;
+            ctx->h_pack_cap[i] = 0;
+            const uint64_t cap = (packed_bytes + 4095) & ~4095ull;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pack[i]), cap, cudaHostAllocDefault));
+            ctx->h_pack_cap[i] = cap;
+        }
+        if (n_exc > ctx->h_exc_cap[i]) {
+            CU(cudaEventSynchronize(ctx->ev_copy[i]));
+            if (ctx->h_exc[i]) cudaFreeHost(ctx->h_exc[i]);
+            ctx->h_exc[i] = nullptr;
+            ctx->h_exc_cap[i] = 0;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_exc[i]), n_exc * sizeof(uint32_t), cudaHostAllocDefault));
+            ctx->h_exc_cap[i] = n_exc;
         }
     }
     return HULK_B200_OK;
@@ -1739,7 +1742,6 @@ static int flush_impl(hulk_b200_ctx *ctx) {
     }
     if (ctx->k1_pending[hs]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k1_last[hs], 0));  // every read of the interval is counted
     if (ctx->k3_pending[fi]) CU(cudaStreamWaitEvent(k2s, ctx->ev_k3_done[fi], 0));  // the sweep two flushes back read this f
-    CU(cudaMemsetAsync(&ctx->d_ctl->nnz[fi], 0, 4, k2s));
     {
     ProfScope prof_scope(ctx, 1, k2s);
     if (peers) {
@@ -1755,15 +1757,14 @@ static int flush_impl(hulk_b200_ctx *ctx) {
             done.flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_arena[p] + ctx->off_gathered) + (size_t)hs * PEER_MAX + ctx->rank;
         }
         k2_mask_count_peers<<<ctx->nblk, K2_MASK_TPB, 0, k2s>>>(src, D, hist, ctx->d_words, ctx->d_word_prefix,
-                                                         ctx->d_block_count, fbits, ctx->d_ctl, fi, done, ctx->d_ticket);
+                                                         ctx->d_block_count, fbits, ctx->d_ctl, fi, done, ctx->d_ticket,
+                                                         ctx->d_block_prefix);
         ctx->peer_dirty[hs] = seq;
     } else {
         k2_mask_count<<<ctx->nblk, K2_MASK_TPB, 0, k2s>>>(hist, D, ctx->d_words, ctx->d_word_prefix, ctx->d_block_count, fbits,
-                                                   ctx->d_ctl, fi);
+                                                   ctx->d_ctl, fi, ctx->d_block_prefix, ctx->d_ticket);
     }
     LAUNCH_CHECK("k2_mask_count");
-    k2_flush_decide<<<1, 256, 0, k2s>>>(ctx->d_block_count, ctx->nblk, ctx->d_block_prefix, D, ctx->d_ctl, fi);
-    LAUNCH_CHECK("k2_flush_decide");
     k2_cms_update<<<(CMS_CELLS * 32 + 255) / 256, 256, 0, k2s>>>(hist, ctx->d_csr_start, ctx->d_csr_bins,
                                                                  ctx->d_words, ctx->d_word_prefix, ctx->d_block_prefix,
                                                                  ctx->d_q, fbits, ctx->d_ctl, fi,
@@ -1976,11 +1977,7 @@ int hulk_b200_add_minimizer_count(hulk_b200_ctx *ctx, uint64_t n) {
 // multi-GPU: peers
 // ------------------------------------------------------------------------------------------
 static int peer_finish_connect(hulk_b200_ctx *ctx, uint32_t world, uint32_t rank) {
-    if (!ctx->d_hist_sum) {
-        CU(dmalloc(&ctx->d_hist_sum, ctx->D));
-        CU(dmalloc(&ctx->d_ticket, 1));
-        CU(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
-    }
+    if (!ctx->d_hist_sum) CU(dmalloc(&ctx->d_hist_sum, ctx->D));
     ctx->world = world;
     ctx->rank = rank;
     return HULK_B200_OK;

@@ -114,48 +114,10 @@ __global__ void k2_sort_csr(const unsigned int *start, int32_t *csr_bins) {
 }
 
 // ---- per flush ----
-// (a) used-bin bitmap, per-32-bin and per-1024-bin used counts, reset of the estimate vector.
-// A block covers 1024 bins with 256 threads (every warp four 32-bin words): small blocks find room next to the counting
-// kernels of the next interval, which a 1024-thread block does not.
-constexpr int K2_MASK_TPB = 256;
-__global__ void __launch_bounds__(K2_MASK_TPB) k2_mask_count(const uint32_t *__restrict__ hist, int32_t D,
-                                                             uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
-                                                             uint32_t *__restrict__ block_count,
-                                                             unsigned long long *__restrict__ fbits, FlushCtl *ctl,
-                                                             const int fi) {
-    __shared__ uint32_t pc[32];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int wd = wid * 4 + j;                                     // word of the block
-        const int64_t i = (int64_t)blockIdx.x * 1024 + wd * 32 + lane;
-        const bool nz = (i < D) && (hist[i] != 0u);
-        if (i < D) fbits[i] = F_EMPTY_BITS;
-        const uint32_t word = __ballot_sync(0xffffffffu, nz);
-        if (lane == 0) {
-            words[(size_t)blockIdx.x * 32 + wd] = word;
-            pc[wd] = __popc(word);
-        }
-    }
-    __syncthreads();
-    if (wid == 0) {
-        const uint32_t v = pc[lane];
-        uint32_t s = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += u;
-        }
-        word_prefix[(size_t)blockIdx.x * 32 + lane] = s - v;   // used bins before this word, inside the block
-        if (lane == 31) {
-            block_count[blockIdx.x] = s;
-            if (s) atomicAdd(&ctl->nnz[fi], s);
-        }
-    }
-}
-// (b) single block: exclusive scan of the per-block counts + the flush decision
-__global__ void __launch_bounds__(256) k2_flush_decide(const uint32_t *__restrict__ block_count, uint32_t nblocks,
-                                                        uint32_t *__restrict__ block_prefix, int32_t D, FlushCtl *ctl,
-                                                        const int fi) {
+// (b) exclusive scan of the per-block counts + the flush decision.  Run by the LAST block of k2_mask_count[_peers] to
+// finish (a ticket counter decides who that is), so the bitmap, the ranks and the decision are one launch.
+__device__ __forceinline__ void k2_decide_tail(const uint32_t *block_count, uint32_t nblocks, uint32_t *__restrict__ block_prefix,
+                                               int32_t D, FlushCtl *ctl, const int fi) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -164,7 +126,7 @@ __global__ void __launch_bounds__(256) k2_flush_decide(const uint32_t *__restric
         if (threadIdx.x < 32) warp_tot[threadIdx.x] = 0;                  // blocks of fewer than 32 warps
         __syncthreads();
         const uint32_t i = base + threadIdx.x;
-        const uint32_t v = (i < nblocks) ? block_count[i] : 0;
+        const uint32_t v = (i < nblocks) ? __ldcg(block_count + i) : 0;   // written by other blocks: read at the L2
         uint32_t s = v;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
@@ -188,7 +150,8 @@ __global__ void __launch_bounds__(256) k2_flush_decide(const uint32_t *__restric
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const unsigned int nnz = ctl->nnz[fi];
+        const unsigned int nnz = carry;                                   // used bins of this flush
+        ctl->nnz[fi] = nnz;
         unsigned int go = 0;
         if (nnz != 0) {                                                   // boss.go:117
             const double prop = (double)nnz / (double)D;                  // kmerspectrum.go:92
@@ -206,7 +169,54 @@ __global__ void __launch_bounds__(256) k2_flush_decide(const uint32_t *__restric
         }
     }
 }
+// true in every thread of the block that finishes last (ticket returns to 0 for the next launch)
+__device__ __forceinline__ bool k2_last_block(unsigned int *ticket) {
+    __shared__ unsigned int last;
+    __threadfence();                                                      // this thread's results first ...
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;   // ... then the ticket
+    __syncthreads();
+    if (last && threadIdx.x == 0) *ticket = 0;
+    return last != 0u;
+}
 
+// (a) used-bin bitmap, per-32-bin and per-1024-bin used counts, reset of the estimate vector.
+// A block covers 1024 bins with 256 threads (every warp four 32-bin words): small blocks find room next to the counting
+// kernels of the next interval, which a 1024-thread block does not.
+constexpr int K2_MASK_TPB = 256;
+__global__ void __launch_bounds__(K2_MASK_TPB) k2_mask_count(const uint32_t *__restrict__ hist, int32_t D,
+                                                             uint32_t *__restrict__ words, uint32_t *__restrict__ word_prefix,
+                                                             uint32_t *__restrict__ block_count,
+                                                             unsigned long long *__restrict__ fbits, FlushCtl *ctl,
+                                                             const int fi, uint32_t *__restrict__ block_prefix,
+                                                             unsigned int *ticket) {
+    __shared__ uint32_t pc[32];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int wd = wid * 4 + j;                                     // word of the block
+        const int64_t i = (int64_t)blockIdx.x * 1024 + wd * 32 + lane;
+        const bool nz = (i < D) && (hist[i] != 0u);
+        if (i < D) fbits[i] = F_EMPTY_BITS;
+        const uint32_t word = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) {
+            words[(size_t)blockIdx.x * 32 + wd] = word;
+            pc[wd] = __popc(word);
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = pc[lane];
+        uint32_t s = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        word_prefix[(size_t)blockIdx.x * 32 + lane] = s - v;   // used bins before this word, inside the block
+        if (lane == 31) block_count[blockIdx.x] = s;
+    }
+    if (k2_last_block(ticket)) k2_decide_tail(block_count, gridDim.x, block_prefix, D, ctl, fi);
+}
 // ---- multi-GPU: the spectrum of a flush is the sum of every GPU's counting buffer --------
 // The GPUs of a node reach each other's memory over NVLink (peer access inside one process, CUDA IPC across processes),
 // so the all-reduce is not a collective call: every GPU reads the other buffers straight from their owners while it
@@ -256,7 +266,8 @@ __global__ void __launch_bounds__(K2_MASK_TPB) k2_mask_count_peers(const PeerSou
                                                                    uint32_t *__restrict__ word_prefix,
                                                                    uint32_t *__restrict__ block_count,
                                                                    unsigned long long *__restrict__ fbits, FlushCtl *ctl,
-                                                                   const int fi, const PeerTargets done, unsigned int *ticket) {
+                                                                   const int fi, const PeerTargets done, unsigned int *ticket,
+                                                                   uint32_t *__restrict__ block_prefix) {
     __shared__ uint32_t pc[32];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -284,23 +295,13 @@ __global__ void __launch_bounds__(K2_MASK_TPB) k2_mask_count_peers(const PeerSou
             if (lane >= o) s += u;
         }
         word_prefix[(size_t)blockIdx.x * 32 + lane] = s - v;
-        if (lane == 31) {
-            block_count[blockIdx.x] = s;
-            if (s) atomicAdd(&ctl->nnz[fi], s);
-        }
+        if (lane == 31) block_count[blockIdx.x] = s;
     }
-    // the last block to finish tells every owner that this GPU is done with its buffer
-    __shared__ unsigned int last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (last) {
-        if (threadIdx.x == 0) *ticket = 0;
+    // the last block to finish tells every owner that this GPU is done with its buffer, then takes the flush decision
+    if (k2_last_block(ticket)) {
         __threadfence_system();
         if (threadIdx.x < done.n) *reinterpret_cast<volatile uint32_t *>(done.flag[threadIdx.x]) = done.seq;
+        k2_decide_tail(block_count, gridDim.x, block_prefix, D, ctl, fi);
     }
 }
 
