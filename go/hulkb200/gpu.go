@@ -15,7 +15,9 @@ import "C"
 import (
 	"fmt"
 	"log"
+	"os"
 	"runtime"
+	"strconv"
 	"unsafe"
 
 	"github.com/will-rowe/hulk/src/helpers"
@@ -39,24 +41,32 @@ func (proc *GPUSketcher) Run() {
 	runtime.LockOSThread() // a context is single-caller (include/hulk_b200.h)
 	defer runtime.UnlockOSThread()
 	s := proc.info.Sketch
-	var ctx *C.hulk_b200_ctx
+	// One handle for 1..16 GPUs of this host (a group of one is the plain context): every interval's reads are split
+	// over the GPUs, the spectra are summed over NVLink inside the flush, the sketch slots are sharded.
+	// HULK_B200_F_PACK_INPUT: each batch crosses PCIe as 2 bits per base, packed by the library on this host's cores
+	// inside push_reads (the Go slices below are free for reuse as soon as the call returns).
+	ngpus := 1
+	if v, err := strconv.Atoi(os.Getenv("HULK_B200_GPUS")); err == nil && v > 0 {
+		ngpus = v
+	}
+	var g *C.hulk_b200_group
 	p := C.hulk_b200_params{k: C.uint32_t(s.KmerSize), w: C.uint32_t(s.WindowSize),
 		sketch_size: C.uint32_t(s.SketchSize), num_bins: C.int32_t(s.SpectrumSize),
-		decay_ratio: C.double(s.DecayRatio)}
+		decay_ratio: C.double(s.DecayRatio), flags: C.HULK_B200_F_PACK_INPUT}
 	check := func(rc C.int) {
 		if rc != 0 {
-			helpers.ErrorCheck(fmt.Errorf("%s", C.GoString(C.hulk_b200_last_error(ctx))))
+			helpers.ErrorCheck(fmt.Errorf("%s", C.GoString(C.hulk_b200_group_last_error(g))))
 		}
 	}
-	check(C.hulk_b200_create(&p, &ctx))
-	defer C.hulk_b200_destroy(ctx)
-	check(C.hulk_b200_generate_cws_tables_async(ctx)) // newCWS (histosketch.go:95-126), drawn on all cores while reads are counted
+	check(C.hulk_b200_group_create(&p, nil, C.uint32_t(ngpus), &g))
+	defer C.hulk_b200_group_destroy(g)
+	check(C.hulk_b200_group_generate_cws_tables(g, 1)) // newCWS (histosketch.go:95-126), drawn on all cores while reads are counted
 
 	bases := make([]byte, 0, batchBytes+1<<20)
 	offsets := []C.uint64_t{0}
 	push := func() {
 		if len(offsets) > 1 {
-			check(C.hulk_b200_push_reads(ctx, (*C.uint8_t)(unsafe.Pointer(&bases[0])),
+			check(C.hulk_b200_group_push_reads(g, (*C.uint8_t)(unsafe.Pointer(&bases[0])),
 				&offsets[0], C.uint64_t(len(offsets)-1)))
 			bases, offsets = bases[:0], offsets[:1]
 		}
@@ -74,22 +84,22 @@ func (proc *GPUSketcher) Run() {
 			push()
 			sketchingInterval++
 			log.Printf("\treached interval %d -> histosketching", sketchingInterval)
-			check(C.hulk_b200_flush(ctx))
+			check(C.hulk_b200_group_flush(g))
 		} else if len(bases) >= batchBytes {
 			push()
 		}
 	}
 	log.Printf("generating final histosketch of k-mer spectra...")
 	push()
-	check(C.hulk_b200_flush(ctx)) // sketch.go:221
+	check(C.hulk_b200_group_flush(g)) // sketch.go:221
 	if seqCount == 0 {
 		helpers.ErrorCheck(fmt.Errorf("no sequences received")) // sketch.go:237-239
 	}
 	mins := make([]C.uint64_t, s.SketchSize)
 	weights := make([]C.double, s.SketchSize)
-	check(C.hulk_b200_finish(ctx, &mins[0], &weights[0]))
+	check(C.hulk_b200_group_finish(g, &mins[0], &weights[0]))
 	var st C.hulk_b200_stats
-	check(C.hulk_b200_get_stats(ctx, &st))
+	check(C.hulk_b200_group_get_stats(g, &st))
 	log.Printf("\tprocessed %d sequences in total\n", seqCount)
 	log.Printf("\tmean sequence length: %d\n", uint(float64(st.n_bases)/float64(seqCount)))
 	log.Printf("\tfound %d minimizers\n", uint64(st.n_minimizers))
