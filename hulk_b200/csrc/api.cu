@@ -136,8 +136,6 @@ struct hulk_b200_ctx {
     bool k1_persistent = false;                // HULK_B200_K1_PERSISTENT=1: scan CTAs loop over tasks handed out by a counter (A/B)
     bool jump_smem = false;                    // HULK_B200_JUMP_SMEM=1: keys handed out through a shared-memory counter (A/B measurements)
     bool jump_fx = true;                       // HULK_B200_JUMP_FX=0: keep the bracketed jump step for every D (A/B measurements)
-    int jump_v = 1;                            // HULK_B200_JUMP_V=2: lane-private key queues + shared remainder (A/B measurements)
-    int jump_tail = 15;                        // HULK_B200_JUMP_TAIL=8|15|25: percent of a warp's segment handed out dynamically
     bool k1_v2 = true;                         // HULK_B200_K1_V2=0: keep the first-generation w = 9 scan (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
     unsigned long long *d_arena_cursor[NBUF] = {};
@@ -635,13 +633,6 @@ static int create_impl(hulk_b200_ctx *ctx) {
         HULK_PRELOAD((k1_jump_queue_fx<4, false>));
         HULK_PRELOAD((k1_jump_queue_fx<3, true>));
         HULK_PRELOAD((k1_jump_queue_fx<4, true>));
-        HULK_PRELOAD((k1_jump_queue_fx2<2, 15>));
-        HULK_PRELOAD((k1_jump_queue_fx2<3, 15>));
-        HULK_PRELOAD((k1_jump_queue_fx2<4, 15>));
-        HULK_PRELOAD((k1_jump_queue_fx2<3, 8>));
-        HULK_PRELOAD((k1_jump_queue_fx2<3, 25>));
-        HULK_PRELOAD((k1_jump_queue_fx2<4, 8>));
-        HULK_PRELOAD((k1_jump_queue_fx2<4, 25>));
 #undef HULK_PRELOAD
     }
     {
@@ -663,10 +654,6 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e == '1') ctx->jump_smem = true;
         e = getenv("HULK_B200_JUMP_FX");
         if (e && *e == '0') ctx->jump_fx = false;
-        e = getenv("HULK_B200_JUMP_V");
-        if (e && (*e == '1' || *e == '2')) ctx->jump_v = *e - '0';
-        e = getenv("HULK_B200_JUMP_TAIL");
-        if (e && (atoi(e) == 8 || atoi(e) == 15 || atoi(e) == 25)) ctx->jump_tail = atoi(e);
         e = getenv("HULK_B200_K1_FUSED");
         ctx->fused_jump = e && *e == '1';
         e = getenv("HULK_B200_K1_V2");
@@ -1138,16 +1125,7 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         LAUNCH_CHECK("k1_minimizer_histogram");
         if (use_queue) {
             const unsigned gridj = (unsigned)(ctx->sm_count * ctx->jump_ctas_per_sm);
-            if (ctx->jump_fx && (uint32_t)ctx->D <= JUMP_FX_MAX_BUCKETS && ctx->jump_v == 2) {
-                const int jb = ctx->jump_batch, jt = ctx->jump_tail;
-                if (jb == 2) k1_jump_queue_fx2<2, 15><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else if (jb == 3 && jt == 8) k1_jump_queue_fx2<3, 8><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else if (jb == 3 && jt == 25) k1_jump_queue_fx2<3, 25><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else if (jb == 3) k1_jump_queue_fx2<3, 15><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else if (jt == 8) k1_jump_queue_fx2<4, 8><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else if (jt == 25) k1_jump_queue_fx2<4, 25><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-                else k1_jump_queue_fx2<4, 15><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
-            } else if (ctx->jump_fx && (uint32_t)ctx->D <= JUMP_FX_MAX_BUCKETS) {          // every k^4-bin spectrum
+            if (ctx->jump_fx && (uint32_t)ctx->D <= JUMP_FX_MAX_BUCKETS) {          // every k^4-bin spectrum
                 if (ctx->jump_smem) {
                     if (ctx->jump_batch == 3) k1_jump_queue_fx<3, true><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
                     else k1_jump_queue_fx<4, true><<<gridj, K1_JUMP_TPB, 0, st>>>(p);

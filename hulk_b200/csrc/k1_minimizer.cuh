@@ -284,102 +284,6 @@ __device__ __forceinline__ void k1_jump_walk_fx(Load load, uint32_t *const next_
     }
 }
 
-// ---- third form of the walks: lane-private key queues, a shared remainder -----------------------------------
-// The hand-out above costs a ballot, two population counts and the index arithmetic per walk and refill point --
-// about a third of the kernel's instructions.  Here walk c of lane l owns keys seg_begin + 2 l + c + 64 n of the
-// warp's segment: a refill is a compare, a load and an add, private to the lane.  Walk lengths vary (13.2 +- 3.5
-// steps), so lanes would run dry at different times; the last part of the segment (from stat_end on) is therefore
-// still handed out by ballot, and only by warps in which some walk has no key waiting -- the balanced tail of the
-// dynamic scheme at the refill cost of the static one.
-template <int BATCH, class Load>
-__device__ __forceinline__ void k1_jump_walk_fx2(Load load, const uint32_t seg_begin, const uint32_t stat_end,
-                                                 const uint32_t total, uint32_t *const hist, const uint32_t nb) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lane_lt = (1u << lane) - 1u;
-    uint64_t key[2] = {0, 0}, spare[2] = {0, 0};
-    constexpr uint32_t NO_BIN = 0xFFFFFFFFu;
-    uint32_t bkt[2] = {NO_BIN, NO_BIN};
-    uint32_t idx[2] = {seg_begin + 2u * lane, seg_begin + 2u * lane + 1u};
-    bool busy[2] = {false, false}, have[2] = {false, false};
-    uint32_t g = stat_end;                                               // next key of the shared remainder (warp-uniform)
-    const double two52m1 = k1_jump_fx_consts[0], two83m = k1_jump_fx_consts[1], one = k1_jump_fx_consts[2];
-    const double ynb = k1_pin(JUMP_TWO32 + (double)nb);
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-        if (idx[c] < stat_end) {
-            spare[c] = load(idx[c]);
-            idx[c] += 64u;
-            have[c] = true;
-        }
-    }
-    for (;;) {
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            if (!busy[c]) {
-                if (bkt[c] != NO_BIN) atomicAdd(&hist[bkt[c]], 1u);      // its walk ended in the last batch
-                key[c] = spare[c];
-                bkt[c] = have[c] ? 0u : NO_BIN;                          // first step of jump.Hash: b = 0
-                busy[c] = have[c];
-                have[c] = false;
-                if (idx[c] < stat_end) {                                 // the lane's own next key, one refill point ahead
-                    spare[c] = load(idx[c]);
-                    idx[c] += 64u;
-                    have[c] = true;
-                }
-            }
-        }
-        if (g < total && __any_sync(0xffffffffu, !have[0] | !have[1])) { // someone ran dry: the shared remainder
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const uint32_t need = __ballot_sync(0xffffffffu, !have[c]);
-                const uint32_t mine = g + __popc(need & lane_lt);
-                g = min(g + (uint32_t)__popc(need), total);
-                if (!have[c] && mine < total) {
-                    spare[c] = load(mine);
-                    have[c] = true;
-                }
-            }
-        }
-        if (!__any_sync(0xffffffffu, busy[0] | busy[1] | have[0] | have[1])) break;
-#pragma unroll
-        for (int it = 0; it < BATCH; it++) {
-            uint32_t nbk[2];
-            bool fin[2], amb[2];
-#pragma unroll
-            for (int c = 0; c < 2; c++) {                                // evaluate: no side effects, the two walks interleave
-                key[c] = key[c] * 2862933555777941757ull + 1ull;
-                const double qd = dbl_make(0x43300000u, (uint32_t)(key[c] >> 33)) - two52m1;   // (double)q
-                const double jd1 = dbl_make(0x45200000u, bkt[c]) - two83m;                     // (b + 1) 2^31, exact
-                const double r0 = rcp_seed(qd);
-                const double e = fma(-qd, r0, one);
-                const double jr = jd1 * r0;
-                const double x = fma(jr, e, jr);                                               // ~ (b + 1) 2^31 / q
-                const double y = x + JUMP_TWO32;                                               // 2^32 + x
-                amb[c] = (uint32_t)(dbl_lo(y) * 4096u + 3u * 4096u) < 6u * 4096u;              // fraction in -3 .. 2 units of 2^-20
-                fin[c] = y >= ynb;
-                nbk[c] = __funnelshift_l(dbl_lo(y), dbl_hi(y), 12);                            // floor(x)
-            }
-            if ((amb[0] && busy[0]) || (amb[1] && busy[1])) {            // ~2^-17 per step: the true division
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    if (amb[c] && busy[c]) {
-                        uint32_t b = bkt[c];
-                        double j1;
-                        fin[c] = jump_step_exact(key[c], b, j1, nb) != 0;
-                        nbk[c] = b;
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 2; c++) {                                // commit
-                const bool adv = busy[c] && !fin[c];
-                bkt[c] = adv ? nbk[c] : bkt[c];
-                busy[c] = adv;
-            }
-        }
-    }
-}
-
 // ---- the part of a warp's work behind the scan: exact per-read sets, then jump-hash binning -------
 // wl: the warp's list block [list_cap][32] (entry e of lane l at wl[e * 32 + l]); n: this lane's number
 // of adjacent-distinct window minima (0 when the read is invalid or was queued for k1_generic).
@@ -847,21 +751,6 @@ __global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue_fx(const K1Params p
     }
     k1_jump_walk_fx<BATCH, SMEM>([&](uint32_t i) { return q[i]; }, &next_key[threadIdx.x >> 5], seg_begin, seg_end, p.hist,
                                  (uint32_t)p.D);
-}
-
-// the same with lane-private key queues and a shared remainder (k1_jump_walk_fx2): the last TAIL_PCT percent of every
-// warp's segment are handed out dynamically
-template <int BATCH, int TAIL_PCT>
-__global__ void __launch_bounds__(K1_JUMP_TPB) k1_jump_queue_fx2(const K1Params p) {
-    const unsigned long long filled = *p.queue_cursor;
-    const uint64_t total = filled < p.queue_cap ? filled : p.queue_cap;
-    const uint64_t nwarps = (uint64_t)gridDim.x * (K1_JUMP_TPB / 32);
-    const uint64_t gw = (uint64_t)blockIdx.x * (K1_JUMP_TPB / 32) + (threadIdx.x >> 5);
-    const uint32_t seg_begin = (uint32_t)(total * gw / nwarps), seg_end = (uint32_t)(total * (gw + 1) / nwarps);
-    const uint32_t len = seg_end - seg_begin;
-    const uint32_t stat_end = seg_begin + ((uint32_t)((uint64_t)len * (100 - TAIL_PCT) / 100) & ~63u);
-    const uint64_t *const q = p.queue;
-    k1_jump_walk_fx2<BATCH>([&](uint32_t i) { return q[i]; }, seg_begin, stat_end, seg_end, p.hist, (uint32_t)p.D);
 }
 
 // reciprocal self-test (parity tap): for q = q0 + i the seed's and the refined reciprocal's relative errors,
