@@ -540,14 +540,16 @@ def run_b200(a):
     e2e_ascii["transport"] = "ASCII bases, one byte each"
     # ... and the default host path: the same call packs the batch to 2 bits per base on the host's cores INSIDE the
     # timed region (hulk_b200_pack_bases) and ships a quarter of the bytes; the device unpacks (k0_unpack)
+    # host threads that pack: this rank's share of the CPUs it may run on, less two for the threads that issue the GPU work
     ncpu = len(os.sched_getaffinity(0))
-    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or max(1, min(32, ncpu - 2 if ncpu > 3 else ncpu))
-    if world > 1 and not affinity:
-        pack_threads = max(1, ncpu // world - 1)
+    share = max(1, min(ncpu, (os.cpu_count() or ncpu) // world))
+    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or max(1, min(32, share - 2 if share > 3 else share))
     hs.set_input_packing(pack_threads)
     e2e, mins_e2e = run_e2e("e2e")
-    e2e["transport"] = ("2 bits per base + positions of non-ACGTU bytes: packed from the host's ASCII buffer by %d host "
-                        "threads inside the timed region, unpacked on the device" % pack_threads)
+    e2e["transport"] = ("most of every batch as 2 bits per base (+ positions of non-ACGTU bytes), packed from the host's ASCII "
+                        "buffer by %d host threads inside the timed region and unpacked on the device, the rest as letters "
+                        "while the cores pack: the split follows the measured balance of cores and link, packed share = "
+                        "(15e6 - h2d bytes per rank and step) / 11.25e6" % pack_threads)
     e2e["pack_threads"] = pack_threads
     hs.set_input_packing(0)
     assert (mins_ascii == mins_e2e).all()

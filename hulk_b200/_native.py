@@ -30,6 +30,7 @@ EXPORTS = [
     "hulk_b200_group_push_reads", "hulk_b200_group_push_reads_fixed", "hulk_b200_group_sync_inputs",
     "hulk_b200_group_flush", "hulk_b200_group_sync", "hulk_b200_group_finish", "hulk_b200_group_reset",
     "hulk_b200_group_get_stats", "hulk_b200_group_sketch_reader",
+    "hulk_b200_generate_cws_tables_device", "hulk_b200_get_cws_tables", "hulk_b200_group_generate_cws_tables_device",
     "hulk_b200_packed_bytes", "hulk_b200_pack_bases", "hulk_b200_push_reads_packed", "hulk_b200_set_input_packing",
 ]
 PEER_HANDLE_BYTES = 64
@@ -153,6 +154,9 @@ def load():
         "hulk_b200_group_reset": (C.c_int, [vp]),
         "hulk_b200_group_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "hulk_b200_group_sketch_reader": (C.c_int, [vp, vp, u64, LOG_FN, vp]),
+        "hulk_b200_generate_cws_tables_device": (C.c_int, [vp]),
+        "hulk_b200_get_cws_tables": (C.c_int, [vp, vp, vp, vp]),
+        "hulk_b200_group_generate_cws_tables_device": (C.c_int, [vp]),
         "hulk_b200_packed_bytes": (u64, [u64]),
         "hulk_b200_pack_bases": (C.c_int, [vp, u64, vp, vp, u64, C.POINTER(u64), i32]),
         "hulk_b200_push_reads_packed": (C.c_int, [vp, vp, vp, u64, vp, u64, u32]),

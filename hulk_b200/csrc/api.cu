@@ -37,6 +37,7 @@
 #include "k1_minimizer.cuh"
 #include "k2_countmin.cuh"
 #include "k3_cws.cuh"
+#include "k4_cwsdraw.cuh"
 
 using namespace hulk;
 
@@ -116,6 +117,10 @@ struct hulk_b200_ctx {
     uint32_t feed_seq[NSTAGE] = {};            // uses of stage buffer b by the feeder path
     uint32_t *d_feed = nullptr;                // [NSTAGE][4]: sequence flag, mode (1 = packed), exceptions, pad
     uint32_t *h_feed = nullptr;                // pinned mirror of mode / exceptions, [NSTAGE][4]
+    cudaEvent_t ev_tail[NSTAGE] = {};          // the letters part of the batch in stage buffer b has arrived
+    double feed_frac = 0.75;                   // share of a batch that travels packed (feeder thread only)
+    double feed_frac_sum = 0.0;
+    bool feed_adapt = true;                    // HULK_B200_PACK_FRACTION=<0..1> pins the share
     std::atomic<uint64_t> feed_h2d{0}, feed_pack_ns{0}, feed_batches{0};
     std::atomic<uint64_t> feed_t_idle{0}, feed_t_evsync{0}, feed_t_enq{0}, feed_t_backpressure{0};   // ns (HULK_B200_FEED_DEBUG)
     CUresult (*cu_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -171,6 +176,7 @@ struct hulk_b200_ctx {
     unsigned long long *d_sketch = nullptr;
     double *d_weights = nullptr;
     bool tables_set = false;
+    uint64_t cws_ties = 0;                     // attempts of the device-side table draw that the host's libm decided
     // generate_cws_tables_async: the host draw runs on its own thread; the first flush (or set/finish) joins it
     std::thread gen_thread;
     std::vector<double> gen_r, gen_c, gen_b;
@@ -331,9 +337,9 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
         ctx->feeder.join();
         host_stats_print();
         if (getenv("HULK_B200_FEED_STATS"))
-            fprintf(stderr, "[feed] requests %llu: feeder idle %.3f ms, waiting for its pinned buffer %.3f, packing %.3f, "
-                            "enqueueing copies %.3f; caller held back %.3f ms\n",
-                    (unsigned long long)ctx->feed_done, ctx->feed_t_idle.load() * 1e-6, ctx->feed_t_evsync.load() * 1e-6,
+            fprintf(stderr, "[feed] requests %llu, %.3f of the bases packed (last split %.3f): feeder idle %.3f ms, waiting for its pinned "
+                            "buffer %.3f, packing %.3f, enqueueing copies %.3f; caller held back %.3f ms\n",
+                    (unsigned long long)ctx->feed_done, ctx->feed_frac_sum / (double)std::max<uint64_t>(1, ctx->feed_done), ctx->feed_frac, ctx->feed_t_idle.load() * 1e-6, ctx->feed_t_evsync.load() * 1e-6,
                     ctx->feed_pack_ns.load() * 1e-6, ctx->feed_t_enq.load() * 1e-6, ctx->feed_t_backpressure.load() * 1e-6);
     }
     cudaSetDevice(ctx->P.device);
@@ -370,6 +376,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     for (int i = 0; i < NSTAGE; i++) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         for (int q = 0; q < 2; q++) if (ctx->ev_k1x[i][q]) cudaEventDestroy(ctx->ev_k1x[i][q]);
+        if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
     }
     for (int i = 0; i < NBUF; i++) {
         if (ctx->ev_k1_last[i]) cudaEventDestroy(ctx->ev_k1_last[i]);
@@ -441,6 +448,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
     for (int i = 0; i < NSTAGE; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
         for (int q = 0; q < 2; q++) CU(cudaEventCreateWithFlags(&ctx->ev_k1x[i][q], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < NBUF; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_k1_last[i], cudaEventDisableTiming));
@@ -661,6 +669,11 @@ static int create_impl(hulk_b200_ctx *ctx) {
         e = getenv("HULK_B200_SERIAL");
         if (e && *e == '1') ctx->overlap = false;
         if (P.flags & HULK_B200_F_PACK_INPUT) ctx->pack_threads = -1;
+        e = getenv("HULK_B200_PACK_FRACTION");
+        if (e && *e) {
+            ctx->feed_frac = std::min(1.0, std::max(0.0, atof(e)));
+            ctx->feed_adapt = false;
+        }
         e = getenv("HULK_B200_PACK_INPUT");                  // A/B runs and the CLI: 1 = on, 0 = off whatever the flag says
         if (e && *e == '1') ctx->pack_threads = -1;
         if (e && *e == '0') ctx->pack_threads = 0;
@@ -911,6 +924,221 @@ static int finish_async_tables(hulk_b200_ctx *ctx) {
     std::vector<double>().swap(ctx->gen_c);
     std::vector<double>().swap(ctx->gen_b);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// newCWS drawn on the device (k4_cwsdraw.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" void hulk_b200_internal_alfg_window(int64_t seed, uint64_t *w);
+extern "C" void hulk_b200_internal_alfg_xpow(uint64_t n, uint64_t *poly);
+extern "C" void hulk_b200_internal_alfg_polymul(const uint64_t *a, const uint64_t *b, uint64_t *out);
+extern "C" int hulk_b200_internal_gamma_accepts(uint64_t raw1, uint64_t raw2);
+
+namespace {
+struct DevBuf {                       // frees what the draw allocated, whichever way it leaves
+    std::vector<void *> dev, host;
+    ~DevBuf() {
+        for (void *p : dev) cudaFree(p);
+        for (void *p : host) cudaFreeHost(p);
+    }
+};
+}  // namespace
+
+// returns 1 when the draw has to be left to the host generator (an output converted to exactly 1.0, too many events)
+static int draw_tables_on_device(hulk_b200_ctx *ctx) {
+    const uint64_t D = (uint64_t)ctx->D;
+    const uint64_t E = (uint64_t)ctx->P.slot_end * D, skip = (uint64_t)ctx->P.slot_begin * D;
+    const uint64_t need = 2 * E;                                          // gamma draws: r, c, r, c, ...
+    const uint64_t n_own = E - skip;
+    cudaStream_t st = ctx->stream;
+    if (E == 0) return HULK_B200_OK;
+    const uint64_t L = K4_CHUNK;
+    // ~4.55 raw outputs per element (1.14 attempts of two uniforms per draw, two draws); any shortfall is one more round
+    uint64_t C = (uint64_t)(4.7 * (double)E / (double)L) + 1;
+    C = std::min<uint64_t>(C, 1024);
+    const uint64_t R = C * L, A = R / 2 + 2;                              // raw outputs and attempts (at most) per round
+    const uint32_t ext_cap = 1u << 16, tie_cap = 1u << 12;
+    const uint32_t nblk = (uint32_t)((A + K4_COUNT_TPB - 1) / K4_COUNT_TPB);
+    DevBuf keep;
+    uint64_t *d_states = nullptr, *d_poly = nullptr, *d_raw = nullptr, *d_ext = nullptr;
+    double *d_xs = nullptr;
+    uint8_t *d_acc = nullptr;
+    K4Tie *d_ties = nullptr;
+    uint32_t *d_bcount = nullptr;
+    unsigned long long *d_bprefix = nullptr, *d_total = nullptr;
+    K4ScanOut *d_scan = nullptr;
+    K4SampleOut *d_samp = nullptr;
+#define K4_ALLOC(ptr, count)                                   \
+    do {                                                       \
+        CU(dmalloc(&ptr, count));                              \
+        keep.dev.push_back(ptr);                               \
+    } while (0)
+    K4_ALLOC(d_states, C * ALFG_LEN);
+    K4_ALLOC(d_poly, ALFG_LEN);
+    K4_ALLOC(d_raw, R + K4_LOOKAHEAD);
+    K4_ALLOC(d_ext, ext_cap);
+    K4_ALLOC(d_xs, A);
+    K4_ALLOC(d_acc, A);
+    K4_ALLOC(d_ties, tie_cap);
+    K4_ALLOC(d_bcount, nblk);
+    K4_ALLOC(d_bprefix, nblk);
+    K4_ALLOC(d_total, 1);
+    K4_ALLOC(d_scan, 1);
+    K4_ALLOC(d_samp, 1);
+#undef K4_ALLOC
+    // generator windows: every block starts from the seeded window and jumps to block * L by binary decomposition
+    {
+        std::vector<uint64_t> w0(ALFG_LEN), all(C * ALFG_LEN), poly(ALFG_LEN);
+        hulk_b200_internal_alfg_window(1, w0.data());                    // DISTRIBUTION_SEED  histosketch.go:20
+        for (uint64_t c = 0; c < C; c++) std::copy(w0.begin(), w0.end(), all.begin() + c * ALFG_LEN);
+        CU(cudaMemcpyAsync(d_states, all.data(), sizeof(uint64_t) * all.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        // Q_i = x^(L 2^i): block c applies the Q_i of its set bits; the jump between two rounds, x^((C - 1) L), is the
+        // product of the Q_i of the set bits of C - 1
+        std::vector<uint64_t> jump(ALFG_LEN, 0);
+        jump[0] = 1;
+        hulk_b200_internal_alfg_xpow(L, poly.data());
+        for (int bit = 0; (1ull << bit) < C; bit++) {
+            if (bit) hulk_b200_internal_alfg_polymul(poly.data(), poly.data(), poly.data());
+            if (((C - 1) >> bit) & 1) hulk_b200_internal_alfg_polymul(jump.data(), poly.data(), jump.data());
+            CU(cudaMemcpyAsync(d_poly, poly.data(), sizeof(uint64_t) * ALFG_LEN, cudaMemcpyHostToDevice, st));
+            k4_apply_poly<<<(unsigned)C, 512, 0, st>>>(d_states, d_poly, bit);
+            LAUNCH_CHECK("k4_apply_poly");
+            CU(cudaStreamSynchronize(st));                                // poly is reused by the next bit
+        }
+        if (C > 1) {                                                      // between rounds: from the end of a chunk to its next one
+            CU(cudaMemcpyAsync(d_poly, jump.data(), sizeof(uint64_t) * ALFG_LEN, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
+    }
+    std::vector<uint64_t> ext;
+    std::vector<K4Tie> ties(tie_cap);
+    uint64_t produced = 0, pos0 = 0, next_start = 0;
+    while (produced < need) {
+        k4_raw<<<(unsigned)C, 288, 0, st>>>(d_states, d_raw, K4_LOOKAHEAD);
+        LAUNCH_CHECK("k4_raw");
+        CU(cudaMemsetAsync(d_scan, 0, sizeof(K4ScanOut), st));
+        k4_scan<<<ctx->sm_count * 8, 256, 0, st>>>(d_raw, R, pos0, d_ext, ext_cap, d_scan, ctx->d_b, skip, E);
+        LAUNCH_CHECK("k4_scan");
+        K4ScanOut so;
+        CU(cudaMemcpyAsync(&so, d_scan, sizeof so, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (so.saw_one || so.n_extreme > ext_cap) return 1;
+        ext.resize(so.n_extreme);
+        if (so.n_extreme) CU(cudaMemcpy(ext.data(), d_ext, sizeof(uint64_t) * so.n_extreme, cudaMemcpyDeviceToHost));
+        std::sort(ext.begin(), ext.end());
+        // the pairing of the round: an attempt starts at next_start; a FIRST uniform outside (1e-7, 0.9999999) is consumed
+        // alone and the next attempt starts right behind it (go_rng's `continue`)
+        K4Segments segs{};
+        const uint64_t end = pos0 + R;
+        uint64_t cur = next_start, attempts = 0;
+        bool too_many = false;
+        auto add_seg = [&](uint64_t start, uint64_t n) {
+            if (!n) return;
+            if (segs.n >= (uint32_t)K4_MAX_SEGMENTS) { too_many = true; return; }
+            segs.seg[segs.n++] = K4Segment{start - pos0, attempts, n};
+            attempts += n;
+        };
+        for (uint64_t e : ext) {
+            if (e < cur) continue;
+            if (((e - cur) & 1) == 0) {                                   // a first uniform
+                add_seg(cur, (e - cur) / 2);
+                cur = e + 1;
+            }
+        }
+        if (end > cur) {
+            const uint64_t n = (end - cur + 1) / 2;                       // the last attempt may take its second uniform from
+            add_seg(cur, n);                                              // the look-ahead
+            next_start = cur + 2 * n;
+        } else {
+            next_start = cur;
+        }
+        if (too_many) return 1;
+        segs.total_attempts = attempts;
+        if (attempts) {
+            CU(cudaMemsetAsync(d_samp, 0, sizeof(K4SampleOut), st));
+            k4_sample<<<ctx->sm_count * 8, 256, 0, st>>>(d_raw, segs, d_xs, d_acc, d_ties, tie_cap, d_samp);
+            LAUNCH_CHECK("k4_sample");
+            K4SampleOut sp;
+            CU(cudaMemcpyAsync(&sp, d_samp, sizeof sp, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (sp.n_ties > tie_cap) return 1;
+            if (sp.n_ties) {                                              // the host's libm decides what is too close to call
+                CU(cudaMemcpy(ties.data(), d_ties, sizeof(K4Tie) * sp.n_ties, cudaMemcpyDeviceToHost));
+                for (uint32_t i = 0; i < sp.n_ties; i++) {
+                    const uint8_t a = (uint8_t)hulk_b200_internal_gamma_accepts(ties[i].raw1, ties[i].raw2);
+                    CU(cudaMemcpy(d_acc + ties[i].attempt, &a, 1, cudaMemcpyHostToDevice));
+                }
+                ctx->cws_ties += sp.n_ties;
+            }
+            const uint32_t nb = (uint32_t)((attempts + K4_COUNT_TPB - 1) / K4_COUNT_TPB);
+            k4_count<<<nb, K4_COUNT_TPB, 0, st>>>(d_acc, attempts, d_bcount);
+            LAUNCH_CHECK("k4_count");
+            k4_scan_counts<<<1, 1024, 0, st>>>(d_bcount, nb, d_bprefix, d_total);
+            LAUNCH_CHECK("k4_scan_counts");
+            k4_scatter<<<nb, K4_COUNT_TPB, 0, st>>>(d_acc, d_xs, attempts, d_bprefix, produced, need, skip, ctx->d_r, ctx->d_c);
+            LAUNCH_CHECK("k4_scatter");
+            unsigned long long total = 0;
+            CU(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            produced += total;
+        }
+        pos0 = end;
+        if (produced < need && C > 1) {
+            k4_apply_poly<<<(unsigned)C, 512, 0, st>>>(d_states, d_poly, -1);
+            LAUNCH_CHECK("k4_apply_poly");
+        }
+    }
+    if (n_own) {
+        k4_scale_b<<<(unsigned)((n_own + 255) / 256), 256, 0, st>>>(ctx->d_b, ctx->d_r, n_own);
+        LAUNCH_CHECK("k4_scale_b");
+    }
+    CU(cudaStreamSynchronize(st));
+    return HULK_B200_OK;
+}
+
+int hulk_b200_generate_cws_tables_device(hulk_b200_ctx *ctx) {
+    if (!ctx) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    const uint64_t n = (uint64_t)ctx->rows * (uint64_t)ctx->D;
+    if (!ctx->d_r) {
+        CU(dmalloc(&ctx->d_r, n));
+        CU(dmalloc(&ctx->d_c, n));
+        CU(dmalloc(&ctx->d_b, n));
+        if (ctx->filter16) CU(dmalloc(&ctx->d_K16, (uint64_t)ctx->rows * ctx->Dp));
+        else CU(dmalloc(&ctx->d_K32, (uint64_t)ctx->rows * ctx->Dp));
+    }
+    const int rc = draw_tables_on_device(ctx);
+    if (rc == 1) return hulk_b200_generate_cws_tables(ctx);               // the rare cases the parallel draw does not cover
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const uint64_t total = (uint64_t)ctx->rows * ctx->Dp;
+    if (total) {
+        if (ctx->filter16)
+            k3_fold16<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
+                                                                       ctx->Dp, ctx->d_K16);
+        else
+            k3_fold<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ctx->d_r, ctx->d_c, ctx->d_b, ctx->rows, ctx->D,
+                                                                     ctx->Dp, ctx->d_K32);
+        LAUNCH_CHECK("k3_fold");
+    }
+    CU(cudaStreamSynchronize(st));
+    ctx->tables_set = true;
+    return HULK_B200_OK;
+}
+
+// parity tap: the float64 tables as they sit on the device (rows x num_bins each)
+int hulk_b200_get_cws_tables(hulk_b200_ctx *ctx, double *r, double *c, double *b) {
+    if (!ctx || !r || !c || !b) return HULK_B200_EARG;
+    if (!ctx->tables_set) return fail(ctx, HULK_B200_ESTATE, "CWS tables not set");
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    const size_t bytes = sizeof(double) * (size_t)ctx->rows * (size_t)ctx->D;
+    CU(cudaMemcpy(r, ctx->d_r, bytes, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(c, ctx->d_c, bytes, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(b, ctx->d_b, bytes, cudaMemcpyDeviceToHost));
+    return HULK_B200_OK;
 }
 
 int hulk_b200_generate_cws_tables(hulk_b200_ctx *ctx) {
@@ -1223,9 +1451,10 @@ __global__ void k0_patch(const uint32_t *__restrict__ exc, uint64_t n, uint32_t 
 // exceptions it has (meta[2]) is only known on the device by the time they run
 __global__ void k0_unpack_fed(const uint32_t *__restrict__ packed, uint64_t n_words, uint4 *__restrict__ ascii,
                               const uint32_t *__restrict__ meta) {
-    if (meta[1] == 0u) return;                               // the batch travelled as ASCII: it is in place already
+    // meta[3]: packed words at the head of the batch (0: it travelled as letters and is in place already); the rest of the
+    // batch arrived as letters behind them
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_words) return;
+    if (t >= n_words || t >= (uint64_t)meta[3]) return;
     const uint32_t x = packed[t];
     uint32_t o[4];
 #pragma unroll
@@ -1275,41 +1504,68 @@ static void feeder_main(hulk_b200_ctx *ctx) {
             }
         };
         const int buf = rq.buf;
-        const uint64_t exc_cap = feed_exc_cap(rq.nb), packed_bytes = (rq.nb + 3) / 4;
+        const uint64_t exc_cap = feed_exc_cap(rq.nb);
         FEED_DBG("feeder: request buf %d seq %u, %llu bases: waiting for the pinned buffer", buf, rq.seq, (unsigned long long)rq.nb);
         cu(cudaEventSynchronize(ctx->ev_copy[buf]), "cudaEventSynchronize");      // the pinned buffers are free again
         lap(ctx->feed_t_evsync);
         FEED_DBG("feeder: packing");
         // (the pinned buffers were sized by the calling thread before it posted the request: nothing in this loop may
         // allocate -- an allocation can wait for the device, and the device may be waiting for this loop)
+        //
+        // Two resources move a batch: the host's cores (packing, bound by their memory bandwidth) and the link.  Packing
+        // everything leaves the link idle three quarters of the time, so the batch is split: its TAIL travels as letters
+        // -- that copy is enqueued first and runs while the HEAD is being packed -- and the head travels packed.  The
+        // split point follows what is observed: if the tail had already arrived when packing ended, the cores are the
+        // bottleneck and the next batch packs a little less; if it was still on the link, a little more.
         uint64_t n_exc = 0, moved = 0;
+        uint64_t n_head = (uint64_t)(ctx->feed_frac * (double)rq.nb) & ~63ull;     // bases that travel packed
+        if (n_head < 4096) n_head = 0;
+        if (rq.nb - n_head < 4096) n_head = rq.nb;
+        // the copy stream holds nothing but this thread's copies, in request order: each waits for the kernels that last
+        // read its stage buffer and for nothing else
+        cu(cudaStreamWaitEvent(ctx->copy_stream, rq.stage_free, 0), "cudaStreamWaitEvent");
+        const bool has_tail = n_head < rq.nb;
+        if (rc == HULK_B200_OK && has_tail) {
+            cu(cudaMemcpyAsync(ctx->d_stage[buf] + n_head, rq.src + n_head, rq.nb - n_head, cudaMemcpyHostToDevice,
+                               ctx->copy_stream), "cudaMemcpyAsync");
+            cu(cudaEventRecord(ctx->ev_tail[buf], ctx->copy_stream), "cudaEventRecord");
+            moved += rq.nb - n_head;
+        }
         bool packed = false;
-        if (rc == HULK_B200_OK) {
+        const uint64_t packed_head_bytes = (n_head + 3) / 4;
+        if (rc == HULK_B200_OK && n_head) {
             const auto t0 = std::chrono::steady_clock::now();
-            const int prc = hulk_b200_pack_bases(rq.src, rq.nb, ctx->h_pack[buf], ctx->h_exc[buf], exc_cap, &n_exc,
+            const int prc = hulk_b200_pack_bases(rq.src, n_head, ctx->h_pack[buf], ctx->h_exc[buf], exc_cap, &n_exc,
                                                  ctx->pack_threads);
             ctx->feed_pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                                      std::chrono::steady_clock::now() - t0).count();
             if (prc) { rc = prc; msg = std::string(hulk_b200_strerror(prc)) + ": pack_bases"; }
             packed = prc == HULK_B200_OK && n_exc <= exc_cap;
+            if (ctx->feed_adapt && rc == HULK_B200_OK) {
+                const bool tail_arrived = !has_tail || cudaEventQuery(ctx->ev_tail[buf]) == cudaSuccess;
+                cudaGetLastError();                                   // cudaErrorNotReady is not an error
+                ctx->feed_frac += tail_arrived ? -1.0 / 64.0 : 1.0 / 64.0;
+                ctx->feed_frac = std::min(1.0, std::max(0.0, ctx->feed_frac));
+            }
+        } else if (ctx->feed_adapt && n_head == 0) {
+            ctx->feed_frac = 1.0 / 16.0;                              // try packing a little again
         }
-        FEED_DBG("feeder: packed (rc %d, %llu exceptions), copying", rc, (unsigned long long)n_exc);
+        ctx->feed_frac_sum += (double)n_head / (double)std::max<uint64_t>(1, rq.nb);
+        FEED_DBG("feeder: packed %llu of %llu bases (rc %d, %llu exceptions), copying", (unsigned long long)n_head,
+                 (unsigned long long)rq.nb, rc, (unsigned long long)n_exc);
         tick = std::chrono::steady_clock::now();
-        // the copy stream holds nothing but this thread's copies, in request order: each waits for the kernels that last
-        // read its stage buffer and for nothing else
-        cu(cudaStreamWaitEvent(ctx->copy_stream, rq.stage_free, 0), "cudaStreamWaitEvent");
         if (rc == HULK_B200_OK) {
             if (packed) {
-                cu(cudaMemcpyAsync(ctx->d_pack[buf], ctx->h_pack[buf], packed_bytes, cudaMemcpyHostToDevice, ctx->copy_stream),
+                cu(cudaMemcpyAsync(ctx->d_pack[buf], ctx->h_pack[buf], packed_head_bytes, cudaMemcpyHostToDevice, ctx->copy_stream),
                    "cudaMemcpyAsync");
                 if (n_exc)
                     cu(cudaMemcpyAsync(ctx->d_exc[buf], ctx->h_exc[buf], sizeof(uint32_t) * n_exc, cudaMemcpyHostToDevice,
                                        ctx->copy_stream), "cudaMemcpyAsync");
-                moved = packed_bytes + sizeof(uint32_t) * n_exc;
+                moved += packed_head_bytes + sizeof(uint32_t) * n_exc;
                 ctx->feed_batches++;
-            } else {                                          // too many foreign bytes: the letters travel as they are
-                cu(cudaMemcpyAsync(ctx->d_stage[buf], rq.src, rq.nb, cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync");
-                moved = rq.nb;
+            } else if (n_head) {                              // too many foreign bytes: the letters travel as they are
+                cu(cudaMemcpyAsync(ctx->d_stage[buf], rq.src, n_head, cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync");
+                moved += n_head;
                 n_exc = 0;
             }
             if (rq.offsets) {
@@ -1323,7 +1579,8 @@ static void feeder_main(hulk_b200_ctx *ctx) {
         uint32_t *hm = ctx->h_feed + 4 * buf;
         hm[1] = (rc == HULK_B200_OK && packed) ? 1u : 0u;
         hm[2] = (uint32_t)n_exc;
-        cu(cudaMemcpyAsync(ctx->d_feed + 4 * buf + 1, hm + 1, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream),
+        hm[3] = (rc == HULK_B200_OK && packed) ? (uint32_t)((n_head + 15) / 16) : 0u;       // packed words to unpack
+        cu(cudaMemcpyAsync(ctx->d_feed + 4 * buf + 1, hm + 1, 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream),
            "cudaMemcpyAsync");
         const CUresult wr = ctx->cu_write32(reinterpret_cast<CUstream>(ctx->copy_stream),
                                             reinterpret_cast<CUdeviceptr>(ctx->d_feed + 4 * buf), rq.seq, 0);

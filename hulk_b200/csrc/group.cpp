@@ -11,6 +11,7 @@
 //   * the count-min update is replicated (tiny), the CWS sweep is sharded by sketch slot: context g owns slots
 //     [g s / G, (g+1) s / G) and only those rows of the CWS tables;
 //   * finish gathers the slots on the host.
+#include <cstdlib>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -144,9 +145,23 @@ static int group_finish_tables(hulk_b200_group *g) {               // join the d
     std::vector<double>().swap(g->gen_b);
     return rc;
 }
+int hulk_b200_group_generate_cws_tables_device(hulk_b200_group *g) {
+    if (!g) return HULK_B200_EARG;
+    for (size_t i = 0; i < g->ctx.size(); i++) {                          // every GPU draws the rows of its own slots
+        const int rc = hulk_b200_generate_cws_tables_device(g->ctx[i]);
+        if (rc) return gfrom(g, i, rc);
+    }
+    return HULK_B200_OK;
+}
 int hulk_b200_group_generate_cws_tables(hulk_b200_group *g, int background) {
     if (!g) return HULK_B200_EARG;
     if (g->gen_pending) return gfail(g, HULK_B200_ESTATE, "table generation already running");
+    {
+        // HULK_B200_CWS_DEVICE=1: draw on the GPUs instead (the values can differ from the host draw in the last bit,
+        // see hulk_b200_generate_cws_tables_device -- which is why it is not the default of a drop-in)
+        const char *e = getenv("HULK_B200_CWS_DEVICE");
+        if (e && *e == '1') return hulk_b200_group_generate_cws_tables_device(g);
+    }
     const size_t n = (size_t)g->P.sketch_size * (size_t)g->D;
     try {
         g->gen_r.resize(n ? n : 1); g->gen_c.resize(n ? n : 1); g->gen_b.resize(n ? n : 1);

@@ -459,6 +459,32 @@ bool new_cws_parallel(uint32_t slot_begin, uint32_t slot_end, int32_t num_bins, 
 
 }  // namespace
 
+// ---- internal (not in include/hulk_b200.h): the pieces of Go's generator the device-side draw needs --------------
+// (hidden visibility: linked from api.cu inside the same library)
+extern "C" void hulk_b200_internal_alfg_window(int64_t seed, uint64_t *w) {
+    // W[i] = S[i - 607]: the 607 values in front of the first output, so that S[n] = S[n - 607] + S[n - 273].
+    // The first outputs are vec[333 - n] + vec[606 - n] (tap starts at 0, feed at 334, both step down).
+    GoSource g(seed);
+    for (int i = 0; i < kRngLen - kRngTap; i++) w[i] = g.vec[kRngLen - kRngTap - 1 - i];
+    for (int i = 0; i < kRngTap; i++) w[kRngLen - kRngTap + i] = g.vec[kRngLen - 1 - i];
+}
+extern "C" void hulk_b200_internal_alfg_xpow(uint64_t n, uint64_t *poly) { GoSource::xpow(n, poly); }
+extern "C" void hulk_b200_internal_alfg_polymul(const uint64_t *a, const uint64_t *b, uint64_t *out) {   // out may alias a or b
+    GoSource::polymul(a, b, out);
+}
+// Cheng's acceptance test for one attempt with the host's libm (the arbiter of near-ties found on the device)
+extern "C" int hulk_b200_internal_gamma_accepts(uint64_t raw1, uint64_t raw2) {
+    static const double kMagic = 1.0 + std::log(4.5);
+    const double alpha = 2.0, ainv = std::sqrt(2.0 * alpha - 1.0), bbb = alpha - std::log(4.0), ccc = alpha + ainv;
+    bool one;
+    const double u1 = GoSource::to_float64(raw1, &one), u2 = 1.0 - GoSource::to_float64(raw2, &one);
+    const double vv = std::log(u1 / (1.0 - u1)) / ainv;
+    const double x = alpha * std::exp(vv);
+    const double z = u1 * u1 * u2;
+    const double rr = bbb + ccc * vv - x;
+    return (rr + kMagic - 4.5 * z >= 0.0 || rr >= std::log(z)) ? 1 : 0;
+}
+
 extern "C" {
 
 // test hook: the parallel draw with an explicit thread count and raw-chunk length; returns 1 when it had to give up

@@ -215,6 +215,17 @@ class HistoSketch:
         self._check(fn(self._ctx))
 
     # -- stage 1+2 ---------------------------------------------------------------------------
+    def generate_tables_device(self):
+        """HistoSketch.newCWS drawn on the GPU (hulk_b200_generate_cws_tables_device)."""
+        self._check(self._L.hulk_b200_generate_cws_tables_device(self._ctx))
+
+    def tables(self):
+        """The float64 CWS tables as they sit on the device: (r, c, b), rows x num_bins each."""
+        shape = (self.slot_end - self.slot_begin, self.num_bins)
+        r, c, b = np.zeros(shape), np.zeros(shape), np.zeros(shape)
+        self._check(self._L.hulk_b200_get_cws_tables(self._ctx, _ptr(r), _ptr(c), _ptr(b)))
+        return r, c, b
+
     def add_reads(self, bases: np.ndarray, offsets: np.ndarray):
         """theBoss.AddSeq for a batch (src/pipeline/boss.go:24-26)."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

@@ -491,6 +491,50 @@ def test_c1_golden_json(hb, fixture_reads):
                    [ln for ln in want.split("\n") if "e" not in ln and "." not in ln]
 
 
+def _ulp_diff(a, b):
+    ia, ib = a.view(np.int64), b.view(np.int64)
+    return np.abs(ia - ib)
+
+
+@pytest.mark.parametrize("k,s,slots", [(11, 16, None), (11, 16, (5, 9)), (21, 3, None), (15, 40, (0, 7))])
+def test_cws_tables_drawn_on_the_device(hb, k, s, slots):
+    """hulk_b200_generate_cws_tables_device against the host generator (hulk_b200_new_cws): the same accept/reject
+    SEQUENCE (a single difference would shift every later entry, so agreement of the last row proves it), values equal
+    to the last bit or two (CUDA's exp/log against glibc's), b = U r from the uniform at the element's fixed position."""
+    D = k ** 4
+    sb, se = slots if slots else (0, s)
+    r0, c0, b0 = hb.new_cws(s, D, sb, se)
+    with hb.HistoSketch(k, 9, s, 1.0, slots=slots) as hs:
+        hs.generate_tables_device()
+        r1, c1, b1 = hs.tables()
+    assert r1.shape == r0.shape
+    # draw = 2 exp(ln(u / (1 - u)) / sqrt 3): one ulp of the logarithm is |v| ulps of the draw -- a few ulps at most
+    for name, x0, x1 in (("r", r0, r1), ("b", b0, b1)):
+        np.testing.assert_allclose(x1, x0, rtol=8e-15, atol=0, err_msg=name)
+        assert (_ulp_diff(x0, x1) == 0).mean() > 0.5, name
+    # c = ln(draw): a draw next to 1 gives a logarithm next to 0, where one ulp of the draw is many ulps of c
+    np.testing.assert_allclose(c1, c0, rtol=1e-14, atol=4e-16)
+    assert (c1 == c0).mean() > 0.5
+
+
+def test_sketch_with_device_drawn_tables_matches_the_oracle(hb, oracle):
+    """Whole path with the tables drawn on the device: mins equal, weights to 1e-12 (the tables differ from the host
+    draw by at most a few ulp)."""
+    k, w, s = 11, 9, 24
+    D = k ** 4
+    r, c, b = hb.new_cws(s, D)
+    reads = hb.synthetic_reads(6000, 150, seed=21)
+    offs = np.arange(6001, dtype=np.uint64) * np.uint64(150)
+    ref = oracle.HistoSketch(k, s, D, 1.0, r, c, b)
+    ref.run(w, reads.reshape(-1), offs, interval=2000, parallel=True)
+    mins_ref, weights_ref = ref.get()
+    with hb.HistoSketch(k, w, s, 1.0) as hs:
+        hs.generate_tables_device()
+        mins, weights, _ = hb.sketch_reads(hs, [(reads.reshape(-1), offs)], interval=2000)
+    np.testing.assert_array_equal(mins, mins_ref)
+    np.testing.assert_allclose(weights, weights_ref, rtol=W_RTOL, atol=0)
+
+
 def test_flush_semantics(hb):
     k, s = 5, 8
     D = k ** 4

@@ -241,6 +241,22 @@ def test_cli_gpus_flag_gives_the_same_json(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_with_tables_drawn_on_the_device(tmp_path):
+    """HULK_B200_CWS_DEVICE=1: `hulk sketch` draws the CWS tables on the GPU (also with --gpus: every member its own rows).
+    Same mins and md5 as the golden sketch; the weights agree to 1e-12 (tables equal to the last bit or two)."""
+    gold = json.load(open(os.path.join(GOLDEN, "c1_k21_s50.json")))
+    for gpus, env in (("1", {}), ("2", {"HULK_B200_GPUS_ON_ONE_DEVICE": "1", "CUDA_DEVICE_MAX_CONNECTIONS": "32"})):
+        out = str(tmp_path / ("dev" + gpus))
+        r = _hulk("sketch", "-f", FIXTURE, "-k", "21", "-s", "50", "--gpus", gpus, "-o", out,
+                  env=dict(env, HULK_B200_CWS_DEVICE="1"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = json.load(open(out + ".json"))
+        g, w = got["signatures"][0]["Sketch"], gold["signatures"][0]["Sketch"]
+        assert g["mins"] == w["mins"] and g["md5sum"] == w["md5sum"]
+        np.testing.assert_allclose(g["weights"], w["weights"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
 def test_cli_reference_fatals(tmp_path):
     short = tmp_path / "short.fq"
     short.write_bytes(b"@r1\n" + b"ACGT" * 30 + b"\n+\n" + b"I" * 120 + b"\n@r2\nACGTACGT\n+\nIIIIIIII\n")
