@@ -29,6 +29,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# one hardware queue per stream (read when the CUDA context is created, i.e. before torch touches the device): the host
+# path orders a counting stream behind its input copy with stream memory operations, see hulk_b200_create
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 

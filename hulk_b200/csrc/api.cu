@@ -106,6 +106,7 @@ struct hulk_b200_ctx {
         uint32_t seq;
         cudaEvent_t stage_free;     // the previous consumers of this stage buffer are done (waited for on the copy stream)
     };
+    bool feeder_allowed = false;               // every stream has a hardware queue of its own (see hulk_b200_create)
     std::thread feeder;
     std::mutex feed_mu;
     std::condition_variable feed_cv;
@@ -494,7 +495,7 @@ static int create_impl(hulk_b200_ctx *ctx) {
         cudaDriverEntryPointQueryResult q1, q2;
         void *f1 = nullptr, *f2 = nullptr;
         const char *off = getenv("HULK_B200_FEEDER");
-        if (!(off && *off == '0') &&
+        if (!(off && *off == '0') && ctx->feeder_allowed &&
             cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &q1) == cudaSuccess &&
             cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &q2) == cudaSuccess &&
             q1 == cudaDriverEntryPointSuccess && q2 == cudaDriverEntryPointSuccess && f1 && f2) {
@@ -697,6 +698,34 @@ int hulk_b200_create(const hulk_b200_params *params, hulk_b200_ctx **out) {
     if (sb == 0 && se == 0) se = params->sketch_size;
     if (sb > se || se > params->sketch_size) return fail(ctx, HULK_B200_EARG, "slot range");
 
+    // The feeder path orders a counting stream behind a copy with stream memory operations, an order CUDA's scheduler does
+    // not see: if the two streams shared a hardware queue, the wait could end up in front of the copy that satisfies it.
+    // Every stream must therefore have its own queue: the context's ~8 streams (plus the caller's) need more than the
+    // default 8 connections.  The setting is read when the device's context is created: it is set here if that has not
+    // happened yet; a context created earlier without it keeps the safe path (packing on the calling thread).
+    bool queues_ok;
+    {
+        const char *mc = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        if (mc) {
+            queues_ok = atoi(mc) >= 16;
+        } else {
+            bool context_exists = true;               // unknown means: assume the worst
+            cudaDriverEntryPointQueryResult q;
+            void *f = nullptr;
+            if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &f, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess && f) {
+                unsigned int flags = 0;
+                int active = 1;
+                auto get_state = reinterpret_cast<CUresult (*)(CUdevice, unsigned int *, int *)>(f);
+                if (get_state((CUdevice)params->device, &flags, &active) == CUDA_SUCCESS) context_exists = active != 0;
+            }
+            cudaGetLastError();
+            if (!context_exists) setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 1);
+            queues_ok = !context_exists;
+        }
+        const char *force = getenv("HULK_B200_FEEDER");
+        if (force && *force == '1') queues_ok = true;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -712,6 +741,7 @@ int hulk_b200_create(const hulk_b200_params *params, hulk_b200_ctx **out) {
     ctx->D = D;
     ctx->s = params->sketch_size;
     ctx->rows = se - sb;
+    ctx->feeder_allowed = queues_ok;
     ctx->drift = (params->decay_ratio != 1.0);                                            // histosketch.go:79-81
     if (params->decay_ratio > 0.0 && params->decay_ratio < 1.0) {                         // countmin.go:50-55
         ctx->apply_scaling = true;
