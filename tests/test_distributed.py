@@ -313,3 +313,9 @@ def test_group_members_on_one_device_take_the_peer_path(oracle, case):
     p = subprocess.run([sys.executable, "-c", ONE_DEVICE_SCRIPT, ROOT, json.dumps(case)], env=env, capture_output=True,
                        text=True, timeout=600)
     assert p.returncode == 0 and "ONE_DEVICE_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+    if case[0] == 11:
+        # the same with every member's share of a batch travelling packed: three feeder threads, one shared packer pool
+        env["HULK_B200_PACK_INPUT"] = "1"
+        p = subprocess.run([sys.executable, "-c", ONE_DEVICE_SCRIPT, ROOT, json.dumps(case)], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert p.returncode == 0 and "ONE_DEVICE_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
