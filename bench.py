@@ -546,7 +546,7 @@ def run_b200(a):
     # host threads that pack: this rank's share of the CPUs it may run on, less two for the threads that issue the GPU work
     ncpu = len(os.sched_getaffinity(0))
     share = max(1, min(ncpu, (os.cpu_count() or ncpu) // world))
-    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or max(1, min(32, share - 2 if share > 3 else share))
+    pack_threads = int(os.environ.get("HULK_B200_PACK_THREADS", "0")) or max(1, min(32, share - 2 if share > 4 else share - 1))
     hs.set_input_packing(pack_threads)
     e2e, mins_e2e = run_e2e("e2e")
     e2e["transport"] = ("most of every batch as 2 bits per base (+ positions of non-ACGTU bytes), packed from the host's ASCII "

@@ -118,7 +118,10 @@ struct hulk_b200_ctx {
     uint32_t feed_seq[NSTAGE] = {};            // uses of stage buffer b by the feeder path
     uint32_t *d_feed = nullptr;                // [NSTAGE][4]: sequence flag, mode (1 = packed), exceptions, pad
     uint32_t *h_feed = nullptr;                // pinned mirror of mode / exceptions, [NSTAGE][4]
-    cudaEvent_t ev_tail[NSTAGE] = {};          // the letters part of the batch in stage buffer b has arrived
+    cudaEvent_t ev_tail0[NSTAGE] = {}, ev_tail[NSTAGE] = {};   // around the copy of the letters part of the batch in stage buffer b
+    int feed_last_tail = -1;                   // stage buffer whose letters copy has not been timed yet
+    uint64_t feed_last_tail_bytes = 0;
+    double feed_bp = 0.0, feed_bl = 0.0;       // measured rates, bytes of bases per second: packing, link (0: not measured yet)
     double feed_frac = 0.75;                   // share of a batch that travels packed (feeder thread only)
     double feed_frac_sum = 0.0;
     bool feed_adapt = true;                    // HULK_B200_PACK_FRACTION=<0..1> pins the share
@@ -338,6 +341,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
         ctx->feeder.join();
         host_stats_print();
         if (getenv("HULK_B200_FEED_STATS"))
+            fprintf(stderr, "[feed] packing %.1f GB/s, link %.1f GB/s\n", ctx->feed_bp * 1e-9, ctx->feed_bl * 1e-9);
             fprintf(stderr, "[feed] requests %llu, %.3f of the bases packed (last split %.3f): feeder idle %.3f ms, waiting for its pinned "
                             "buffer %.3f, packing %.3f, enqueueing copies %.3f; caller held back %.3f ms\n",
                     (unsigned long long)ctx->feed_done, ctx->feed_frac_sum / (double)std::max<uint64_t>(1, ctx->feed_done), ctx->feed_frac, ctx->feed_t_idle.load() * 1e-6, ctx->feed_t_evsync.load() * 1e-6,
@@ -378,6 +382,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         for (int q = 0; q < 2; q++) if (ctx->ev_k1x[i][q]) cudaEventDestroy(ctx->ev_k1x[i][q]);
         if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
+        if (ctx->ev_tail0[i]) cudaEventDestroy(ctx->ev_tail0[i]);
     }
     for (int i = 0; i < NBUF; i++) {
         if (ctx->ev_k1_last[i]) cudaEventDestroy(ctx->ev_k1_last[i]);
@@ -449,7 +454,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
     for (int i = 0; i < NSTAGE; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
         for (int q = 0; q < 2; q++) CU(cudaEventCreateWithFlags(&ctx->ev_k1x[i][q], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming));
+        CU(cudaEventCreate(&ctx->ev_tail0[i]));
+        CU(cudaEventCreate(&ctx->ev_tail[i]));
     }
     for (int i = 0; i < NBUF; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_k1_last[i], cudaEventDisableTiming));
@@ -1545,9 +1551,25 @@ static void feeder_main(hulk_b200_ctx *ctx) {
         // Two resources move a batch: the host's cores (packing, bound by their memory bandwidth) and the link.  Packing
         // everything leaves the link idle three quarters of the time, so the batch is split: its TAIL travels as letters
         // -- that copy is enqueued first and runs while the HEAD is being packed -- and the head travels packed.  The
-        // split point follows what is observed: if the tail had already arrived when packing ended, the cores are the
-        // bottleneck and the next batch packs a little less; if it was still on the link, a little more.
+        // split follows the two rates as measured (packing: bases per second of this thread's pack calls; link: CUDA events
+        // around the previous tail copy): with a share f packed, packing takes f n / Bp and the link carries
+        // (1 - 0.75 f) n / Bl; they finish together at f = Bp / (Bl + 0.75 Bp).
         uint64_t n_exc = 0, moved = 0;
+        if (ctx->feed_adapt && ctx->feed_last_tail >= 0 && cudaEventQuery(ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev_tail0[ctx->feed_last_tail], ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess &&
+                ms > 0.f) {
+                const double bl = (double)ctx->feed_last_tail_bytes / (ms * 1e-3);
+                ctx->feed_bl = ctx->feed_bl > 0.0 ? 0.75 * ctx->feed_bl + 0.25 * bl : bl;
+            }
+            ctx->feed_last_tail = -1;
+        }
+        cudaGetLastError();                                           // cudaErrorNotReady is not an error
+        if (ctx->feed_adapt && ctx->feed_bp > 0.0 && ctx->feed_bl > 0.0) {
+            const double f = ctx->feed_bp / (ctx->feed_bl + 0.75 * ctx->feed_bp);
+            // both rates have to stay observable: never less than 1/32 packed, never less than 1/32 as letters
+            ctx->feed_frac = std::min(31.0 / 32.0, std::max(1.0 / 32.0, 0.5 * ctx->feed_frac + 0.5 * f));
+        }
         uint64_t n_head = (uint64_t)(ctx->feed_frac * (double)rq.nb) & ~63ull;     // bases that travel packed
         if (n_head < 4096) n_head = 0;
         if (rq.nb - n_head < 4096) n_head = rq.nb;
@@ -1556,10 +1578,15 @@ static void feeder_main(hulk_b200_ctx *ctx) {
         cu(cudaStreamWaitEvent(ctx->copy_stream, rq.stage_free, 0), "cudaStreamWaitEvent");
         const bool has_tail = n_head < rq.nb;
         if (rc == HULK_B200_OK && has_tail) {
+            cu(cudaEventRecord(ctx->ev_tail0[buf], ctx->copy_stream), "cudaEventRecord");
             cu(cudaMemcpyAsync(ctx->d_stage[buf] + n_head, rq.src + n_head, rq.nb - n_head, cudaMemcpyHostToDevice,
                                ctx->copy_stream), "cudaMemcpyAsync");
             cu(cudaEventRecord(ctx->ev_tail[buf], ctx->copy_stream), "cudaEventRecord");
             moved += rq.nb - n_head;
+            if (rq.nb - n_head >= (1u << 20)) {                       // long enough to time
+                ctx->feed_last_tail = buf;
+                ctx->feed_last_tail_bytes = rq.nb - n_head;
+            }
         }
         bool packed = false;
         const uint64_t packed_head_bytes = (n_head + 3) / 4;
@@ -1567,18 +1594,15 @@ static void feeder_main(hulk_b200_ctx *ctx) {
             const auto t0 = std::chrono::steady_clock::now();
             const int prc = hulk_b200_pack_bases(rq.src, n_head, ctx->h_pack[buf], ctx->h_exc[buf], exc_cap, &n_exc,
                                                  ctx->pack_threads);
-            ctx->feed_pack_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
-                                     std::chrono::steady_clock::now() - t0).count();
+            const uint64_t ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                    std::chrono::steady_clock::now() - t0).count();
+            ctx->feed_pack_ns += ns;
             if (prc) { rc = prc; msg = std::string(hulk_b200_strerror(prc)) + ": pack_bases"; }
             packed = prc == HULK_B200_OK && n_exc <= exc_cap;
-            if (ctx->feed_adapt && rc == HULK_B200_OK) {
-                const bool tail_arrived = !has_tail || cudaEventQuery(ctx->ev_tail[buf]) == cudaSuccess;
-                cudaGetLastError();                                   // cudaErrorNotReady is not an error
-                ctx->feed_frac += tail_arrived ? -1.0 / 64.0 : 1.0 / 64.0;
-                ctx->feed_frac = std::min(1.0, std::max(0.0, ctx->feed_frac));
+            if (ns && n_head >= (1u << 20)) {
+                const double bp = (double)n_head / (ns * 1e-9);
+                ctx->feed_bp = ctx->feed_bp > 0.0 ? 0.75 * ctx->feed_bp + 0.25 * bp : bp;
             }
-        } else if (ctx->feed_adapt && n_head == 0) {
-            ctx->feed_frac = 1.0 / 16.0;                              // try packing a little again
         }
         ctx->feed_frac_sum += (double)n_head / (double)std::max<uint64_t>(1, rq.nb);
         FEED_DBG("feeder: packed %llu of %llu bases (rc %d, %llu exceptions), copying", (unsigned long long)n_head,
