@@ -309,26 +309,27 @@ __device__ __forceinline__ void k1_finish_lists(const K1Params &p, uint64_t *wl,
     // in between: rare.  So the lists are first only TESTED -- loads and compares, four independent accumulators,
     // nothing stored -- and the set construction below runs for a warp where the test fires (a false alarm from
     // stale entries behind a short list only costs that pass).
+    // The test looks at the LOW WORDS only (one 32-bit load and one integer compare-and-accumulate per pair instead of a
+    // 64-bit load and a 64-bit compare): two different values share a low word once in 2^24 pairs (the span byte is
+    // the same for nearly all of them), which again only costs the set pass.
     bool maybe_dup = false;
     {
         const uint32_t n_max = __reduce_max_sync(0xffffffffu, n);
+        const uint32_t *const lo = reinterpret_cast<const uint32_t *>(my_list);       // entry e: lo[e * 64] (little endian)
         for (uint32_t a = 0; a < n_max; a += 4) {
-            uint64_t x[4];
+            uint32_t x[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = (a + u < n) ? my_list[(a + u) * 32] : NONE - 1u - (uint64_t)u;   // distinct pads
+            for (int u = 0; u < 4; u++) x[u] = (a + u < n) ? lo[(a + u) * 64] : 0xFFFFFFFFu - (uint32_t)u;   // distinct pads
             for (uint32_t b = 0; b < a; b += 4) {                        // a is a multiple of four
-                uint64_t y[4];
+                uint32_t y[4];
 #pragma unroll
-                for (int v = 0; v < 4; v++) y[v] = my_list[(b + v) * 32];
-                bool hit = false;
+                for (int v = 0; v < 4; v++) y[v] = lo[(b + v) * 64];
 #pragma unroll
                 for (int v = 0; v < 4; v++)
 #pragma unroll
-                    for (int u = 0; u < 4; u++) hit |= ueq64<FP>(y[v], x[u]);
-                maybe_dup |= hit;
+                    for (int u = 0; u < 4; u++) maybe_dup |= y[v] == x[u];
             }
-            maybe_dup |= ueq64<FP>(x[1], x[0]) | ueq64<FP>(x[2], x[0]) | ueq64<FP>(x[2], x[1]) | ueq64<FP>(x[3], x[0]) |
-                         ueq64<FP>(x[3], x[1]) | ueq64<FP>(x[3], x[2]);
+            maybe_dup |= (x[1] == x[0]) | (x[2] == x[0]) | (x[2] == x[1]) | (x[3] == x[0]) | (x[3] == x[1]) | (x[3] == x[2]);
         }
     }
     const bool exact = __any_sync(0xffffffffu, maybe_dup);

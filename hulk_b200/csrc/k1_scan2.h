@@ -120,10 +120,11 @@ struct K1List {
 // every read, so its blocks are the same code with the position-dependent parts folded at compile time:
 // PH = 3: in front of the first k-mer (roll only); PH = 1: the block that holds position k-1 (offset U0: no
 // k-mer before it, spans k-8.. from there, minimizer.go:127-131); PH = 2: the block after it (the remaining
-// partial spans, then k).
+// partial spans, then k).  PH = 4: the LAST block of a read whose length is not a multiple of 8: an interior block of
+// which only the first `rem` positions exist (the codes behind them are arbitrary; what is computed from them is dropped).
 template <int K, int STRIDE, int PH>
 HULK_HD void k1_fast_block(const uint32_t codes0, const uint32_t codes1, uint32_t &f_lo, uint32_t &f_hi, uint32_t &r_lo,
-                           uint32_t &r_hi, double (&A)[8], K1List<STRIDE> &L) {
+                           uint32_t &r_hi, double (&A)[8], K1List<STRIDE> &L, const int32_t rem = 8) {
     using R = K1Repr<K>;
     static_assert(K >= 17 && K <= 31 && (K & 1), "fast block: odd k, two-word k-mers");
     constexpr int U0 = (K - 1) & 7;                // offset of position k-1 in its block
@@ -142,7 +143,7 @@ HULK_UNROLL
         r_hi = (r_hi + (rc << RSH)) >> 2;
         r_lo = nr_lo;
         if (PH == 3 || (PH == 1 && u < U0)) continue;                     // minimizer.go:140-142
-        const int span = PH == 0 ? K : PH == 1 ? K - 8 + (u - U0) : (u < U0 ? K - U0 + u : K);   // :127-131
+        const int span = (PH == 0 || PH == 4) ? K : PH == 1 ? K - 8 + (u - U0) : (u < U0 ? K - U0 + u : K);   // :127-131
         const bool lt = dbl_make(f_hi, f_lo) < dbl_make(r_hi, r_lo);      // k-mers as bit patterns: tiny positive doubles
         uint32_t lo = lt ? f_lo : r_lo, hi = lt ? f_hi : r_hi;            // minimizer.go:150-153
         // hash64 (minimizer.go:33-42), masks deferred into the xor-shifts
@@ -193,12 +194,22 @@ HULK_UNROLL
         if (t > T0) pref = k1_vmin<R::ARITH>(pref, X[t]);
         const double m = k1_vmin<R::ARITH>(A[t], pref);                   // suffix of the previous block, prefix of this one
         A[t] = X[t];
+        if (PH == 4) {
+            const bool fresh = t < rem && m != L.last;                    // positions at or behind the read's end: nothing
+            if (fresh) {
+                L.base[(size_t)L.n * STRIDE] = dbl_bits(m);
+                L.n++;
+                L.last = m;
+            }
+            continue;
+        }
         if (m != L.last) {                                                // minimizer.go:186-199 (room for 8 was checked)
             L.base[(size_t)L.n * STRIDE] = dbl_bits(m);
             L.n++;
         }
         L.last = m;
     }
+    if (PH == 4) return;                                                  // nothing behind the last block
 HULK_UNROLL
     for (int x = 6; x >= 0; x--) A[x] = k1_vmin<R::ARITH>(A[x], A[x + 1]);   // suffix minima in place
 }
@@ -292,14 +303,24 @@ HULK_UNROLL
         uint32_t w0, w1, bad0, bad1;
         src.next(w0, w1);
         uint32_t c0 = nt4x4b(w0, bad0), c1 = nt4x4b(w1, bad1);
-        if (bad0 | bad1) {                                                // N, IUPAC, raw 0..3 bytes, ... (or bytes past the end)
+        const int32_t rem = len - i0;                                     // positions of this block inside the read
+        if (rem < 8) {                                                    // bytes at or past the end say nothing about the read
+            const uint32_t keep0 = rem >= 4 ? 0xFFFFFFFFu : (1u << (8 * rem)) - 1u;
+            const uint32_t keep1 = rem <= 4 ? 0u : (1u << (8 * (rem - 4))) - 1u;
+            bad0 &= keep0;
+            bad1 &= keep1;
+        }
+        if (bad0 | bad1) {                                                // N, IUPAC, raw 0..3 bytes, ...
             c0 = nt4_bytes(w0);
             c1 = nt4_bytes(w1);
             fast_from = i0 + K + 9;                                       // a code 4 lives k steps in fwd, k + 1 in rev
         }
         constexpr int32_t HEAD = 8 * ((K - 1) >> 3);                       // start of the block that holds position k-1
-        const bool quick = HAS_FAST && i0 + 8 <= len && L.n + 8u <= L.cap;
-        if (quick && i0 >= fast_from) {
+        const bool room = HAS_FAST && L.n + 8u <= L.cap;
+        const bool quick = room && rem >= 8;
+        if (room && rem < 8 && i0 >= fast_from) {                         // the read's last, partial block
+            if constexpr (HAS_FAST) k1_fast_block<K, STRIDE, 4>(c0, c1, f_lo, f_hi, r_lo, r_hi, A, L, rem);
+        } else if (quick && i0 >= fast_from) {
             if constexpr (HAS_FAST) k1_fast_block<K, STRIDE, 0>(c0, c1, f_lo, f_hi, r_lo, r_hi, A, L);
         } else if (quick && fast_from == K + 7) {                         // head of a read without any foreign byte so far
             if constexpr (HAS_FAST) {
