@@ -994,6 +994,13 @@ static int draw_tables_on_device(hulk_b200_ctx *ctx) {
     C = std::min<uint64_t>(C, 1024);
     const uint64_t R = C * L, A = R / 2 + 2;                              // raw outputs and attempts (at most) per round
     const uint32_t ext_cap = 1u << 16, tie_cap = 1u << 12;
+    // how close to its boundary an acceptance test has to be for the host to decide it (tests widen the band to drive
+    // attempts through that path: HULK_B200_CWS_TIE_EPS)
+    double tie_eps = 1e-9;
+    {
+        const char *e = getenv("HULK_B200_CWS_TIE_EPS");
+        if (e && atof(e) > 0.0) tie_eps = atof(e);
+    }
     const uint32_t nblk = (uint32_t)((A + K4_COUNT_TPB - 1) / K4_COUNT_TPB);
     DevBuf keep;
     uint64_t *d_states = nullptr, *d_poly = nullptr, *d_raw = nullptr, *d_ext = nullptr;
@@ -1093,7 +1100,7 @@ static int draw_tables_on_device(hulk_b200_ctx *ctx) {
         segs.total_attempts = attempts;
         if (attempts) {
             CU(cudaMemsetAsync(d_samp, 0, sizeof(K4SampleOut), st));
-            k4_sample<<<ctx->sm_count * 8, 256, 0, st>>>(d_raw, segs, d_xs, d_acc, d_ties, tie_cap, d_samp);
+            k4_sample<<<ctx->sm_count * 8, 256, 0, st>>>(d_raw, segs, d_xs, d_acc, d_ties, tie_cap, d_samp, tie_eps);
             LAUNCH_CHECK("k4_sample");
             K4SampleOut sp;
             CU(cudaMemcpyAsync(&sp, d_samp, sizeof sp, cudaMemcpyDeviceToHost, st));

@@ -149,7 +149,7 @@ struct K4SampleOut {
 // Cheng's sampler for alpha = 2, beta = 1 as go_rng ports it from CPython's random.gammavariate
 __global__ void k4_sample(const uint64_t *__restrict__ raw, const K4Segments segs, double *__restrict__ xs,
                           uint8_t *__restrict__ accept, K4Tie *__restrict__ ties, const uint32_t ties_cap,
-                          K4SampleOut *__restrict__ out) {
+                          K4SampleOut *__restrict__ out, const double tie_eps) {
     const double alpha = 2.0;
     const double ainv = sqrt(2.0 * alpha - 1.0), bbb = alpha - log(4.0), ccc = alpha + ainv, magic = 1.0 + log(4.5);
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < segs.total_attempts;
@@ -166,7 +166,7 @@ __global__ void k4_sample(const uint64_t *__restrict__ raw, const K4Segments seg
         const double t1 = r + magic - 4.5 * z, t2 = r - log(z);
         const bool acc = t1 >= 0.0 || t2 >= 0.0;
         // a test this close to its boundary could come out the other way with another libm: the host decides
-        const bool tie = (fabs(t1) < 1e-9 && !(t2 >= 1e-9)) || (fabs(t2) < 1e-9 && !(t1 >= 1e-9));
+        const bool tie = (fabs(t1) < tie_eps && !(t2 >= tie_eps)) || (fabs(t2) < tie_eps && !(t1 >= tie_eps));
         if (tie) {
             const unsigned int at = atomicAdd(&out->n_ties, 1u);
             if (at < ties_cap) ties[at] = K4Tie{g, raw1, raw2};

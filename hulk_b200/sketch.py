@@ -445,6 +445,10 @@ class GroupSketch:
                 raise HulkError(N.EARG, f"table shape {t.shape}, expected {want}")
         self._check(self._L.hulk_b200_group_set_cws_tables(self._g, _ptr(r), _ptr(c), _ptr(b)))
 
+    def generate_tables_device(self):
+        """Every member draws the rows of its slots on its own GPU (hulk_b200_group_generate_cws_tables_device)."""
+        self._check(self._L.hulk_b200_group_generate_cws_tables_device(self._g))
+
     def generate_tables(self, background: bool = False):
         self._check(self._L.hulk_b200_group_generate_cws_tables(self._g, int(background)))
 

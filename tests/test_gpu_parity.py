@@ -496,7 +496,7 @@ def _ulp_diff(a, b):
     return np.abs(ia - ib)
 
 
-@pytest.mark.parametrize("k,s,slots", [(11, 16, None), (11, 16, (5, 9)), (21, 3, None), (15, 40, (0, 7))])
+@pytest.mark.parametrize("k,s,slots", [(11, 16, None), (11, 16, (5, 9)), (21, 3, None), (15, 40, (0, 7)), (21, 128, (100, 128))])
 def test_cws_tables_drawn_on_the_device(hb, k, s, slots):
     """hulk_b200_generate_cws_tables_device against the host generator (hulk_b200_new_cws): the same accept/reject
     SEQUENCE (a single difference would shift every later entry, so agreement of the last row proves it), values equal
@@ -515,6 +515,21 @@ def test_cws_tables_drawn_on_the_device(hb, k, s, slots):
     # c = ln(draw): a draw next to 1 gives a logarithm next to 0, where one ulp of the draw is many ulps of c
     np.testing.assert_allclose(c1, c0, rtol=1e-14, atol=4e-16)
     assert (c1 == c0).mean() > 0.5
+
+
+def test_cws_device_draw_lets_the_host_decide_what_is_close(hb, monkeypatch):
+    """With the band widened to 2e-3, about one attempt in a thousand goes through the host's re-decision: the tables
+    must not change (the host decides as the device would have, except on true near-ties)."""
+    k, s = 11, 16
+    D = k ** 4
+    r0, c0, b0 = hb.new_cws(s, D)
+    monkeypatch.setenv("HULK_B200_CWS_TIE_EPS", "2e-3")
+    with hb.HistoSketch(k, 9, s, 1.0) as hs:
+        hs.generate_tables_device()
+        r1, c1, b1 = hs.tables()
+    np.testing.assert_allclose(r1, r0, rtol=8e-15, atol=0)
+    np.testing.assert_allclose(c1, c0, rtol=1e-14, atol=4e-16)
+    np.testing.assert_allclose(b1, b0, rtol=8e-15, atol=0)
 
 
 def test_sketch_with_device_drawn_tables_matches_the_oracle(hb, oracle):
