@@ -41,8 +41,8 @@
 
 using namespace hulk;
 
-// k values served by the second-generation w = 9 scan (k1_scan2.h: odd k with two-word k-mers)
-#define K1_V2_FOR_EACH_K(X) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31)
+// k values served by the second-generation w = 9 scan (k1_scan2.h: odd k with two-word k-mers; k = 9, 11 in one word)
+#define K1_V2_FOR_EACH_K(X) X(9) X(11) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31)
 
 constexpr int NBUF = 4;     // spectrum buffers allocated; ctx->nbuf of them are cycled = intervals in flight at once
 constexpr int NSTAGE = 4;   // host-input staging buffers (ring)

@@ -285,12 +285,128 @@ HULK_UNROLL
     }
 };
 
+// ---- k = 9, 11 (odd, 2k + 8 <= 32): everything fits one 32-bit word -----------------------------------------
+// The k-mer pair is one word each, hash64 works on 2k <= 22 bits -- its `>> 24` and `>> 28` xor-shifts and its last
+// multiplication (key + key << 31) are the identity there -- X = hash << 8 | span has at most 30 bits, and a minimum is one
+// integer instruction.  Same block decomposition and the same phases as k1_fast_block; the state between blocks is the
+// k-mer pair and eight suffix minima as 32-bit words.  The list still holds the 64-bit stored form (2^52 + X).
+constexpr uint32_t K1_SENT32 = 0xFFFFFFFFu;                                // larger than any X
+template <int K, int STRIDE, int PH>
+HULK_HD void k1_fast_block32(const uint32_t codes0, const uint32_t codes1, uint32_t &f, uint32_t &r, uint32_t (&A)[8],
+                             uint32_t &last, K1List<STRIDE> &L, const int32_t rem = 8) {
+    static_assert((K == 9 || K == 11), "32-bit block: odd k with 2k + 8 <= 32 and k - 1 >= 8");
+    constexpr int U0 = (K - 1) & 7;
+    constexpr uint32_t M = (1u << (2 * K)) - 1u;
+    constexpr int SH = 2 * (K - 1);
+    uint32_t X[8];
+HULK_UNROLL
+    for (int u = 0; u < 8; u++) {
+        const uint32_t c = ((u < 4 ? codes0 : codes1) >> (8 * (u & 3))) & 0xffu;
+        f = ((f << 2) | c) & M;                                           // minimizer.go:134
+        r = (r >> 2) | ((3u ^ c) << SH);                                  // :137
+        if (PH == 3 || (PH == 1 && u < U0)) continue;                     // :140-142
+        const int span = (PH == 0 || PH == 4) ? K : PH == 1 ? K - 8 + (u - U0) : (u < U0 ? K - U0 + u : K);   // :127-131
+        uint32_t key = f < r ? f : r;                                     // :150-153 (odd k: never equal)
+        key = key * 2097151u + 0xFFFFFFFFu;                               // hash64 (:33-42), masks deferred to the xor-shift
+        key = key * 265u;
+        key &= M;
+        key ^= key >> 14;
+        key = key * 21u;
+        X[u] = ((key << 8) & (M << 8)) | (uint32_t)span;                  // :156-159
+    }
+    if (PH == 3) return;
+    constexpr int T0 = PH == 1 ? U0 : 0;
+    uint32_t pref = X[T0];
+HULK_UNROLL
+    for (int t = 0; t < 8; t++) {
+        if (t < T0) {
+            A[t] = K1_SENT32;
+            continue;
+        }
+        if (t > T0) pref = pref < X[t] ? pref : X[t];
+        const uint32_t m = A[t] < pref ? A[t] : pref;
+        A[t] = X[t];
+        const bool fresh = (PH != 4 || t < rem) && m != last;             // minimizer.go:186-199 (room for 8 was checked)
+        if (fresh) {
+            L.base[(size_t)L.n * STRIDE] = K1Repr<K>::PREFIX | (uint64_t)m;
+            L.n++;
+            last = m;
+        }
+    }
+    if (PH == 4) return;
+HULK_UNROLL
+    for (int x = 6; x >= 0; x--) A[x] = A[x] < A[x + 1] ? A[x] : A[x + 1];
+}
+
+template <int K, int STRIDE, class Src>
+HULK_HD void k1_scan_read_w9_32(Src src, const int32_t len, K1List<STRIDE> &L) {
+    using R = K1Repr<K>;
+    uint32_t f = 0, r = 0, last = K1_SENT32;
+    uint32_t A[8];
+HULK_UNROLL
+    for (int x = 0; x < 8; x++) A[x] = K1_SENT32;
+    L.last = bits_dbl(R::SENT);
+    int32_t fast_from = K + 7;
+    for (int32_t i0 = 0; i0 < len; i0 += 8) {
+        uint32_t w0, w1, bad0, bad1;
+        src.next(w0, w1);
+        uint32_t c0 = nt4x4b(w0, bad0), c1 = nt4x4b(w1, bad1);
+        const int32_t rem = len - i0;
+        if (rem < 8) {
+            const uint32_t keep0 = rem >= 4 ? 0xFFFFFFFFu : (1u << (8 * rem)) - 1u;
+            const uint32_t keep1 = rem <= 4 ? 0u : (1u << (8 * (rem - 4))) - 1u;
+            bad0 &= keep0;
+            bad1 &= keep1;
+        }
+        if (bad0 | bad1) {
+            c0 = nt4_bytes(w0);
+            c1 = nt4_bytes(w1);
+            fast_from = i0 + K + 9;
+        }
+        constexpr int32_t HEAD = 8 * ((K - 1) >> 3);
+        const bool room = L.n + 8u <= L.cap;
+        const bool quick = room && rem >= 8;
+        if (room && rem < 8 && i0 >= fast_from) {
+            k1_fast_block32<K, STRIDE, 4>(c0, c1, f, r, A, last, L, rem);
+        } else if (quick && i0 >= fast_from) {
+            k1_fast_block32<K, STRIDE, 0>(c0, c1, f, r, A, last, L);
+        } else if (quick && fast_from == K + 7) {
+            if (i0 < HEAD) k1_fast_block32<K, STRIDE, 3>(c0, c1, f, r, A, last, L);
+            else if (i0 == HEAD) k1_fast_block32<K, STRIDE, 1>(c0, c1, f, r, A, last, L);
+            else k1_fast_block32<K, STRIDE, 2>(c0, c1, f, r, A, last, L);
+        } else {
+            // the reference's loop on the 64-bit state (a code 4 makes rev outgrow 2k bits: minimizer.go:137 does not mask it)
+            uint64_t fwd = f, rev = r;
+            double Ad[8];
+HULK_UNROLL
+            for (int x = 0; x < 8; x++) Ad[x] = A[x] == K1_SENT32 ? bits_dbl(R::SENT) : bits_dbl(R::PREFIX | (uint64_t)A[x]);
+            L.last = last == K1_SENT32 ? bits_dbl(R::SENT) : bits_dbl(R::PREFIX | (uint64_t)last);
+            k1_general_block<K, STRIDE>(c0, c1, i0, len, fwd, rev, Ad, L);
+            // back to words: a pair that no longer fits (a code 4 still inside it) keeps the general block until it has left
+            if ((fwd | rev) >> 32) fast_from = i0 + K + 9 > fast_from ? i0 + K + 9 : fast_from;
+            f = (uint32_t)fwd;
+            r = (uint32_t)rev;
+HULK_UNROLL
+            for (int x = 0; x < 8; x++) {
+                const uint64_t bits = dbl_bits(Ad[x]);
+                A[x] = bits == R::SENT ? K1_SENT32 : (uint32_t)R::to_x(bits);
+            }
+            const uint64_t lb = dbl_bits(L.last);
+            last = lb == R::SENT ? K1_SENT32 : (uint32_t)R::to_x(lb);
+        }
+    }
+}
+
 // Scan one read of at least 9 + k - 1 bases (the caller applied minimizer.go:62-76); the candidates end up in L
 // (stored form of K1Repr<K>, position order, adjacent duplicates removed).  8 <= k <= 31.
 template <int K, int STRIDE, class Src>
 HULK_HD void k1_scan_read_w9_v2(Src src, const int32_t len, K1List<STRIDE> &L) {
     using R = K1Repr<K>;
     static_assert(K >= 8 && K <= 31, "w = 9 needs k >= 8 for a non-negative span");
+    if constexpr (K == 9 || K == 11) {                                    // one-word k-mers and values
+        k1_scan_read_w9_32<K, STRIDE>(src, len, L);
+        return;
+    }
     constexpr bool HAS_FAST = (K & 1) && K >= 17;
     const double SENT = bits_dbl(R::SENT);
     uint32_t f_lo = 0, f_hi = 0, r_lo = 0, r_hi = 0;
