@@ -1590,7 +1590,7 @@ static void feeder_main(hulk_b200_ctx *ctx) {
                                ctx->copy_stream), "cudaMemcpyAsync");
             cu(cudaEventRecord(ctx->ev_tail[buf], ctx->copy_stream), "cudaEventRecord");
             moved += rq.nb - n_head;
-            if (rq.nb - n_head >= (1u << 20)) {                       // long enough to time
+            if (rq.nb - n_head >= (1u << 18)) {                       // long enough to time
                 ctx->feed_last_tail = buf;
                 ctx->feed_last_tail_bytes = rq.nb - n_head;
             }
@@ -1606,7 +1606,7 @@ static void feeder_main(hulk_b200_ctx *ctx) {
             ctx->feed_pack_ns += ns;
             if (prc) { rc = prc; msg = std::string(hulk_b200_strerror(prc)) + ": pack_bases"; }
             packed = prc == HULK_B200_OK && n_exc <= exc_cap;
-            if (ns && n_head >= (1u << 20)) {
+            if (ns && n_head >= (1u << 18)) {
                 const double bp = (double)n_head / (ns * 1e-9);
                 ctx->feed_bp = ctx->feed_bp > 0.0 ? 0.75 * ctx->feed_bp + 0.25 * bp : bp;
             }
