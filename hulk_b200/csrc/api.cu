@@ -45,7 +45,7 @@ using namespace hulk;
 #define K1_V2_FOR_EACH_K(X) X(9) X(11) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31)
 
 constexpr int NBUF = 4;     // spectrum buffers allocated; ctx->nbuf of them are cycled = intervals in flight at once
-constexpr int NSTAGE = 4;   // host-input staging buffers (ring)
+constexpr int NSTAGE = 6;   // host-input staging buffers (ring): deep enough that the feeder never waits for the copy that last used one
 
 struct hulk_b200_ctx {
     hulk_b200_params P{};
