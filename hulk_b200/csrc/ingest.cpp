@@ -300,6 +300,9 @@ struct hulk_b200_reader {
             size_t total = 0;
             Tail tail = END;
             std::atomic<bool> bad{false};
+            std::mutex bad_mu;                              // first bad member of the window and what is wrong with it
+            size_t bad_idx = (size_t)-1;
+            std::string bad_msg;
         } win[2];
         size_t off = 0, win_bytes = 64u << 20;
         if (const char *e = getenv("HULK_B200_BGZF_WINDOW")) win_bytes = std::max<size_t>(1, strtoull(e, nullptr, 10));   // tests
@@ -308,6 +311,8 @@ struct hulk_b200_reader {
             w.blks.clear();
             w.total = 0;
             w.bad = false;
+            w.bad_idx = (size_t)-1;
+            w.bad_msg.clear();
             w.tail = END;
             while (off < size) {
                 if (w.total >= win_bytes) { w.tail = MORE; break; }
@@ -343,6 +348,16 @@ struct hulk_b200_reader {
                     const uint32_t crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
                     if (ist != pgz::ST_OK || got != b.isize || used != b.bsize - b.hdr - 8 ||
                         (uint32_t)crc32(0L, scratch.p, (uInt)got) != crc) {
+                        // what compress/gzip would have said at this member: the inflater's own error first, then the
+                        // trailer checks (gzip.ErrChecksum covers both the CRC and the length)
+                        std::string why = ist == pgz::ST_EOF ? "unexpected EOF"
+                                          : ist != pgz::ST_OK ? "flate: corrupt input (" + msg + ")"
+                                                              : "gzip: invalid checksum";
+                        std::lock_guard<std::mutex> lk(w.bad_mu);
+                        if (i < w.bad_idx) {
+                            w.bad_idx = i;
+                            w.bad_msg = why;
+                        }
                         w.bad = true;
                         continue;
                     }
@@ -366,7 +381,13 @@ struct hulk_b200_reader {
                 ahead = std::thread([&, wi] { inflate_window(win[wi ^ 1]); });
             }
             if (stop) ok = false;
-            else if (w.bad) ok = fail(HULK_B200_EIO, "gzip: invalid checksum");
+            else if (w.bad) {
+                // the members in front of the first bad one are good data: they are delivered (and may raise a framing
+                // error of their own) before the stream fails where a streaming reader would have failed
+                const size_t good = w.blks[w.bad_idx].out;
+                ok = good ? feed(w.data.data(), good, carry) : true;
+                if (ok) ok = fail(HULK_B200_EIO, w.bad_msg);
+            }
             else if (w.total) ok = feed(w.data.data(), w.total, carry);
             if (ahead.joinable()) ahead.join();
             if (!ok || fasta_stop) break;

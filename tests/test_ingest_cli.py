@@ -397,6 +397,43 @@ def _bgzf(data, block=0xff00, level=6):
     return bytes(out)
 
 
+def test_bgzf_bad_member_delivers_what_came_before(tmp_path):
+    """A damaged member in the middle of a BGZF file: the parallel path hands on the reads of the members in front of it
+    and then fails with the text the one-thread path (compress/gzip's rules) gives -- not the whole window dropped, not
+    every failure called a checksum error."""
+    import struct
+    reads = random_reads(6000, 150, seed=33)
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
+    good = bytearray(_bgzf(rec))
+    # member boundaries from the BSIZE fields
+    offs, o = [], 0
+    while o < len(good):
+        offs.append(o)
+        o += struct.unpack_from("<H", good, o + 16)[0] + 1
+    assert len(offs) > 12
+    m = offs[7]
+    size = offs[8] - offs[7]
+    cases = {}
+    crc = bytearray(good); crc[m + size - 8] ^= 1                                  # CRC-32 of member 7
+    cases["crc"] = (bytes(crc), "gzip: invalid checksum")
+    isz = bytearray(good); isz[m + size - 4] ^= 1                                  # ISIZE of member 7
+    cases["isize"] = (bytes(isz), "gzip: invalid checksum")
+    body = bytearray(good); body[m + 18 + 40] ^= 0xFF; body[m + 18 + 41] ^= 0xFF   # deflate data of member 7
+    cases["body"] = (bytes(body), None)
+    for name, (data, want_msg) in cases.items():
+        f = tmp_path / (name + ".fastq.gz")
+        f.write_bytes(data)
+        one = _native_env([f], {"HULK_B200_PARALLEL_READER": "0"}).split(" ", 4)
+        par = _native_env([f], {"HULK_B200_PARALLEL_READER": "1", "HULK_B200_BGZF_WINDOW": "300000"}).split(" ", 4)
+        assert one[0] == par[0] == "ERR", (name, one, par)
+        n_one, n_par = int(one[1]), int(par[1])
+        assert n_par > 0 and abs(n_one - n_par) <= 450, (name, n_one, n_par)      # at most one member's worth of reads apart
+        if want_msg:
+            assert one[4] == par[4] == want_msg, (name, one[4], par[4])
+        else:
+            assert par[4] in ("gzip: invalid checksum", "unexpected EOF") or par[4].startswith("flate: corrupt input"), par[4]
+
+
 def test_bgzf_reader_equals_plain_gzip(tmp_path):
     reads = random_reads(20000, 150, seed=21, ragged=50)
     rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
