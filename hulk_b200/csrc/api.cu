@@ -123,6 +123,8 @@ struct hulk_b200_ctx {
     uint64_t feed_last_tail_bytes = 0;
     double feed_bp = 0.0, feed_bl = 0.0;       // measured rates, bytes of bases per second: packing, link (0: not measured yet)
     double feed_frac = 0.75;                   // share of a batch that travels packed (feeder thread only)
+    double feed_step = 1.0 / 16.0;             // how far the split moves per batch
+    int feed_dir = 0;
     double feed_frac_sum = 0.0;
     bool feed_adapt = true;                    // HULK_B200_PACK_FRACTION=<0..1> pins the share
     std::atomic<uint64_t> feed_h2d{0}, feed_pack_ns{0}, feed_batches{0};
@@ -1558,11 +1560,13 @@ static void feeder_main(hulk_b200_ctx *ctx) {
         // Two resources move a batch: the host's cores (packing, bound by their memory bandwidth) and the link.  Packing
         // everything leaves the link idle three quarters of the time, so the batch is split: its TAIL travels as letters
         // -- that copy is enqueued first and runs while the HEAD is being packed -- and the head travels packed.  The
-        // split follows the two rates as measured (packing: bases per second of this thread's pack calls; link: CUDA events
-        // around the previous tail copy): with a share f packed, packing takes f n / Bp and the link carries
-        // (1 - 0.75 f) n / Bl; they finish together at f = Bp / (Bl + 0.75 Bp).
+        // split point follows what is observed at the end of every pack call: if the tail had already arrived, the cores
+        // are the bottleneck and the next batch packs less; if it was still on the link, more.  The step starts at 1/16
+        // and halves (down to 1/64) whenever the direction turns.  (A split computed from the two measured rates,
+        // f = Bp / (Bl + 0.75 Bp), was tried: both rates sag when the other side runs -- they share the host's memory
+        // system -- and it settled 5-8 % slower at one rank per host.  The rates are still measured, for the record.)
         uint64_t n_exc = 0, moved = 0;
-        if (ctx->feed_adapt && ctx->feed_last_tail >= 0 && cudaEventQuery(ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess) {
+        if (ctx->feed_last_tail >= 0 && cudaEventQuery(ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ctx->ev_tail0[ctx->feed_last_tail], ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess &&
                 ms > 0.f) {
@@ -1572,11 +1576,6 @@ static void feeder_main(hulk_b200_ctx *ctx) {
             ctx->feed_last_tail = -1;
         }
         cudaGetLastError();                                           // cudaErrorNotReady is not an error
-        if (ctx->feed_adapt && ctx->feed_bp > 0.0 && ctx->feed_bl > 0.0) {
-            const double f = ctx->feed_bp / (ctx->feed_bl + 0.75 * ctx->feed_bp);
-            // both rates have to stay observable: never less than 1/32 packed, never less than 1/32 as letters
-            ctx->feed_frac = std::min(31.0 / 32.0, std::max(1.0 / 32.0, 0.5 * ctx->feed_frac + 0.5 * f));
-        }
         uint64_t n_head = (uint64_t)(ctx->feed_frac * (double)rq.nb) & ~63ull;     // bases that travel packed
         if (n_head < 4096) n_head = 0;
         if (rq.nb - n_head < 4096) n_head = rq.nb;
@@ -1610,6 +1609,16 @@ static void feeder_main(hulk_b200_ctx *ctx) {
                 const double bp = (double)n_head / (ns * 1e-9);
                 ctx->feed_bp = ctx->feed_bp > 0.0 ? 0.75 * ctx->feed_bp + 0.25 * bp : bp;
             }
+            if (ctx->feed_adapt && rc == HULK_B200_OK) {
+                const bool tail_arrived = !has_tail || cudaEventQuery(ctx->ev_tail[buf]) == cudaSuccess;
+                cudaGetLastError();
+                const int dir = tail_arrived ? -1 : 1;
+                if (dir != ctx->feed_dir) ctx->feed_step = std::max(ctx->feed_step * 0.5, 1.0 / 64.0);
+                ctx->feed_dir = dir;
+                ctx->feed_frac = std::min(1.0, std::max(0.0, ctx->feed_frac + dir * ctx->feed_step));
+            }
+        } else if (ctx->feed_adapt && n_head == 0) {
+            ctx->feed_frac = 1.0 / 16.0;                              // try packing a little again
         }
         ctx->feed_frac_sum += (double)n_head / (double)std::max<uint64_t>(1, rq.nb);
         FEED_DBG("feeder: packed %llu of %llu bases (rc %d, %llu exceptions), copying", (unsigned long long)n_head,
