@@ -45,9 +45,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--k", type=int, default=21)
+    ap.add_argument("--k", "--kmer-size", dest="k", type=int, default=21)
     ap.add_argument("--w", type=int, default=9)
-    ap.add_argument("--s", type=int, default=512)
+    ap.add_argument("--s", "--sketch-size", dest="s", type=int, default=512,
+                    help="(under torchrun use --sketch-size: its own parser takes --s for an abbreviation)")
     ap.add_argument("--interval", type=int, default=100_000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--decay", type=float, default=1.0)

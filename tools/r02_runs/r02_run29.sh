@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 300 python __graft_entry__.py > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -20 gpurun_out/build.log; }
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29511 --nproc-per-node 2"
 for k in 11 21 31; do for s in 128 512 2048; do
-  timeout 200 $TR bench.py --gpus 2 --scaling strong --k $k --s $s --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/c5g2_${k}_${s}.log 2> gpurun_out/c5g2_${k}_${s}.err || echo "k=$k s=$s failed"
+  timeout 200 $TR bench.py --gpus 2 --scaling strong --kmer-size $k --sketch-size $s --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/c5g2_${k}_${s}.log 2> gpurun_out/c5g2_${k}_${s}.err || echo "k=$k s=$s failed"
 done; done
 python - <<'PY' > gpurun_out/r02r_c5_strong_g2.txt
 import json
