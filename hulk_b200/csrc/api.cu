@@ -1564,9 +1564,9 @@ static void feeder_main(hulk_b200_ctx *ctx) {
         // are the bottleneck and the next batch packs less; if it was still on the link, more.  The step starts at 1/16
         // and halves (down to 1/64) whenever the direction turns.  (A split computed from the two measured rates,
         // f = Bp / (Bl + 0.75 Bp), was tried: both rates sag when the other side runs -- they share the host's memory
-        // system -- and it settled 5-8 % slower at one rank per host.  The rates are still measured, for the record.)
+        // system -- and it settled 5-8 % slower at one rank per host.  With HULK_B200_FEED_STATS=1 the rates are still measured.)
         uint64_t n_exc = 0, moved = 0;
-        if (ctx->feed_last_tail >= 0 && cudaEventQuery(ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess) {
+        if (g_host_stats && ctx->feed_last_tail >= 0 && cudaEventQuery(ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ctx->ev_tail0[ctx->feed_last_tail], ctx->ev_tail[ctx->feed_last_tail]) == cudaSuccess &&
                 ms > 0.f) {
@@ -1584,12 +1584,12 @@ static void feeder_main(hulk_b200_ctx *ctx) {
         cu(cudaStreamWaitEvent(ctx->copy_stream, rq.stage_free, 0), "cudaStreamWaitEvent");
         const bool has_tail = n_head < rq.nb;
         if (rc == HULK_B200_OK && has_tail) {
-            cu(cudaEventRecord(ctx->ev_tail0[buf], ctx->copy_stream), "cudaEventRecord");
+            if (g_host_stats) cu(cudaEventRecord(ctx->ev_tail0[buf], ctx->copy_stream), "cudaEventRecord");   // link rate, for the record
             cu(cudaMemcpyAsync(ctx->d_stage[buf] + n_head, rq.src + n_head, rq.nb - n_head, cudaMemcpyHostToDevice,
                                ctx->copy_stream), "cudaMemcpyAsync");
             cu(cudaEventRecord(ctx->ev_tail[buf], ctx->copy_stream), "cudaEventRecord");
             moved += rq.nb - n_head;
-            if (rq.nb - n_head >= (1u << 18)) {                       // long enough to time
+            if (g_host_stats && rq.nb - n_head >= (1u << 18)) {       // long enough to time
                 ctx->feed_last_tail = buf;
                 ctx->feed_last_tail_bytes = rq.nb - n_head;
             }
