@@ -37,7 +37,7 @@ import (
 	"os"
 	"sort"
 
-	"github.com/leesper/go_rng"
+	rng "github.com/leesper/go_rng"
 	"github.com/will-rowe/hulk/src/countmin"
 	"github.com/will-rowe/hulk/src/histosketch"
 	"github.com/will-rowe/hulk/src/kmerspectrum"
