@@ -35,6 +35,7 @@
 
 #include "../../include/hulk_b200.h"
 #include "k1_minimizer.cuh"
+#include "k1_long.cuh"
 #include "k2_countmin.cuh"
 #include "k3_cws.cuh"
 #include "k4_cwsdraw.cuh"
@@ -140,6 +141,7 @@ struct hulk_b200_ctx {
     int k1_ctas_per_sm = 4;                    // scan CTAs per SM in queue mode (tasks are handed out dynamically):
                                                // one short of what fits, so the flush chain always finds SM room
     uint64_t batch_max_len = 0;                // longest read of the batch being pushed (0: unknown)
+    uint64_t batch_long_entries = 0;           // arena entries the sets of its long sequences take (k1_long.cuh)
     uint64_t max_launch_reads = 1ull << 22;    // reads per k1 launch (HULK_B200_MAX_LAUNCH_READS)
     int jump_ctas_per_sm = K1_JUMP_CTAS_PER_SM;
     int jump_batch = 4;                        // jump steps between two refill points of k1_jump_queue
@@ -149,6 +151,9 @@ struct hulk_b200_ctx {
     bool jump_fx = true;                       // HULK_B200_JUMP_FX=0: keep the bracketed jump step for every D (A/B measurements)
     bool k1_v2 = true;                         // HULK_B200_K1_V2=0: keep the first-generation w = 9 scan (A/B measurements)
     uint64_t *d_arena[NBUF] = {};
+    K1LongTask *d_long_tasks[NBUF] = {};       // long sequences of the launch in flight on each k1 stream (k1_long.cuh)
+    K1LongCtl *d_long_ctl[NBUF] = {};
+    bool long_path = true;                     // HULK_B200_LONG=0: long sequences stay with k1_generic (A/B)
     unsigned long long *d_arena_cursor[NBUF] = {};
     uint64_t arena_entries[NBUF] = {};
 
@@ -357,7 +362,7 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < NBUF; i++) {
         void *per[] = {ctx->d_ovf_count[i], ctx->d_ovf_list[i], ctx->d_arena[i], ctx->d_arena_cursor[i],
-                       ctx->d_queue[i], ctx->d_queue_cursor[i]};
+                       ctx->d_queue[i], ctx->d_queue_cursor[i], ctx->d_long_tasks[i], ctx->d_long_ctl[i]};
         for (void *p : per)
             if (p) cudaFree(p);
     }
@@ -518,6 +523,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(dmalloc(&ctx->d_ovf_list[i], ctx->ovf_cap));
         CU(dmalloc(&ctx->d_arena_cursor[i], 1));
         CU(dmalloc(&ctx->d_queue_cursor[i], 2));
+        CU(dmalloc(&ctx->d_long_tasks[i], K1_LONG_TASKS));
+        CU(dmalloc(&ctx->d_long_ctl[i], 1));
     }
     CU(dmalloc(&ctx->d_ctl, 1));
     CU(dmalloc(&ctx->d_cols, (uint64_t)D * CMS_DEPTH));
@@ -643,6 +650,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
         HULK_PRELOAD(k0_patch_fed);
         HULK_PRELOAD(k1_generic<false>);
         HULK_PRELOAD(k1_generic<true>);
+        HULK_PRELOAD(k1_long_plan);
+        HULK_PRELOAD(k1_long_zero);
+        HULK_PRELOAD(k1_long_scan<false>);
+        HULK_PRELOAD(k1_long_scan<true>);
         HULK_PRELOAD((k1_jump_queue<2>));
         HULK_PRELOAD((k1_jump_queue<4>));
         HULK_PRELOAD((k1_jump_queue_fx<2, false>));
@@ -657,6 +668,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         ctx->force_tile_path = e && *e == '1';
         e = getenv("HULK_B200_K1_CTAS");
         if (e && *e >= '1' && *e <= '0' + K1_W9_CTAS_PER_SM) ctx->k1_ctas_per_sm = *e - '0';
+        e = getenv("HULK_B200_LONG");
+        ctx->long_path = !(e && *e == '0');
         e = getenv("HULK_B200_MAX_LAUNCH_READS");
         if (e && atoll(e) >= 32) ctx->max_launch_reads = (uint64_t)atoll(e);
         e = getenv("HULK_B200_JUMP_CTAS");
@@ -1283,18 +1296,28 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     p.dump = d_dump;
     p.dump_cap = dump_cap;
     p.dump_counts = d_dump_counts;
+    // sequences of K1_LONG_MIN bases or more go to the sliced scan (k1_long.cuh) whenever the host cannot rule them
+    // out: each takes a table of at most four entries per base behind k1_generic's allocations
+    const bool long_on = ctx->long_path && (ctx->batch_max_len ? ctx->batch_max_len >= K1_LONG_MIN
+                                                               : (d_offsets != nullptr && fixed_len == 0));
+    p.long_min = long_on ? (uint64_t)K1_LONG_MIN : ~0ull;
+    p.long_seg = k1_long_seg(ctx->P.k, ctx->P.w);
+    p.long_cap = K1_LONG_TASKS;
+    p.long_tasks = ctx->d_long_tasks[hs];
+    p.long_ctl = ctx->d_long_ctl[hs];
     // scratch arena of the generic path: 4 table slots per base of the batch, at least 4 Mi entries
     uint64_t want = std::max<uint64_t>(1ull << 22, 4 * total_bytes + (n_reads << 7));
     // only reserve the large arena when the generic path will take whole batches ...
     uint64_t arena_cap = 1ull << 26;
-    if (ctx->batch_max_len > (1u << 20)) {
-        // ... or a very long sequence (a chromosome in --fasta mode) is in the batch: room for its
-        // open-addressing table (two slots per k-mer, a power of two), twice over
+    if (!long_on && ctx->batch_max_len > (1u << 20)) {
+        // ... or a very long sequence (a chromosome in --fasta mode) is in the batch and the sliced scan is off: room
+        // for its open-addressing table (two slots per k-mer, a power of two), twice over
         uint64_t t = 64;
         while (t < 2 * ctx->batch_max_len) t <<= 1;
         arena_cap = std::max<uint64_t>(arena_cap, 2 * t);
     }
     if (ctx->P.w <= (uint32_t)K1_W_FAST) want = std::min<uint64_t>(want, arena_cap);
+    if (long_on && ctx->batch_max_len) want += ctx->batch_long_entries + 8;
     if (want > ctx->arena_entries[hs]) {
         // grow the scratch of EVERY spectrum buffer at once: the next intervals will need the same, and an
         // allocation (a device-wide synchronisation) belongs in front of the pipeline, not inside it
@@ -1416,6 +1439,14 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         k1_generic<DUMP><<<grid, 64, 0, st>>>(p, false);
         LAUNCH_CHECK("k1_generic");
     }
+    if (long_on) {
+        k1_long_plan<<<1, K1_LONG_PLAN_TPB, 0, st>>>(p, fast);
+        LAUNCH_CHECK("k1_long_plan");
+        k1_long_zero<<<ctx->sm_count * 4, 256, 0, st>>>(p);
+        LAUNCH_CHECK("k1_long_zero");
+        k1_long_scan<DUMP><<<ctx->sm_count * 8, K1_LONG_TPB, 0, st>>>(p);
+        LAUNCH_CHECK("k1_long_scan");
+    }
     return HULK_B200_OK;
 }
 
@@ -1466,6 +1497,22 @@ static int before_first_k1(hulk_b200_ctx *ctx, int hs, cudaStream_t ks) {
         ctx->peer_dirty[hs] = 0;
     }
     return HULK_B200_OK;
+}
+
+// What the host knows about the lengths of the batch it is about to launch: the longest read, and the room the sets of
+// its long sequences need (offsets == nullptr: n_reads reads of fixed_len bases).
+static void note_batch_lengths(hulk_b200_ctx *ctx, const uint64_t *offsets, uint64_t n_reads, uint32_t fixed_len) {
+    ctx->batch_max_len = fixed_len;
+    ctx->batch_long_entries = 0;
+    if (offsets) {
+        for (uint64_t i = 0; i < n_reads; i++) {
+            const uint64_t len = offsets[i + 1] - offsets[i];
+            ctx->batch_max_len = std::max(ctx->batch_max_len, len);
+            if (len >= K1_LONG_MIN) ctx->batch_long_entries += k1_long_table_entries(len, (int32_t)ctx->P.k);
+        }
+    } else if (fixed_len >= K1_LONG_MIN) {
+        ctx->batch_long_entries = n_reads * k1_long_table_entries(fixed_len, (int32_t)ctx->P.k);
+    }
 }
 
 static const uint64_t kMaxBatchBytes = 256ull << 20;   // staging granularity of one H2D copy + k1 launch
@@ -1757,9 +1804,7 @@ static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
             b1 = upto * (uint64_t)fixed_len;
         }
         const uint64_t nb = b1 - b0, nr = upto - done;
-        ctx->batch_max_len = fixed_len;
-        if (offsets)
-            for (uint64_t i = done; i < upto; i++) ctx->batch_max_len = std::max(ctx->batch_max_len, offsets[i + 1] - offsets[i]);
+        note_batch_lengths(ctx, offsets ? offsets + done : nullptr, nr, fixed_len);
         const int buf = ctx->cur_buf;
         int rc = ensure_stage(ctx, buf, nb + 16, offsets ? nr + 1 : 0);
         if (rc) return rc;
@@ -1996,7 +2041,7 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
         total_bytes = ends[1] - ends[0];
     }
     const int hs = ctx->cur_hist;
-    ctx->batch_max_len = read_len;             // read lengths behind device offsets are not known on the host
+    note_batch_lengths(ctx, nullptr, n_reads, read_len);   // (read lengths behind device offsets are not known on the host)
     cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
     if (ctx->overlap && !(ctx->P.flags & HULK_B200_F_INPUT_READY)) {          // order behind whatever produced the input on the main stream
         CU(cudaEventRecord(ctx->ev_main, ctx->stream));
@@ -2415,6 +2460,7 @@ int hulk_b200_minimizers(hulk_b200_ctx *ctx, const uint8_t *bases, const uint64_
     CU(cudaMemcpyAsync(d_offsets, offsets, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_reads, st));
     const uint64_t saved_reads = ctx->st.n_reads;
+    note_batch_lengths(ctx, offsets, n_reads, 0);
     int rc = launch_k1<true>(ctx, 0, st, d_bases, (nb + 15) & ~15ull, d_offsets, b0, 0, n_reads, nb, d_dump, cap,
                              d_counts);
     ctx->st.n_reads = saved_reads;

@@ -34,6 +34,17 @@ namespace hulk {
 constexpr int K1_TPB = 128;       // threads (= reads) per CTA tile
 constexpr int K1_W_FAST = 32;     // largest w handled by the shared-memory path
 
+// A long sequence (k1_long.cuh): its slices are scanned by many threads that share one set.
+struct K1LongTask {
+    uint64_t r, b0, len;           // read index in the batch, first byte, length
+    uint64_t tab, cap;             // its open-addressing table: first arena entry, entries (power of two; flag at [cap])
+    uint64_t seg_first, n_seg;     // its slices are the batch's slices seg_first .. seg_first + n_seg - 1
+};
+struct K1LongCtl {
+    unsigned long long n_tasks, n_segs;
+    unsigned long long zero_begin, zero_end;   // arena entries the tables of this launch occupy
+};
+
 struct K1Params {
     const uint8_t *bases;          // device
     uint64_t bases_bytes;          // bytes that may legally be read starting at `bases`
@@ -65,6 +76,12 @@ struct K1Params {
     uint64_t *arena;
     unsigned long long *arena_cursor;
     uint64_t arena_entries;
+    // sequences of long_min bases or more are left to k1_long.cuh by every other kernel (~0: there are none)
+    uint64_t long_min;
+    uint32_t long_seg;             // positions per slice
+    uint32_t long_cap;             // entries of long_tasks
+    K1LongTask *long_tasks;
+    K1LongCtl *long_ctl;
 };
 
 constexpr uint32_t K1_ERR_EMPTY = 3;   // HULK_B200_EEMPTYSEQ
@@ -471,6 +488,9 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
                 k1_report(p, r, K1_ERR_EMPTY);                                   // minimizer.go:71-73
             } else if (len64 < (uint64_t)(p.w + p.k - 1)) {
                 k1_report(p, r, K1_ERR_SHORT);                                   // minimizer.go:74-76
+            } else if (len64 >= p.long_min) {
+                valid = true;                                                    // k1_long.cuh takes it: queued below
+                n = list_cap + 1u;
             } else {
                 valid = true;
                 const uint64_t src = *tile_src;
@@ -584,6 +604,9 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
                 k1_report(p, r, K1_ERR_EMPTY);                                   // minimizer.go:71-73
             } else if (len64 < (uint64_t)(9 + p.k - 1)) {
                 k1_report(p, r, K1_ERR_SHORT);                                   // minimizer.go:74-76
+            } else if (len64 >= p.long_min) {
+                valid = true;                                                    // k1_long.cuh takes it: queued below
+                n = list_cap + 1u;
             } else {
                 valid = true;
                 uint64_t last = Sentinel<FP>::value;                             // never a minimizer
@@ -692,6 +715,9 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_scan_w9_v2(const
                 k1_report(p, r, K1_ERR_EMPTY);                                   // minimizer.go:71-73
             } else if (len64 < (uint64_t)(9 + K - 1)) {
                 k1_report(p, r, K1_ERR_SHORT);                                   // minimizer.go:74-76
+            } else if (len64 >= p.long_min) {
+                valid = true;                                                    // k1_long.cuh takes it: queued below
+                n = list_cap + 1u;
             } else {
                 valid = true;
                 K1List<32> L{my_list, list_cap, 0u, 0.0};
@@ -800,6 +826,7 @@ __global__ void __launch_bounds__(64) k1_generic(const K1Params p, const bool us
         const uint64_t b0 = k1_read_off(p, r), b1 = k1_read_off(p, r + 1);
         const uint64_t len64 = b1 - b0;
         if (DUMP) p.dump_counts[r] = 0;
+        if (len64 >= p.long_min) continue;                                       // k1_long.cuh takes it
         if (len64 < 1) { k1_report(p, r, K1_ERR_EMPTY); continue; }
         if (len64 < (uint64_t)(p.w + p.k - 1)) { k1_report(p, r, K1_ERR_SHORT); continue; }
         // table capacity: power of two >= 2 * (number of k-mers)

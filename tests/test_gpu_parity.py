@@ -73,6 +73,53 @@ def test_long_reads_take_the_generic_path(hb, oracle):
     np.testing.assert_array_equal(h, ho.astype(np.uint32))
 
 
+@pytest.mark.parametrize("k,w", [(21, 9), (31, 9), (11, 9), (7, 40), (21, 200), (30, 256)])
+def test_long_sequences_take_the_sliced_scan(hb, oracle, k, w):
+    # sequences of 2^14 bases or more (--fasta contigs, long reads) are cut into slices that share one set per
+    # sequence (k1_long.cuh); next to them: reads for the fast kernels and reads for k1_generic, N runs, lower case,
+    # a sequence of exactly the threshold length and one a base short of it
+    reads = (random_reads(3, 40_000, seed=k + w, n_frac=0.002, lower_frac=0.1, ragged=30_000)
+             + [random_reads(1, 16_384, seed=5)[0], random_reads(1, 16_383, seed=6)[0], b"ACGTAC" * 5000,
+                b"N" * 9000 + random_reads(1, 12_000, seed=7)[0] + b"N" * 300 + b"acgt" * 2000, b"A" * 20_000]
+             + random_reads(50, 400, seed=8, ragged=3000) + random_reads(100, 300, seed=9))
+    cap = 70_000
+    with hb.HistoSketch(k, w, 4) as hs:
+        sets, counts = hs.minimizers(reads, cap=cap)
+        for r, got, n in zip(reads, sets, counts):
+            want = np.sort(oracle.minimizers(k, w, r))
+            assert n == want.size, (k, w, len(r))
+            np.testing.assert_array_equal(got, want)
+        hs.add_seqs(reads)
+        hs.add_seqs(reads[:2])                       # a second batch: tables and slice numbers start over
+        h = hs.histogram()
+        st = hs.stats()
+    ho, nm = oracle.count_reads(k, w, k ** 4, *oracle.pack_reads(reads + reads[:2]))
+    np.testing.assert_array_equal(h, ho.astype(np.uint32))
+    assert st["n_minimizers"] == nm
+
+
+def test_long_sequences_fixed_length_and_device_offsets(hb, oracle):
+    # the two other ways a batch arrives: fixed-length reads (the host knows the one length) and offsets that only
+    # exist on the device (the host cannot rule long sequences out, so the sliced scan's launches are made)
+    import torch
+    reads = random_reads(6, 20_000, seed=31, n_frac=0.001)
+    ho, nm = oracle.count_reads(21, 9, 21 ** 4, *oracle.pack_reads(reads))
+    with hb.HistoSketch(21, 9, 4) as hs:
+        hs.add_reads_fixed(np.frombuffer(b"".join(reads), dtype=np.uint8).copy(), len(reads), 20_000)
+        np.testing.assert_array_equal(hs.histogram(), ho.astype(np.uint32))
+        assert hs.stats()["n_minimizers"] == nm
+    ragged = random_reads(4, 18_000, seed=32, ragged=9000) + random_reads(200, 150, seed=33, ragged=100)
+    bases, offsets = oracle.pack_reads(ragged)
+    ho, nm = oracle.count_reads(21, 9, 21 ** 4, bases, offsets)
+    with hb.HistoSketch(21, 9, 4) as hs:
+        d_b = torch.from_numpy(np.concatenate([bases, np.zeros(64, np.uint8)])).cuda()
+        d_o = torch.from_numpy(offsets.astype(np.int64)).cuda()
+        torch.cuda.synchronize()
+        hs.add_reads_device(d_b.data_ptr(), d_o.data_ptr(), len(ragged), 0)
+        np.testing.assert_array_equal(hs.histogram(), ho.astype(np.uint32))
+        assert hs.stats()["n_minimizers"] == nm
+
+
 def test_chromosome_sized_sequence(hb, oracle):
     # --fasta mode hands whole contigs to AddSeq: a 20 Mbp sequence needs a 2^26-entry table, more than the
     # default scratch arena holds next to its neighbours, and must still give the reference's set

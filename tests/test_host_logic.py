@@ -378,6 +378,79 @@ def test_kernel_scan_and_fast_jump_compiled_for_host_match_oracle(oracle, tmp_pa
     assert n_amb < n_jump
 
 
+LONG_TEST_SRC = r"""
+#include <algorithm>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "k1_scan.h"
+#include "k1_long.h"
+struct VH { uint64_t* b; uint64_t& operator()(int t) const { return b[t]; } };
+int main() {
+    // stdin: "k w seg seq" -> the slices of k1_long.h, put end to end, against one pass of k1_scan.h over the sequence;
+    // prints the sorted distinct minima (or MISMATCH)
+    int k, w, seg; static char buf[1 << 20];
+    while (scanf("%d %d %d %1048575s", &k, &w, &seg, buf) == 4) {
+        const int len = (int)strlen(buf);
+        for (int i = 0; i < len; i++) if (buf[i] >= '0' && buf[i] <= '3') buf[i] -= '0';   // raw 0..3 bytes
+        std::vector<uint64_t> whole, sliced, vh(w + 1);
+        hulk::k1_scan_read<false>(hulk::ByteSrc{(const uint8_t*)buf, len}, len, k, w, VH{vh.data()},
+                                  [&](uint64_t m, bool on) { if (on) whole.push_back(m); });
+        for (int64_t b = 0; b < len; b += seg)
+            hulk::k1_scan_range((const uint8_t*)buf, len, k, w, b, b + seg, VH{vh.data()},
+                                [&](uint64_t m) { sliced.push_back(m); });
+        if (sliced != whole) { printf("MISMATCH\n"); continue; }
+        // a range that ends past the sequence, an empty range, and the table size rule
+        std::vector<uint64_t> tail;
+        hulk::k1_scan_range((const uint8_t*)buf, len, k, w, len - 1, (int64_t)len + 1000, VH{vh.data()},
+                            [&](uint64_t m) { tail.push_back(m); });
+        hulk::k1_scan_range((const uint8_t*)buf, len, k, w, len, (int64_t)len + 5, VH{vh.data()},
+                            [&](uint64_t m) { tail.push_back(~0ull); });
+        if (tail.size() > 1 || (tail.size() == 1 && (whole.empty() || tail[0] != whole.back()))) { printf("MISMATCH_TAIL\n"); continue; }
+        const uint64_t e = hulk::k1_long_table_entries((uint64_t)len, k) - 8;
+        if ((e & (e - 1)) || e < 2 * (uint64_t)(len - k + 1) || e < 64) { printf("MISMATCH_CAP\n"); continue; }
+        std::sort(whole.begin(), whole.end());
+        whole.erase(std::unique(whole.begin(), whole.end()), whole.end());
+        printf("%zu", whole.size());
+        for (uint64_t x : whole) printf(" %llu", (unsigned long long)x);
+        printf("\n");
+    }
+    return 0;
+}
+"""
+
+
+def test_long_sequence_slices_compiled_for_host_match_one_pass_and_oracle(oracle, tmp_path):
+    # k1_long.h is the exact source k1_long_scan compiles: a slice of a long sequence restarts the rolling k-mers and
+    # the window k + w positions early and must emit what the sequential pass (minimizer.go:96-204) emits there
+    src = tmp_path / "long_test.cpp"
+    src.write_text(LONG_TEST_SRC)
+    exe = tmp_path / "long_test"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "hulk_b200", "csrc"),
+                    "-o", str(exe), str(src)], check=True)
+    from conftest import random_reads
+    lines, want = [], []
+    cases = [(21, 9, 2000, 256), (21, 9, 1500, 1), (21, 9, 700, 7), (31, 9, 3000, 320), (11, 9, 1000, 160), (4, 4, 300, 64),
+             (21, 1, 400, 50), (15, 32, 1200, 376), (5, 9, 500, 33), (7, 40, 900, 100), (21, 200, 2500, 1768),
+             (2, 2, 60, 3), (28, 9, 800, 296), (1, 9, 200, 16), (30, 256, 4000, 2288), (3, 7, 90, 90), (21, 9, 5000, 4999)]
+    for k, w, L, seg in cases:
+        reads = (random_reads(2, L, seed=k * 1000 + w) + random_reads(3, L, seed=k + w + seg, n_frac=0.03, lower_frac=0.3)
+                 + [b"A" * L, (b"ACGTU" * L)[:L], (b"acgn0123RYKM" * L)[:L], (b"AC" * L)[:L],
+                    (b"N" * (L // 2)) + random_reads(1, L - L // 2, seed=seg)[0]])
+        for rd in reads:
+            lines.append("%d %d %d %s" % (k, w, seg, rd.decode()))
+            raw = bytes((c - 48) if 48 <= c <= 51 else c for c in rd)
+            m = np.sort(oracle.minimizers(k, w, raw))
+            want.append(" ".join([str(len(m))] + [str(int(x)) for x in m]))
+    out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+    got = out.strip().split("\n")
+    assert len(got) == len(want)
+    for ln, g, w_ in zip(lines, got, want):
+        assert g == w_, ln[:40]
+
+
 def test_bench_generators_on_cpu(monkeypatch):
     """bench.py's device-side generators, run here on torch's CPU device: the i.i.d. reads equal the host definition
     (hulk_b200.synthetic_reads) and the realism variant draws every read
