@@ -22,6 +22,7 @@ import (
 
 	"github.com/will-rowe/hulk/src/helpers"
 	"github.com/will-rowe/hulk/src/histosketch"
+	"github.com/will-rowe/hulk/src/minhash"
 	"github.com/will-rowe/hulk/src/seqio"
 	"github.com/will-rowe/hulk/src/sketchio"
 )
@@ -61,6 +62,13 @@ func (proc *GPUSketcher) Run() {
 	check(C.hulk_b200_group_create(&p, nil, C.uint32_t(ngpus), &g))
 	defer C.hulk_b200_group_destroy(g)
 	check(C.hulk_b200_group_generate_cws_tables(g, 1)) // newCWS (histosketch.go:95-126), drawn on all cores while reads are counted
+	// --kmv / --khf: the reference's boss never feeds the two MinHash sketches (boss.go:18-19); with
+	// HULK_B200_FEED_MINHASH=1 the library feeds them from the same minimizer stream (include/hulk_b200.h)
+	feedMinhash := os.Getenv("HULK_B200_FEED_MINHASH") == "1" && (s.KMV || s.KHF)
+	if feedMinhash {
+		b2i := map[bool]C.int{false: 0, true: 1}
+		check(C.hulk_b200_group_minhash_enable(g, b2i[s.KMV], b2i[s.KHF]))
+	}
 
 	bases := make([]byte, 0, batchBytes+1<<20)
 	offsets := []C.uint64_t{0}
@@ -115,6 +123,25 @@ func (proc *GPUSketcher) Run() {
 	hs := histosketch.FromSlots(s.KmerSize, s.SpectrumSize, s.DecayRatio != 1.0, sk, wt)
 	hulkData := sketchio.NewHULKdata()
 	helpers.ErrorCheck(hulkData.Add(hs))
+	if feedMinhash && s.KMV { // sketch.go:227-230: KMVsketch.AddHash keeps what it is given when it fits (kmv.go:57-59)
+		vals := make([]C.uint64_t, s.SketchSize)
+		var n C.uint32_t
+		check(C.hulk_b200_group_get_kmv(g, &vals[0], &n))
+		kmv := minhash.NewKMVsketch(s.KmerSize, s.SketchSize)
+		for _, v := range vals[:n] {
+			kmv.AddHash(uint64(v))
+		}
+		helpers.ErrorCheck(hulkData.Add(kmv))
+	}
+	if feedMinhash && s.KHF { // sketch.go:231-234
+		vals := make([]C.uint64_t, s.SketchSize)
+		check(C.hulk_b200_group_get_khf(g, &vals[0]))
+		khf := minhash.NewKHFsketch(s.KmerSize, s.SketchSize)
+		for i, v := range vals {
+			khf.Sketch[i] = uint64(v)
+		}
+		helpers.ErrorCheck(hulkData.Add(khf))
+	}
 	hulkData.FileName, hulkData.Banner = s.FileName, s.BannerLabel
 	hulkData.WriteJSON(s.OutFile + ".json")
 	log.Printf("\twritten sketch to disk: %v\n", s.OutFile+".json")

@@ -32,6 +32,8 @@ EXPORTS = [
     "hulk_b200_group_get_stats", "hulk_b200_group_sketch_reader",
     "hulk_b200_generate_cws_tables_device", "hulk_b200_get_cws_tables", "hulk_b200_group_generate_cws_tables_device",
     "hulk_b200_packed_bytes", "hulk_b200_pack_bases", "hulk_b200_push_reads_packed", "hulk_b200_set_input_packing",
+    "hulk_b200_minhash_enable", "hulk_b200_get_khf", "hulk_b200_get_kmv",
+    "hulk_b200_group_minhash_enable", "hulk_b200_group_get_khf", "hulk_b200_group_get_kmv",
 ]
 PEER_HANDLE_BYTES = 64
 
@@ -161,6 +163,12 @@ def load():
         "hulk_b200_pack_bases": (C.c_int, [vp, u64, vp, vp, u64, C.POINTER(u64), i32]),
         "hulk_b200_push_reads_packed": (C.c_int, [vp, vp, vp, u64, vp, u64, u32]),
         "hulk_b200_set_input_packing": (C.c_int, [vp, i32]),
+        "hulk_b200_minhash_enable": (C.c_int, [vp, C.c_int, C.c_int]),
+        "hulk_b200_get_khf": (C.c_int, [vp, vp]),
+        "hulk_b200_get_kmv": (C.c_int, [vp, vp, C.POINTER(u32)]),
+        "hulk_b200_group_minhash_enable": (C.c_int, [vp, C.c_int, C.c_int]),
+        "hulk_b200_group_get_khf": (C.c_int, [vp, vp]),
+        "hulk_b200_group_get_kmv": (C.c_int, [vp, vp, C.POINTER(u32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

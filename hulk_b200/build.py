@@ -13,7 +13,7 @@ CLI = os.path.join(HERE, "bin", "hulk")
 
 CUDA_SOURCES = ["api.cu", "smash.cu"]
 HOST_SOURCES = ["host_io.cpp", "ingest.cpp", "sketch_json.cpp", "group.cpp", "pack.cpp"]
-DEPS = CUDA_SOURCES + HOST_SOURCES + ["hd_math.h", "pgzip.h", "ptx_util.cuh", "k1_minimizer.cuh", "k1_scan.h", "k1_scan2.h", "k1_long.h", "k1_long.cuh", "k2_countmin.cuh",
+DEPS = CUDA_SOURCES + HOST_SOURCES + ["hd_math.h", "pgzip.h", "ptx_util.cuh", "k1_minimizer.cuh", "k1_scan.h", "k1_scan2.h", "k1_long.h", "k1_long.cuh", "k1_minhash.cuh", "k2_countmin.cuh",
                                       "k3_cws.cuh", "go_rng_cooked.inc", "../../include/hulk_b200.h"]
 CLI_SOURCES = ["cli/hulk_main.cpp"]
 

@@ -36,6 +36,7 @@
 #include "../../include/hulk_b200.h"
 #include "k1_minimizer.cuh"
 #include "k1_long.cuh"
+#include "k1_minhash.cuh"
 #include "k2_countmin.cuh"
 #include "k3_cws.cuh"
 #include "k4_cwsdraw.cuh"
@@ -153,7 +154,17 @@ struct hulk_b200_ctx {
     uint64_t *d_arena[NBUF] = {};
     K1LongTask *d_long_tasks[NBUF] = {};       // long sequences of the launch in flight on each k1 stream (k1_long.cuh)
     K1LongCtl *d_long_ctl[NBUF] = {};
+    unsigned long long *d_lenstat = nullptr;   // k1_length_stats' two words
+    uint64_t long_cap[NBUF] = {};              // entries of d_long_tasks
+    // MinHash side sketches fed from the minimizer queue (k1_minhash.cuh; hulk_b200_minhash_enable)
+    bool mh_kmv = false, mh_khf = false;
+    unsigned long long *d_khf = nullptr;       // [s]
+    K1KmvState *d_kmv_state[NBUF] = {};        // one bottom-s pool per k1 stream, merged when read
+    uint64_t *d_kmv_pool[NBUF] = {};           // [2][s]
+    uint64_t *d_kmv_cand[NBUF] = {};           // [kmv_cand_cap]
+    uint64_t kmv_cand_cap[NBUF] = {};
     bool long_path = true;                     // HULK_B200_LONG=0: long sequences stay with k1_generic (A/B)
+    uint64_t long_min = K1_LONG_MIN;           // sequences this long take the sliced scan (HULK_B200_LONG_MIN, >= 1024)
     unsigned long long *d_arena_cursor[NBUF] = {};
     uint64_t arena_entries[NBUF] = {};
 
@@ -362,7 +373,8 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < NBUF; i++) {
         void *per[] = {ctx->d_ovf_count[i], ctx->d_ovf_list[i], ctx->d_arena[i], ctx->d_arena_cursor[i],
-                       ctx->d_queue[i], ctx->d_queue_cursor[i], ctx->d_long_tasks[i], ctx->d_long_ctl[i]};
+                       ctx->d_queue[i], ctx->d_queue_cursor[i], ctx->d_long_tasks[i], ctx->d_long_ctl[i],
+                       ctx->d_kmv_state[i], ctx->d_kmv_pool[i], ctx->d_kmv_cand[i]};
         for (void *p : per)
             if (p) cudaFree(p);
     }
@@ -377,6 +389,8 @@ void hulk_b200_destroy(hulk_b200_ctx *ctx) {
     for (uint32_t p = 0; p < PEER_MAX; p++)
         if (ctx->peer_ipc[p] && ctx->peer_arena[p]) cudaIpcCloseMemHandle(ctx->peer_arena[p]);
     if (ctx->h_feed) cudaFreeHost(ctx->h_feed);
+    if (ctx->d_khf) cudaFree(ctx->d_khf);
+    if (ctx->d_lenstat) cudaFree(ctx->d_lenstat);
     void *ptrs[] = {ctx->d_feed, ctx->arena, ctx->d_hist_sum, ctx->d_ticket, ctx->d_nmin, ctx->d_errword, ctx->d_ctl,
                     ctx->d_cols, ctx->d_csr_start, ctx->d_csr_bins, ctx->d_words, ctx->d_word_prefix,
                     ctx->d_block_count, ctx->d_block_prefix, ctx->d_q, ctx->d_fbits[0], ctx->d_fbits[1], ctx->d_invf[0],
@@ -523,9 +537,9 @@ static int create_impl(hulk_b200_ctx *ctx) {
         CU(dmalloc(&ctx->d_ovf_list[i], ctx->ovf_cap));
         CU(dmalloc(&ctx->d_arena_cursor[i], 1));
         CU(dmalloc(&ctx->d_queue_cursor[i], 2));
-        CU(dmalloc(&ctx->d_long_tasks[i], K1_LONG_TASKS));
         CU(dmalloc(&ctx->d_long_ctl[i], 1));
     }
+    CU(dmalloc(&ctx->d_lenstat, 2));
     CU(dmalloc(&ctx->d_ctl, 1));
     CU(dmalloc(&ctx->d_cols, (uint64_t)D * CMS_DEPTH));
     CU(dmalloc(&ctx->d_csr_start, CMS_CELLS + 1));
@@ -651,6 +665,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
         HULK_PRELOAD(k1_generic<false>);
         HULK_PRELOAD(k1_generic<true>);
         HULK_PRELOAD(k1_long_plan);
+        HULK_PRELOAD(k1_length_stats);
+        HULK_PRELOAD(k1_khf_queue);
+        HULK_PRELOAD(k1_kmv_filter);
+        HULK_PRELOAD(k1_kmv_select);
         HULK_PRELOAD(k1_long_zero);
         HULK_PRELOAD(k1_long_scan<false>);
         HULK_PRELOAD(k1_long_scan<true>);
@@ -670,8 +688,10 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e >= '1' && *e <= '0' + K1_W9_CTAS_PER_SM) ctx->k1_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_LONG");
         ctx->long_path = !(e && *e == '0');
+        e = getenv("HULK_B200_LONG_MIN");
+        if (e && atoll(e) >= 1024) ctx->long_min = (uint64_t)atoll(e);
         e = getenv("HULK_B200_MAX_LAUNCH_READS");
-        if (e && atoll(e) >= 32) ctx->max_launch_reads = (uint64_t)atoll(e);
+        if (e && atoll(e) >= 32) ctx->max_launch_reads = std::min<uint64_t>((uint64_t)atoll(e), 1ull << 30);
         e = getenv("HULK_B200_JUMP_CTAS");
         if (e && *e >= '1' && *e <= '8') ctx->jump_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_JUMP_BATCH");
@@ -848,6 +868,71 @@ int hulk_b200_set_cws_tables_device(hulk_b200_ctx *ctx, const double *d_r, const
     return HULK_B200_OK;
 }
 
+// both side sketches as their constructors leave them: KHF slots at MaxUint64 (khf.go:20-32), an empty KMV heap
+// (kmv.go:24-38)
+static int minhash_clear(hulk_b200_ctx *ctx) {
+    cudaStream_t st = ctx->stream;                           // (callers have drained every stream of the context)
+    if (ctx->d_khf) CU(cudaMemsetAsync(ctx->d_khf, 0xff, sizeof(unsigned long long) * ctx->s, st));
+    for (int i = 0; i < NBUF; i++)
+        if (ctx->d_kmv_state[i]) CU(cudaMemsetAsync(ctx->d_kmv_state[i], 0, sizeof(K1KmvState), st));
+    CU(cudaStreamSynchronize(st));
+    return HULK_B200_OK;
+}
+
+int hulk_b200_minhash_enable(hulk_b200_ctx *ctx, int kmv, int khf) {
+    if (!ctx) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    if (ctx->st.n_reads) return fail(ctx, HULK_B200_ESTATE, "minhash_enable after reads were pushed");
+    if (khf && !ctx->d_khf) CU(dmalloc(&ctx->d_khf, ctx->s));
+    if (kmv) {
+        for (int i = 0; i < NBUF; i++) {
+            if (!ctx->d_kmv_state[i]) CU(dmalloc(&ctx->d_kmv_state[i], 1));
+            if (!ctx->d_kmv_pool[i]) CU(dmalloc(&ctx->d_kmv_pool[i], 2 * (uint64_t)ctx->s));
+        }
+    }
+    ctx->mh_kmv = kmv != 0;
+    ctx->mh_khf = khf != 0;
+    return minhash_clear(ctx);
+}
+
+int hulk_b200_get_khf(hulk_b200_ctx *ctx, uint64_t *mins) {
+    if (!ctx || !mins) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    if (!ctx->mh_khf || !ctx->d_khf) {                       // never fed: the constructor's state (khf.go:20-32)
+        for (uint32_t i = 0; i < ctx->s; i++) mins[i] = ~0ull;
+        return HULK_B200_OK;
+    }
+    CU(cudaMemcpy(mins, ctx->d_khf, sizeof(uint64_t) * ctx->s, cudaMemcpyDeviceToHost));
+    return HULK_B200_OK;
+}
+
+int hulk_b200_get_kmv(hulk_b200_ctx *ctx, uint64_t *mins, uint32_t *n) {
+    if (!ctx || !mins || !n) return HULK_B200_EARG;
+    CU(cudaSetDevice(ctx->P.device));
+    { const int rc = sync_all(ctx); if (rc) return rc; }
+    *n = 0;
+    if (!ctx->mh_kmv) return HULK_B200_OK;                   // never fed: an empty heap (kmv.go:24-38)
+    // bottom-s of a union is the bottom-s of the parts' bottom-s: the pools of the k1 streams are merged here
+    std::vector<uint64_t> all;
+    for (int i = 0; i < NBUF; i++) {
+        if (!ctx->d_kmv_state[i]) continue;
+        K1KmvState st;
+        CU(cudaMemcpy(&st, ctx->d_kmv_state[i], sizeof(st), cudaMemcpyDeviceToHost));
+        const size_t have = all.size(), np = (size_t)std::min<unsigned long long>(st.n_pool, ctx->s);
+        all.resize(have + np);
+        if (np)
+            CU(cudaMemcpy(all.data() + have, ctx->d_kmv_pool[i] + (size_t)st.cur * ctx->s, sizeof(uint64_t) * np,
+                          cudaMemcpyDeviceToHost));
+    }
+    std::sort(all.begin(), all.end());                       // SetSketch: low -> high (kmv.go:160-168)
+    if (all.size() > ctx->s) all.resize(ctx->s);
+    std::copy(all.begin(), all.end(), mins);
+    *n = (uint32_t)all.size();
+    return HULK_B200_OK;
+}
+
 int hulk_b200_reset(hulk_b200_ctx *ctx) {
     if (!ctx) return HULK_B200_EARG;
     CU(cudaSetDevice(ctx->P.device));
@@ -883,7 +968,7 @@ int hulk_b200_reset(hulk_b200_ctx *ctx) {
     ctx->feed_batches = 0;
     ctx->extra_minimizers = 0;
     ctx->err.clear();
-    return HULK_B200_OK;
+    return minhash_clear(ctx);
 }
 
 int hulk_b200_set_overlap(hulk_b200_ctx *ctx, int enable) {
@@ -1298,17 +1383,33 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     p.dump_counts = d_dump_counts;
     // sequences of K1_LONG_MIN bases or more go to the sliced scan (k1_long.cuh) whenever the host cannot rule them
     // out: each takes a table of at most four entries per base behind k1_generic's allocations
-    const bool long_on = ctx->long_path && (ctx->batch_max_len ? ctx->batch_max_len >= K1_LONG_MIN
+    const bool long_on = ctx->long_path && (ctx->batch_max_len ? ctx->batch_max_len >= ctx->long_min
                                                                : (d_offsets != nullptr && fixed_len == 0));
-    p.long_min = long_on ? (uint64_t)K1_LONG_MIN : ~0ull;
+    p.long_min = long_on ? ctx->long_min : ~0ull;
     p.long_seg = k1_long_seg(ctx->P.k, ctx->P.w);
-    p.long_cap = K1_LONG_TASKS;
+    if (long_on) {
+        // room for every sequence of the launch that can be that long
+        const uint64_t need = std::min<uint64_t>(n_reads, total_bytes / ctx->long_min + 2);
+        if (need > ctx->long_cap[hs]) {
+            { const int rc = sync_all(ctx); if (rc) return rc; }
+            const uint64_t cap = std::max<uint64_t>(need, 4096);
+            for (int i = 0; i < ctx->nbuf; i++) {
+                if (cap <= ctx->long_cap[i]) continue;
+                if (ctx->d_long_tasks[i]) cudaFree(ctx->d_long_tasks[i]);
+                ctx->d_long_tasks[i] = nullptr;
+                ctx->long_cap[i] = 0;
+                CU(dmalloc(&ctx->d_long_tasks[i], cap));
+                ctx->long_cap[i] = cap;
+            }
+        }
+    }
+    p.long_cap = (uint32_t)std::min<uint64_t>(ctx->long_cap[hs], 0xffffffffull);
     p.long_tasks = ctx->d_long_tasks[hs];
     p.long_ctl = ctx->d_long_ctl[hs];
     // scratch arena of the generic path: 4 table slots per base of the batch, at least 4 Mi entries
     uint64_t want = std::max<uint64_t>(1ull << 22, 4 * total_bytes + (n_reads << 7));
     // only reserve the large arena when the generic path will take whole batches ...
-    uint64_t arena_cap = 1ull << 26;
+    uint64_t arena_cap = 1ull << 25;
     if (!long_on && ctx->batch_max_len > (1u << 20)) {
         // ... or a very long sequence (a chromosome in --fasta mode) is in the batch and the sliced scan is off: room
         // for its open-addressing table (two slots per k-mer, a power of two), twice over
@@ -1318,6 +1419,20 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     }
     if (ctx->P.w <= (uint32_t)K1_W_FAST) want = std::min<uint64_t>(want, arena_cap);
     if (long_on && ctx->batch_max_len) want += ctx->batch_long_entries + 8;
+    // in front of that: one table per k1_generic thread, reused read after read -- however many reads of a few hundred
+    // to a few thousand bases a batch holds, their sets never run the arena dry.  Its size follows the longest read of
+    // the batch (two entries per k-mer, a power of two) up to K1_SLAB_MAX; sets that need more use the part behind
+    const bool fast = ctx->P.w <= (uint32_t)K1_W_FAST;
+    const unsigned generic_grid = fast ? (unsigned)(ctx->sm_count * 2)
+                                       : (unsigned)std::min<uint64_t>((n_reads + 63) / 64, (uint64_t)ctx->sm_count * 8);
+    p.slab_size = 2048;
+    if (ctx->batch_max_len) {
+        const uint64_t nk = ctx->batch_max_len >= ctx->P.k ? ctx->batch_max_len - ctx->P.k + 1 : 1;
+        p.slab_size = 64;
+        while (p.slab_size < K1_SLAB_MAX && p.slab_size < 2 * nk) p.slab_size <<= 1;
+    }
+    p.slab_entries = (uint64_t)generic_grid * 64 * p.slab_size;
+    want += p.slab_entries;
     if (want > ctx->arena_entries[hs]) {
         // grow the scratch of EVERY spectrum buffer at once: the next intervals will need the same, and an
         // allocation (a device-wide synchronisation) belongs in front of the pipeline, not inside it
@@ -1334,12 +1449,15 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         }
     }
     // minimizer queue of the batch: at most list_cap keys per read (longer lists go to k1_generic)
-    const bool fast = ctx->P.w <= (uint32_t)K1_W_FAST;
-    const bool use_queue = fast && !DUMP && !ctx->fused_jump;
+    // (with the MinHash feed on, every kernel's minimizers go through the queue: k1_generic and k1_long_scan append
+    // theirs -- at most one per k-mer -- behind the fast kernels')
+    const bool feed = !DUMP && (ctx->mh_kmv || ctx->mh_khf);
+    const bool use_queue = fast && !DUMP && (!ctx->fused_jump || feed);
     size_t smem = 0;
     if (fast) k1_geometry(ctx, n_reads, total_bytes, &p.tile_cap, &p.list_cap, &smem);
-    if (use_queue) {
-        const uint64_t need = n_reads * (uint64_t)p.list_cap;
+    p.feed_queue = feed ? 1u : 0u;
+    if (use_queue || feed) {
+        const uint64_t need = (use_queue ? n_reads * (uint64_t)p.list_cap : 0) + (feed ? total_bytes + n_reads : 0);
         if (need >= (1ull << 31)) return fail(ctx, HULK_B200_EARG, "batch too large for one minimizer queue");
         if (need > ctx->queue_cap[hs]) {
             { const int rc = sync_all(ctx); if (rc) return rc; }
@@ -1356,6 +1474,17 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         p.queue_cursor = ctx->d_queue_cursor[hs];
         p.queue_cap = ctx->queue_cap[hs];
         CU(cudaMemsetAsync(ctx->d_queue_cursor[hs], 0, 16, st));
+        if (feed && ctx->mh_kmv && ctx->kmv_cand_cap[hs] < ctx->queue_cap[hs]) {
+            { const int rc = sync_all(ctx); if (rc) return rc; }
+            for (int i = 0; i < ctx->nbuf; i++) {
+                if (ctx->kmv_cand_cap[i] >= ctx->queue_cap[i]) continue;
+                if (ctx->d_kmv_cand[i]) cudaFree(ctx->d_kmv_cand[i]);
+                ctx->d_kmv_cand[i] = nullptr;
+                ctx->kmv_cand_cap[i] = 0;
+                CU(dmalloc(&ctx->d_kmv_cand[i], ctx->queue_cap[i]));
+                ctx->kmv_cand_cap[i] = ctx->queue_cap[i];
+            }
+        }
     }
     p.arena = ctx->d_arena[hs];
     p.arena_cursor = ctx->d_arena_cursor[hs];
@@ -1432,11 +1561,10 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
             else k1_jump_queue<4><<<gridj, K1_JUMP_TPB, 0, st>>>(p);
             LAUNCH_CHECK("k1_jump_queue");
         }
-        k1_generic<DUMP><<<ctx->sm_count * 2, 64, 0, st>>>(p, true);
+        k1_generic<DUMP><<<generic_grid, 64, 0, st>>>(p, true);
         LAUNCH_CHECK("k1_generic");
     } else {
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_reads + 63) / 64, (uint64_t)ctx->sm_count * 8);
-        k1_generic<DUMP><<<grid, 64, 0, st>>>(p, false);
+        k1_generic<DUMP><<<generic_grid, 64, 0, st>>>(p, false);
         LAUNCH_CHECK("k1_generic");
     }
     if (long_on) {
@@ -1446,6 +1574,27 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
         LAUNCH_CHECK("k1_long_zero");
         k1_long_scan<DUMP><<<ctx->sm_count * 8, K1_LONG_TPB, 0, st>>>(p);
         LAUNCH_CHECK("k1_long_scan");
+    }
+    if (feed) {
+        K1MinhashParams m{};
+        m.queue = p.queue;
+        m.queue_cursor = p.queue_cursor;
+        m.queue_cap = p.queue_cap;
+        m.s = ctx->s;
+        m.khf = ctx->d_khf;
+        m.kmv = ctx->d_kmv_state[hs];
+        m.kmv_pool = ctx->d_kmv_pool[hs];
+        m.kmv_cand = ctx->d_kmv_cand[hs];
+        if (ctx->mh_khf) {
+            k1_khf_queue<<<ctx->sm_count * 4, K1_KHF_TPB, 0, st>>>(m);
+            LAUNCH_CHECK("k1_khf_queue");
+        }
+        if (ctx->mh_kmv) {
+            k1_kmv_filter<<<ctx->sm_count * 4, 256, 0, st>>>(m);
+            LAUNCH_CHECK("k1_kmv_filter");
+            k1_kmv_select<<<1, K1_KMV_SELECT_TPB, 0, st>>>(m);
+            LAUNCH_CHECK("k1_kmv_select");
+        }
     }
     return HULK_B200_OK;
 }
@@ -1508,9 +1657,9 @@ static void note_batch_lengths(hulk_b200_ctx *ctx, const uint64_t *offsets, uint
         for (uint64_t i = 0; i < n_reads; i++) {
             const uint64_t len = offsets[i + 1] - offsets[i];
             ctx->batch_max_len = std::max(ctx->batch_max_len, len);
-            if (len >= K1_LONG_MIN) ctx->batch_long_entries += k1_long_table_entries(len, (int32_t)ctx->P.k);
+            if (len >= ctx->long_min) ctx->batch_long_entries += k1_long_table_entries(len, (int32_t)ctx->P.k);
         }
-    } else if (fixed_len >= K1_LONG_MIN) {
+    } else if (fixed_len >= ctx->long_min) {
         ctx->batch_long_entries = n_reads * k1_long_table_entries(fixed_len, (int32_t)ctx->P.k);
     }
 }
@@ -2032,16 +2181,26 @@ int hulk_b200_push_reads_device(hulk_b200_ctx *ctx, const uint8_t *d_bases, cons
         d_offsets = nullptr;
     } else {
         if (!d_offsets) return fail(ctx, HULK_B200_EARG, "d_offsets is NULL and read_len is 0");
+        // the two ends of the byte range, the longest read and the room the sets of long sequences need: one round trip
         uint64_t ends[2];
+        unsigned long long lens[2] = {0, 0};
+        CU(cudaMemsetAsync(ctx->d_lenstat, 0, 16, ctx->stream));
+        k1_length_stats<<<(unsigned)std::min<uint64_t>((n_reads + 255) / 256, (uint64_t)ctx->sm_count * 4), 256, 0, ctx->stream>>>(
+            d_offsets, n_reads, ctx->long_min, (int32_t)ctx->P.k, ctx->d_lenstat);
+        LAUNCH_CHECK("k1_length_stats");
         CU(cudaMemcpyAsync(&ends[0], d_offsets, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(&ends[1], d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(lens, ctx->d_lenstat, 16, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (ends[1] < ends[0]) return fail(ctx, HULK_B200_EARG, "offsets must be non-decreasing");
         extent = ends[1];
         total_bytes = ends[1] - ends[0];
+        if (lens[0] > total_bytes) return fail(ctx, HULK_B200_EARG, "offsets must be non-decreasing");
+        ctx->batch_max_len = lens[0];
+        ctx->batch_long_entries = lens[1];
     }
     const int hs = ctx->cur_hist;
-    note_batch_lengths(ctx, nullptr, n_reads, read_len);   // (read lengths behind device offsets are not known on the host)
+    if (read_len) note_batch_lengths(ctx, nullptr, n_reads, read_len);
     cudaStream_t ks = ctx->overlap ? ctx->k1_stream[hs] : ctx->stream;
     if (ctx->overlap && !(ctx->P.flags & HULK_B200_F_INPUT_READY)) {          // order behind whatever produced the input on the main stream
         CU(cudaEventRecord(ctx->ev_main, ctx->stream));

@@ -9,7 +9,8 @@
 //   cmd/sketch.go:185-214    sketchParamCheck
 //   src/pipeline/sketch.go:182-301  SeqMinimizer.Run / Sketcher.Run log lines and the output file
 //   cmd/smash.go             `hulk smash`: flags, checks, the similarity matrix CSV
-// Not here (out of scope): --profiling (pprof), KMV/KHF side sketches
+// Not here (out of scope): --profiling (pprof); KMV/KHF side sketches are unfed as in the reference
+// unless HULK_B200_FEED_MINHASH=1
 // (unwired in the reference, src/pipeline/boss.go:18-19: the flags are accepted and logged, like there).
 #include <dirent.h>
 #include <sys/stat.h>
@@ -406,6 +407,14 @@ int run_sketch(int argc, char **argv) {
     if (rc) fatal(hulk_b200_group_last_error(nullptr));
     rc = hulk_b200_group_generate_cws_tables(ctx, 1);       // NewHistoSketch -> newCWS, drawn while the reads are counted
     if (rc) fatal(hulk_b200_group_last_error(ctx));
+    // HULK_B200_FEED_MINHASH=1 (not a reference flag): --kmv / --khf get the sketches the two types were written to
+    // produce -- every minimizer also goes to their AddHash -- instead of the reference's unfed ones (see below)
+    const char *feed_env = getenv("HULK_B200_FEED_MINHASH");
+    const bool feed_minhash = feed_env && *feed_env == '1' && (o.add_kmv || o.add_khf);
+    if (feed_minhash) {
+        rc = hulk_b200_group_minhash_enable(ctx, o.add_kmv ? 1 : 0, o.add_khf ? 1 : 0);
+        if (rc) fatal(hulk_b200_group_last_error(ctx));
+    }
 
     rc = hulk_b200_group_sketch_reader(ctx, rd, o.interval, log_line, nullptr);
     if (rc) {
@@ -439,11 +448,27 @@ int run_sketch(int argc, char **argv) {
     // (src/pipeline/sketch.go:227-234,289-294); the KHF sketch is written with its initial MaxUint64 in every slot
     // (src/minhash/khf.go:20-32).
     if (P.sketch_size == 0) fatal("no sketch was generated by the histosketch algorithm");
-    if (o.add_kmv) fatal("no sketch was generated by the kmv algorithm");
-    std::vector<uint64_t> khf;
-    if (o.add_khf) khf.assign(P.sketch_size, ~0ull);
+    std::vector<uint64_t> khf, kmv;
+    uint32_t kmv_n = 0;
+    if (feed_minhash) {
+        if (o.add_kmv) {
+            kmv.assign(P.sketch_size, 0);
+            rc = hulk_b200_group_get_kmv(ctx, kmv.data(), &kmv_n);
+            if (rc) fatal(hulk_b200_group_last_error(ctx));
+            if (kmv_n == 0) fatal("no sketch was generated by the kmv algorithm");
+        }
+        if (o.add_khf) {
+            khf.assign(P.sketch_size, ~0ull);
+            rc = hulk_b200_group_get_khf(ctx, khf.data());
+            if (rc) fatal(hulk_b200_group_last_error(ctx));
+        }
+    } else {
+        if (o.add_kmv) fatal("no sketch was generated by the kmv algorithm");
+        if (o.add_khf) khf.assign(P.sketch_size, ~0ull);
+    }
     rc = hulk_b200_write_json_minhash(out_json.c_str(), file_name.c_str(), o.banner_label.c_str(), P.k, mins.data(),
-                                      weights.data(), P.sketch_size, spectrum, o.decay_ratio != 1.0, nullptr, 0,
+                                      weights.data(), P.sketch_size, spectrum, o.decay_ratio != 1.0,
+                                      kmv_n ? kmv.data() : nullptr, kmv_n,
                                       o.add_khf ? khf.data() : nullptr, (uint32_t)khf.size());
     if (rc == HULK_B200_ENOSKETCH) fatal("no sketch was generated by the histosketch algorithm");
     if (rc == HULK_B200_EARG) fatal("json: unsupported value: a sketch weight is not finite");

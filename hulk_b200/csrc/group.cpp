@@ -281,6 +281,44 @@ int hulk_b200_group_get_stats(hulk_b200_group *g, hulk_b200_stats *out) {
     return HULK_B200_OK;
 }
 
+// ---- MinHash side sketches over the group: each member sketches its share, the parts are merged on the host
+int hulk_b200_group_minhash_enable(hulk_b200_group *g, int kmv, int khf) {
+    if (!g) return HULK_B200_EARG;
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        const int rc = hulk_b200_minhash_enable(g->ctx[i], kmv, khf);
+        if (rc) return gfrom(g, i, rc);
+    }
+    return HULK_B200_OK;
+}
+int hulk_b200_group_get_khf(hulk_b200_group *g, uint64_t *mins) {
+    if (!g || !mins) return HULK_B200_EARG;
+    const uint32_t s = g->P.sketch_size;
+    std::vector<uint64_t> part(s);
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        const int rc = hulk_b200_get_khf(g->ctx[i], i == 0 ? mins : part.data());
+        if (rc) return gfrom(g, i, rc);
+        if (i)
+            for (uint32_t j = 0; j < s; j++) mins[j] = std::min(mins[j], part[j]);      // KHFsketch.Merge, khf.go:47-55
+    }
+    return HULK_B200_OK;
+}
+int hulk_b200_group_get_kmv(hulk_b200_group *g, uint64_t *mins, uint32_t *n) {
+    if (!g || !mins || !n) return HULK_B200_EARG;
+    const uint32_t s = g->P.sketch_size;
+    std::vector<uint64_t> all, part(s);
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        uint32_t np = 0;
+        const int rc = hulk_b200_get_kmv(g->ctx[i], part.data(), &np);
+        if (rc) return gfrom(g, i, rc);
+        all.insert(all.end(), part.begin(), part.begin() + np);
+    }
+    std::sort(all.begin(), all.end());
+    if (all.size() > s) all.resize(s);
+    std::copy(all.begin(), all.end(), mins);
+    *n = (uint32_t)all.size();
+    return HULK_B200_OK;
+}
+
 // SeqMinimizer.Run's loop over a reader (src/pipeline/sketch.go:197-224), the group's form of hulk_b200_sketch_reader
 int hulk_b200_group_sketch_reader(hulk_b200_group *g, hulk_b200_reader *rd, uint64_t interval, hulk_b200_log_fn log,
                                   void *user) {

@@ -15,7 +15,7 @@
 //
 // Three launches, only made when the host knows (or cannot rule out) that the batch holds such a sequence:
 //   k1_long_plan   one CTA: collects the long sequences the other kernels passed over, gives each its table
-//                  (arena bump allocation behind k1_generic's) and its range of slice numbers;
+//                  (arena bump allocation behind k1_generic's) and its range of slice numbers (two prefix sums);
 //   k1_long_zero   clears the tables;
 //   k1_long_scan   one thread per slice, grid-stride.
 #pragma once
@@ -26,8 +26,9 @@
 
 namespace hulk {
 
-constexpr uint32_t K1_LONG_MIN = 1u << 14;      // sequences this long go to the sliced scan
-constexpr uint32_t K1_LONG_TASKS = 1u << 16;    // long sequences per launch
+// Sequences this long go to the sliced scan.  Measured (profiles/r02w_long_reads.txt, push + sync of 100-160 Mbases):
+// reads of ~2000 bases 2.2 -> 5.5 Gbases/s, of ~8000 bases 1.4 -> 6.0 Gbases/s against one k1_generic thread per read.
+constexpr uint32_t K1_LONG_MIN = 1u << 10;
 constexpr int K1_LONG_PLAN_TPB = 1024;
 constexpr int K1_LONG_TPB = 128;
 
@@ -37,14 +38,46 @@ __host__ __device__ inline uint32_t k1_long_seg(uint32_t k, uint32_t w) {
     return s < 256u ? 256u : s;
 }
 
+// exclusive prefix sum over the CTA's 1024 threads (every thread calls it); `total` is the sum over the CTA
+__device__ __forceinline__ unsigned long long k1_plan_scan(const unsigned long long v, unsigned long long *ws /* [33] */,
+                                                           unsigned long long &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = ws[lane];
+        unsigned long long winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        ws[lane] = winc - w;
+        if (lane == 31) ws[32] = winc;
+    }
+    __syncthreads();
+    const unsigned long long r = ws[warp] + inc - v;
+    total = ws[32];
+    __syncthreads();                                             // ws is reused by the next call
+    return r;
+}
+
 // use_list: the candidates are the reads queued by the fast kernels; otherwise every read of the batch (w > 32)
 __global__ void __launch_bounds__(K1_LONG_PLAN_TPB) k1_long_plan(const K1Params p, const bool use_list) {
     __shared__ unsigned int s_n;
+    __shared__ unsigned long long s_end;
+    __shared__ unsigned long long ws[33];
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const uint64_t total = use_list ? (uint64_t)min(*p.ovf_count, p.ovf_cap) : p.n_reads;
     for (uint64_t q = threadIdx.x; q < total; q += K1_LONG_PLAN_TPB) {
-        const uint64_t r = use_list ? p.ovf_list[q] : q;
+        const uint64_t r = use_list ? (p.ovf_list[q] & 0xffffffffull) : q;      // (the high word is k1_generic's size hint)
         const uint64_t b0 = k1_read_off(p, r), len = k1_read_off(p, r + 1) - b0;
         if (len < p.long_min) continue;
         const unsigned int slot = atomicAdd(&s_n, 1u);
@@ -59,35 +92,65 @@ __global__ void __launch_bounds__(K1_LONG_PLAN_TPB) k1_long_plan(const K1Params 
         }
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
     const uint32_t n = s_n < p.long_cap ? s_n : p.long_cap;
-    unsigned long long cursor = *p.arena_cursor;                 // k1_generic is done: nobody else allocates now
-    cursor = (cursor + 7ull) & ~7ull;
-    const unsigned long long zero_begin = cursor;
-    unsigned long long segs = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        K1LongTask t = p.long_tasks[i];
-        const uint64_t entries = k1_long_table_entries(t.len, (int32_t)p.k);
-        t.seg_first = segs;
-        if (cursor + entries > p.arena_entries) {
-            k1_report(p, t.r, K1_ERR_OVF);
-            t.n_seg = 0;
-        } else {
-            t.tab = cursor;
+    // tables behind k1_generic's allocations (it is done: nobody else allocates now), slices numbered in task order
+    const unsigned long long base = (p.slab_entries + *p.arena_cursor + 7ull) & ~7ull;
+    if (threadIdx.x == 0) s_end = base;
+    __syncthreads();
+    unsigned long long carry_e = 0, carry_s = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += K1_LONG_PLAN_TPB) {
+        const uint32_t i = c0 + threadIdx.x;
+        const bool have = i < n;
+        K1LongTask t{};
+        if (have) t = p.long_tasks[i];
+        const unsigned long long entries = have ? k1_long_table_entries(t.len, (int32_t)p.k) : 0ull;
+        unsigned long long tot_e, tot_s;
+        const unsigned long long tab = base + carry_e + k1_plan_scan(entries, ws, tot_e);
+        const bool fits = have && tab + entries <= p.arena_entries;       // (once one does not fit, none behind it does)
+        const unsigned long long nseg = fits ? (t.len + p.long_seg - 1) / p.long_seg : 0ull;
+        const unsigned long long first = carry_s + k1_plan_scan(nseg, ws, tot_s);
+        if (have) {
+            t.tab = tab;
             t.cap = entries - 8;
-            t.n_seg = (t.len + p.long_seg - 1) / p.long_seg;
-            cursor += entries;
-            segs += t.n_seg;
+            t.seg_first = first;
+            t.n_seg = nseg;
+            p.long_tasks[i] = t;
+            if (fits) atomicMax(&s_end, tab + entries);
+            else k1_report(p, t.r, K1_ERR_OVF);
         }
-        p.long_tasks[i] = t;
+        carry_e += tot_e;
+        carry_s += tot_s;
     }
-    *p.arena_cursor = cursor;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    *p.arena_cursor = s_end - p.slab_entries;
     K1LongCtl c;
     c.n_tasks = n;
-    c.n_segs = segs;
-    c.zero_begin = zero_begin;
-    c.zero_end = cursor;
+    c.n_segs = carry_s;
+    c.zero_begin = base;
+    c.zero_end = s_end;
     *p.long_ctl = c;
+}
+
+// What the host wants to know about a batch whose offsets only exist on the device: out[0] = the longest read,
+// out[1] = the arena entries the sets of its long sequences take (both start at 0)
+__global__ void __launch_bounds__(256) k1_length_stats(const uint64_t *offsets, const uint64_t n_reads, const uint64_t long_min,
+                                                       const int32_t k, unsigned long long *out) {
+    unsigned long long mx = 0, ent = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        mx = len > mx ? len : mx;
+        if (len >= long_min) ent += k1_long_table_entries(len, k);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long m2 = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx;
+        ent += __shfl_down_sync(0xffffffffu, ent, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&out[0], mx);
+        if (ent) atomicAdd(&out[1], ent);
+    }
 }
 
 __global__ void __launch_bounds__(256) k1_long_zero(const K1Params p) {
@@ -144,6 +207,7 @@ __global__ void __launch_bounds__(K1_LONG_TPB) k1_long_scan(const K1Params p) {
                 if (e < p.dump_cap) p.dump[t.r * p.dump_cap + e] = m;
             } else {
                 atomicAdd(&p.hist[jump_hash(m, p.D)], 1u);
+                if (p.feed_queue) k1_feed_queue(p, t.r, m);
             }
             n_new++;
         });

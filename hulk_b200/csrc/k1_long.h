@@ -62,7 +62,7 @@ HULK_HD void k1_scan_range(const uint8_t *seq, int64_t len, int32_t k, int32_t w
 HULK_HD uint64_t k1_long_table_entries(uint64_t len, int32_t k) {            // entries to reserve, flag entry included
     const uint64_t nk = len - (uint64_t)k + 1;
     uint64_t cap = 64;
-    while (cap < 2 * nk) cap <<= 1;
+    while (cap < 2 * nk && cap < (1ull << 62)) cap <<= 1;                    // (terminates on garbage lengths too)
     return cap + 8;                                                          // (keeps every table 64-byte aligned)
 }
 HULK_HD uint64_t k1_long_slot(uint64_t m) { return (m * 0x9E3779B97F4A7C15ull) >> 17; }

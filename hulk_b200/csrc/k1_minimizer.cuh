@@ -73,17 +73,24 @@ struct K1Params {
     unsigned long long *queue_cursor;      // [0]: keys appended so far, [1]: next 32-read task (dynamic scheduling)
     uint64_t queue_cap;
     // generic path scratch
+    // (arena entries [0, slab_entries) are the k1_generic threads' own tables, slab_size each; the rest is handed out
+    // through arena_cursor)
     uint64_t *arena;
     unsigned long long *arena_cursor;
     uint64_t arena_entries;
+    uint64_t slab_entries;
+    uint32_t slab_size;
     // sequences of long_min bases or more are left to k1_long.cuh by every other kernel (~0: there are none)
     uint64_t long_min;
     uint32_t long_seg;             // positions per slice
     uint32_t long_cap;             // entries of long_tasks
     K1LongTask *long_tasks;
     K1LongCtl *long_ctl;
+    // MinHash feed (k1_minhash.cuh): the kernels that bin their minimizers themselves also append them to the queue
+    uint32_t feed_queue;
 };
 
+constexpr uint32_t K1_SLAB_MAX = 8192;   // most entries of a k1_generic thread's own table (sets of up to 4096 values)
 constexpr uint32_t K1_ERR_EMPTY = 3;   // HULK_B200_EEMPTYSEQ
 constexpr uint32_t K1_ERR_SHORT = 4;   // HULK_B200_ESHORTSEQ
 constexpr uint32_t K1_ERR_OVF = 31;    // overflow queue / arena exhausted -> HULK_B200_ENOMEM
@@ -93,6 +100,12 @@ __device__ __forceinline__ uint64_t k1_read_off(const K1Params &p, uint64_t r) {
 }
 __device__ __forceinline__ void k1_report(const K1Params &p, uint64_t r, uint32_t code) {
     atomicMin(p.err_word, (unsigned long long)(((p.read_base + r) << 8) | code));
+}
+// one more member of read r's set for the batch queue (the queue is sized for them when feed_queue is set)
+__device__ __forceinline__ void k1_feed_queue(const K1Params &p, uint64_t r, uint64_t m) {
+    const unsigned long long at = atomicAdd(p.queue_cursor, 1ull);
+    if (at < p.queue_cap) p.queue[at] = m;
+    else k1_report(p, r, K1_ERR_OVF);
 }
 
 struct K1SmemVH {
@@ -515,7 +528,7 @@ __global__ void __launch_bounds__(K1_TPB) k1_minimizer_histogram(const K1Params 
         if (overflow) {
             // hand the read to the generic kernel (exact de-dup with an unbounded set)
             const unsigned int slot = atomicAdd(p.ovf_count, 1u);
-            if (slot < p.ovf_cap) p.ovf_list[slot] = r;
+            if (slot < p.ovf_cap) p.ovf_list[slot] = ((unsigned long long)n << 32) | r;   // (r < 2^32 per launch)
             else k1_report(p, r, K1_ERR_OVF);
             n = 0;
             valid = false;
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_minimizer_histog
         const bool overflow = valid && n > list_cap;
         if (overflow) {
             const unsigned int slot = atomicAdd(p.ovf_count, 1u);
-            if (slot < p.ovf_cap) p.ovf_list[slot] = r;
+            if (slot < p.ovf_cap) p.ovf_list[slot] = ((unsigned long long)n << 32) | r;   // (r < 2^32 per launch)
             else k1_report(p, r, K1_ERR_OVF);
             n = 0;
             valid = false;
@@ -728,7 +741,7 @@ __global__ void __launch_bounds__(K1_TPB, K1_W9_CTAS_PER_SM) k1_scan_w9_v2(const
         const bool overflow = valid && n > list_cap;
         if (overflow) {
             const unsigned int slot = atomicAdd(p.ovf_count, 1u);
-            if (slot < p.ovf_cap) p.ovf_list[slot] = r;
+            if (slot < p.ovf_cap) p.ovf_list[slot] = ((unsigned long long)n << 32) | r;   // (r < 2^32 per launch)
             else k1_report(p, r, K1_ERR_OVF);
             n = 0;
             valid = false;
@@ -819,23 +832,33 @@ template <bool DUMP>
 __global__ void __launch_bounds__(64) k1_generic(const K1Params p, const bool use_queue) {
     uint64_t vhbuf[257];
     const uint64_t total = use_queue ? (uint64_t)min(*p.ovf_count, p.ovf_cap) : p.n_reads;
+    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long local_minimizers = 0;
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-         q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = use_queue ? p.ovf_list[q] : q;
+    for (uint64_t q = gt; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+        // a queued read comes with the number of values its scan produced (an upper bound of its set's size)
+        const unsigned long long entry = use_queue ? p.ovf_list[q] : 0ull;
+        const uint64_t r = use_queue ? (entry & 0xffffffffull) : q;
+        const uint64_t n_hint = entry >> 32;
         const uint64_t b0 = k1_read_off(p, r), b1 = k1_read_off(p, r + 1);
         const uint64_t len64 = b1 - b0;
         if (DUMP) p.dump_counts[r] = 0;
         if (len64 >= p.long_min) continue;                                       // k1_long.cuh takes it
         if (len64 < 1) { k1_report(p, r, K1_ERR_EMPTY); continue; }
         if (len64 < (uint64_t)(p.w + p.k - 1)) { k1_report(p, r, K1_ERR_SHORT); continue; }
-        // table capacity: power of two >= 2 * (number of k-mers)
+        // table capacity: power of two >= 2 * (values that can be inserted: at most one per k-mer).  Tables of up to
+        // slab_size entries live in this thread's own slab, read after read; larger ones come from the shared cursor
         const uint64_t nk = len64 - p.k + 1;
+        const uint64_t n_max = (n_hint && n_hint < nk) ? n_hint : nk;
         uint64_t cap = 64;
-        while (cap < 2 * nk) cap <<= 1;
-        const unsigned long long at = atomicAdd(p.arena_cursor, (unsigned long long)cap);
-        if (at + cap > p.arena_entries) { k1_report(p, r, K1_ERR_OVF); continue; }
-        uint64_t *tab = p.arena + at;
+        while (cap < 2 * n_max && cap < (1ull << 62)) cap <<= 1;
+        uint64_t *tab;
+        if (cap <= p.slab_size && (gt + 1) * p.slab_size <= p.slab_entries) {
+            tab = p.arena + gt * p.slab_size;
+        } else {
+            const unsigned long long at = p.slab_entries + atomicAdd(p.arena_cursor, (unsigned long long)cap);
+            if (at + cap > p.arena_entries) { k1_report(p, r, K1_ERR_OVF); continue; }
+            tab = p.arena + at;
+        }
         for (uint64_t x = 0; x < cap; x++) tab[x] = 0;        // 0 = empty; the value 0 itself is tracked apart
         bool seen_zero = false;
         uint32_t n_set = 0;
@@ -865,6 +888,7 @@ __global__ void __launch_bounds__(64) k1_generic(const K1Params p, const bool us
                 if (n_set < p.dump_cap) p.dump[r * p.dump_cap + n_set] = m;
             } else {
                 atomicAdd(&p.hist[jump_hash(m, p.D)], 1u);
+                if (p.feed_queue) k1_feed_queue(p, r, m);
             }
             n_set++;
         });

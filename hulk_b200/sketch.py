@@ -277,6 +277,24 @@ class HistoSketch:
         self._check(self._L.hulk_b200_get_stats(self._ctx, C.byref(st)))
         return {n: int(getattr(st, n)) for n, _ in N.Stats._fields_}
 
+    # -- MinHash side sketches (src/minhash; unfed in the reference, src/pipeline/boss.go:18-19) ---------------
+    def enable_minhash(self, kmv: bool = True, khf: bool = True):
+        """Feed every minimizer to KMVsketch.AddHash / KHFsketch.AddHash as well (before the first read)."""
+        self._check(self._L.hulk_b200_minhash_enable(self._ctx, int(kmv), int(khf)))
+
+    def khf(self) -> np.ndarray:
+        """KHFsketch.GetSketch (src/minhash/khf.go:58-60)."""
+        mins = np.zeros(self.sketch_size, dtype=np.uint64)
+        self._check(self._L.hulk_b200_get_khf(self._ctx, _ptr(mins)))
+        return mins
+
+    def kmv(self) -> np.ndarray:
+        """KMVsketch.GetSketch (src/minhash/kmv.go:160-176): at most sketch_size values, low -> high."""
+        mins = np.zeros(self.sketch_size, dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._check(self._L.hulk_b200_get_kmv(self._ctx, _ptr(mins), C.byref(n)))
+        return mins[:n.value].copy()
+
     # -- multi-GPU plumbing ------------------------------------------------------------------
     def histogram_device_ptr(self) -> int:
         p = C.c_void_p()
@@ -485,6 +503,20 @@ class GroupSketch:
         st = N.Stats()
         self._check(self._L.hulk_b200_group_get_stats(self._g, C.byref(st)))
         return {n: int(getattr(st, n)) for n, _ in N.Stats._fields_}
+
+    def enable_minhash(self, kmv: bool = True, khf: bool = True):
+        self._check(self._L.hulk_b200_group_minhash_enable(self._g, int(kmv), int(khf)))
+
+    def khf(self) -> np.ndarray:
+        mins = np.zeros(self.sketch_size, dtype=np.uint64)
+        self._check(self._L.hulk_b200_group_get_khf(self._g, _ptr(mins)))
+        return mins
+
+    def kmv(self) -> np.ndarray:
+        mins = np.zeros(self.sketch_size, dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._check(self._L.hulk_b200_group_get_kmv(self._g, _ptr(mins), C.byref(n)))
+        return mins[:n.value].copy()
 
     @property
     def concept_drift(self) -> bool:

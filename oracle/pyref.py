@@ -337,3 +337,96 @@ def smash_matrix(mins, weights, metric: str):
     n = len(mins)
     sim = [[100 - (get_distance(mins[i], mins[j], weights[i], metric) * 100) for j in range(n)] for i in range(n)]
     return sim, [["%.2f" % v for v in row] for row in sim]
+
+
+# ---- src/minhash: the two MinHash side sketches ------------------------------------------------------
+# The reference constructs both next to the k-mer spectrum (src/pipeline/boss.go:70-71) and never feeds them
+# (boss.go:18-19, "not used yet").  These are the types as written, for the feed the library can switch on
+# (hulk_b200_minhash_enable): every minimizer the collector receives goes to AddHash.
+class KHFsketch:
+    """src/minhash/khf.go:11-60"""
+
+    def __init__(self, k: int, s: int):
+        self.k, self.s = k, s
+        self.sketch = [M64] * s                                   # khf.go:20-32
+
+    def add_hash(self, hv: int):                                  # khf.go:35-45
+        for i in range(self.s):
+            val = (hv + ((i * hv) & M64)) & M64
+            if val < self.sketch[i]:
+                self.sketch[i] = val
+
+    def merge(self, other: "KHFsketch"):                          # khf.go:47-55
+        for i, m in enumerate(other.sketch):
+            if m < self.sketch[i]:
+                self.sketch[i] = m
+
+    def get_sketch(self):
+        return self.sketch
+
+    def similarity(self, other) -> float:                         # khf.go:82-100
+        a, b = self.get_sketch(), other.get_sketch()
+        n = min(len(a), len(b))
+        return sum(1.0 for i in range(n) if a[i] == b[i]) / float(n)
+
+
+class KMVsketch:
+    """src/minhash/kmv.go:11-176 with container/heap over IntHeap (src/minhash/heap.go: Less is '>', so the LARGEST
+    value sits at index 0)."""
+
+    def __init__(self, k: int, s: int):
+        self.k, self.s = k, s
+        self.heap = []
+        self.multiplicity_sum = 0
+
+    # container/heap's up/down for a heap whose Less(i, j) is h[i] > h[j]
+    def _up(self, j: int):
+        h = self.heap
+        while True:
+            i = (j - 1) // 2
+            if i == j or j <= 0 or not (h[j] > h[i]):
+                break
+            h[i], h[j] = h[j], h[i]
+            j = i
+
+    def _down(self, i0: int, n: int) -> bool:
+        h = self.heap
+        i = i0
+        while True:
+            j1 = 2 * i + 1
+            if j1 >= n or j1 < 0:
+                break
+            j = j1
+            j2 = j1 + 1
+            if j2 < n and h[j2] > h[j1]:
+                j = j2
+            if not (h[j] > h[i]):
+                break
+            h[i], h[j] = h[j], h[i]
+            i = j
+        return i > i0
+
+    def add_hash(self, hv: int):                                  # kmv.go:40-71
+        self.multiplicity_sum += 1
+        if len(self.heap) < self.s:
+            self.heap.append(hv)                                  # heap.Push
+            self._up(len(self.heap) - 1)
+        elif hv < self.heap[0]:
+            self.heap[0] = hv
+            if not self._down(0, len(self.heap)):                 # heap.Fix(h, 0)
+                self._up(0)
+
+    def get_sketch(self):                                         # kmv.go:160-176
+        return sorted(self.heap)
+
+    def similarity(self, other: "KMVsketch") -> float:            # kmv.go:118-157
+        longer, shorter = (self.heap, other.heap) if len(self.heap) > len(other.heap) else (other.heap, self.heap)
+        counts = {}
+        for v in longer:
+            counts[v] = counts.get(v, 0) + 1
+        intersect = 0
+        for m in shorter:
+            if counts.get(m, 0) > 0:
+                counts[m] -= 1
+                intersect += 1
+        return float(intersect) / float(len(longer))

@@ -73,13 +73,28 @@ def test_long_reads_take_the_generic_path(hb, oracle):
     np.testing.assert_array_equal(h, ho.astype(np.uint32))
 
 
+def test_many_reads_of_a_few_hundred_bases(hb, oracle):
+    # tens of thousands of reads whose candidate lists overflow (merged pairs, 454, short nanopore): every k1_generic
+    # thread reuses its own table, so the number of such reads in a batch does not matter (round 2 ran out of scratch
+    # memory at ~33 000 of them)
+    reads = random_reads(45_000, 400, seed=91, n_frac=0.001, ragged=800) + random_reads(2000, 150, seed=92)
+    with hb.HistoSketch(21, 9, 4) as hs:
+        hs.add_seqs(reads)
+        h = hs.histogram()
+        st = hs.stats()
+    ho, nm = oracle.count_reads(21, 9, 21 ** 4, *oracle.pack_reads(reads))
+    np.testing.assert_array_equal(h, ho.astype(np.uint32))
+    assert st["n_minimizers"] == nm
+
+
 @pytest.mark.parametrize("k,w", [(21, 9), (31, 9), (11, 9), (7, 40), (21, 200), (30, 256)])
 def test_long_sequences_take_the_sliced_scan(hb, oracle, k, w):
-    # sequences of 2^14 bases or more (--fasta contigs, long reads) are cut into slices that share one set per
+    # sequences of 1024 bases or more (--fasta contigs, long reads) are cut into slices that share one set per
     # sequence (k1_long.cuh); next to them: reads for the fast kernels and reads for k1_generic, N runs, lower case,
     # a sequence of exactly the threshold length and one a base short of it
     reads = (random_reads(3, 40_000, seed=k + w, n_frac=0.002, lower_frac=0.1, ragged=30_000)
-             + [random_reads(1, 16_384, seed=5)[0], random_reads(1, 16_383, seed=6)[0], b"ACGTAC" * 5000,
+             + [random_reads(1, 1024, seed=5)[0], random_reads(1, 1023, seed=6)[0], random_reads(1, 16_384, seed=4)[0],
+                b"ACGTAC" * 5000,
                 b"N" * 9000 + random_reads(1, 12_000, seed=7)[0] + b"N" * 300 + b"acgt" * 2000, b"A" * 20_000]
              + random_reads(50, 400, seed=8, ragged=3000) + random_reads(100, 300, seed=9))
     cap = 70_000

@@ -300,6 +300,26 @@ def test_cli_khf_and_kmv_flags_behave_like_the_reference(tmp_path):
         assert "cleaning up..." in r.stdout and not os.path.exists(out + ".json")
 
 
+@pytest.mark.gpu
+def test_cli_feeds_khf_and_kmv_when_asked(tmp_path, oracle, fixture_reads):
+    """HULK_B200_FEED_MINHASH=1 (an extension, not a reference flag): every minimizer the collector receives also goes to
+    KMVsketch.AddHash / KHFsketch.AddHash (src/minhash/kmv.go:40-71, khf.go:35-45); the histosketch signature is
+    untouched and the two MinHash signatures follow in the reference's order (src/pipeline/sketch.go:227-234)."""
+    out = str(tmp_path / "fed")
+    r = _hulk("sketch", "-f", FIXTURE, "-k", "21", "-s", "50", "--kmv", "--khf", "-o", out,
+              env={"HULK_B200_FEED_MINHASH": "1"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    doc = json.loads(open(out + ".json").read())
+    assert [g["Algorithm"] for g in doc["signatures"]] == ["histosketch", "kmv", "khf"]
+    ws = json.loads(open(os.path.join(GOLDEN, "c1_k21_s50.json")).read())["signatures"][0]["Sketch"]
+    assert doc["signatures"][0]["Sketch"]["mins"] == ws["mins"]
+    keys = np.concatenate([oracle.minimizers(21, 9, rd) for rd in fixture_reads]).astype(np.uint64)
+    kmv, khf = doc["signatures"][1]["Sketch"], doc["signatures"][2]["Sketch"]
+    assert kmv["mins"] == np.sort(keys)[:50].tolist() and kmv["num"] == 50 and kmv["ksize"] == 21
+    assert khf["mins"] == [int((keys * np.uint64(i + 1)).min()) for i in range(50)] and khf["num"] == 50
+    assert kmv["md5sum"] == hulk_b200.md5_mins(np.array(kmv["mins"], dtype=np.uint64))
+
+
 # ---- the parallel parse of plain FASTQ files (csrc/ingest.cpp produce_parallel) -----------------------
 def _native_env(paths, env):
     """Read through the native reader in a subprocess (the mode switches are read from the environment at open)."""
