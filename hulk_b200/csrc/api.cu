@@ -164,6 +164,7 @@ struct hulk_b200_ctx {
     uint64_t *d_kmv_cand[NBUF] = {};           // [kmv_cand_cap]
     uint64_t kmv_cand_cap[NBUF] = {};
     bool long_path = true;                     // HULK_B200_LONG=0: long sequences stay with k1_generic (A/B)
+    uint32_t list_cap_w9 = 192;                // longest candidate list of the w = 9 kernels (HULK_B200_LIST_CAP, 16..192)
     uint64_t long_min = K1_LONG_MIN;           // sequences this long take the sliced scan (HULK_B200_LONG_MIN, >= 1024)
     unsigned long long *d_arena_cursor[NBUF] = {};
     uint64_t arena_entries[NBUF] = {};
@@ -688,6 +689,8 @@ static int create_impl(hulk_b200_ctx *ctx) {
         if (e && *e >= '1' && *e <= '0' + K1_W9_CTAS_PER_SM) ctx->k1_ctas_per_sm = *e - '0';
         e = getenv("HULK_B200_LONG");
         ctx->long_path = !(e && *e == '0');
+        e = getenv("HULK_B200_LIST_CAP");
+        if (e && atoi(e) >= 16 && atoi(e) <= 192) ctx->list_cap_w9 = (uint32_t)atoi(e);
         e = getenv("HULK_B200_LONG_MIN");
         if (e && atoll(e) >= 1024) ctx->long_min = (uint64_t)atoll(e);
         e = getenv("HULK_B200_MAX_LAUNCH_READS");
@@ -1302,7 +1305,7 @@ int hulk_b200_generate_cws_tables(hulk_b200_ctx *ctx) {
 // ------------------------------------------------------------------------------------------
 // stage 1+2
 // ------------------------------------------------------------------------------------------
-static void k1_geometry(const hulk_b200_ctx *ctx, uint64_t n_reads, uint64_t total_bytes, uint32_t *tile_cap,
+static void k1_geometry(const hulk_b200_ctx *ctx, uint64_t n_reads, uint64_t total_bytes, bool w9, uint32_t *tile_cap,
                         uint32_t *list_cap, size_t *smem) {
     const double avg = n_reads ? (double)total_bytes / (double)n_reads : 0.0;
     uint64_t tc = (uint64_t)(avg * K1_TPB * 1.05) + 64;
@@ -1310,7 +1313,9 @@ static void k1_geometry(const hulk_b200_ctx *ctx, uint64_t n_reads, uint64_t tot
     if (tc > 64 * 1024) tc = 64 * 1024;
     const double nk = std::max(1.0, avg - ctx->P.k + 1);
     uint32_t lc = (uint32_t)(0.28 * nk * (9.0 + 1.0) / (ctx->P.w + 1.0)) + 5;    // ~2/(w+1) candidates per k-mer
-    lc = std::max(16u, std::min(lc, 96u));
+    // (the w = 9 kernels keep nothing but the lists in shared memory: batches of reads of several hundred bases get
+    // lists of up to 192 entries -- one CTA per SM then, still an order of magnitude faster than k1_generic)
+    lc = std::max(16u, std::min(lc, w9 ? ctx->list_cap_w9 : 96u));
     *tile_cap = (uint32_t)tc;
     *list_cap = lc;
     // tile (+16 bytes slack) | window buffers [w + 1][128] | lists [4 warps][lc][32] | mbarrier
@@ -1454,7 +1459,7 @@ static int launch_k1_one(hulk_b200_ctx *ctx, int hs, cudaStream_t st, const uint
     const bool feed = !DUMP && (ctx->mh_kmv || ctx->mh_khf);
     const bool use_queue = fast && !DUMP && (!ctx->fused_jump || feed);
     size_t smem = 0;
-    if (fast) k1_geometry(ctx, n_reads, total_bytes, &p.tile_cap, &p.list_cap, &smem);
+    if (fast) k1_geometry(ctx, n_reads, total_bytes, ctx->P.w == 9 && !ctx->force_tile_path, &p.tile_cap, &p.list_cap, &smem);
     p.feed_queue = feed ? 1u : 0u;
     if (use_queue || feed) {
         const uint64_t need = (use_queue ? n_reads * (uint64_t)p.list_cap : 0) + (feed ? total_bytes + n_reads : 0);

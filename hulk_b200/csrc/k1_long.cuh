@@ -26,8 +26,8 @@
 
 namespace hulk {
 
-// Sequences this long go to the sliced scan.  Measured (profiles/r02w_long_reads.txt, push + sync of 100-160 Mbases):
-// reads of ~2000 bases 2.2 -> 5.5 Gbases/s, of ~8000 bases 1.4 -> 6.0 Gbases/s against one k1_generic thread per read.
+// Sequences this long go to the sliced scan.  Measured (profiles/r02x_long_reads.txt, 100-160 Mbases resident in HBM):
+// reads of ~2000 bases 2.8 -> 11.0 Gbases/s, of ~8000 bases 1.7 -> 13.7 Gbases/s against one k1_generic thread per read.
 constexpr uint32_t K1_LONG_MIN = 1u << 10;
 constexpr int K1_LONG_PLAN_TPB = 1024;
 constexpr int K1_LONG_TPB = 128;

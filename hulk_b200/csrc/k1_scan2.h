@@ -209,9 +209,10 @@ HULK_UNROLL
         }
         L.last = m;
     }
-    if (PH == 4) return;                                                  // nothing behind the last block
+    if (PH != 4) {                                                        // (nothing comes behind a read's last block)
 HULK_UNROLL
-    for (int x = 6; x >= 0; x--) A[x] = k1_vmin<R::ARITH>(A[x], A[x + 1]);   // suffix minima in place
+        for (int x = 6; x >= 0; x--) A[x] = k1_vmin<R::ARITH>(A[x], A[x + 1]);   // suffix minima in place
+    }
 }
 
 // ---- GENERAL block: the reference's loop, position by position, in the same representation -----
@@ -333,9 +334,10 @@ HULK_UNROLL
             last = m;
         }
     }
-    if (PH == 4) return;
+    if (PH != 4) {
 HULK_UNROLL
-    for (int x = 6; x >= 0; x--) A[x] = A[x] < A[x + 1] ? A[x] : A[x + 1];
+        for (int x = 6; x >= 0; x--) A[x] = A[x] < A[x + 1] ? A[x] : A[x + 1];
+    }
 }
 
 template <int K, int STRIDE, class Src>
