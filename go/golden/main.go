@@ -23,6 +23,9 @@
 //                 (src/countmin/countmin.go:103-147)
 //   histosketch   Sketch / SketchWeights after feeding the spectrum's non-zero bins in ascending order once
 //                 (k = 21, s = 50, decay 1.0 and 0.02): src/histosketch/histosketch.go:129-155 over the tables of newCWS
+//   minhash       KMVsketch / KHFsketch (s = 50) after AddHash of every minimizer above, in read order -- the feed the
+//                 reference's boss never makes (src/pipeline/boss.go:18-19) and hulk_b200_minhash_enable does
+//                 (src/minhash/kmv.go:40-71,160-176, khf.go:35-45)
 package main
 
 import (
@@ -41,6 +44,7 @@ import (
 	"github.com/will-rowe/hulk/src/countmin"
 	"github.com/will-rowe/hulk/src/histosketch"
 	"github.com/will-rowe/hulk/src/kmerspectrum"
+	"github.com/will-rowe/hulk/src/minhash"
 	"github.com/will-rowe/hulk/src/minimizer"
 )
 
@@ -73,6 +77,8 @@ type pins struct {
 	SpectrumFreq []float64  `json:"spectrum_freq"`
 	CountMin     []cmsPin   `json:"countmin"`
 	HistoSketch  []hskPin   `json:"histosketch"`
+	KMV          []uint64   `json:"minhash_kmv"`
+	KHF          []uint64   `json:"minhash_khf"`
 }
 
 func check(err error) {
@@ -117,6 +123,7 @@ func main() {
 	// minimizers and the spectrum
 	spectrum, err := kmerspectrum.NewKmerSpectrum(numBins)
 	check(err)
+	kmv, khf := minhash.NewKMVsketch(k, s), minhash.NewKHFsketch(k, s)
 	for _, seq := range readFastq(*fastq) {
 		ms, err := minimizer.NewMinimizerSketch(k, w, seq)
 		check(err)
@@ -124,11 +131,14 @@ func main() {
 		for m := range ms.GetMinimizers() {
 			set = append(set, m.(uint64))
 			check(spectrum.AddHash(m.(uint64)))
+			kmv.AddHash(m.(uint64))
+			khf.AddHash(m.(uint64))
 		}
 		sort.Slice(set, func(a, b int) bool { return set[a] < set[b] })
 		out.Minimizers = append(out.Minimizers, set)
 	}
 	out.UsedBins = spectrum.Cardinality()
+	out.KMV, out.KHF = kmv.GetSketch(), khf.GetSketch()
 	counts := make([]byte, 4*int(numBins))
 	dump, err := spectrum.Dump()
 	check(err)

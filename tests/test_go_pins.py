@@ -84,3 +84,19 @@ def test_histosketch_of_the_fixture(pins, oracle):
         mins, weights = hs.get()
         np.testing.assert_array_equal(mins, np.array(pin["mins"], dtype=np.uint64))
         np.testing.assert_allclose(weights, _f64(pin["weights_bits"]), rtol=1e-12, atol=0)
+
+
+def test_minhash_sketches_of_the_fixture(pins, oracle, fixture_reads):
+    """KMVsketch / KHFsketch fed with every minimizer of the fixture (src/minhash/kmv.go:40-71, khf.go:35-45): the feed
+    hulk_b200_minhash_enable switches on, against the restatement in oracle/pyref.py."""
+    if "minhash_kmv" not in pins:
+        pytest.skip("go_pins.json was produced by an older go/golden/main.go")
+    from oracle import pyref as P
+    s = len(pins["minhash_khf"])
+    kmv, khf = P.KMVsketch(pins["k"], s), P.KHFsketch(pins["k"], s)
+    for seq in fixture_reads:
+        for m in oracle.minimizers(pins["k"], pins["w"], seq):
+            kmv.add_hash(int(m))
+            khf.add_hash(int(m))
+    assert kmv.get_sketch() == pins["minhash_kmv"]
+    assert khf.get_sketch() == pins["minhash_khf"]
