@@ -119,6 +119,15 @@ def test_native_reader_fasta(tmp_path):
     seq = random_reads(1, 300000, seed=9)[0]
     big.write_bytes(b">chr\n" + b"\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + b"\n")
     assert _native([big], fasta=True, batch_bytes=8192) == [seq]
+    # chromosome-sized records (what the sliced scan of k1_long.cuh is for) arrive as one sequence each, plain and gzipped
+    rng = np.random.default_rng(10)
+    chrom = np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, 6_000_000)].tobytes()
+    body = b">chr1 six megabases\n" + b"\n".join(chrom[i:i + 60] for i in range(0, len(chrom), 60)) + b"\n>plasmid\nACGTACGT\nAC\n"
+    for name, data in (("chrom.fa", body), ("chrom.fa.gz", gzip.compress(body, 1))):
+        path = tmp_path / name
+        path.write_bytes(data)
+        got = _native([path], fasta=True)
+        assert len(got) == 2 and got[0] == chrom and got[1] == b"ACGTACGTAC"
     none = tmp_path / "none.fa"
     none.write_bytes(b"ACGT\n")
     with pytest.raises(ValueError):
