@@ -444,6 +444,17 @@ def test_long_sequence_slices_compiled_for_host_match_one_pass_and_oracle(oracle
             raw = bytes((c - 48) if 48 <= c <= 51 else c for c in rd)
             m = np.sort(oracle.minimizers(k, w, raw))
             want.append(" ".join([str(len(m))] + [str(int(x)) for x in m]))
+    # and shapes nobody picked: random k, w, slice length (down to 1, up to past the end), sequence length and N density
+    rng = np.random.default_rng(2024)
+    for case in range(80):
+        k = int(rng.integers(1, 32))
+        w = int(rng.choice([1, 2, 5, 9, 9, 9, 16, 33, 100, 256]))
+        L = int(rng.integers(k + w - 1, k + w + 3000))
+        seg = int(rng.choice([1, 2, 17, 64, 256, 8 * (k + w), L, L + 7, int(rng.integers(1, L + 1))]))
+        rd = random_reads(1, L, seed=5000 + case, n_frac=float(rng.choice([0.0, 0.01, 0.2])), lower_frac=0.2)[0]
+        lines.append("%d %d %d %s" % (k, w, seg, rd.decode()))
+        m = np.sort(oracle.minimizers(k, w, rd))
+        want.append(" ".join([str(len(m))] + [str(int(x)) for x in m]))
     out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
     got = out.strip().split("\n")
     assert len(got) == len(want)
