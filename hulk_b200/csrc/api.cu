@@ -1982,7 +1982,8 @@ static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
             n_exc = (uint64_t)(e1 - e0);
             rc = ensure_pack_stage(ctx, buf, packed_bytes, n_exc, false);
             if (rc) return rc;
-        } else if (ctx->pack_threads != 0 && nb >= 4096 && (ctx->P.flags & HULK_B200_F_ASYNC_INPUT) && ctx->cu_wait32) {
+        } else if (ctx->pack_threads != 0 && nb >= 4096 && nb < (1ull << 32) && (ctx->P.flags & HULK_B200_F_ASYNC_INPUT) &&
+                   ctx->cu_wait32) {                   // (code-4 positions are 32-bit: a larger batch -- one giant sequence -- goes as letters)
             // ---- the feeder thread packs and copies; this thread only enqueues the consumers behind the batch's number
             if (!ctx->feeder.joinable()) ctx->feeder = std::thread(feeder_main, ctx);
             FEED_DBG("push: buf %d, %llu bases", buf, (unsigned long long)nb);
@@ -2047,7 +2048,7 @@ static int push_host(hulk_b200_ctx *ctx, const HostBatch &hb) {
             ctx->cur_buf = (ctx->cur_buf + 1) % NSTAGE;
             done = upto;
             continue;
-        } else if (ctx->pack_threads != 0 && nb >= 4096) {
+        } else if (ctx->pack_threads != 0 && nb >= 4096 && nb < (1ull << 32)) {
             const uint64_t exc_cap = std::max<uint64_t>(1024, nb / 32);
             packed_bytes = (nb + 3) / 4;
             rc = ensure_pack_stage(ctx, buf, packed_bytes, exc_cap, true);
