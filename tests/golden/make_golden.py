@@ -5,6 +5,9 @@ c1_anchors.json   histogram anchors of the reference fixture at k=21, w=9
 c1_k21_s50.json   the complete sketch `hulk sketch -f c1_reads.fq.gz -k 21 -s 50` would write, computed by the
                   CPU oracle with Go-compatible CWS tables (race-free flush semantics)
 c1_k21_s50_x02_i250.json   same input with -x 0.2 -i 250 (concept drift + four interval flushes)
+c1_k21_s50_minhash.json    KMVsketch / KHFsketch (s = 50) fed with every minimizer of the fixture in read order, by the
+                  literal restatement of src/minhash (oracle/pyref.py): what `hulk sketch --kmv --khf` writes with the
+                  MinHash feed on (HULK_B200_FEED_MINHASH=1)
 """
 import gzip
 import hashlib
@@ -41,3 +44,13 @@ for name, decay, interval in (("c1_k21_s50.json", 1.0, 0), ("c1_k21_s50_x02_i250
     doc = P.sketch_json("testing/test-reads-small.fq.gz,", k, mins, weights, D, decay != 1.0)
     open(os.path.join(HERE, name), "w").write(doc)
     print(name, P.md5_of_mins(mins))
+
+kmv, khf = P.KMVsketch(k, s), P.KHFsketch(k, s)
+for rd in reads:
+    for m in sorted(int(x) for x in O.minimizers(k, w, rd)):
+        kmv.add_hash(m)
+        khf.add_hash(m)
+json.dump({"k": k, "w": w, "s": s, "n_added": kmv.multiplicity_sum, "kmv": kmv.get_sketch(), "khf": khf.get_sketch(),
+           "kmv_md5": P.md5_of_mins(kmv.get_sketch()), "khf_md5": P.md5_of_mins(khf.get_sketch())},
+          open(os.path.join(HERE, "c1_k21_s50_minhash.json"), "w"), indent=1)
+print("c1_k21_s50_minhash.json", kmv.multiplicity_sum)

@@ -327,6 +327,9 @@ def test_cli_feeds_khf_and_kmv_when_asked(tmp_path, oracle, fixture_reads):
     assert kmv["mins"] == np.sort(keys)[:50].tolist() and kmv["num"] == 50 and kmv["ksize"] == 21
     assert khf["mins"] == [int((keys * np.uint64(i + 1)).min()) for i in range(50)] and khf["num"] == 50
     assert kmv["md5sum"] == hulk_b200.md5_mins(np.array(kmv["mins"], dtype=np.uint64))
+    gold = json.loads(open(os.path.join(GOLDEN, "c1_k21_s50_minhash.json")).read())
+    assert kmv["mins"] == gold["kmv"] and khf["mins"] == gold["khf"]
+    assert kmv["md5sum"] == gold["kmv_md5"] and khf["md5sum"] == gold["khf_md5"]
 
 
 # ---- the parallel parse of plain FASTQ files (csrc/ingest.cpp produce_parallel) -----------------------

@@ -84,6 +84,18 @@ def test_minhash_restatement_is_order_independent(seed, n, s, hi):
     assert h1.get_sketch() == khf.get_sketch()
 
 
+def test_minhash_golden_of_the_reference_fixture(oracle, fixture_reads):
+    # tests/golden/c1_k21_s50_minhash.json (make_golden.py: the literal restatement, read by read) against the
+    # order-independent definitions the GPU tests use
+    from conftest import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "c1_k21_s50_minhash.json")))
+    keys = np.concatenate([oracle.minimizers(g["k"], g["w"], rd) for rd in fixture_reads]).astype(np.uint64)
+    assert keys.size == g["n_added"] == 17040                    # total minimizers of the fixture
+    assert kmv_numpy(keys, g["s"]).tolist() == g["kmv"] and khf_numpy(keys, g["s"]).tolist() == g["khf"]
+    assert len(set(g["kmv"])) < len(g["kmv"])                    # equal values from different reads are kept (kmv.go:40-71)
+    assert P.md5_of_mins(g["kmv"]) == g["kmv_md5"] and P.md5_of_mins(g["khf"]) == g["khf_md5"]
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def hb():
